@@ -1,0 +1,406 @@
+"""NumPy restatement of nbkode's explicit hot path (TEST INFRASTRUCTURE, not product code).
+
+This module is an *oracle*: a single-trajectory CPU restatement of the algorithms the
+reference (hgrecco/numbakit-ode, ``/root/reference``) runs for ForwardEuler,
+AdamsBashforth1..5, RungeKutta23 and RungeKutta45.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import it; the
+product package ``nbkode_b200`` never does.
+
+Parity status: PINNED.  ``tests/golden/*.json`` were produced by running the live
+reference in this container (``tests/golden/make_golden.py``); ``tests/test_oracle_np.py``
+checks this restatement against them bit-for-bit for vector-valued systems
+(it uses the same NumPy primitives in the same association order as the reference).
+
+Each function cites the reference lines it restates (paths relative to /root/reference).
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Tableaux (nbkode/runge_kutta/explicit.py:146-151 RK23, :185-239 RK45).  The values are
+# the published Bogacki-Shampine 3(2) and Dormand-Prince 5(4) coefficients.
+# --------------------------------------------------------------------------------------
+
+
+class BS23:
+    name = "RungeKutta23"
+    q = 2  # error_estimator_order
+    C = np.array([0, 1 / 2, 3 / 4], dtype=float)
+    A = np.array([[0, 0, 0], [1 / 2, 0, 0], [0, 3 / 4, 0]], dtype=float)
+    B = np.array([2 / 9, 1 / 3, 4 / 9], dtype=float)
+    B2 = np.array([7 / 24, 1 / 4, 1 / 3, 1 / 8], dtype=float)
+    # FSAL.E (explicit.py:54-58): E = -B2; E[:-1] += B
+    E = -B2.copy()
+    E[:-1] += B
+    P = np.array([[1, -4 / 3, 5 / 9], [0, 1, -2 / 3], [0, 4 / 3, -8 / 9], [0, -1, 1]])
+
+
+class DP45:
+    name = "RungeKutta45"
+    q = 4
+    C = np.array([0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1])
+    A = np.array(
+        [
+            [0, 0, 0, 0, 0, 0],
+            [1 / 5, 0, 0, 0, 0, 0],
+            [3 / 40, 9 / 40, 0, 0, 0, 0],
+            [44 / 45, -56 / 15, 32 / 9, 0, 0, 0],
+            [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729, 0, 0],
+            [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656, 0],
+        ]
+    )
+    B = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84])
+    E = np.array([-71 / 57600, 0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40])
+    P = np.array(
+        [
+            [1, -8048581381 / 2820520608, 8663915743 / 2820520608, -12715105075 / 11282082432],
+            [0, 0, 0, 0],
+            [0, 131558114200 / 32700410799, -68118460800 / 10900136933, 87487479700 / 32700410799],
+            [0, -1754552775 / 470086768, 14199869525 / 1410260304, -10690763975 / 1880347072],
+            [0, 127303824393 / 49829197408, -318862633887 / 49829197408, 701980252875 / 199316789632],
+            [0, -282668133 / 205662961, 2019193451 / 616988883, -1453857185 / 822651844],
+            [0, 40617522 / 29380423, -110615467 / 29380423, 69997945 / 29380423],
+        ]
+    )
+
+
+RK_METHODS = {"RungeKutta23": BS23, "RungeKutta45": DP45}
+
+# Adams-Bashforth weights exactly as listed by the reference classes
+# (nbkode/multistep/adams_bashforth.py:20,31,44,57,61).  NB the reference applies B[0]
+# to the OLDEST derivative in the window (multistep/core.py:101,109 + buffer.py:48-56).
+AB_B = {
+    1: np.array([1.0]),
+    2: np.array([3, -1]) / 2,
+    3: np.array([23, -16, 5]) / 12,
+    4: np.array([55, -59, 37, -9]) / 24,
+    5: np.array([1901, -2774, 2616, -1274, 251]) / 720,
+}
+
+
+def _rms(x):
+    # scipy.integrate._ivp.common.norm: ||x||_2 / sqrt(size)
+    return np.linalg.norm(x) / x.size**0.5
+
+
+def select_initial_step(rhs, t0, y0, f0, order, rtol, atol):
+    """scipy.integrate._ivp.common.select_initial_step with direction=+1 and unbounded
+    interval / max_step, as called from nbkode/core.py:695-705."""
+    if y0.size == 0:
+        return np.inf
+    scale = atol + np.abs(y0) * rtol
+    d0 = _rms(y0 / scale)
+    d1 = _rms(f0 / scale)
+    if d0 < 1e-5 or d1 < 1e-5:
+        h0 = 1e-6
+    else:
+        h0 = 0.01 * d0 / d1
+    y1 = y0 + h0 * 1 * f0
+    f1 = rhs(t0 + h0 * 1, y1)
+    d2 = _rms((f1 - f0) / scale) / h0
+    if d1 <= 1e-15 and d2 <= 1e-15:
+        h1 = max(1e-6, h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1 / (order + 1))
+    return min(100 * h0, h1)
+
+
+class History:
+    """Sliding window oldest->newest of (t, y, f); nbkode/buffer.py:12-56."""
+
+    def __init__(self, length, t, y, f):
+        n = y.size
+        self.ts = np.empty(length)
+        self.ys = np.empty((length, n))
+        self.fs = np.empty((length, n))
+        for _ in range(length):
+            self.push(t, y, f)
+
+    def push(self, t, y, f):
+        self.ts[:-1] = self.ts[1:]
+        self.ts[-1] = t
+        self.ys[:-1] = self.ys[1:]
+        self.ys[-1] = y
+        self.fs[:-1] = self.fs[1:]
+        self.fs[-1] = f
+
+    @property
+    def t(self):
+        return self.ts[-1]
+
+    @property
+    def y(self):
+        return self.ys[-1]
+
+    @property
+    def f(self):
+        return self.fs[-1]
+
+
+def _bind(rhs, params):
+    if params is None:
+        return rhs
+    params = np.ascontiguousarray(params)
+    return lambda t, y: rhs(t, y, params)
+
+
+class AdaptiveRK:
+    """RungeKutta23 / RungeKutta45 of the reference (FSAL pairs).
+
+    ctor: nbkode/core.py:106-141, :687-706; runge_kutta/core.py:25-27.
+    attempt: runge_kutta/explicit.py:60-79; error/norm/controller: runge_kutta/core.py:73-99;
+    accept loop: explicit.py:81-99; t_bound guard: core.py:176-184;
+    dense output: explicit.py:354-403.
+    """
+
+    def __init__(
+        self,
+        method,
+        rhs,
+        t0,
+        y0,
+        params=None,
+        *,
+        rtol=1e-3,
+        atol=1e-6,
+        first_step=None,
+        t_bound=np.inf,
+        min_factor=0.2,
+        max_factor=10.0,
+        safety_factor=0.9,
+    ):
+        self.M = RK_METHODS[method] if isinstance(method, str) else method
+        self.rhs = _bind(rhs, params)
+        self.rtol, self.atol = rtol, atol
+        self.min_factor, self.max_factor, self.safety = min_factor, max_factor, safety_factor
+        self.t_bound = t_bound
+        t0 = float(t0)
+        y0 = np.array(y0, dtype=float, ndmin=1)
+        self.cache = History(2, t0, y0, self.rhs(t0, y0))
+        self.S = len(self.M.A)  # stages without the FSAL one
+        self.K = np.zeros((self.S + 1, y0.size))
+        if first_step is None:
+            first_step = select_initial_step(
+                self.rhs, self.cache.t, self.cache.y, self.cache.f, self.M.q, rtol, atol
+            )
+        self.h = np.array(first_step, dtype=float)
+        self.n_accepted = 0
+        self.n_rejected = 0
+
+    t = property(lambda self: self.cache.t)
+    y = property(lambda self: self.cache.y)
+    f = property(lambda self: self.cache.f)
+
+    def _attempt(self):
+        M, K, c, h = self.M, self.K, self.cache, self.h
+        t, y = c.t, c.y
+        K[0] = c.f
+        for s in range(1, self.S):
+            dy = M.A[s, :s] @ K[:s]
+            K[s] = self.rhs(t + h * M.C[s], y + h * dy)
+        t_new = t + h
+        y_new = y + h * M.B @ K[:-1]
+        K[-1] = self.rhs(t_new, y_new)
+        return t_new, y_new
+
+    def step(self, bound=None):
+        """One accepted step. Returns False (without stepping) if t + h > bound."""
+        bound = self.t_bound if bound is None else bound
+        c = self.cache
+        if c.t + self.h > bound:
+            return False
+        while True:
+            t_new, y_new = self._attempt()
+            err = self.h * (self.M.E @ self.K)
+            scale = self.atol + self.rtol * np.maximum(np.abs(y_new), np.abs(c.y))
+            norm = np.sqrt(np.mean((err / scale) ** 2))
+            if norm == 0:
+                self.h *= self.max_factor
+                ok = True
+            else:
+                factor = self.safety / norm ** (1 / (self.M.q + 1))
+                self.h *= min(self.max_factor, max(self.min_factor, factor))
+                ok = norm < 1
+            if ok:
+                c.push(t_new, y_new, self.K[-1])
+                self.n_accepted += 1
+                return True
+            self.n_rejected += 1
+
+    def interpolate(self, t_eval):
+        c = self.cache
+        if t_eval == c.ts[-1]:
+            return c.ys[-1].copy()
+        if t_eval == c.ts[-2]:
+            return c.ys[-2].copy()
+        Q = self.K.T.dot(self.M.P)
+        t_old, y_old = c.ts[-2], c.ys[-2]
+        H = c.ts[-1] - t_old
+        x = (t_eval - t_old) / H
+        p = np.cumprod(np.repeat(x, Q.shape[1]))
+        return H * np.dot(Q, p) + y_old
+
+
+class AdamsBashforth:
+    """AdamsBashforth-k (k=1..5; ForwardEuler == AB1) with the reference's semantics.
+
+    ctor/start-up: nbkode/multistep/core.py:37-65; step: :71-80, :90-112;
+    coefficients: multistep/adams_bashforth.py; window Hermite: nbkode/core.py:577-596.
+    ``first_stepper`` is None, "RungeKutta45"/"auto" (adaptive start-up, default
+    tolerances) or an int k' (AdamsBashforth-k' fixed-step start-up).
+    """
+
+    def __init__(self, order, rhs, t0, y0, params=None, *, h=None, t_bound=np.inf, first_stepper="auto"):
+        self.order = order
+        self.B = AB_B[order]
+        self.L = max(order, 2)
+        self.rhs = _bind(rhs, params)
+        self.raw_rhs, self.params = rhs, params
+        self.t_bound = t_bound
+        self.h = np.array(h, dtype=float) if h is not None else 1
+        t0 = float(t0)
+        y0 = np.array(y0, dtype=float, ndmin=1)
+        self.cache = History(self.L, t0, y0, self.rhs(t0, y0))
+        c = self.cache
+        if first_stepper is None or order == 1:
+            return
+        if first_stepper == "auto":
+            first_stepper = "RungeKutta45"
+        if isinstance(first_stepper, int):
+            sub = AdamsBashforth(first_stepper, self.rhs, c.t, c.y, h=self.h)
+            for _ in range(order - 1):
+                sub.step()
+                c.push(sub.t, sub.y, sub.f)
+        else:
+            sub = AdaptiveRK(first_stepper, self.rhs, c.t, c.y)
+            for ti in np.arange(1, order) * self.h:
+                while sub.t < ti:
+                    sub.step()
+                yi = sub.interpolate(ti)
+                c.push(ti, yi, self.rhs(ti, yi))
+
+    t = property(lambda self: self.cache.t)
+    y = property(lambda self: self.cache.y)
+    f = property(lambda self: self.cache.f)
+
+    def step(self, bound=None):
+        bound = self.t_bound if bound is None else bound
+        c, k = self.cache, self.order
+        if c.t + self.h > bound:
+            return False
+        A = np.zeros_like(self.B)
+        A[-1] = -1
+        t_new = c.t + self.h
+        y_new = self.h * self.B @ c.fs[self.L - k :] - A @ c.ys[self.L - k :]
+        c.push(t_new, y_new, self.rhs(t_new, y_new))
+        return True
+
+    def interpolate(self, t_eval):
+        c = self.cache
+        t0, y0 = c.ts[0], c.ys[0]
+        if t_eval == t0:
+            return y0.copy()
+        dt, dy = c.t - t0, c.y - y0
+        f0, f1 = c.fs[0], c.f
+        T = (t_eval - t0) / dt
+        return y0 + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * f0 + T * f1))
+
+
+def run(solver, ts):
+    """nbkode/core.py:598-619 (_run_eval) for points ahead of solver.t, preceded by the
+    past-point branch of run_events (core.py:401-408).  ``ts`` must be sorted."""
+    ts = np.atleast_1d(ts).astype(np.float64)
+    out = []
+    for ti in ts:
+        if ti > solver.t:
+            while solver.t < ti:
+                if not solver.step():
+                    return ts[: len(out)], np.array(out)
+        out.append(solver.interpolate(ti))
+    return ts, np.array(out).reshape(len(ts), -1)
+
+
+def steps(solver, n=None, upto_t=None):
+    """nbkode/core.py:214-267 step(n=, upto_t=) -> (t[k], y[k, n])."""
+    tt, yy = [], []
+    bound = solver.t_bound if upto_t is None else upto_t
+    while n is None or len(tt) < n:
+        if not solver.step(bound):
+            break
+        tt.append(solver.t)
+        yy.append(solver.y.copy())
+    return np.array(tt), np.array(yy).reshape(len(tt), -1)
+
+
+# --------------------------------------------------------------------------------------
+# RHS catalogue used by the configs in BASELINE.json.
+# --------------------------------------------------------------------------------------
+
+
+def rhs_decay(t, y, p):
+    return -p * y
+
+
+def rhs_lorenz(t, y, p):
+    return np.array([p[0] * (y[1] - y[0]), y[0] * (p[1] - y[2]) - y[1], y[0] * y[1] - p[2] * y[2]])
+
+
+def rhs_vdp(t, y, p):
+    return np.array([y[1], p[0] * (1 - y[0] * y[0]) * y[1] - y[0]])
+
+
+def rhs_linear(t, y, A):
+    return A @ y
+
+
+def rhs_rd1d(t, y, p):
+    """Periodic 1-D reaction diffusion: d*(y[i+1]-2y[i]+y[i-1]) + r*y[i]*(1-y[i])."""
+    d, r = p[0], p[1]
+    return d * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + r * y * (1 - y)
+
+
+RHS = {"decay": rhs_decay, "lorenz": rhs_lorenz, "vdp": rhs_vdp, "linear": rhs_linear, "rd1d": rhs_rd1d}
+
+
+def lorenz_ensemble(B, seed=0):
+    """C2 generator of SURVEY.md section 8(d): draw order x0,y0,z0,sigma,rho,beta."""
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(-15, 15, B)
+    y0 = rng.uniform(-20, 20, B)
+    z0 = rng.uniform(5, 45, B)
+    sg = rng.uniform(8, 12, B)
+    rh = rng.uniform(20, 36, B)
+    be = rng.uniform(2, 3.5, B)
+    return np.stack([x0, y0, z0], 1), np.stack([sg, rh, be], 1)
+
+
+def vdp_ensemble(B, seed=1):
+    """C3 generator of SURVEY.md section 8(d)."""
+    rng = np.random.default_rng(seed)
+    mu = np.linspace(0.1, 5, B)
+    y0 = np.stack([rng.uniform(-2.5, 2.5, B), rng.uniform(-2.5, 2.5, B)], 1)
+    return y0, mu[:, None].copy()
+
+
+def linear_ensemble(B, n=128, seed=2):
+    """C4 generator: A = G/sqrt(n) - I (shared), y0 ~ N(0,1)."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n)) / math.sqrt(n) - np.eye(n)
+    y0 = rng.standard_normal((B, n))
+    return y0, A
+
+
+def rd1d_ensemble(B, n=2048, seed=3):
+    """C5 generator: kappa~U(0.5e-4,2e-4), r~U(0.5,2), y0=0.5+0.4 sin(2 pi x + phi)."""
+    rng = np.random.default_rng(seed)
+    kappa = rng.uniform(0.5e-4, 2e-4, B)
+    r = rng.uniform(0.5, 2, B)
+    phi = rng.uniform(0, 2 * np.pi, B)
+    x = np.arange(n) / n
+    y0 = 0.5 + 0.4 * np.sin(2 * np.pi * x[None, :] + phi[:, None])
+    d = kappa * n * n  # kappa / dx^2
+    return y0, np.stack([d, r], 1)
