@@ -1,0 +1,148 @@
+/*
+ * nbkode_b200.h -- C-ABI of libnbkode_b200.so, the B200-native batched ODE-ensemble engine
+ * behind the nbkode solver API (hgrecco/numbakit-ode).
+ *
+ * The reference has no FFI: its boundary is the Python class API.
+ * Each entry point below replaces the reference call chain named in its comment (paths are
+ * relative to the reference repository); the Python shell nbkode_b200/ binds them with ctypes
+ * exactly as INTEGRATION.md shows.
+ *
+ * Conventions
+ *  - plain C types only; every pointer marked "device" is a CUDA device pointer owned by the
+ *    caller (the Python shell passes torch.Tensor.data_ptr()); the library owns only its handle,
+ *    compiled programs and a small work-queue counter;
+ *  - every function returns 0 on success, a negative NBK_E* code otherwise; the message is
+ *    available from nbk_last_error() (thread-local);
+ *  - kernels are launched on the caller's stream (cudaStream_t passed as void*) and never
+ *    synchronise; a handle is not re-entrant, different handles may be used from different
+ *    host threads / devices;
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    NBK_ECUDA.
+ *
+ * Ensemble state layout (struct nbk_state; B = batch, n = state size, trajectory index
+ * fastest so that consecutive lanes touch consecutive addresses):
+ *    ts [L][B]  ys [L][n][B]  fs [L][n][B]   history window, oldest -> newest
+ *                                            (nbkode/buffer.py:5-56, AlignedBuffer)
+ *    K  [S+1][n][B]                          stage derivatives of the last accepted step
+ *                                            (nbkode/runge_kutta/core.py:25-27), RK only
+ *    h  [B]                                  next step size (nbkode/core.py:706)
+ *    params [np][B] or [np]                  nbkode/core.py:118-119
+ *    n_accepted, n_rejected [B], status [B], n_out [B]   (no reference counterpart)
+ *  L and S+1 come from nbk_layout().
+ */
+#ifndef NBKODE_B200_H
+#define NBKODE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBK_VERSION 1
+
+/* error codes */
+#define NBK_OK 0
+#define NBK_EINVAL (-1)   /* bad argument (maps to ValueError) */
+#define NBK_ECUDA (-2)    /* CUDA runtime / driver failure, or no device */
+#define NBK_ECOMPILE (-3) /* NVRTC failed; nbk_last_error() carries the compiler log */
+#define NBK_ENOTFOUND (-4)/* unknown built-in right-hand side */
+
+/* methods: nbkode class names -> ids */
+#define NBK_RK23 23 /* RungeKutta23   nbkode/runge_kutta/explicit.py:132-164 */
+#define NBK_RK45 45 /* RungeKutta45   nbkode/runge_kutta/explicit.py:167-253 */
+#define NBK_AB1 1   /* AdamsBashforth1 / ForwardEuler  multistep/adams_bashforth.py:17-20, euler.py:19-27 */
+#define NBK_AB2 2   /* AdamsBashforth2..5              multistep/adams_bashforth.py:23-61 */
+#define NBK_AB3 3
+#define NBK_AB4 4
+#define NBK_AB5 5
+
+/* per-trajectory status */
+#define NBK_TRAJ_OK 0
+#define NBK_TRAJ_BOUND 1       /* stopped by the t_bound / upto_t guard, nbkode/core.py:176-184 */
+#define NBK_TRAJ_NONFINITE 2   /* non-finite error norm or collapsed step (the reference spins forever) */
+#define NBK_TRAJ_MAXATTEMPTS 3 /* attempt budget of the call exhausted */
+
+typedef struct nbk_solver nbk_solver;
+
+typedef struct {
+    int method;           /* NBK_RK23, NBK_RK45, NBK_AB1..5 */
+    int n;                /* state size */
+    int n_params;         /* parameters per trajectory (0 allowed) */
+    int params_shared;    /* 1: one parameter vector for the whole ensemble */
+    long long batch;      /* B */
+    const char *rhs;      /* built-in right-hand side: "lorenz", "vdp", "decay"; or NULL */
+    const char *rhs_src;  /* CUDA C source defining
+                               NBK_RHS nbk_rhs(double t, const double* y, const double* p, double* dy)
+                             compiled by NVRTC into the integrator kernels; or NULL.
+                             Replaces numba.njit(rhs) of nbkode/core.py:125-132. */
+    /* VariableStepOptions, nbkode/core.py:661-679 (min_step/max_step are never enforced by
+       the reference and therefore absent) */
+    double rtol, atol, min_factor, max_factor, safety_factor;
+    int first_stepper;    /* multistep start-up (nbkode/multistep/core.py:37-65):
+                             0 none, NBK_RK45 ("auto"), NBK_RK23, NBK_AB1..5 */
+    int device;           /* CUDA device ordinal */
+} nbk_config;
+
+typedef struct {          /* all device pointers, see the layout above */
+    double *ts, *ys, *fs, *K, *h, *params;
+    long long *n_accepted, *n_rejected;
+    int *status, *n_out;
+} nbk_state;
+
+int nbk_version(void);
+const char *nbk_last_error(void);
+
+/* Replaces class construction + numba JIT of the step closures
+   (nbkode/core.py:143-184 __init_subclass__, :125-132 rhs jitting). Built-in right-hand sides
+   use kernels compiled ahead of time by nvcc; rhs_src goes through NVRTC (sm_100a). */
+int nbk_create(const nbk_config *cfg, nbk_solver **out);
+void nbk_destroy(nbk_solver *s);
+
+/* History length L and number of stage rows S+1 (0 for multistep) the caller must allocate. */
+int nbk_layout(const nbk_solver *s, int *len_history, int *stage_rows);
+/* 1 if the kernels came from NVRTC, 0 if from the ahead-of-time catalogue. */
+int nbk_is_jit(const nbk_solver *s);
+
+/* Replaces Solver.__init__ / VariableStep.__init__ / Multistep.__init__
+   (nbkode/core.py:106-141, :687-706, nbkode/multistep/core.py:37-65): f0 = rhs(t0, y0), history
+   filled with (t0, y0, f0), h = select_initial_step(...) when h is NaN (adaptive), multistep
+   start-up.  y0 element (b, c) is read from y0[b*y0_sb + c*y0_sc] (device); params likewise
+   (ignored when n_params == 0; for params_shared the np values are read from params[c*p_sc]).
+   h_per_traj (device, [B]) overrides h when not NULL. */
+int nbk_init(nbk_solver *s, const nbk_state *st, double t0, const double *y0, long long y0_sb,
+             long long y0_sc, const double *params, long long p_sb, long long p_sc, double h,
+             const double *h_per_traj, void *stream);
+
+/* Replaces Solver.run -> _run_eval (nbkode/core.py:315-332, :598-619) including the past-point
+   branch of run_events (:401-408): for each sorted grid time ts[k] (device, [m]) advance every
+   trajectory while t < ts[k] (steps are never clipped) and write the dense output
+   (RkInterpolator.evaluate explicit.py:371-403 / Solver._interpolate core.py:577-596) to
+   y_out[b*o_sb + k*o_sk + c*o_sc] (device).  A step starts only if t + h <= t_bound;
+   trajectories stopped by that guard report NBK_TRAJ_BOUND and n_out < m. */
+int nbk_run(nbk_solver *s, const nbk_state *st, const double *ts, int m, double t_bound,
+            double *y_out, long long o_sb, long long o_sk, long long o_sc, long long max_attempts,
+            void *stream);
+
+/* Replaces Solver.step / Solver.skip -> _nsteps/_steps/_nskip/_skip (nbkode/core.py:214-313,
+   :483-575): up to n_steps accepted steps per trajectory, each starting only if
+   t + h <= bound (bound = upto_t or t_bound).  With emit != 0 step j of trajectory b is written
+   to t_out[b*to_sb + j] and y_out[b*o_sb + j*o_sk + c*o_sc]; st->n_out[b] receives the number
+   of steps taken. */
+int nbk_step(nbk_solver *s, const nbk_state *st, long long n_steps, double bound, int emit,
+             double *t_out, long long to_sb, double *y_out, long long o_sb, long long o_sk,
+             long long o_sc, long long max_attempts, void *stream);
+
+/* Launch geometry of the most recent nbk_run / nbk_step (for reporting). */
+int nbk_last_launch(const nbk_solver *s, int *grid, int *block, int *regs_per_thread);
+
+/* NVRTC front half only (no device needed): compiles the kernels of cfg for sm_100a and returns
+   the cubin size; used by the CPU test-suite and to pre-warm the program cache. */
+int nbk_jit_compile_only(const nbk_config *cfg, long long *cubin_bytes);
+
+/* FP64 vector-pipe roofline denominator: runs a register-resident DFMA chain kernel for
+   `iters` iterations and returns the achieved TFLOP/s (2 FLOP per DFMA) and its duration. */
+int nbk_fp64_peak(int device, int iters, double *tflops, double *millis);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

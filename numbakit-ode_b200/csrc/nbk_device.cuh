@@ -1,0 +1,903 @@
+// nbk_device.cuh -- device side of the B200 ODE-ensemble engine (sm_100a, FP64).
+//
+// One trajectory per thread; the state vector, the stage derivatives K0..K_S and the
+// parameters live in registers (every loop below has a compile-time trip count and is fully
+// unrolled, so all array indices are static).  HBM is touched only to load a trajectory,
+// to emit dense output and to retire the trajectory.  The adaptive kernels are persistent:
+// a lane that finishes its trajectory pulls the next one from a global queue so that
+// per-trajectory step-count variance (adaptive-step divergence) does not idle the warp.
+//
+// The same file is compiled by nvcc (built-in right-hand sides, nbk_program.cu) and by
+// NVRTC at run time (user right-hand sides), so it must not include host headers.
+//
+// Reference behaviour restated here (paths under /root/reference):
+//   FSAL stage loop            nbkode/runge_kutta/explicit.py:60-79
+//   error estimate, norm       nbkode/runge_kutta/core.py:73-83
+//   I-controller               nbkode/runge_kutta/core.py:85-99
+//   accept/retry loop          nbkode/runge_kutta/explicit.py:81-99
+//   t_bound guard              nbkode/core.py:176-184
+//   RK dense output            nbkode/runge_kutta/explicit.py:354-403
+//   initial step               nbkode/core.py:695-705 (scipy select_initial_step)
+//   history window             nbkode/buffer.py:12-56
+//   Adams-Bashforth step       nbkode/multistep/core.py:90-112, multistep/adams_bashforth.py
+//   multistep start-up         nbkode/multistep/core.py:37-65
+//   window Hermite             nbkode/core.py:577-596
+//   run(ts) / step driver      nbkode/core.py:483-537, 598-619
+#ifndef NBK_DEVICE_CUH
+#define NBK_DEVICE_CUH
+
+#include "nbk_kargs.h"
+
+#define NBK_DEV __device__ __forceinline__
+#define NBK_HD __host__ __device__ constexpr
+
+#ifndef NBK_REFILL_MIN
+#define NBK_REFILL_MIN 2  // idle lanes needed before a warp stops to refill from the queue
+#endif
+#ifndef NBK_BLOCK
+#define NBK_BLOCK 128
+#endif
+#ifdef NBK_HOST_EMUL
+#define NBK_LOG2F(x) log2f(x)
+#else
+#define NBK_LOG2F(x) __log2f(x)
+#endif
+#ifndef NBK_FULL_MASK
+#define NBK_FULL_MASK 0xffffffffu  // tests/emul compiles the kernels for the host as 1-lane warps
+#endif
+
+namespace nbk {
+
+NBK_DEV double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+NBK_DEV double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+NBK_DEV bool d_finite(double x) { return fabs(x) < d_inf(); }
+
+// =====================================================================================
+// Tableaux.  constexpr accessors: after unrolling every coefficient is an immediate /
+// constant-bank operand and zero entries cost nothing.
+// =====================================================================================
+
+struct tab_rk23 {  // Bogacki-Shampine 3(2), nbkode/runge_kutta/explicit.py:146-151
+    static constexpr int S = 3, Q = 2, M = 3, ROOT = 6, ID = 23;
+    static NBK_HD double a(int i, int j) {
+        constexpr double A[3][3] = {{0, 0, 0}, {1.0 / 2, 0, 0}, {0, 3.0 / 4, 0}};
+        return A[i][j];
+    }
+    static NBK_HD double b(int j) {
+        constexpr double Bv[3] = {2.0 / 9, 1.0 / 3, 4.0 / 9};
+        return Bv[j];
+    }
+    static NBK_HD double c(int j) {
+        constexpr double Cv[3] = {0, 1.0 / 2, 3.0 / 4};
+        return Cv[j];
+    }
+    static NBK_HD double e(int j) {  // FSAL.E = [B,0] - B2 (explicit.py:54-58)
+        constexpr double Ev[4] = {2.0 / 9 - 7.0 / 24, 1.0 / 3 - 1.0 / 4, 4.0 / 9 - 1.0 / 3, -1.0 / 8};
+        return Ev[j];
+    }
+    static NBK_HD double p(int j, int k) {
+        constexpr double Pv[4][3] = {{1, -4.0 / 3, 5.0 / 9}, {0, 1, -2.0 / 3}, {0, 4.0 / 3, -8.0 / 9}, {0, -1, 1}};
+        return Pv[j][k];
+    }
+};
+
+struct tab_rk45 {  // Dormand-Prince 5(4), nbkode/runge_kutta/explicit.py:185-239
+    static constexpr int S = 6, Q = 4, M = 4, ROOT = 10, ID = 45;
+    static NBK_HD double a(int i, int j) {
+        constexpr double A[6][6] = {
+            {0, 0, 0, 0, 0, 0},
+            {1.0 / 5, 0, 0, 0, 0, 0},
+            {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+            {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+            {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+            {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0}};
+        return A[i][j];
+    }
+    static NBK_HD double b(int j) {
+        constexpr double Bv[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+        return Bv[j];
+    }
+    static NBK_HD double c(int j) {
+        constexpr double Cv[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1};
+        return Cv[j];
+    }
+    static NBK_HD double e(int j) {
+        constexpr double Ev[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+        return Ev[j];
+    }
+    static NBK_HD double p(int j, int k) {
+        constexpr double Pv[7][4] = {
+            {1, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
+            {0, 0, 0, 0},
+            {0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
+            {0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
+            {0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
+            {0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
+            {0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+        return Pv[j][k];
+    }
+};
+
+// Adams-Bashforth weights exactly as the reference lists them; index 0 multiplies the OLDEST
+// derivative of the window (nbkode/multistep/core.py:101,109).
+template <int ORDER>
+struct tab_ab {
+    static constexpr int ID = ORDER, LEN = ORDER > 2 ? ORDER : 2;
+    static NBK_HD double b(int j) {
+        constexpr double Bv[6][5] = {
+            {0, 0, 0, 0, 0},
+            {1.0, 0, 0, 0, 0},
+            {3.0 / 2, -1.0 / 2, 0, 0, 0},
+            {23.0 / 12, -16.0 / 12, 5.0 / 12, 0, 0},
+            {55.0 / 24, -59.0 / 24, 37.0 / 24, -9.0 / 24, 0},
+            {1901.0 / 720, -2774.0 / 720, 2616.0 / 720, -1274.0 / 720, 251.0 / 720}};
+        return Bv[ORDER][j];
+    }
+};
+
+// runtime-order copy for the (cold) multistep start-up with an Adams-Bashforth first stepper
+NBK_DEV double ab_weight(int order, int j) {
+    const double Bv[6][5] = {
+        {0, 0, 0, 0, 0},
+        {1.0, 0, 0, 0, 0},
+        {3.0 / 2, -1.0 / 2, 0, 0, 0},
+        {23.0 / 12, -16.0 / 12, 5.0 / 12, 0, 0},
+        {55.0 / 24, -59.0 / 24, 37.0 / 24, -9.0 / 24, 0},
+        {1901.0 / 720, -2774.0 / 720, 2616.0 / 720, -1274.0 / 720, 251.0 / 720}};
+    return Bv[order][j];
+}
+
+// =====================================================================================
+// Built-in right-hand sides (the catalogue of BASELINE.json's configs that fit one thread).
+// A right-hand side is a struct with N, NP and
+//   static void eval(double t, const double (&y)[N], const double (&p)[NPX], double (&dy)[N]).
+// =====================================================================================
+
+template <int N_, int NP_>
+struct rhs_decay {  // y' = -k*y, k scalar (NP=1) or element-wise (NP=N): README.rst:44-50
+    static constexpr int N = N_, NP = NP_;
+    static NBK_DEV void eval(double, const double (&y)[N_], const double (&p)[NP_], double (&dy)[N_]) {
+#pragma unroll
+        for (int i = 0; i < N_; ++i) dy[i] = -p[NP_ == 1 ? 0 : i] * y[i];
+    }
+};
+
+typedef rhs_decay<1, 1> rhs_decay11;  // catalogue instance (nvcc -D cannot carry a comma)
+
+struct rhs_lorenz {  // Lorenz-63: [sigma (y-x), x (rho-z) - y, x y - beta z]
+    static constexpr int N = 3, NP = 3;
+    static NBK_DEV void eval(double, const double (&y)[3], const double (&p)[3], double (&dy)[3]) {
+        dy[0] = p[0] * (y[1] - y[0]);
+        dy[1] = y[0] * (p[1] - y[2]) - y[1];
+        dy[2] = y[0] * y[1] - p[2] * y[2];
+    }
+};
+
+struct rhs_vdp {  // Van der Pol: [v, mu (1-x^2) v - x]
+    static constexpr int N = 2, NP = 1;
+    static NBK_DEV void eval(double, const double (&y)[2], const double (&p)[1], double (&dy)[2]) {
+        dy[0] = y[1];
+        dy[1] = p[0] * (1 - y[0] * y[0]) * y[1] - y[0];
+    }
+};
+
+#ifdef NBK_USER_RHS
+// User right-hand side compiled by NVRTC: the user source defines
+//   __device__ void nbk_rhs(double t, const double* y, const double* p, double* dy)
+// with NBK_N state variables and NBK_NP parameters.
+struct rhs_user {
+    static constexpr int N = NBK_N, NP = NBK_NP;
+    static NBK_DEV void eval(double t, const double (&y)[NBK_N], const double (&p)[NBK_NP > 0 ? NBK_NP : 1],
+                             double (&dy)[NBK_N]) {
+        nbk_rhs(t, y, p, dy);
+    }
+};
+#endif
+
+// =====================================================================================
+// Arithmetic helpers
+// =====================================================================================
+
+// 1/x for positive normal x: MUFU seed + two Newton steps (4 DFMA) instead of the ~12
+// instruction IEEE division sequence.  Error <= ~1 ulp (the result is not correctly rounded).
+NBK_DEV double fast_rcp(double x) {
+    double r;
+#ifdef NBK_HOST_EMUL
+    r = (double)(float)(1.0 / x);  // stands in for the ~2^-23 MUFU seed
+#else
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// x^(-1/R) for x within float range: single-precision seed (ex2/lg2 MUFU) polished by two FP64
+// Newton steps on g(y) = y^-R - x, i.e. y <- y + y (1 - x y^R) / R (quadratic convergence:
+// 1e-6 -> 5e-12 -> 1e-22), so the step-size factor is FP64-accurate to ~2 ulp.
+template <int R>
+NBK_DEV double inv_root(double x) {  // x in [1e-30, 1e30]
+    const float xf = (float)x;
+    double y = (double)exp2f(NBK_LOG2F(xf) * (-1.0f / R));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        double y2 = y * y, yr;
+        if (R == 10) {
+            const double y4 = y2 * y2, y8 = y4 * y4;
+            yr = y8 * y2;
+        } else if (R == 6) {
+            const double y4 = y2 * y2;
+            yr = y4 * y2;
+        } else {
+            yr = 1.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) yr *= y;
+        }
+        const double r = fma(-x, yr, 1.0);
+        y = fma(y * (1.0 / R), r, y);
+    }
+    return y;
+}
+
+// rms(x / scale) of scipy.integrate._ivp.common.norm (cold path: IEEE division and sqrt)
+template <int N>
+NBK_DEV double rms_scaled(const double (&x)[N], const double (&sc)[N]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double v = x[i] / sc[i];
+        acc = fma(v, v, acc);
+    }
+    return sqrt(acc) / sqrt((double)N);
+}
+
+// =====================================================================================
+// One FSAL attempt: K[0] must hold f(t, y).  Produces K[1..S], y_new and the squared
+// scaled RMS error  err2 = mean((h E.K / (atol + rtol max(|y_new|,|y|)))^2).
+// Algorithmic FLOPs: RK45 6R + 66N + 18, RK23 3R + 27N + 18.
+// =====================================================================================
+template <class Tab, class Rhs>
+NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&K)[Tab::S + 1][Rhs::N],
+                        const double (&p)[Rhs::NP > 0 ? Rhs::NP : 1], double (&ynew)[Rhs::N], double &err2,
+                        double rtol, double atol) {
+    constexpr int N = Rhs::N, S = Tab::S;
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+        double ys[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                if (Tab::a(s, j) != 0.0) {
+                    acc = first ? Tab::a(s, j) * K[j][i] : fma(Tab::a(s, j), K[j][i], acc);
+                    first = false;
+                }
+            }
+            ys[i] = fma(h, acc, y[i]);
+        }
+        Rhs::eval(fma(h, Tab::c(s), t), ys, p, K[s]);
+    }
+    // y_new = y + (h*B) . K[:S]   (the vector h*B is formed first, as the reference does)
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double acc = y[i];
+#pragma unroll
+        for (int j = 0; j < S; ++j)
+            if (Tab::b(j) != 0.0) acc = fma(h * Tab::b(j), K[j][i], acc);
+        ynew[i] = acc;
+    }
+    Rhs::eval(t + h, ynew, p, K[S]);
+    double acc2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double e = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j <= S; ++j) {
+            if (Tab::e(j) != 0.0) {
+                e = first ? Tab::e(j) * K[j][i] : fma(Tab::e(j), K[j][i], e);
+                first = false;
+            }
+        }
+        e *= h;
+        const double sc = fma(rtol, fmax(fabs(ynew[i]), fabs(y[i])), atol);
+        const double r = e * fast_rcp(sc);
+        acc2 = fma(r, r, acc2);
+    }
+    err2 = acc2 * (1.0 / N);
+}
+
+// I-controller of the reference: h *= clip(safety * norm^(-1/(q+1)), min_factor, max_factor)
+// on accept AND reject; accept iff norm < 1 (norm == 0 -> max_factor, accept).  Works on the
+// squared norm: norm^(-1/(q+1)) == err2^(-1/(2(q+1))), and sqrt(x) < 1 <=> x < 1.
+// [x_lo, x_hi] (host-computed from the options, nbk_api.cu) brackets the range of err2 in which
+// the clip is not already decided; clamping into it keeps the single-precision seed in range.
+template <class Tab>
+NBK_DEV double step_factor(double err2, double safety, double min_factor, double max_factor, double x_lo,
+                           double x_hi) {
+    const double xc = fmin(fmax(err2, x_lo), x_hi);
+    const double f = safety * inv_root<Tab::ROOT>(xc);
+    return fmin(max_factor, fmax(min_factor, f));
+}
+
+// Dense output inside the last accepted step [t_old, t_new] (RkInterpolator.evaluate).
+template <class Tab, int N>
+NBK_DEV void rk_dense(double te, double t_old, double t_new, const double (&y_old)[N], const double (&y_new)[N],
+                      const double (&K)[Tab::S + 1][N], double (&out)[N]) {
+    if (te == t_new) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = y_new[i];
+        return;
+    }
+    if (te == t_old) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = y_old[i];
+        return;
+    }
+    const double H = t_new - t_old;
+    const double x = (te - t_old) / H;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double acc = 0.0, pw = x;
+#pragma unroll
+        for (int k = 0; k < Tab::M; ++k) {
+            double q = 0.0;
+#pragma unroll
+            for (int j = 0; j <= Tab::S; ++j)
+                if (Tab::p(j, k) != 0.0) q = fma(K[j][i], Tab::p(j, k), q);
+            acc = fma(q, pw, acc);
+            pw *= x;
+        }
+        out[i] = fma(H, acc, y_old[i]);
+    }
+}
+
+// scipy select_initial_step (direction +1, unbounded interval), SURVEY.md row a4.
+template <class Rhs>
+NBK_DEV double initial_step(double t0, const double (&y0)[Rhs::N], const double (&f0)[Rhs::N],
+                            const double (&p)[Rhs::NP > 0 ? Rhs::NP : 1], int q, double rtol, double atol) {
+    constexpr int N = Rhs::N;
+    double sc[N], y1[N], f1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) sc[i] = atol + fabs(y0[i]) * rtol;
+    const double d0 = rms_scaled<N>(y0, sc), d1 = rms_scaled<N>(f0, sc);
+    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) y1[i] = y0[i] + h0 * f0[i];
+    Rhs::eval(t0 + h0, y1, p, f1);
+#pragma unroll
+    for (int i = 0; i < N; ++i) f1[i] -= f0[i];
+    const double d2 = rms_scaled<N>(f1, sc) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(d1, d2), 1.0 / (q + 1));
+    return fmin(100 * h0, h1);
+}
+
+// -------------------------------------------------------------------------------------
+// parameter fetch: SoA [np][B] or shared [np]
+// -------------------------------------------------------------------------------------
+template <int NP>
+NBK_DEV void load_params(const nbk_kargs &a, long long idx, double (&p)[NP > 0 ? NP : 1]) {
+    if (NP == 0) {
+        p[0] = 0.0;
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < NP; ++c) p[c] = a.params_shared ? __ldg(a.params + c) : __ldg(a.params + (long long)c * a.B + idx);
+}
+
+
+// =====================================================================================
+// Adaptive advance kernel body (RungeKutta23 / RungeKutta45), persistent with lane refill.
+// MODE RUN : for ti in tgrid: while t < ti: step; emit dense(ti)      (core.py:598-619)
+// MODE STEP: up to n_steps accepted steps, each emitted as (t, y)      (core.py:483-537)
+// Every loop iteration is one ATTEMPT for every running lane; accept/reject is resolved with
+// selects, so lanes of a warp only diverge when a trajectory is loaded, emits or retires.
+// =====================================================================================
+template <class Tab, class Rhs, int MODE>
+NBK_DEV void advance_adaptive(const nbk_kargs &a) {
+    constexpr int N = Rhs::N, NP = Rhs::NP, NPX = NP > 0 ? NP : 1, S = Tab::S;
+    const unsigned FULL = NBK_FULL_MASK;
+    const int lane = threadIdx.x & 31;
+    const long long B = a.B;
+    const double rtol = a.rtol, atol = a.atol;
+    const double safety = a.safety, min_factor = a.min_factor, max_factor = a.max_factor;
+    const double bound = a.bound;
+
+    long long idx = -1;
+    bool running = false, finishing = false, queue_empty = false;
+    double t = 0, h = 0, t_old = 0, te_next = 0;
+    double y[N], y_old[N], K[S + 1][N], p[NPX];
+    int nacc = 0, nrej = 0;  // of this call
+    int kout = 0;            // RUN: next grid index
+    bool fresh = true;       // the next attempt opens a new step (K[S] holds f(t, y))
+    int status = NBK_TRAJ_OK;
+
+    for (;;) {
+        // ---------------------------------------------------------------- (1) retire
+        if (finishing) {
+            if (nacc > 0) {
+                const bool clean = status == NBK_TRAJ_OK || status == NBK_TRAJ_BOUND;
+                a.ts[idx] = t_old;
+                a.ts[B + idx] = t;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    a.ys[(long long)c * B + idx] = y_old[c];
+                    a.ys[(long long)(N + c) * B + idx] = y[c];
+                    a.fs[(long long)c * B + idx] = K[0][c];
+                    a.fs[(long long)(N + c) * B + idx] = clean ? K[S][c] : K[0][c];
+                }
+#pragma unroll
+                for (int s = 0; s <= S; ++s)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) a.K[((long long)s * N + c) * B + idx] = K[s][c];
+            }
+            a.h[idx] = h;
+            a.n_acc[idx] += nacc;
+            a.n_rej[idx] += nrej;
+            a.status[idx] = status;
+            a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nacc;
+            finishing = false;
+            idx = -1;
+        }
+        // ---------------------------------------------------------------- (2) refill
+        const unsigned idle = __ballot_sync(FULL, !running);
+        if (idle) {
+            if (queue_empty) {
+                if (idle == FULL) break;
+            } else if (__popc(idle) >= NBK_REFILL_MIN) {
+                const int nidle = __popc(idle);
+                unsigned long long base = 0;
+                const int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(a.work_counter, (unsigned long long)nidle);
+                base = __shfl_sync(FULL, base, leader);
+                if ((long long)(base + nidle) >= B) queue_empty = true;
+                const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
+                if (!running && mine < B) {
+                    idx = mine;
+                    t_old = a.ts[idx];
+                    t = a.ts[B + idx];
+                    h = a.h[idx];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        y_old[c] = a.ys[(long long)c * B + idx];
+                        y[c] = a.ys[(long long)(N + c) * B + idx];
+                    }
+#pragma unroll
+                    for (int s = 0; s <= S; ++s)
+#pragma unroll
+                        for (int c = 0; c < N; ++c) K[s][c] = a.K[((long long)s * N + c) * B + idx];
+                    load_params<NP>(a, idx, p);
+                    nacc = nrej = 0;
+                    kout = 0;
+                    fresh = true;
+                    status = NBK_TRAJ_OK;
+                    running = true;
+                    if (MODE == NBK_MODE_RUN) {
+                        // grid points inside the stored last step are answered from history
+                        // without stepping (core.py:401-408)
+                        while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                            double out[N];
+                            rk_dense<Tab, N>(__ldg(a.tgrid + kout), t_old, t, y_old, y, K, out);
+#pragma unroll
+                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                            ++kout;
+                        }
+                        running = kout < a.m;
+                        te_next = running ? __ldg(a.tgrid + kout) : d_inf();
+                    } else {
+                        running = a.n_steps > 0;
+                    }
+                    // f(t, y) of the stored state becomes K[0] of the first attempt
+#pragma unroll
+                    for (int c = 0; c < N; ++c) K[S][c] = a.fs[(long long)(N + c) * B + idx];
+                    finishing = !running;
+                }
+            }
+        }
+        // ---------------------------------------------------------------- (3) one attempt
+        if (running) {
+            if (fresh && (t + h > bound)) {
+                // t_bound / upto_t guard: tested once per step with the proposed h (core.py:176-184)
+                status = NBK_TRAJ_BOUND;
+                running = false;
+                finishing = true;
+            } else {
+                if (fresh) {  // FSAL: last stage of the accepted step opens the next one
+#pragma unroll
+                    for (int c = 0; c < N; ++c) K[0][c] = K[S][c];
+                }
+                double ynew[N], err2;
+                rk_attempt<Tab, Rhs>(t, h, y, K, p, ynew, err2, rtol, atol);
+                const bool accept = err2 < 1.0;
+                const double t_new = t + h;
+                h *= step_factor<Tab>(err2, safety, min_factor, max_factor, a.x_lo, a.x_hi);
+                t_old = accept ? t : t_old;
+                t = accept ? t_new : t;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    y_old[c] = accept ? y[c] : y_old[c];
+                    y[c] = accept ? ynew[c] : y[c];
+                }
+                nacc += accept ? 1 : 0;
+                nrej += accept ? 0 : 1;
+                fresh = accept;
+                bool done = false;
+                if (MODE == NBK_MODE_RUN) {
+                    if (accept && t >= te_next) {
+                        do {
+                            double out[N];
+                            rk_dense<Tab, N>(te_next, t_old, t, y_old, y, K, out);
+#pragma unroll
+                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                            ++kout;
+                            te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                        } while (t >= te_next);
+                        done = kout >= a.m;
+                    }
+                } else {
+                    if (accept) {
+                        if (a.emit) {
+                            a.t_out[idx * a.to_sb + (nacc - 1)] = t;
+#pragma unroll
+                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + (nacc - 1) * a.o_sk + c * a.o_sc] = y[c];
+                        }
+                        done = nacc >= a.n_steps;
+                    }
+                }
+                // guards the reference does not have (it would spin forever): non-finite error
+                // norm, collapsed step size, attempt budget.
+                if (!(err2 < d_inf()) || !(h > 0.0)) {
+                    status = NBK_TRAJ_NONFINITE;
+                    done = true;
+                } else if (!done && (long long)nacc + nrej >= a.max_attempts) {
+                    status = NBK_TRAJ_MAXATTEMPTS;
+                    done = true;
+                }
+                if (done) {
+                    running = false;
+                    finishing = true;
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// Adams-Bashforth-k advance (ForwardEuler == k=1).  All trajectories take (nearly) the same
+// number of steps, so the mapping is static: thread i owns trajectory i and consecutive
+// lanes read/write consecutive addresses of every SoA array.
+// =====================================================================================
+template <int L, int N>
+NBK_DEV void hermite_window(double te, const double (&ts)[L], const double (&ys)[L][N], const double (&fs)[L][N],
+                            double (&out)[N]) {
+    const double t0 = ts[0];
+    if (te == t0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = ys[0][i];
+        return;
+    }
+    const double dt = ts[L - 1] - t0;
+    const double T = (te - t0) / dt;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double dy = ys[L - 1][i] - ys[0][i];
+        out[i] = ys[0][i] + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * fs[0][i] + T * fs[L - 1][i]));
+    }
+}
+
+template <int ORDER, class Rhs, int MODE>
+NBK_DEV void advance_ab(const nbk_kargs &a) {
+    constexpr int N = Rhs::N, NP = Rhs::NP, NPX = NP > 0 ? NP : 1, L = tab_ab<ORDER>::LEN;
+    const long long B = a.B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B) return;
+    double ts[L], ys[L][N], fs[L][N], p[NPX];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        ts[l] = a.ts[(long long)l * B + idx];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            ys[l][c] = a.ys[((long long)l * N + c) * B + idx];
+            fs[l][c] = a.fs[((long long)l * N + c) * B + idx];
+        }
+    }
+    const double h = a.h[idx];
+    load_params<NP>(a, idx, p);
+    double hB[ORDER];
+#pragma unroll
+    for (int j = 0; j < ORDER; ++j) hB[j] = h * tab_ab<ORDER>::b(j);
+
+    int kout = 0, status = NBK_TRAJ_OK;
+    long long nsteps = 0;
+    double te_next = d_inf();
+    bool running;
+    if (MODE == NBK_MODE_RUN) {
+        while (kout < a.m && __ldg(a.tgrid + kout) <= ts[L - 1]) {
+            double out[N];
+            hermite_window<L, N>(__ldg(a.tgrid + kout), ts, ys, fs, out);
+#pragma unroll
+            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+            ++kout;
+        }
+        running = kout < a.m;
+        if (running) te_next = __ldg(a.tgrid + kout);
+    } else {
+        running = a.n_steps > 0;
+    }
+    while (running) {
+        if (ts[L - 1] + h > a.bound) {
+            status = NBK_TRAJ_BOUND;
+            break;
+        }
+        const double t_new = ts[L - 1] + h;
+        double ynew[N], fnew[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            double acc = hB[0] * fs[L - ORDER][c];
+#pragma unroll
+            for (int j = 1; j < ORDER; ++j) acc = fma(hB[j], fs[L - ORDER + j][c], acc);
+            ynew[c] = acc + ys[L - 1][c];
+        }
+        Rhs::eval(t_new, ynew, p, fnew);
+        // push: shift the window by one (register renaming after unrolling)
+#pragma unroll
+        for (int l = 0; l < L - 1; ++l) {
+            ts[l] = ts[l + 1];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                ys[l][c] = ys[l + 1][c];
+                fs[l][c] = fs[l + 1][c];
+            }
+        }
+        ts[L - 1] = t_new;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            ys[L - 1][c] = ynew[c];
+            fs[L - 1][c] = fnew[c];
+        }
+        ++nsteps;
+        if (MODE == NBK_MODE_RUN) {
+            while (t_new >= te_next) {
+                double out[N];
+                hermite_window<L, N>(te_next, ts, ys, fs, out);
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                ++kout;
+                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+            }
+            running = kout < a.m;
+        } else {
+            if (a.emit) {
+                a.t_out[idx * a.to_sb + (nsteps - 1)] = t_new;
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + (nsteps - 1) * a.o_sk + c * a.o_sc] = ynew[c];
+            }
+            running = nsteps < a.n_steps;
+        }
+        if (running && nsteps >= a.max_attempts) {
+            status = NBK_TRAJ_MAXATTEMPTS;
+            break;
+        }
+    }
+    if (nsteps > 0) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            a.ts[(long long)l * B + idx] = ts[l];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                a.ys[((long long)l * N + c) * B + idx] = ys[l][c];
+                a.fs[((long long)l * N + c) * B + idx] = fs[l][c];
+            }
+        }
+        a.n_acc[idx] += nsteps;
+    }
+    a.status[idx] = status;
+    a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
+}
+
+// =====================================================================================
+// Construction kernels (one thread per trajectory; cold path: IEEE division / sqrt / pow)
+// =====================================================================================
+template <class Rhs>
+NBK_DEV void load_initial(const nbk_kargs &a, long long idx, double (&y)[Rhs::N],
+                          double (&p)[Rhs::NP > 0 ? Rhs::NP : 1]) {
+    constexpr int N = Rhs::N, NP = Rhs::NP;
+#pragma unroll
+    for (int c = 0; c < N; ++c) y[c] = a.y0[idx * a.y0_sb + c * a.y0_sc];
+    if (NP == 0) p[0] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+        if (a.params_shared) {
+            p[c] = a.params[c];  // the host already placed the shared vector
+        } else {
+            p[c] = a.p0[idx * a.p0_sb + c * a.p0_sc];
+            a.params[(long long)c * a.B + idx] = p[c];  // SoA copy used by the advance kernels
+        }
+    }
+}
+
+template <class Tab, class Rhs>
+NBK_DEV void init_adaptive(const nbk_kargs &a) {
+    constexpr int N = Rhs::N, NPX = Rhs::NP > 0 ? Rhs::NP : 1, S = Tab::S;
+    const long long B = a.B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B) return;
+    double y[N], f[N], p[NPX];
+    load_initial<Rhs>(a, idx, y, p);
+    Rhs::eval(a.t0, y, p, f);
+    double h = a.h0 ? a.h0[idx] : a.h_init;
+    if (!(h == h)) h = initial_step<Rhs>(a.t0, y, f, p, Tab::Q, a.rtol, a.atol);
+    a.ts[idx] = a.t0;
+    a.ts[B + idx] = a.t0;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        a.ys[(long long)c * B + idx] = y[c];
+        a.ys[(long long)(N + c) * B + idx] = y[c];
+        a.fs[(long long)c * B + idx] = f[c];
+        a.fs[(long long)(N + c) * B + idx] = f[c];
+    }
+#pragma unroll
+    for (int s = 0; s <= S; ++s)
+#pragma unroll
+        for (int c = 0; c < N; ++c) a.K[((long long)s * N + c) * B + idx] = 0.0;
+    a.h[idx] = h;
+    a.n_acc[idx] = 0;
+    a.n_rej[idx] = 0;
+    a.status[idx] = NBK_TRAJ_OK;
+}
+
+// Start-up points of an adaptive first stepper with DEFAULT tolerances (rtol 1e-3, atol 1e-6):
+// dense output at the absolute times hfix, 2 hfix, ..., npts*hfix (multistep/core.py:60-65).
+template <class Tab, class Rhs>
+NBK_DEV bool rk_startup_points(double t0, const double (&y0)[Rhs::N], const double (&f0)[Rhs::N],
+                               const double (&p)[Rhs::NP > 0 ? Rhs::NP : 1], double hfix, int npts, double *pt,
+                               double (*py)[Rhs::N], double (*pf)[Rhs::N]) {
+    constexpr int N = Rhs::N, S = Tab::S;
+    const double rtol = 1e-3, atol = 1e-6;
+    double t = t0, t_old = t0, y[N], y_old[N], K[S + 1][N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        y[c] = y_old[c] = y0[c];
+#pragma unroll
+        for (int s = 0; s <= S; ++s) K[s][c] = 0.0;
+        K[S][c] = f0[c];
+    }
+    double h = initial_step<Rhs>(t0, y0, f0, p, Tab::Q, rtol, atol);
+    bool fresh = true;
+    int budget = 1000000;
+    for (int j = 1; j <= npts; ++j) {
+        const double ti = j * hfix;
+        while (t < ti) {
+            if (fresh) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) K[0][c] = K[S][c];
+            }
+            double ynew[N], err2;
+            rk_attempt<Tab, Rhs>(t, h, y, K, p, ynew, err2, rtol, atol);
+            const bool accept = err2 < 1.0;
+            const double t_new = t + h;
+            h *= step_factor<Tab>(err2, 0.9, 0.2, 10.0, 1e-13, 1e8);
+            if (accept) {
+                t_old = t;
+                t = t_new;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    y_old[c] = y[c];
+                    y[c] = ynew[c];
+                }
+            }
+            fresh = accept;
+            if (!(err2 < d_inf()) || !(h > 0.0) || --budget < 0) return false;
+        }
+        double out[N];
+        rk_dense<Tab, N>(ti, t_old, t, y_old, y, K, out);
+        pt[j - 1] = ti;
+#pragma unroll
+        for (int c = 0; c < N; ++c) py[j - 1][c] = out[c];
+        Rhs::eval(ti, out, p, pf[j - 1]);
+    }
+    return true;
+}
+
+template <int ORDER, class Rhs>
+NBK_DEV void init_ab(const nbk_kargs &a) {
+    constexpr int N = Rhs::N, NPX = Rhs::NP > 0 ? Rhs::NP : 1, L = tab_ab<ORDER>::LEN;
+    const long long B = a.B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B) return;
+    double y[N], f[N], p[NPX];
+    load_initial<Rhs>(a, idx, y, p);
+    Rhs::eval(a.t0, y, p, f);
+    const double h = a.h0 ? a.h0[idx] : a.h_init;
+    // history: L copies of (t0, y0, f0) (buffer.py:14-19), then ORDER-1 start-up points pushed
+    double pt[4], py[4][N], pf[4][N];
+    int npush = 0, status = NBK_TRAJ_OK;
+    const int fsr = a.first_stepper;
+    if (ORDER > 1 && fsr != 0) {
+        bool ok = true;
+        if (fsr == 45) {
+            ok = rk_startup_points<tab_rk45, Rhs>(a.t0, y, f, p, h, ORDER - 1, pt, py, pf);
+        } else if (fsr == 23) {
+            ok = rk_startup_points<tab_rk23, Rhs>(a.t0, y, f, p, h, ORDER - 1, pt, py, pf);
+        } else {
+            // fixed-step first stepper AdamsBashforth-k' built with ITS default start-up
+            // (RungeKutta45), then ORDER-1 steps of it (multistep/core.py:54-59)
+            const int k2 = fsr, L2 = k2 > 2 ? k2 : 2;
+            double st[5], sy[5][N], sf[5][N];
+            for (int l = 0; l < L2; ++l) {
+                st[l] = a.t0;
+                for (int c = 0; c < N; ++c) {
+                    sy[l][c] = y[c];
+                    sf[l][c] = f[c];
+                }
+            }
+            if (k2 > 1) {
+                double qt[4], qy[4][N], qf[4][N];
+                ok = rk_startup_points<tab_rk45, Rhs>(a.t0, y, f, p, h, k2 - 1, qt, qy, qf);
+                for (int j = 0; j < k2 - 1; ++j) {
+                    for (int l = 0; l < L2 - 1; ++l) {
+                        st[l] = st[l + 1];
+                        for (int c = 0; c < N; ++c) {
+                            sy[l][c] = sy[l + 1][c];
+                            sf[l][c] = sf[l + 1][c];
+                        }
+                    }
+                    st[L2 - 1] = qt[j];
+                    for (int c = 0; c < N; ++c) {
+                        sy[L2 - 1][c] = qy[j][c];
+                        sf[L2 - 1][c] = qf[j][c];
+                    }
+                }
+            }
+            for (int j = 0; j < ORDER - 1; ++j) {
+                const double t_new = st[L2 - 1] + h;
+                double yn[N], fn[N];
+                for (int c = 0; c < N; ++c) {
+                    double acc = (h * ab_weight(k2, 0)) * sf[L2 - k2][c];
+                    for (int i = 1; i < k2; ++i) acc = fma(h * ab_weight(k2, i), sf[L2 - k2 + i][c], acc);
+                    yn[c] = acc + sy[L2 - 1][c];
+                }
+                Rhs::eval(t_new, yn, p, fn);
+                for (int l = 0; l < L2 - 1; ++l) {
+                    st[l] = st[l + 1];
+                    for (int c = 0; c < N; ++c) {
+                        sy[l][c] = sy[l + 1][c];
+                        sf[l][c] = sf[l + 1][c];
+                    }
+                }
+                st[L2 - 1] = t_new;
+                pt[j] = t_new;
+                for (int c = 0; c < N; ++c) {
+                    sy[L2 - 1][c] = yn[c];
+                    sf[L2 - 1][c] = fn[c];
+                    py[j][c] = yn[c];
+                    pf[j][c] = fn[c];
+                }
+            }
+        }
+        npush = ORDER - 1;
+        if (!ok) status = NBK_TRAJ_NONFINITE;
+    }
+    // window after npush pushes: (L - npush) copies of the initial point, then the pushed ones
+    for (int l = 0; l < L; ++l) {
+        const int j = l - (L - npush);
+        a.ts[(long long)l * B + idx] = j < 0 ? a.t0 : pt[j];
+        for (int c = 0; c < N; ++c) {
+            a.ys[((long long)l * N + c) * B + idx] = j < 0 ? y[c] : py[j][c];
+            a.fs[((long long)l * N + c) * B + idx] = j < 0 ? f[c] : pf[j][c];
+        }
+    }
+    a.h[idx] = h;
+    a.n_acc[idx] = 0;
+    a.n_rej[idx] = 0;
+    a.status[idx] = status;
+}
+
+}  // namespace nbk
+#endif

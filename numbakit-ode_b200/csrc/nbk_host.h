@@ -1,0 +1,13 @@
+// nbk_host.h -- host-side internals shared by nbk_api.cu, nbk_jit.cpp and nbk_program.cu.
+#ifndef NBK_HOST_H
+#define NBK_HOST_H
+
+struct nbk_static_program {
+    int method;            // 23, 45, 1..5
+    int n, n_params;
+    const void *k_init;    // host stubs of the __global__ kernels (cudaLaunchKernel)
+    const void *k_run;
+    const void *k_step;
+};
+
+#endif

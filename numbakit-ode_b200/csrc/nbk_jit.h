@@ -1,0 +1,35 @@
+// nbk_jit.h -- NVRTC program cache + CUDA driver-API loader (internal).
+#ifndef NBK_JIT_H
+#define NBK_JIT_H
+
+#include <string>
+#include <vector>
+
+struct nbk_jit_request {
+    int method;             // 23, 45, 1..5
+    int n, n_params;
+    std::string rhs_type;   // C++ type name of a built-in rhs (e.g. "nbk::rhs_decay<2,2>") or empty
+    std::string user_src;   // user source defining nbk_rhs(...) (used when rhs_type is empty)
+};
+
+struct nbk_jit_module {
+    void *module = nullptr;  // CUmodule
+    void *k_init = nullptr;  // CUfunction
+    void *k_run = nullptr;
+    void *k_step = nullptr;
+};
+
+// Compile (or fetch from the in-process cache) the cubin of a request. Needs no GPU.
+// Returns false and fills err (with the NVRTC log) on failure.
+bool nbk_jit_compile(const nbk_jit_request &rq, std::vector<char> &cubin, std::string &err);
+
+// Load a cubin into the current context and resolve the three kernels.
+bool nbk_jit_load(const std::vector<char> &cubin, nbk_jit_module &mod, std::string &err);
+void nbk_jit_unload(nbk_jit_module &mod);
+
+// cuLaunchKernel with a single by-value argument block.
+bool nbk_jit_launch(void *func, unsigned grid, unsigned block, void *arg_block, void *stream, std::string &err);
+// cuOccupancyMaxActiveBlocksPerMultiprocessor / register count of a CUfunction.
+bool nbk_jit_occupancy(void *func, int block, int *blocks_per_sm, int *regs, std::string &err);
+
+#endif

@@ -1,0 +1,57 @@
+// nbk_kargs.h -- kernel argument block shared by the host launcher (nbk_api.cu) and the
+// device programs (nbk_device.cuh, compiled by nvcc for the built-in catalogue and by NVRTC
+// for user right-hand sides).  Plain C types only: NVRTC compiles this without host headers.
+#ifndef NBK_KARGS_H
+#define NBK_KARGS_H
+
+// status codes per trajectory (also exported through include/nbkode_b200.h)
+#define NBK_TRAJ_OK 0          // reached the end of the request
+#define NBK_TRAJ_BOUND 1       // stopped by the t_bound / upto_t guard (nbkode/core.py:176-184)
+#define NBK_TRAJ_NONFINITE 2   // non-finite error norm or step size collapsed to 0
+#define NBK_TRAJ_MAXATTEMPTS 3 // attempt budget of this call exhausted
+
+// advance modes
+#define NBK_MODE_RUN 0   // run(ts): emit dense output at the shared grid tgrid[0..m)
+#define NBK_MODE_STEP 1  // step(n, upto_t) / skip: emit (t, y) after every accepted step
+
+struct nbk_kargs {
+    // ---- ensemble state, SoA with the trajectory index fastest (see DESIGN.md "HBM layout")
+    long long B;          // trajectories
+    double *ts;           // [L][B]      history times, oldest -> newest
+    double *ys;           // [L][n][B]   history states
+    double *fs;           // [L][n][B]   history derivatives
+    double *K;            // [S+1][n][B] stage derivatives of the last accepted step (RK only)
+    double *h;            // [B]         next step size
+    double *params;       // [np][B] (or [np] when params_shared)
+    long long *n_acc;     // [B] accepted steps so far
+    long long *n_rej;     // [B] rejected attempts so far
+    int *status;          // [B] NBK_TRAJ_*
+    int params_shared;
+    int first_stepper;    // multistep start-up: 0 none, 23/45 adaptive RK, 1..5 Adams-Bashforth-k
+    // ---- init inputs (user layout: element (b, c) at base[b*sb + c*sc])
+    const double *y0;
+    long long y0_sb, y0_sc;
+    const double *p0;
+    long long p0_sb, p0_sc;
+    const double *h0;     // optional per-trajectory first step / fixed step ([B]); NULL -> h_init
+    double t0;
+    double h_init;        // NaN -> select_initial_step (adaptive); fixed step for multistep
+    // ---- controller options (nbkode/core.py:661-679)
+    double rtol, atol, min_factor, max_factor, safety;
+    double x_lo, x_hi;    // clamp of the squared error norm outside which the factor clip decides
+    // ---- advance request
+    double bound;         // t_bound or upto_t: a step starts only if t + h <= bound
+    const double *tgrid;  // [m] sorted output times shared by all trajectories (RUN)
+    int m;
+    int emit;             // STEP: 0 = skip (no outputs)
+    long long n_steps;    // STEP: accepted steps to take (per trajectory)
+    double *y_out;        // RUN: (b,k,c) at y_out[b*o_sb + k*o_sk + c*o_sc]; STEP: k = step index
+    long long o_sb, o_sk, o_sc;
+    double *t_out;        // STEP: (b,k) at t_out[b*to_sb + k]
+    long long to_sb;
+    int *n_out;           // [B] grid points emitted (RUN) / steps taken (STEP) in this call
+    long long max_attempts;
+    unsigned long long *work_counter;  // persistent-kernel trajectory queue head
+};
+
+#endif

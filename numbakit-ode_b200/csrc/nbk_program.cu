@@ -1,0 +1,67 @@
+// nbk_program.cu -- one "program" = the init / run / step kernels of one (method, RHS) pair.
+//
+// Compiled once per built-in pair by nvcc (see Makefile: -DNBK_METHOD=.. -DNBK_RHS_T=..
+// -DNBK_TAG=..) and at run time by NVRTC for user right-hand sides (nbk_jit.cpp passes the
+// same macros plus -DNBK_USER_RHS and prepends the user's nbk_rhs definition).
+//
+// NBK_METHOD: 23 / 45 = RungeKutta23 / RungeKutta45; 1..5 = AdamsBashforth-k (1 == ForwardEuler).
+#include "nbk_device.cuh"
+
+#define NBK_CAT2(a, b) a##b
+#define NBK_CAT(a, b) NBK_CAT2(a, b)
+#define NBK_KERNEL(stem) NBK_CAT(NBK_CAT(nbk_, stem), NBK_CAT(_, NBK_TAG))
+
+typedef NBK_RHS_T nbk_rhs_t;
+
+#if NBK_METHOD == 45
+typedef nbk::tab_rk45 nbk_tab_t;
+#define NBK_ADAPTIVE 1
+#elif NBK_METHOD == 23
+typedef nbk::tab_rk23 nbk_tab_t;
+#define NBK_ADAPTIVE 1
+#elif NBK_METHOD >= 1 && NBK_METHOD <= 5
+#define NBK_ADAPTIVE 0
+#else
+#error "NBK_METHOD must be 23, 45 or 1..5"
+#endif
+
+#ifndef NBK_MIN_BLOCKS
+#define NBK_MIN_BLOCKS 1
+#endif
+
+extern "C" __global__ void __launch_bounds__(NBK_BLOCK) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
+#if NBK_ADAPTIVE
+    nbk::init_adaptive<nbk_tab_t, nbk_rhs_t>(a);
+#else
+    nbk::init_ab<NBK_METHOD, nbk_rhs_t>(a);
+#endif
+}
+
+extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
+#if NBK_ADAPTIVE
+    nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_RUN>(a);
+#else
+    nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN>(a);
+#endif
+}
+
+extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
+#if NBK_ADAPTIVE
+    nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_STEP>(a);
+#else
+    nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_STEP>(a);
+#endif
+}
+
+#ifndef __CUDACC_RTC__
+#include "nbk_host.h"
+// registration record picked up by nbk_api.cu (static catalogue)
+extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
+    out->method = NBK_METHOD;
+    out->n = nbk_rhs_t::N;
+    out->n_params = nbk_rhs_t::NP;
+    out->k_init = (const void *)&NBK_KERNEL(init);
+    out->k_run = (const void *)&NBK_KERNEL(run);
+    out->k_step = (const void *)&NBK_KERNEL(step);
+}
+#endif

@@ -1,0 +1,157 @@
+"""TEST INFRASTRUCTURE: run the CUDA kernel *source* on the host (one-lane warps).
+
+``numbakit-ode_b200/csrc/nbk_program.cu`` is compiled with g++ against
+``cuda_host_shim.h`` so that the logic of the device code -- trajectory queue, retire,
+t_bound guard, controller, dense output, multistep start-up -- is covered by
+``pytest -m "not gpu"``.  It checks the same source the GPU runs, but it is NOT a product
+path: nothing under ``nbkode_b200`` imports it, and it says nothing about GPU-only aspects
+(warp refill with 32 lanes, MUFU seeds, FMA contraction), which the ``-m gpu`` parity tests cover.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "numbakit-ode_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+
+_CTYPES = {
+    "long long": C.c_longlong, "int": C.c_int, "double": C.c_double,
+}
+
+
+def _kargs_struct():
+    """ctypes mirror of struct nbk_kargs, parsed from the header so it cannot drift."""
+    text = open(os.path.join(CSRC, "nbk_kargs.h")).read()
+    body = text[text.index("struct nbk_kargs {") + len("struct nbk_kargs {"): text.index("};")]
+    body = re.sub(r"//[^\n]*", "", body)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"(const\s+)?(unsigned long long|long long|double|int)\s*(.*)", decl)
+        assert m, decl
+        base = m.group(2)
+        for name in m.group(3).split(","):
+            name = name.strip()
+            if name.startswith("*"):
+                fields.append((name.lstrip("* "), C.c_void_p))
+            else:
+                fields.append((name, _CTYPES[base]))
+    return type("KArgs", (C.Structure,), {"_fields_": fields})
+
+
+KArgs = _kargs_struct()
+
+RHS_TYPES = {"lorenz": ("nbk::rhs_lorenz", 3, 3), "vdp": ("nbk::rhs_vdp", 2, 1)}
+METHOD_IDS = {
+    "RungeKutta23": 23, "RungeKutta45": 45, "ForwardEuler": 1, "AdamsBashforth1": 1, "AdamsBashforth2": 2,
+    "AdamsBashforth3": 3, "AdamsBashforth4": 4, "AdamsBashforth5": 5,
+}
+_libs = {}
+
+
+def _program(method, rhs, n, npar):
+    if rhs == "decay":
+        # typedef through a forced include: a -D value cannot carry the template comma portably
+        rtype, tag = f"nbk::rhs_decay<{n},{npar}>", f"m{method}_decay_{n}_{npar}"
+    else:
+        rtype, tag = RHS_TYPES[rhs][0], f"m{method}_{rhs}"
+    if tag in _libs:
+        return _libs[tag]
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, f"libemul_{tag}.so")
+    deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_kargs.h", "nbk_program.cu")]
+    deps += [os.path.join(HERE, f) for f in ("nbk_emul.cpp", "cuda_host_shim.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        pre = os.path.join(BUILD, f"pre_{tag}.h")
+        with open(pre, "w") as fh:
+            fh.write(f"#define NBK_METHOD {method}\n#define NBK_RHS_T {rtype}\n#define NBK_TAG {tag}\n")
+        subprocess.check_call([
+            "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
+            "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", "-include", pre,
+            os.path.join(HERE, "nbk_emul.cpp"), "-o", so,
+        ])
+    lib = C.CDLL(so)
+    fn = getattr(lib, f"emul_{tag}")
+    fn.argtypes = [C.c_int, C.POINTER(KArgs), C.c_longlong]
+    _libs[tag] = fn
+    return fn
+
+
+class EmulEnsemble:
+    """Host mirror of what nbkode_b200.core.Solver does around the C-ABI, on NumPy arrays."""
+
+    def __init__(self, method, rhs, y0, params, *, t0=0.0, h=None, first_step=None, rtol=1e-3, atol=1e-6,
+                 min_factor=0.2, max_factor=10.0, safety_factor=0.9, first_stepper=45, params_shared=False):
+        self.mid = METHOD_IDS[method] if isinstance(method, str) else method
+        y0 = np.ascontiguousarray(np.atleast_2d(np.asarray(y0, float)))
+        self.B, self.n = y0.shape
+        params = np.ascontiguousarray(np.asarray(params, float))
+        params = params.reshape(1, -1) if params_shared else params.reshape(self.B, -1)
+        self.np_ = params.shape[1]
+        self.fn = _program(self.mid, rhs, self.n, self.np_)
+        adaptive = self.mid in (23, 45)
+        self.L = 2 if adaptive else max(self.mid, 2)
+        self.SR = {23: 4, 45: 7}.get(self.mid, 0)
+        B, n = self.B, self.n
+        self.ts = np.zeros((self.L, B)); self.ys = np.zeros((self.L, n, B)); self.fs = np.zeros((self.L, n, B))
+        self.K = np.zeros((max(self.SR, 1), n, B)); self.h = np.zeros(B)
+        self.p = np.zeros((self.np_,) if params_shared else (self.np_, B))
+        if params_shared:
+            self.p[:] = params[0]
+        self.nacc = np.zeros(B, np.int64); self.nrej = np.zeros(B, np.int64)
+        self.status = np.zeros(B, np.int32); self.nout = np.zeros(B, np.int32)
+        self.counter = np.zeros(1, np.uint64)
+        root = 10 if self.mid == 45 else 6
+        self.base = dict(
+            B=B, ts=self.ts.ctypes.data, ys=self.ys.ctypes.data, fs=self.fs.ctypes.data, K=self.K.ctypes.data,
+            h=self.h.ctypes.data, params=self.p.ctypes.data, n_acc=self.nacc.ctypes.data, n_rej=self.nrej.ctypes.data,
+            status=self.status.ctypes.data, n_out=self.nout.ctypes.data, params_shared=int(params_shared),
+            first_stepper=first_stepper or 0, rtol=rtol, atol=atol, min_factor=min_factor, max_factor=max_factor,
+            safety=safety_factor, x_lo=0.5 * (safety_factor / max_factor) ** root,
+            x_hi=2.0 * (safety_factor / min_factor) ** root, bound=math.inf, max_attempts=2**31 - 1,
+            work_counter=self.counter.ctypes.data,
+        )
+        hh = first_step if adaptive else (1.0 if h is None else h)
+        a = KArgs(**self.base)
+        a.y0, a.y0_sb, a.y0_sc = y0.ctypes.data, n, 1
+        a.p0, a.p0_sb, a.p0_sc = params.ctypes.data, self.np_, 1
+        a.t0, a.h_init = t0, (math.nan if hh is None else hh)
+        self._keep = (y0, params)
+        self.fn(0, C.byref(a), B)
+
+    def run(self, ts, t_bound=math.inf):
+        ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
+        m = ts.size
+        out = np.full((self.B, m, self.n), np.nan)
+        a = KArgs(**self.base)
+        a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
+        a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
+        self.counter[0] = 0
+        self.fn(1, C.byref(a), self.B)
+        return out
+
+    def step(self, n_steps, bound=math.inf, emit=True):
+        t_out = np.full((self.B, max(n_steps, 1)), np.nan)
+        y_out = np.full((self.B, max(n_steps, 1), self.n), np.nan)
+        a = KArgs(**self.base)
+        a.bound, a.n_steps, a.emit = bound, n_steps, int(emit)
+        a.t_out, a.to_sb = t_out.ctypes.data, max(n_steps, 1)
+        a.y_out, a.o_sb, a.o_sk, a.o_sc = y_out.ctypes.data, max(n_steps, 1) * self.n, self.n, 1
+        self.counter[0] = 0
+        self.fn(2, C.byref(a), self.B)
+        return t_out, y_out, self.nout.copy()
+
+    t = property(lambda self: self.ts[-1].copy())
+    y = property(lambda self: self.ys[-1].T.copy())
+    f = property(lambda self: self.fs[-1].T.copy())

@@ -1,0 +1,155 @@
+"""Kernel-logic tests without a GPU: the CUDA kernel source (csrc/nbk_device.cuh,
+nbk_program.cu) compiled for the host as one-lane warps (tests/emul) against the reference's
+golden vectors and the C oracle.  GPU-only aspects are covered by the -m gpu parity tests."""
+
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+from emul import EmulEnsemble  # noqa: E402
+
+from oracle import nbk_oracle_c as oc  # noqa: E402
+from oracle import nbk_oracle_np as onp  # noqa: E402
+
+from conftest import load_golden  # noqa: E402
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape
+    return float(np.max(np.abs(a - b))) / max(1.0, float(np.max(np.abs(b))))
+
+
+ADAPTIVE = [c for c in load_golden("adaptive_single.json") if c["rhs"] in ("lorenz", "vdp", "decay")]
+
+
+@pytest.mark.parametrize("c", ADAPTIVE, ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_adaptive_single_vs_reference(c):
+    e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], **c["kw"])
+    assert rel(e.h[0], c["h0"]) < 1e-14
+    assert rel(e.f[0], c["f0"]) < 1e-15
+    ys = e.run(c["ts"])
+    tol = 1e-9 if c["rhs"] == "lorenz" else 1e-11
+    assert e.nacc[0] == c["n_accepted"]
+    assert rel(ys[0], c["ys"]) < tol
+    assert rel(e.t[0], c["t_end"]) < 1e-8 and rel(e.y[0], c["y_end"]) < 1e-8 and rel(e.h[0], c["h_end"]) < 1e-8
+    assert rel(e.K[:, :, 0], c["K_end"]) < 1e-7
+    assert rel(e.ts[0, 0], c["t_old"]) < 1e-8 and rel(e.ys[0, :, 0], c["y_old"]) < 1e-8
+    assert e.status[0] == 0 and e.nout[0] == len(c["ts"])
+
+
+FIXED = [c for c in load_golden("fixed_single.json")]
+
+
+def _fs(kw):
+    fs = kw.get("first_stepper_cls", "auto")
+    if fs is None or fs == "None":
+        return 0
+    return {"auto": 45, "RungeKutta23": 23, "RungeKutta45": 45}.get(fs) or int(fs[-1])
+
+
+@pytest.mark.parametrize("c", FIXED, ids=lambda c: f"{c['cls']}-{c['rhs']}-{c['kw']}")
+def test_fixed_single_vs_reference(c):
+    """Fixed-step bar of the north star: 1e-12 relative (per trajectory, max-norm scaled)."""
+    e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], h=c["h"], first_stepper=_fs(c["kw"]))
+    assert rel(e.ts[:, 0], c["init_ts"]) < 1e-15
+    tol0 = 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    assert rel(e.ys[:, :, 0], c["init_ys"]) < tol0 and rel(e.fs[:, :, 0], c["init_fs"]) < tol0
+    ys = e.run(c["ts"])
+    assert rel(ys[0], c["ys"]) < tol0
+    assert e.t[0] == c["t_end"]
+    assert rel(e.y[0], c["y_end"]) < tol0 and rel(e.ts[:, 0], c["end_ts"]) < 1e-15
+
+
+def test_lorenz_ensemble_queue():
+    g = load_golden("lorenz_ensemble_rk45.json")
+    rows = g["rows"]
+    y0 = np.array([r["y0"] for r in rows])
+    p = np.array([r["p"] for r in rows])
+    e = EmulEnsemble("RungeKutta45", "lorenz", y0, p, rtol=g["rtol"], atol=g["atol"])
+    ys = e.run([g["T"]])
+    assert np.array_equal(e.nacc, [r["n_accepted"] for r in rows])
+    assert rel(ys[:, 0], [r["ys"][0] for r in rows]) < 1e-8
+    assert rel(e.h, [r["h_end"] for r in rows]) < 1e-6
+    assert (e.status == 0).all() and (e.nout == 1).all()
+    assert e.counter[0] >= len(rows)  # every trajectory went through the work queue
+
+
+def test_vdp_dense_output_rk23_and_ab4():
+    g = load_golden("vdp_ensemble.json")
+    ts = np.linspace(0, 20, g["n_ts"])
+    y0 = np.array([r["y0"] for r in g["rk23"]])
+    p = np.array([r["p"] for r in g["rk23"]])
+    e = EmulEnsemble("RungeKutta23", "vdp", y0, p, rtol=1e-6, atol=1e-9)
+    ys = e.run(ts)
+    assert np.array_equal(e.nacc, [r["n_accepted"] for r in g["rk23"]])
+    assert rel(ys[:, g["keep"]], [r["ys"] for r in g["rk23"]]) < 1e-9
+    e = EmulEnsemble("AdamsBashforth4", "vdp", y0, p, h=0.01)
+    ys = e.run(ts)
+    assert rel(ys[:, g["keep"]], [r["ys"] for r in g["ab4"]]) < 1e-12
+    assert np.array_equal(e.t, [r["t_end"] for r in g["ab4"]])
+
+
+def test_resumed_run_equals_single_run():
+    y0, p = onp.lorenz_ensemble(8, seed=7)
+    ts = np.linspace(0.5, 4, 8)
+    a = EmulEnsemble("RungeKutta45", "lorenz", y0, p, rtol=1e-6, atol=1e-9)
+    ya = a.run(ts)
+    b = EmulEnsemble("RungeKutta45", "lorenz", y0, p, rtol=1e-6, atol=1e-9)
+    yb1 = b.run(ts[:3])
+    yb2 = b.run(ts[3:])
+    assert np.array_equal(ya, np.concatenate([yb1, yb2], 1))
+    assert np.array_equal(a.nacc, b.nacc) and np.array_equal(a.t, b.t)
+    # points inside the stored last step are answered from history without stepping
+    c = EmulEnsemble("RungeKutta45", "lorenz", y0[:1], p[:1], rtol=1e-6, atol=1e-9)
+    c.run([1.0])
+    nacc, t_in = c.nacc.copy(), 0.5 * (c.ts[0, 0] + c.ts[1, 0])
+    yi = c.run([t_in, c.ts[1, 0]])
+    assert np.array_equal(c.nacc, nacc) and np.array_equal(yi[0, 1], c.y[0])
+    o = onp.AdaptiveRK("RungeKutta45", onp.rhs_lorenz, 0.0, y0[0], p[0], rtol=1e-6, atol=1e-9)
+    onp.run(o, [1.0])
+    assert rel(yi[0, 0], o.interpolate(t_in)) < 1e-10
+
+
+def test_step_semantics_match_oracle():
+    for method, mk in (
+        ("RungeKutta45", lambda: onp.AdaptiveRK("RungeKutta45", onp.rhs_vdp, 0.0, [2.0, 0.0], np.array([1.0]))),
+        ("AdamsBashforth3", lambda: onp.AdamsBashforth(3, onp.rhs_vdp, 0.0, [2.0, 0.0], np.array([1.0]), h=0.05, first_stepper=None)),
+    ):
+        kw = dict(h=0.05, first_stepper=0) if method.startswith("Adams") else {}
+        e = EmulEnsemble(method, "vdp", [[2.0, 0.0]], [[1.0]], **kw)
+        o = mk()
+        t_ref, y_ref = onp.steps(o, n=12)
+        t_out, y_out, cnt = e.step(12)
+        assert cnt[0] == 12 and rel(t_out[0], t_ref) < 1e-12 and rel(y_out[0], y_ref) < 1e-10
+        # upto_t: stops before the step that would cross the bound (proposed h)
+        bound = float(t_ref[-1]) + 0.4
+        t_ref2, y_ref2 = onp.steps(o, upto_t=bound)
+        t_out, y_out, cnt = e.step(64, bound=bound)
+        assert cnt[0] == len(t_ref2) and e.status[0] == 1
+        assert rel(t_out[0, : cnt[0]], t_ref2) < 1e-12
+        assert np.isnan(t_out[0, cnt[0]:]).all()
+        # skip == step without outputs
+        t_ref3, _ = onp.steps(o, n=5)
+        _, _, cnt = e.step(5, emit=False)
+        assert cnt[0] == 5 and rel(e.t[0], t_ref3[-1]) < 1e-12
+
+
+def test_t_bound_guard_prefix():
+    e = EmulEnsemble("AdamsBashforth2", "decay", [[1.0]], [[0.1]], h=0.1, first_stepper=0)
+    ys = e.run([0.5, 1.0, 1.5, 2.0], t_bound=1.25)
+    r = oc.run_ensemble("AdamsBashforth2", "decay", [[1.0]], [0.1], [0.5, 1.0, 1.5, 2.0], h=0.1, t_bound=1.25, first_stepper=None)
+    assert e.status[0] == 1 and e.nout[0] == 2 == r["n_out"][0]
+    assert rel(ys[0, :2], r["ys"][0, :2]) < 1e-14 and np.isnan(ys[0, 2:]).all()
+    assert e.t[0] == r["t_end"][0]
+
+
+def test_nonfinite_guard_terminates():
+    # blow-up: y' = -k y with k = -1e308 overflows immediately -> status NONFINITE, no hang
+    e = EmulEnsemble("RungeKutta45", "decay", [[1.0]], [[-1e308]], first_step=1.0)
+    e.run([10.0])
+    assert e.status[0] == 2
