@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of BASELINE.json: accepted RK45 steps/s on the Lorenz-63
+ensemble (configs[1]: 1M trajectories per GPU, random y0, sigma/rho/beta sweep, rtol=1e-6,
+atol=1e-9, t in [0, 10], FP64).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path over the ensemble: constructor kernel (f0 + initial
+step size) and the persistent RK45 kernel to t = 10.  Under torchrun every rank integrates its
+own 1M-trajectory ensemble (weak scaling, no data-path collective).
+
+Printed JSON line (rank 0): see the contract in the task statement; additionally
+  roofline     FP64 vector pipe: algorithmic FLOPs (264 per attempted step)
+               / run-kernel time, against the DFMA peak measured in this run (nbk_fp64_peak)
+  cpu_baseline the C oracle (oracle/nbk_oracle.c, a port of the reference's algorithm) on all
+               host cores over a bounded sample of the same ensemble
+  e2e          the same metric through the public API with pinned HOST buffers in and out
+`--impl reference` times the oracle port alone (the reference is pure Python + numba and
+cannot travel to the GPU box).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "numbakit-ode_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+B_PER_GPU = 1_000_000
+T_END = 10.0
+RTOL, ATOL = 1e-6, 1e-9
+FLOP_PER_ATTEMPT = 264  # 6R + 66n + 18 with R = 8, n = 3
+METRIC = "accepted RK45 steps/s, 1M-traj Lorenz FP64"
+UNIT = "accepted steps/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "Lorenz-63 ensemble, RungeKutta45 rtol=1e-6 atol=1e-9, t in [0,10], run([10.0])",
+        "trajectories_per_gpu": B_PER_GPU,
+        "trajectories_total": B_PER_GPU * n_gpus,
+        "parallelism": f"trajectory sharding x{n_gpus}, no collective",
+        "l2": "working set (inputs 48 MB + state 344 MB per GPU) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+# ----------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_sm = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_oracle_throughput(y0, p, budget_s=12.0, threads=None):
+    """C oracle (port of the reference algorithm) on all host cores over a bounded sample."""
+    from oracle import nbk_oracle_c as oc
+
+    threads = threads or os.cpu_count() or 1
+    probe = min(len(y0), 4096 * max(1, threads // 4))
+    t0 = time.perf_counter()
+    r = oc.run_ensemble("RungeKutta45", "lorenz", y0[:probe], p[:probe], [T_END], rtol=RTOL, atol=ATOL, nthreads=threads, dense=False)
+    dt = time.perf_counter() - t0
+    rate = r["n_accepted"].sum() / dt
+    n = int(min(len(y0), max(probe, budget_s * probe / max(dt, 1e-6))))
+    t0 = time.perf_counter()
+    r = oc.run_ensemble("RungeKutta45", "lorenz", y0[:n], p[:n], [T_END], rtol=RTOL, atol=ATOL, nthreads=threads, dense=False)
+    dt = time.perf_counter() - t0
+    return {
+        "value": float(r["n_accepted"].sum() / dt), "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": f"first {n} trajectories of the rank-0 ensemble, {dt:.2f} s wall, C oracle (oracle/nbk_oracle.c) with pthreads",
+        "probe_rate": float(rate),
+    }
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    from oracle import nbk_oracle_c as oc
+    from oracle import nbk_oracle_np as onp
+
+    threads = os.cpu_count() or 1
+    y0, p = onp.lorenz_ensemble(B_PER_GPU, seed=0)
+    # bounded sample per step: ~3 s of CPU work
+    probe = 8192
+    t0 = time.perf_counter()
+    oc.run_ensemble("RungeKutta45", "lorenz", y0[:probe], p[:probe], [T_END], rtol=RTOL, atol=ATOL, nthreads=threads, dense=False)
+    dt = time.perf_counter() - t0
+    n = int(min(B_PER_GPU, max(probe, 3.0 * probe / dt)))
+    total_steps, times = 0, []
+    for it in range(args.warmup + args.steps):
+        lo = (it * n) % max(1, B_PER_GPU - n)
+        t0 = time.perf_counter()
+        r = oc.run_ensemble("RungeKutta45", "lorenz", y0[lo:lo + n], p[lo:lo + n], [T_END], rtol=RTOL, atol=ATOL,
+                            nthreads=threads, dense=True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            total_steps += int(r["n_accepted"].sum())
+    value = total_steps / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {**workload_config(args.gpus), "sample_trajectories_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} trajectories per step, C oracle port of nbkode's RK45 path (pthreads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import nbkode_b200 as nbk
+    from oracle import nbk_oracle_np as onp  # input generator only (SURVEY.md 8(d) distribution)
+
+    B = args.batch
+    y0_np, p_np = onp.lorenz_ensemble(B, seed=rank)
+    # host inputs live in pinned memory (e2e arm); device-resident copies for the kernel-only arm
+    y0_host = torch.from_numpy(y0_np).pin_memory()
+    p_host = torch.from_numpy(p_np).pin_memory()
+    y0_dev, p_dev = y0_host.to(dev), p_host.to(dev)
+
+    def one_pass(y0, p):
+        s = nbk.RungeKutta45("lorenz", 0.0, y0, p, rtol=RTOL, atol=ATOL, device=local_rank)
+        return s, s.run([T_END])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    peak_tf, _ = nbk.fp64_peak(local_rank, 20000)
+
+    # ------------------------------------------------------------ kernel-only arm (inputs resident in HBM)
+    for _ in range(max(args.warmup, 3)):
+        s, (t, y) = one_pass(y0_dev, p_dev)
+    launch = s.last_launch()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    run_ev = []
+    steps_acc = torch.zeros((), dtype=torch.int64, device=dev)
+    attempts = torch.zeros((), dtype=torch.int64, device=dev)
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        s = nbk.RungeKutta45("lorenz", 0.0, y0_dev, p_dev, rtol=RTOL, atol=ATOL, device=local_rank)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t, y = s.run([T_END])
+        e1.record()
+        run_ev.append((e0, e1))
+        steps_acc += s._nacc.sum()
+        attempts += s._nacc.sum() + s._nrej.sum()
+    ev[1].record()
+    barrier()
+    clocks = sampler.finish()
+    ms_total = ev[0].elapsed_time(ev[1])
+    ms_run = sum(a.elapsed_time(b) for a, b in run_ev)
+    tm = torch.tensor([ms_total, ms_run], dtype=torch.float64, device=dev)
+    cnt = torch.stack([steps_acc, attempts]).to(torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total, ms_run = float(tm[0]), float(tm[1])
+    total_steps, total_attempts = float(cnt[0]), float(cnt[1])
+    value = total_steps / (ms_total * 1e-3)
+
+    # ------------------------------------------------------------ e2e arm (pinned host buffers in and out)
+    for _ in range(2):
+        s, (t, y) = one_pass(y0_host, p_host)
+        _ = s.n_accepted
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    for _ in range(args.steps):
+        s, (t, y) = one_pass(y0_host, p_host)
+        nacc = s.n_accepted  # pinned host tensor: the step's result (final states y + step counts)
+        e2e_steps += int(nacc.sum())
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_n = torch.tensor([float(e2e_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_n[0]) / float(e2e_t[0])
+    h2d = y0_host.numel() * 8 + p_host.numel() * 8
+    d2h = y.numel() * 8 + nacc.numel() * 8
+
+    if rank == 0:
+        achieved_tf = (total_attempts / world) * FLOP_PER_ATTEMPT / (ms_run * 1e-3) / 1e12  # per GPU
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {**workload_config(world), "trajectories_per_gpu": B},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": None,
+                "note": "FP64 vector (DFMA) pipe; achieved = attempted steps x 264 algorithmic FLOP / persistent-kernel time "
+                        "(CUDA events); peak = nbk_fp64_peak DFMA chain measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                "kernel": "nbk_run_rk45_lorenz", "kernel_ms_per_step": ms_run / args.steps,
+                "kernel_share_of_step": ms_run / ms_total, "attempts_per_step": total_attempts / world / args.steps,
+                "launch": launch,
+            },
+            "accepted_steps_per_pass": total_steps / world / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_oracle_throughput(y0_np, p_np)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,7 @@ class NbkConfig(C.Structure):
 
 class NbkState(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in
-                ("ts", "ys", "fs", "K", "h", "params", "n_accepted", "n_rejected", "status", "n_out")]
+                ("ts", "ys", "fs", "K", "h", "params", "n_accepted", "n_rejected", "status", "n_out", "work_counter")]
 
 
 class NbkError(RuntimeError):

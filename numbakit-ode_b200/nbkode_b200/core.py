@@ -185,10 +185,11 @@ class Solver(ABC):
         self._nrej = torch.empty((B,), dtype=torch.int64, device=dev)
         self._status = torch.empty((B,), dtype=torch.int32, device=dev)
         self._nout = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self._queue = torch.zeros((1,), dtype=torch.int64, device=dev)
         ptr = lambda x: x.data_ptr() if x is not None else None  # noqa: E731
         self._state = _lib.NbkState(
             ptr(self._ts), ptr(self._ys), ptr(self._fs), ptr(self._K), ptr(self._h), ptr(self._p),
-            ptr(self._nacc), ptr(self._nrej), ptr(self._status), ptr(self._nout),
+            ptr(self._nacc), ptr(self._nrej), ptr(self._status), ptr(self._nout), ptr(self._queue),
         )
 
         # ---- f0, initial step, multistep start-up: one kernel
@@ -236,9 +237,16 @@ class Solver(ABC):
         return torch.from_numpy(arr).to(self._device, non_blocking=True)
 
     def _out(self, x):
-        """Device tensor -> the caller's array type."""
+        """Device tensor -> the caller's array type (NumPy, or a torch tensor on the device the
+        inputs came from; host tensors are returned in pinned memory)."""
         if self._torch_out:
-            return x if self._out_device.type == "cuda" else x.to(self._out_device)
+            if self._out_device.type == "cuda":
+                return x
+            torch = _torch()
+            host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            host.copy_(x, non_blocking=True)
+            torch.cuda.current_stream(self._device).synchronize()
+            return host
         return x.detach().cpu().numpy()
 
     def _host(self, x):
