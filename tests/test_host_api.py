@@ -1,0 +1,205 @@
+"""Host-side tests (no GPU): registry (port of nbkode/testsuite/test_introspection.py and
+test_util.py for the explicit subset), the Python->CUDA tracer, the C-ABI library's exports,
+NVRTC compilation of user right-hand sides, and the loud failure without a device."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nbkode_b200 as nbkode
+from nbkode_b200 import _lib, rhs
+from nbkode_b200.util import CaseInsensitiveDict
+
+from conftest import ROOT
+
+N_SOLVERS = 8  # ForwardEuler, AdamsBashforth1..5, RungeKutta23, RungeKutta45 (the explicit hot path)
+
+
+# ------------------------------------------------------------------ registry
+def test_get_solvers():
+    assert len(nbkode.get_solvers()) == N_SOLVERS
+
+
+def test_get_solvers_groups():
+    assert len(nbkode.get_solvers("Euler")) == 1  # BackwardEuler is implicit: out of scope
+    assert len(nbkode.get_solvers("euler")) == 1
+    assert len(nbkode.get_solvers("adams-bashforth")) == 5
+    assert len(nbkode.get_solvers("Runge-Kutta")) == 2
+    assert nbkode.get_groups() == ("Adams-Bashforth", "Euler", "Runge-Kutta")
+    with pytest.raises(KeyError):
+        nbkode.get_solvers("not-a-group")
+
+
+def test_get_solvers_filters():
+    for solver in nbkode.get_solvers(implicit=False):
+        assert solver.IMPLICIT is False
+    assert nbkode.get_solvers(implicit=True) == ()
+    for solver in nbkode.get_solvers(fixed_step=True):
+        assert solver.FIXED_STEP is True
+    for solver in nbkode.get_solvers(fixed_step=False):
+        assert solver.FIXED_STEP is False
+    assert set(nbkode.get_solvers(fixed_step=False) + nbkode.get_solvers(fixed_step=True)) == set(nbkode.get_solvers())
+    assert set(nbkode.get_solvers(runge_kutta=True)) == {nbkode.RungeKutta23, nbkode.RungeKutta45}
+    assert len(nbkode.get_solvers(multistep=True)) == 6
+    # README.rst:63 -- with the corrected IMPLICIT flag the explicit fixed-step solvers are listed
+    assert nbkode.ForwardEuler in nbkode.get_solvers(implicit=False, fixed_step=True)
+
+
+def test_get_solver():
+    assert nbkode.get_solver("forwardeuler") is nbkode.get_solver("ForwardEuler")
+    assert nbkode.get_solver("euler") is nbkode.get_solver("ForwardEuler")
+    with pytest.raises(ValueError):
+        nbkode.get_solver("not_a_solver")
+
+
+def test_module_facade():
+    assert len(dir(nbkode)) == N_SOLVERS + 4
+    with pytest.warns(UserWarning):
+        sol = nbkode.__getattr__("euler")
+    assert sol is nbkode.get_solver("ForwardEuler")
+    with pytest.raises(AttributeError):
+        nbkode.not_a_solver
+    assert getattr(nbkode, "ForwardEuler") is nbkode.get_solver("ForwardEuler")
+    assert "Euler (alias of ForwardEuler)" in nbkode.list_solvers()
+
+
+def test_class_attributes_match_reference_tableaux():
+    from oracle import nbk_oracle_np as onp
+
+    for cls, tab in ((nbkode.RungeKutta23, onp.BS23), (nbkode.RungeKutta45, onp.DP45)):
+        for name in "ABCEP":
+            assert np.array_equal(getattr(cls, name), getattr(tab, name)), (cls.__name__, name)
+        assert cls.error_estimator_order == tab.q and cls.stages == len(tab.A) + 1
+        assert cls.LEN_HISTORY == 2 and cls.FIXED_STEP is False
+    for k in range(1, 6):
+        cls = getattr(nbkode, f"AdamsBashforth{k}")
+        assert np.array_equal(cls.B, onp.AB_B[k]) and cls.ORDER == k and cls.LEN_HISTORY == max(k, 2)
+        assert cls.A[-1] == -1 and np.count_nonzero(cls.A) == 1
+    assert nbkode.ForwardEuler.GROUP == "Euler" and nbkode.ForwardEuler.ALIASES == ("Euler",)
+
+
+# ------------------------------------------------------------------ CaseInsensitiveDict (test_util.py)
+def test_case_insensitive_dict():
+    cid = CaseInsensitiveDict({"Accept": "application/json"}, user="x")
+    assert cid["aCCEPT"] == "application/json" and "ACCEPT" in cid and list(cid) == ["Accept", "user"]
+    cid["ACCEPT"] = "text/plain"
+    assert len(cid) == 2 and list(cid) == ["ACCEPT", "user"] and cid.get("accept") == "text/plain"
+    assert cid == {"accept": "text/plain", "USER": "x"} and cid != {"accept": "other", "user": "x"}
+    del cid["accept"]
+    assert "Accept" not in cid and dict(cid.lower_items()) == {"user": "x"}
+    cp = cid.copy()
+    cp["z"] = 1
+    assert "z" not in cid and repr(cid) == "{'user': 'x'}"
+    with pytest.raises(KeyError):
+        cid["missing"]
+
+
+# ------------------------------------------------------------------ tracer
+def test_trace_arithmetic_and_ufuncs():
+    def f(t, y, p):
+        return np.array([p[0] * (y[1] - y[0]) + np.sin(t), -y[0] ** 2 / p[1], abs(y[2]) ** 0.5 + 2])
+
+    src = rhs.trace(f, 3, (2,), True).source
+    assert "nbk_rhs" in src and "sin(t)" in src and "fabs(" in src and "pow(" in src and src.count("dy[") == 3
+
+    def g(t, y):
+        return -0.5 * y
+
+    assert "dy[0]" in rhs.trace(g, 1, (), False).source
+
+    def mat(t, y, A):
+        return A @ y
+
+    src = rhs.trace(mat, 4, (4, 4), True).source
+    assert "p[15]" in src
+
+
+def test_trace_rejects_untraceable():
+    def branching(t, y):
+        return y if y[0] > 0 else -y
+
+    with pytest.raises(rhs.TraceError):
+        rhs.trace(branching, 1, (), False)
+
+    def wrong_size(t, y):
+        return np.array([y[0], y[0]])
+
+    with pytest.raises(rhs.TraceError):
+        rhs.trace(wrong_size, 1, (), False)
+    with pytest.raises(ValueError):
+        rhs.resolve("no_such_builtin", 1, (), False)
+    with pytest.raises(ValueError):
+        rhs.CudaRHS("void f() {}")
+
+
+# ------------------------------------------------------------------ C-ABI
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "nbkode_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nbk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = _declared_functions()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(_lib.EXPORTS)
+    assert lib.nbk_version() == 1
+
+
+def _cfg(method, n, npar, rhs_name=None, src=None, **kw):
+    return _lib.NbkConfig(method, n, npar, 0, 16, rhs_name, src, kw.get("rtol", 1e-6), kw.get("atol", 1e-9),
+                          kw.get("min_factor", 0.2), kw.get("max_factor", 10.0), 0.9, kw.get("first_stepper", 0), 0)
+
+
+def test_nvrtc_compiles_user_and_builtin_programs_for_sm100a():
+    lib = _lib.lib()
+    sz = C.c_longlong(0)
+
+    def f(t, y, p):
+        return np.array([y[1], p[0] * (1 - y[0] ** 2) * y[1] - y[0]])
+
+    src = rhs.trace(f, 2, (1,), True).source.encode()
+    for method in (45, 23, 4, 1):
+        _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(method, 2, 1, src=src)), C.byref(sz)))
+        assert sz.value > 10_000
+    _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 5, 5, rhs_name=b"decay")), C.byref(sz)))
+    with pytest.raises(_lib.CompileError) as ei:
+        _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 1, 0, src=b"NBK_RHS nbk_rhs(double t, const double* y, const double* p, double* dy) { dy[0] = undefined_symbol; }")), C.byref(sz)))
+    assert "undefined_symbol" in str(ei.value)
+    with pytest.raises(KeyError):
+        _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 3, 3, rhs_name=b"nonexistent")), C.byref(sz)))
+    with pytest.raises(ValueError):
+        _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(99, 3, 3, rhs_name=b"lorenz")), C.byref(sz)))
+    with pytest.raises(ValueError):
+        _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 3, 3, rhs_name=b"lorenz", rtol=-1.0)), C.byref(sz)))
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.NbkError):
+        nbkode.RungeKutta45("lorenz", 0.0, [1.0, 1.0, 1.0], [10.0, 28.0, 8 / 3])
+    handle = C.c_void_p()
+    rc = _lib.lib().nbk_create(C.byref(_cfg(45, 3, 3, rhs_name=b"lorenz")), C.byref(handle))
+    assert rc == _lib.NBK_ECUDA and not handle.value
+    with pytest.raises(_lib.NbkError):
+        nbkode.fp64_peak(0, 10)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "numbakit-ode_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "build.py", os.path.join(dirpath, f)
