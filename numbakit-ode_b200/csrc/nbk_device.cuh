@@ -39,14 +39,24 @@
 #endif
 #ifdef NBK_HOST_EMUL
 #define NBK_LOG2F(x) log2f(x)
+#define NBK_EXP2F(x) exp2f(x)
 #else
-#define NBK_LOG2F(x) __log2f(x)
+// single MUFU.LG2 / MUFU.EX2 (the argument is a normal float well inside the range)
+static __device__ __forceinline__ float nbk_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+static __device__ __forceinline__ float nbk_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#define NBK_LOG2F(x) nbk_lg2(x)
+#define NBK_EXP2F(x) nbk_ex2(x)
 #endif
 #ifndef NBK_FULL_MASK
 #define NBK_FULL_MASK 0xffffffffu  // tests/emul compiles the kernels for the host as 1-lane warps
 #endif
 
 namespace nbk {
+
+// max/min as one DSETP + selects.  fmax()/fmin() cost ~7 instructions each for their NaN rules;
+// every caller below tests finiteness separately, so a NaN may fall through either way.
+NBK_DEV double dmax(double a, double b) { return a > b ? a : b; }
+NBK_DEV double dmin(double a, double b) { return a < b ? a : b; }
 
 NBK_DEV double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 NBK_DEV double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -57,8 +67,11 @@ NBK_DEV bool d_finite(double x) { return fabs(x) < d_inf(); }
 // constant-bank operand and zero entries cost nothing.
 // =====================================================================================
 
+struct cbank_rk23;
+struct cbank_rk45;
 struct tab_rk23 {  // Bogacki-Shampine 3(2), nbkode/runge_kutta/explicit.py:146-151
     static constexpr int S = 3, Q = 2, M = 3, ROOT = 6, ID = 23;
+    static __device__ __forceinline__ const cbank_rk23 &cb();
     static NBK_HD double a(int i, int j) {
         constexpr double A[3][3] = {{0, 0, 0}, {1.0 / 2, 0, 0}, {0, 3.0 / 4, 0}};
         return A[i][j];
@@ -83,6 +96,7 @@ struct tab_rk23 {  // Bogacki-Shampine 3(2), nbkode/runge_kutta/explicit.py:146-
 
 struct tab_rk45 {  // Dormand-Prince 5(4), nbkode/runge_kutta/explicit.py:185-239
     static constexpr int S = 6, Q = 4, M = 4, ROOT = 10, ID = 45;
+    static __device__ __forceinline__ const cbank_rk45 &cb();
     static NBK_HD double a(int i, int j) {
         constexpr double A[6][6] = {
             {0, 0, 0, 0, 0, 0},
@@ -117,6 +131,39 @@ struct tab_rk45 {  // Dormand-Prince 5(4), nbkode/runge_kutta/explicit.py:185-23
         return Pv[j][k];
     }
 };
+
+// Constant-bank copies of the same numbers.  The constexpr accessors above decide at compile
+// time WHICH terms exist (zero entries are skipped); the values themselves are read as
+// c[bank][offset] operands of the DFMA/DMUL, which costs no instruction -- an immediate
+// double would need two UMOVs each (measured: 61 UMOVs per RK45 attempt, profiles/r01).
+struct cbank_rk23 { double a[3][3], b[3], c[3], e[4], p[4][3]; };
+struct cbank_rk45 { double a[6][6], b[6], c[6], e[7], p[7][4]; };
+static __constant__ cbank_rk23 nbk_c23 = {
+    {{0, 0, 0}, {1.0 / 2, 0, 0}, {0, 3.0 / 4, 0}},
+    {2.0 / 9, 1.0 / 3, 4.0 / 9},
+    {0, 1.0 / 2, 3.0 / 4},
+    {2.0 / 9 - 7.0 / 24, 1.0 / 3 - 1.0 / 4, 4.0 / 9 - 1.0 / 3, -1.0 / 8},
+    {{1, -4.0 / 3, 5.0 / 9}, {0, 1, -2.0 / 3}, {0, 4.0 / 3, -8.0 / 9}, {0, -1, 1}}};
+static __constant__ cbank_rk45 nbk_c45 = {
+    {{0, 0, 0, 0, 0, 0},
+     {1.0 / 5, 0, 0, 0, 0, 0},
+     {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+     {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+     {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+     {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0}},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84},
+    {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1},
+    {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40},
+    {{1, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
+     {0, 0, 0, 0},
+     {0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
+     {0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
+     {0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
+     {0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
+     {0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}}};
+
+__device__ __forceinline__ const cbank_rk23 &tab_rk23::cb() { return nbk_c23; }
+__device__ __forceinline__ const cbank_rk45 &tab_rk45::cb() { return nbk_c45; }
 
 // Adams-Bashforth weights exactly as the reference lists them; index 0 multiplies the OLDEST
 // derivative of the window (nbkode/multistep/core.py:101,109).
@@ -220,7 +267,7 @@ NBK_DEV double fast_rcp(double x) {
 template <int R>
 NBK_DEV double inv_root(double x) {  // x in [1e-30, 1e30]
     const float xf = (float)x;
-    double y = (double)exp2f(NBK_LOG2F(xf) * (-1.0f / R));
+    double y = (double)NBK_EXP2F(NBK_LOG2F(xf) * (-1.0f / R));
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         double y2 = y * y, yr;
@@ -273,13 +320,13 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 #pragma unroll
             for (int j = 0; j < s; ++j) {
                 if (Tab::a(s, j) != 0.0) {
-                    acc = first ? Tab::a(s, j) * K[j][i] : fma(Tab::a(s, j), K[j][i], acc);
+                    acc = first ? Tab::cb().a[s][j] * K[j][i] : fma(Tab::cb().a[s][j], K[j][i], acc);
                     first = false;
                 }
             }
             ys[i] = fma(h, acc, y[i]);
         }
-        Rhs::eval(fma(h, Tab::c(s), t), ys, p, K[s]);
+        Rhs::eval(fma(h, Tab::cb().c[s], t), ys, p, K[s]);
     }
     // y_new = y + (h*B) . K[:S]   (the vector h*B is formed first, as the reference does)
 #pragma unroll
@@ -287,7 +334,7 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
         double acc = y[i];
 #pragma unroll
         for (int j = 0; j < S; ++j)
-            if (Tab::b(j) != 0.0) acc = fma(h * Tab::b(j), K[j][i], acc);
+            if (Tab::b(j) != 0.0) acc = fma(h * Tab::cb().b[j], K[j][i], acc);
         ynew[i] = acc;
     }
     Rhs::eval(t + h, ynew, p, K[S]);
@@ -299,12 +346,12 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 #pragma unroll
         for (int j = 0; j <= S; ++j) {
             if (Tab::e(j) != 0.0) {
-                e = first ? Tab::e(j) * K[j][i] : fma(Tab::e(j), K[j][i], e);
+                e = first ? Tab::cb().e[j] * K[j][i] : fma(Tab::cb().e[j], K[j][i], e);
                 first = false;
             }
         }
         e *= h;
-        const double sc = fma(rtol, fmax(fabs(ynew[i]), fabs(y[i])), atol);
+        const double sc = fma(rtol, dmax(fabs(ynew[i]), fabs(y[i])), atol);
         const double r = e * fast_rcp(sc);
         acc2 = fma(r, r, acc2);
     }
@@ -319,9 +366,9 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 template <class Tab>
 NBK_DEV double step_factor(double err2, double safety, double min_factor, double max_factor, double x_lo,
                            double x_hi) {
-    const double xc = fmin(fmax(err2, x_lo), x_hi);
+    const double xc = dmin(dmax(err2, x_lo), x_hi);
     const double f = safety * inv_root<Tab::ROOT>(xc);
-    return fmin(max_factor, fmax(min_factor, f));
+    return dmin(max_factor, dmax(min_factor, f));
 }
 
 // Dense output inside the last accepted step [t_old, t_new] (RkInterpolator.evaluate).
@@ -348,7 +395,7 @@ NBK_DEV void rk_dense(double te, double t_old, double t_new, const double (&y_ol
             double q = 0.0;
 #pragma unroll
             for (int j = 0; j <= Tab::S; ++j)
-                if (Tab::p(j, k) != 0.0) q = fma(K[j][i], Tab::p(j, k), q);
+                if (Tab::p(j, k) != 0.0) q = fma(K[j][i], Tab::cb().p[j][k], q);
             acc = fma(q, pw, acc);
             pw *= x;
         }

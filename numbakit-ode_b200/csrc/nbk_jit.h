@@ -31,5 +31,7 @@ void nbk_jit_unload(nbk_jit_module &mod);
 bool nbk_jit_launch(void *func, unsigned grid, unsigned block, void *arg_block, void *stream, std::string &err);
 // cuOccupancyMaxActiveBlocksPerMultiprocessor / register count of a CUfunction.
 bool nbk_jit_occupancy(void *func, int block, int *blocks_per_sm, int *regs, std::string &err);
+// block size the kernel was compiled for (__launch_bounds__ -> CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK)
+bool nbk_jit_block_size(void *func, int *block, std::string &err);
 
 #endif

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnbkode_b200.so")
+LIB_PATH = os.environ.get("NBK_LIB_PATH") or os.path.join(HERE, "libnbkode_b200.so")
 
 NBK_OK, NBK_EINVAL, NBK_ECUDA, NBK_ECOMPILE, NBK_ENOTFOUND = 0, -1, -2, -3, -4
 TRAJ_OK, TRAJ_BOUND, TRAJ_NONFINITE, TRAJ_MAXATTEMPTS = 0, 1, 2, 3

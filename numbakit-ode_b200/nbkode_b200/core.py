@@ -211,7 +211,6 @@ class Solver(ABC):
                 h_scalar, ptr(h_vec), self._stream(),
             ))
         self._keepalive = (y0_t, p_t, h_vec)
-        self.cache = _Cache(self)
         if self.FIXED_STEP:
             # like the reference, a fixed-step solver keeps the user's value (or the integer 1)
             self.h = np.array(h, dtype=float) if h is not None and np.ndim(h) == 0 else (1 if h is None else h)
@@ -265,6 +264,12 @@ class Solver(ABC):
             raise ValueError(f"Time {t} is larger than solver bound time t_bound={self.t_bound}")
 
     # ------------------------------------------------------------------ state
+    @property
+    def cache(self):
+        # built on demand: a stored view would form a reference cycle and keep the ensemble's HBM
+        # alive until the cyclic garbage collector runs
+        return _Cache(self)
+
     @property
     def t(self):
         cur = self._ts[-1]

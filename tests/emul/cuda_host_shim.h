@@ -13,6 +13,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __global__
+#define __constant__
 #define __grid_constant__
 #define __launch_bounds__(...)
 

@@ -38,3 +38,12 @@ for _ in range(3):
     t0 = tick("torch.zeros", t0)
     del a, b, z
 print("fp64 peak", nbk.fp64_peak(0, 20000))
+import cProfile, pstats
+pr = cProfile.Profile()
+sync()
+pr.enable()
+for _ in range(5):
+    s = nbk.RungeKutta45("lorenz", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
+    sync()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
