@@ -60,7 +60,9 @@ NBK_DEV double dmin(double a, double b) { return a < b ? a : b; }
 
 NBK_DEV double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 NBK_DEV double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
-NBK_DEV bool d_finite(double x) { return fabs(x) < d_inf(); }
+// inf/NaN and "h <= 0 or denormal" tests on the integer pipe (the FP64 pipe is the busy one)
+NBK_DEV bool d_nonfinite(double x) { return (__double2hiint(x) & 0x7ff00000) == 0x7ff00000; }
+NBK_DEV bool d_collapsed(double h) { return __double2hiint(h) < 0x00100000; }
 
 // =====================================================================================
 // Tableaux.  constexpr accessors: after unrolling every coefficient is an immediate /
@@ -245,47 +247,51 @@ struct rhs_user {
 // Arithmetic helpers
 // =====================================================================================
 
-// 1/x for positive normal x: MUFU seed + two Newton steps (4 DFMA) instead of the ~12
-// instruction IEEE division sequence.  Error <= ~1 ulp (the result is not correctly rounded).
+// 1/x for positive normal x: MUFU.RCP64H seed (relative error e <= 2^-23) and ONE third-order
+// step r (1 + e + e^2), whose truncation error e^3 <= 2^-69 is below double rounding: three
+// dependent DFMA instead of the ~12 instruction IEEE division sequence (result within ~1 ulp,
+// not correctly rounded).
 NBK_DEV double fast_rcp(double x) {
     double r;
 #ifdef NBK_HOST_EMUL
-    r = (double)(float)(1.0 / x);  // stands in for the ~2^-23 MUFU seed
+    r = (double)(float)(1.0 / x);  // stands in for the MUFU seed
 #else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    const double q = fma(e, e, e);
+    return fma(r, q, r);
 }
 
-// x^(-1/R) for x within float range: single-precision seed (ex2/lg2 MUFU) polished by two FP64
-// Newton steps on g(y) = y^-R - x, i.e. y <- y + y (1 - x y^R) / R (quadratic convergence:
-// 1e-6 -> 5e-12 -> 1e-22), so the step-size factor is FP64-accurate to ~2 ulp.
+// x^(-1/R) for a positive normal x inside float range ([1e-30, 1e30], guaranteed by the clamp in
+// step_factor).  Seed: the top bits of x reinterpreted as a float (integer ops, no F2F), then
+// lg2/ex2 MUFU: relative error eps ~ 2e-7.  Polish: ONE third-order step on g(y) = y^-R - x,
+//   r = 1 - x y^R,   y <- y (1 + r/R + (R+1) r^2 / (2 R^2)),
+// i.e. the Taylor series of (1-r)^(-1/R); with |r| ~ R eps ~ 2e-6 the dropped r^3 term is ~3e-19,
+// so the step-size factor is accurate to double rounding (a few ulp).
 template <int R>
-NBK_DEV double inv_root(double x) {  // x in [1e-30, 1e30]
-    const float xf = (float)x;
-    double y = (double)NBK_EXP2F(NBK_LOG2F(xf) * (-1.0f / R));
+NBK_DEV double inv_root(double x) {
+    const int hi = __double2hiint(x);
+    const unsigned lo = (unsigned)__double2loint(x);
+    const float xf = __int_as_float(((hi - 0x38000000) << 3) | (int)(lo >> 29));
+    const int sb = __float_as_int(NBK_EXP2F(NBK_LOG2F(xf) * (-1.0f / R)));
+    const double y = __hiloint2double((sb >> 3) + 0x38000000, sb << 29);
+    const double y2 = y * y;
+    double yr;
+    if (R == 10) {
+        const double y4 = y2 * y2, y8 = y4 * y4;
+        yr = y8 * y2;
+    } else if (R == 6) {
+        const double y4 = y2 * y2;
+        yr = y4 * y2;
+    } else {
+        yr = 1.0;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        double y2 = y * y, yr;
-        if (R == 10) {
-            const double y4 = y2 * y2, y8 = y4 * y4;
-            yr = y8 * y2;
-        } else if (R == 6) {
-            const double y4 = y2 * y2;
-            yr = y4 * y2;
-        } else {
-            yr = 1.0;
-#pragma unroll
-            for (int k = 0; k < R; ++k) yr *= y;
-        }
-        const double r = fma(-x, yr, 1.0);
-        y = fma(y * (1.0 / R), r, y);
+        for (int k = 0; k < R; ++k) yr *= y;
     }
-    return y;
+    const double r = fma(-x, yr, 1.0);
+    const double q = fma(r, (R + 1.0) / (2.0 * R * R), 1.0 / R) * r;
+    return fma(y, q, y);
 }
 
 // rms(x / scale) of scipy.integrate._ivp.common.norm (cold path: IEEE division and sqrt)
@@ -599,7 +605,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 }
                 // guards the reference does not have (it would spin forever): non-finite error
                 // norm, collapsed step size, attempt budget.
-                if (!(err2 < d_inf()) || !(h > 0.0)) {
+                if (d_nonfinite(err2) || d_collapsed(h)) {
                     status = NBK_TRAJ_NONFINITE;
                     done = true;
                 } else if (!done && (long long)nacc + nrej >= a.max_attempts) {
@@ -840,7 +846,7 @@ NBK_DEV bool rk_startup_points(double t0, const double (&y0)[Rhs::N], const doub
                 }
             }
             fresh = accept;
-            if (!(err2 < d_inf()) || !(h > 0.0) || --budget < 0) return false;
+            if (d_nonfinite(err2) || d_collapsed(h) || --budget < 0) return false;
         }
         double out[N];
         rk_dense<Tab, N>(ti, t_old, t, y_old, y, K, out);
