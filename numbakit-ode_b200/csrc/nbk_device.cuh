@@ -58,6 +58,16 @@ namespace nbk {
 NBK_DEV double dmax(double a, double b) { return a > b ? a : b; }
 NBK_DEV double dmin(double a, double b) { return a < b ? a : b; }
 
+// The same for operands known to be non-negative: IEEE doubles >= 0 order like their bit patterns,
+// so the comparison runs on the integer pipe and leaves the FP64 pipe (the bottleneck) alone.
+NBK_DEV bool pos_less(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
+NBK_DEV double pos_max(double a, double b) { return pos_less(a, b) ? b : a; }
+NBK_DEV double pos_min(double a, double b) { return pos_less(a, b) ? a : b; }
+NBK_DEV double abs_max(double a, double b) {
+    const long long ia = __double_as_longlong(a) & 0x7fffffffffffffffLL, ib = __double_as_longlong(b) & 0x7fffffffffffffffLL;
+    return __longlong_as_double(ia < ib ? ib : ia);
+}
+
 NBK_DEV double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 NBK_DEV double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 // inf/NaN and "h <= 0 or denormal" tests on the integer pipe (the FP64 pipe is the busy one)
@@ -334,14 +344,20 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
         }
         Rhs::eval(fma(h, Tab::cb().c[s], t), ys, p, K[s]);
     }
-    // y_new = y + (h*B) . K[:S]   (the vector h*B is formed first, as the reference does)
+    // y_new = y + h (B . K[:S]).  (The reference forms the vector h*B first; the difference is one
+    // rounding, far inside the parity bars, and saves the S scalar multiplies.)
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        double acc = y[i];
+        double acc = 0.0;
+        bool first = true;
 #pragma unroll
-        for (int j = 0; j < S; ++j)
-            if (Tab::b(j) != 0.0) acc = fma(h * Tab::cb().b[j], K[j][i], acc);
-        ynew[i] = acc;
+        for (int j = 0; j < S; ++j) {
+            if (Tab::b(j) != 0.0) {
+                acc = first ? Tab::cb().b[j] * K[j][i] : fma(Tab::cb().b[j], K[j][i], acc);
+                first = false;
+            }
+        }
+        ynew[i] = fma(h, acc, y[i]);
     }
     Rhs::eval(t + h, ynew, p, K[S]);
     double acc2 = 0.0;
@@ -356,12 +372,11 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
                 first = false;
             }
         }
-        e *= h;
-        const double sc = fma(rtol, dmax(fabs(ynew[i]), fabs(y[i])), atol);
+        const double sc = fma(rtol, abs_max(ynew[i], y[i]), atol);
         const double r = e * fast_rcp(sc);
         acc2 = fma(r, r, acc2);
     }
-    err2 = acc2 * (1.0 / N);
+    err2 = acc2 * (h * h * (1.0 / N));  // h factored out of the N components
 }
 
 // I-controller of the reference: h *= clip(safety * norm^(-1/(q+1)), min_factor, max_factor)
@@ -372,9 +387,9 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 template <class Tab>
 NBK_DEV double step_factor(double err2, double safety, double min_factor, double max_factor, double x_lo,
                            double x_hi) {
-    const double xc = dmin(dmax(err2, x_lo), x_hi);
+    const double xc = pos_min(pos_max(err2, x_lo), x_hi);  // err2 >= 0 (or NaN, caught by the caller)
     const double f = safety * inv_root<Tab::ROOT>(xc);
-    return dmin(max_factor, dmax(min_factor, f));
+    return pos_min(max_factor, pos_max(min_factor, f));
 }
 
 // Dense output inside the last accepted step [t_old, t_new] (RkInterpolator.evaluate).
@@ -567,7 +582,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 }
                 double ynew[N], err2;
                 rk_attempt<Tab, Rhs>(t, h, y, K, p, ynew, err2, rtol, atol);
-                const bool accept = err2 < 1.0;
+                const bool accept = pos_less(err2, 1.0);  // NaN's bit pattern is 'large': rejected
                 const double t_new = t + h;
                 h *= step_factor<Tab>(err2, safety, min_factor, max_factor, a.x_lo, a.x_hi);
                 t_old = accept ? t : t_old;
@@ -833,7 +848,7 @@ NBK_DEV bool rk_startup_points(double t0, const double (&y0)[Rhs::N], const doub
             }
             double ynew[N], err2;
             rk_attempt<Tab, Rhs>(t, h, y, K, p, ynew, err2, rtol, atol);
-            const bool accept = err2 < 1.0;
+            const bool accept = pos_less(err2, 1.0);
             const double t_new = t + h;
             h *= step_factor<Tab>(err2, 0.9, 0.2, 10.0, 1e-13, 1e8);
             if (accept) {

@@ -25,6 +25,7 @@ static inline int __double2loint(double d) { long long v; std::memcpy(&v, &d, 8)
 static inline double __hiloint2double(int hi, int lo) { unsigned long long v = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double d; std::memcpy(&d, &v, 8); return d; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
