@@ -506,8 +506,13 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     for (int c = 0; c < N; ++c) a.K[((long long)s * N + c) * B + idx] = K[s][c];
             }
             a.h[idx] = h;
-            a.n_acc[idx] += nacc;
-            a.n_rej[idx] += nrej;
+            if (a.pristine) {
+                a.n_acc[idx] = nacc;
+                a.n_rej[idx] = nrej;
+            } else {
+                a.n_acc[idx] += nacc;
+                a.n_rej[idx] += nrej;
+            }
             a.status[idx] = status;
             a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nacc;
             finishing = false;
@@ -528,18 +533,28 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
                 if (!running && mine < B) {
                     idx = mine;
-                    t_old = a.ts[idx];
                     t = a.ts[B + idx];
                     h = a.h[idx];
 #pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        y_old[c] = a.ys[(long long)c * B + idx];
-                        y[c] = a.ys[(long long)(N + c) * B + idx];
+                    for (int c = 0; c < N; ++c) y[c] = a.ys[(long long)(N + c) * B + idx];
+                    if (a.pristine) {
+                        // fresh from the init kernel: both history slots hold (t0, y0), K is zero
+                        t_old = t;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) y_old[c] = y[c];
+#pragma unroll
+                        for (int s = 0; s <= S; ++s)
+#pragma unroll
+                            for (int c = 0; c < N; ++c) K[s][c] = 0.0;
+                    } else {
+                        t_old = a.ts[idx];
+#pragma unroll
+                        for (int c = 0; c < N; ++c) y_old[c] = a.ys[(long long)c * B + idx];
+#pragma unroll
+                        for (int s = 0; s <= S; ++s)
+#pragma unroll
+                            for (int c = 0; c < N; ++c) K[s][c] = a.K[((long long)s * N + c) * B + idx];
                     }
-#pragma unroll
-                    for (int s = 0; s <= S; ++s)
-#pragma unroll
-                        for (int c = 0; c < N; ++c) K[s][c] = a.K[((long long)s * N + c) * B + idx];
                     load_params<NP>(a, idx, p);
                     nacc = nrej = 0;
                     kout = 0;

@@ -28,6 +28,8 @@ struct nbk_kargs {
     int *status;          // [B] NBK_TRAJ_*
     int params_shared;
     int first_stepper;    // multistep start-up: 0 none, 23/45 adaptive RK, 1..5 Adams-Bashforth-k
+    int pristine;         // the state is exactly what the init kernel wrote (no step taken yet):
+                          // the advance kernel then skips loading the K rows / old history slot
     // ---- init inputs (user layout: element (b, c) at base[b*sb + c*sc])
     const double *y0;
     long long y0_sb, y0_sc;

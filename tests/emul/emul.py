@@ -129,6 +129,7 @@ class EmulEnsemble:
         a.t0, a.h_init = t0, (math.nan if hh is None else hh)
         self._keep = (y0, params)
         self.fn(0, C.byref(a), B)
+        self._pristine = True  # mirrors nbk_api.cu: the first advance after init may skip loading K / old history
 
     def run(self, ts, t_bound=math.inf):
         ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
@@ -136,6 +137,7 @@ class EmulEnsemble:
         out = np.full((self.B, m, self.n), np.nan)
         a = KArgs(**self.base)
         a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
+        a.pristine, self._pristine = int(self._pristine), False
         a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
         self.counter[0] = 0
         self.fn(1, C.byref(a), self.B)
@@ -146,6 +148,7 @@ class EmulEnsemble:
         y_out = np.full((self.B, max(n_steps, 1), self.n), np.nan)
         a = KArgs(**self.base)
         a.bound, a.n_steps, a.emit = bound, n_steps, int(emit)
+        a.pristine, self._pristine = int(self._pristine), False
         a.t_out, a.to_sb = t_out.ctypes.data, max(n_steps, 1)
         a.y_out, a.o_sb, a.o_sk, a.o_sc = y_out.ctypes.data, max(n_steps, 1) * self.n, self.n, 1
         self.counter[0] = 0
