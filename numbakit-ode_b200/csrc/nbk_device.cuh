@@ -37,6 +37,9 @@
 #ifndef NBK_BLOCK
 #define NBK_BLOCK 128
 #endif
+#ifndef NBK_INNER
+#define NBK_INNER 4  // attempts between two looks at the trajectory queue
+#endif
 #ifdef NBK_HOST_EMUL
 #define NBK_LOG2F(x) log2f(x)
 #define NBK_EXP2F(x) exp2f(x)
@@ -476,12 +479,16 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     const double rtol = a.rtol, atol = a.atol;
     const double safety = a.safety, min_factor = a.min_factor, max_factor = a.max_factor;
     const double bound = a.bound;
+    const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
 
+    // Loop-carried per-lane state: t, h, y, K (K[0] = f at the start of the step, K[S] = f at its
+    // end) and the parameters.  The OLD end of the last accepted step (history slot 0) is not
+    // carried: it is written to HBM at the moment a trajectory finishes, when it is still live.
     long long idx = -1;
     bool running = false, finishing = false, queue_empty = false;
-    double t = 0, h = 0, t_old = 0, te_next = 0;
-    double y[N], y_old[N], K[S + 1][N], p[NPX];
-    int nacc = 0, nrej = 0;  // of this call
+    double t = 0, h = 0, te_next = 0;
+    double y[N], K[S + 1][N], p[NPX];
+    int nacc = 0, natt = 0;  // accepted steps / attempts of this call
     int kout = 0;            // RUN: next grid index
     bool fresh = true;       // the next attempt opens a new step (K[S] holds f(t, y))
     int status = NBK_TRAJ_OK;
@@ -491,11 +498,9 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
         if (finishing) {
             if (nacc > 0) {
                 const bool clean = status == NBK_TRAJ_OK || status == NBK_TRAJ_BOUND;
-                a.ts[idx] = t_old;
                 a.ts[B + idx] = t;
 #pragma unroll
                 for (int c = 0; c < N; ++c) {
-                    a.ys[(long long)c * B + idx] = y_old[c];
                     a.ys[(long long)(N + c) * B + idx] = y[c];
                     a.fs[(long long)c * B + idx] = K[0][c];
                     a.fs[(long long)(N + c) * B + idx] = clean ? K[S][c] : K[0][c];
@@ -508,10 +513,10 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
             a.h[idx] = h;
             if (a.pristine) {
                 a.n_acc[idx] = nacc;
-                a.n_rej[idx] = nrej;
+                a.n_rej[idx] = natt - nacc;
             } else {
                 a.n_acc[idx] += nacc;
-                a.n_rej[idx] += nrej;
+                a.n_rej[idx] += natt - nacc;
             }
             a.status[idx] = status;
             a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nacc;
@@ -537,11 +542,11 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     h = a.h[idx];
 #pragma unroll
                     for (int c = 0; c < N; ++c) y[c] = a.ys[(long long)(N + c) * B + idx];
+                    double t_old = t, y_old[N];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) y_old[c] = y[c];
                     if (a.pristine) {
                         // fresh from the init kernel: both history slots hold (t0, y0), K is zero
-                        t_old = t;
-#pragma unroll
-                        for (int c = 0; c < N; ++c) y_old[c] = y[c];
 #pragma unroll
                         for (int s = 0; s <= S; ++s)
 #pragma unroll
@@ -556,7 +561,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                             for (int c = 0; c < N; ++c) K[s][c] = a.K[((long long)s * N + c) * B + idx];
                     }
                     load_params<NP>(a, idx, p);
-                    nacc = nrej = 0;
+                    nacc = natt = 0;
                     kout = 0;
                     fresh = true;
                     status = NBK_TRAJ_OK;
@@ -579,58 +584,55 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     // f(t, y) of the stored state becomes K[0] of the first attempt
 #pragma unroll
                     for (int c = 0; c < N; ++c) K[S][c] = a.fs[(long long)(N + c) * B + idx];
+                    // t_bound / upto_t guard of the first step (core.py:176-184); later steps are
+                    // guarded right after the step before them is accepted
+                    if (running && (t + h > bound)) {
+                        status = NBK_TRAJ_BOUND;
+                        running = false;
+                    }
                     finishing = !running;
                 }
             }
         }
-        // ---------------------------------------------------------------- (3) one attempt
-        if (running) {
-            if (fresh && (t + h > bound)) {
-                // t_bound / upto_t guard: tested once per step with the proposed h (core.py:176-184)
-                status = NBK_TRAJ_BOUND;
-                running = false;
-                finishing = true;
-            } else {
+        // ---------------------------------------------------------------- (3) attempts
+        // NBK_INNER attempts per queue check: a finished lane waits at most NBK_INNER-1 attempts
+        // (of ~500 per trajectory) and the vote/branch overhead is paid once per NBK_INNER.
+#pragma unroll 1
+        for (int rep = 0; rep < NBK_INNER; ++rep) {
+            if (running) {
                 if (fresh) {  // FSAL: last stage of the accepted step opens the next one
 #pragma unroll
                     for (int c = 0; c < N; ++c) K[0][c] = K[S][c];
                 }
                 double ynew[N], err2;
                 rk_attempt<Tab, Rhs>(t, h, y, K, p, ynew, err2, rtol, atol);
-                const bool accept = pos_less(err2, 1.0);  // NaN's bit pattern is 'large': rejected
+                // err2 >= 0 or NaN: err2 < 1  <=>  high word below that of 1.0 (unsigned: a NaN with the
+                // sign bit set must not pass)
+                const bool accept = (unsigned)__double2hiint(err2) < 0x3ff00000u;
                 const double t_new = t + h;
                 h *= step_factor<Tab>(err2, safety, min_factor, max_factor, a.x_lo, a.x_hi);
-                t_old = accept ? t : t_old;
-                t = accept ? t_new : t;
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    y_old[c] = accept ? y[c] : y_old[c];
-                    y[c] = accept ? ynew[c] : y[c];
-                }
-                nacc += accept ? 1 : 0;
-                nrej += accept ? 0 : 1;
-                fresh = accept;
+                ++natt;
                 bool done = false;
-                if (MODE == NBK_MODE_RUN) {
-                    if (accept && t >= te_next) {
-                        do {
-                            double out[N];
-                            rk_dense<Tab, N>(te_next, t_old, t, y_old, y, K, out);
+                if (accept) {
+                    if (MODE == NBK_MODE_RUN) {
+                        if (t_new >= te_next) {
+                            do {
+                                double out[N];
+                                rk_dense<Tab, N>(te_next, t, t_new, y, ynew, K, out);
 #pragma unroll
-                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
-                            ++kout;
-                            te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
-                        } while (t >= te_next);
-                        done = kout >= a.m;
-                    }
-                } else {
-                    if (accept) {
-                        if (a.emit) {
-                            a.t_out[idx * a.to_sb + (nacc - 1)] = t;
-#pragma unroll
-                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + (nacc - 1) * a.o_sk + c * a.o_sc] = y[c];
+                                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                                ++kout;
+                                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                            } while (t_new >= te_next);
+                            done = kout >= a.m;
                         }
-                        done = nacc >= a.n_steps;
+                    } else {
+                        if (a.emit) {
+                            a.t_out[idx * a.to_sb + nacc] = t_new;
+#pragma unroll
+                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + nacc * a.o_sk + c * a.o_sc] = ynew[c];
+                        }
+                        done = nacc + 1 >= a.n_steps;
                     }
                 }
                 // guards the reference does not have (it would spin forever): non-finite error
@@ -638,14 +640,31 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 if (d_nonfinite(err2) || d_collapsed(h)) {
                     status = NBK_TRAJ_NONFINITE;
                     done = true;
-                } else if (!done && (long long)nacc + nrej >= a.max_attempts) {
+                } else if (!done && natt >= max_att) {
                     status = NBK_TRAJ_MAXATTEMPTS;
                     done = true;
                 }
+                // t_bound / upto_t guard of the NEXT step, with the proposed h (core.py:176-184)
+                if (accept && !done && (t_new + h > bound)) {
+                    status = NBK_TRAJ_BOUND;
+                    done = true;
+                }
                 if (done) {
+                    // history slot 0 = start of the last accepted step.  After an accepted attempt that is
+                    // the pre-commit (t, y); after an abnormal stop on a rejected attempt the window
+                    // degenerates to the current point.
+                    a.ts[idx] = t;
+#pragma unroll
+                    for (int c = 0; c < N; ++c) a.ys[(long long)c * B + idx] = y[c];
                     running = false;
                     finishing = true;
                 }
+                // commit (selects, no divergence)
+                t = accept ? t_new : t;
+#pragma unroll
+                for (int c = 0; c < N; ++c) y[c] = accept ? ynew[c] : y[c];
+                nacc += accept ? 1 : 0;
+                fresh = accept;
             }
         }
     }
