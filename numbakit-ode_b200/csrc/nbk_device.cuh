@@ -38,7 +38,7 @@
 #define NBK_BLOCK 128
 #endif
 #ifndef NBK_INNER
-#define NBK_INNER 4  // attempts between two looks at the trajectory queue
+#define NBK_INNER 8  // attempts between two looks at the trajectory queue (measured: 1 -> 7.48 ms, 4 -> 7.31, 8 -> 7.26)
 #endif
 #ifdef NBK_HOST_EMUL
 #define NBK_LOG2F(x) log2f(x)
