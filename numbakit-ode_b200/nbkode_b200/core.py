@@ -214,7 +214,9 @@ class Solver(ABC):
         if self.FIXED_STEP:
             # like the reference, a fixed-step solver keeps the user's value (or the integer 1)
             self.h = np.array(h, dtype=float) if h is not None and np.ndim(h) == 0 else (1 if h is None else h)
-        self._raise_on_failure("constructor")
+        # the constructor kernel's status is checked at the first synchronising call (run / step /
+        # any property read), so constructing a solver does not stall the stream
+        self._unchecked = "constructor"
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
@@ -252,6 +254,7 @@ class Solver(ABC):
         return x.detach().cpu().numpy()
 
     def _raise_on_failure(self, where):
+        self._unchecked = None
         bad = int((self._status >= _lib.TRAJ_NONFINITE).sum().item())
         if bad:
             raise RuntimeError(
@@ -309,6 +312,8 @@ class Solver(ABC):
     # ------------------------------------------------------------------ step / skip
     def _advance(self, n_steps, bound, emit):
         torch = _torch()
+        if self._unchecked:
+            self._raise_on_failure(self._unchecked)
         B, n, dev = self.B, self.n, self._device
         t_out = y_out = None
         if emit:
@@ -410,7 +415,12 @@ class Solver(ABC):
         if not is_sorted:
             ndx = np.argsort(t)
             t = t[ndx]
-        oldest = float(self._ts[0].max().item())
+        torch = _torch()
+        pre = torch.stack([self._ts[0].max(), (self._status >= _lib.TRAJ_NONFINITE).sum().to(torch.float64)]).tolist()
+        oldest = pre[0]
+        if pre[1]:
+            self._raise_on_failure(self._unchecked or "a previous call")
+        self._unchecked = None
         if t[0] < oldest:
             raise ValueError(
                 f"Cannot interpolate at t={t[0]} as it is smaller than the current smallest value in history ({oldest})"
@@ -438,6 +448,8 @@ class Solver(ABC):
 
     def interpolate(self, t: float):
         """Dense output inside the recorded history (nbkode/core.py:449-472)."""
+        if self._unchecked:
+            self._raise_on_failure(self._unchecked)
         lo, hi = float(self._ts[0].max().item()), float(self._ts[-1].min().item())
         if not (lo <= t <= hi):
             raise ValueError(f"Time {t} to interpolate outside range ([{lo}, {hi}])")
