@@ -25,7 +25,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -54,55 +53,61 @@ def workload_config(n_gpus):
 
 
 # ----------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU while the timed region runs."""
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs, with the
+    profiling guide's recipe: `nvidia-smi --query-gpu=... -lms 200` in a separate process (NVML
+    calls from a thread of this process were measured to delay kernel launches by ~2 ms/step)."""
 
-    def __init__(self, index, period=0.05):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.sm, self.reasons, self.max_sm = [], set(), None
-        self._stop_evt = threading.Event()
-        self.ok = False
-        try:
-            import pynvml
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
 
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception:  # noqa: BLE001
-            self.nv = None
+    def __init__(self, index, period_ms=100):
+        self.index, self.period_ms, self.proc = index, period_ms, None
 
-    def run(self):
-        if not self.ok:
+    def start(self):
+        import shutil
+        import subprocess
+
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
             return
-        nv = self.nv
-        names = {
-            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
-        }
-        while not self._stop_evt.is_set():
-            try:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
-            except Exception:  # noqa: BLE001
-                break
-            time.sleep(self.period)
+        try:
+            self.proc = subprocess.Popen(
+                [exe, f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 f"-lms={self.period_ms}"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
 
     def finish(self):
-        self._stop_evt.set()
-        if self.is_alive():
-            self.join(timeout=2)
-        if not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "note": "NVML unavailable"}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
-                "samples": len(self.sm)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.25)  # let at least one more sample land
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, mx, power, reasons = [], None, [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "note": "no samples"}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
 
 
 # ----------------------------------------------------------------------------------------
@@ -240,6 +245,7 @@ def main():
         attempts += s._nacc.sum() + s._nrej.sum()
     ev[1].record()
     barrier()
+    s.raise_for_status()  # device-resident results are checked lazily: do it once, outside the timed region
     clocks = sampler.finish()
     ms_total = ev[0].elapsed_time(ev[1])
     ms_run = sum(a.elapsed_time(b) for a, b in run_ev)

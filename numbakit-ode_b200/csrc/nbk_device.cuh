@@ -564,9 +564,13 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     nacc = natt = 0;
                     kout = 0;
                     fresh = true;
-                    status = NBK_TRAJ_OK;
+                    // a trajectory that failed earlier (non-finite / budget) stays failed: the host may
+                    // check the status lazily, after queueing further calls
+                    status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
                     running = true;
-                    if (MODE == NBK_MODE_RUN) {
+                    if (status != NBK_TRAJ_OK) {
+                        running = false;
+                    } else if (MODE == NBK_MODE_RUN) {
                         // grid points inside the stored last step are answered from history
                         // without stepping (core.py:401-408)
                         while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
@@ -591,6 +595,10 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                         running = false;
                     }
                     finishing = !running;
+                    if (status >= NBK_TRAJ_NONFINITE && MODE == NBK_MODE_RUN) {
+                        for (int k = 0; k < a.m; ++k)
+                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + k * a.o_sk + c * a.o_sc] = d_nan();
+                    }
                 }
             }
         }
@@ -715,11 +723,17 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
 #pragma unroll
     for (int j = 0; j < ORDER; ++j) hB[j] = h * tab_ab<ORDER>::b(j);
 
-    int kout = 0, status = NBK_TRAJ_OK;
+    int kout = 0, status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
     long long nsteps = 0;
     double te_next = d_inf();
     bool running;
-    if (MODE == NBK_MODE_RUN) {
+    if (status != NBK_TRAJ_OK) {
+        // failed earlier (start-up): stays failed, outputs are NaN
+        running = false;
+        if (MODE == NBK_MODE_RUN)
+            for (int k = 0; k < a.m; ++k)
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + k * a.o_sk + c * a.o_sc] = d_nan();
+    } else if (MODE == NBK_MODE_RUN) {
         while (kout < a.m && __ldg(a.tgrid + kout) <= ts[L - 1]) {
             double out[N];
             hermite_window<L, N>(__ldg(a.tgrid + kout), ts, ys, fs, out);

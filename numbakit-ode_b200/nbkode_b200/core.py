@@ -217,6 +217,7 @@ class Solver(ABC):
         # the constructor kernel's status is checked at the first synchronising call (run / step /
         # any property read), so constructing a solver does not stall the stream
         self._unchecked = "constructor"
+        self._oldest_host = float(t0)  # oldest history time, known on the host until the first advance
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
@@ -252,6 +253,11 @@ class Solver(ABC):
 
     def _host(self, x):
         return x.detach().cpu().numpy()
+
+    def raise_for_status(self):
+        """Synchronise and raise if a kernel queued earlier reported failed trajectories (the check
+        is deferred while results stay on the GPU, like CUDA's own asynchronous error model)."""
+        self._raise_on_failure(self._unchecked or "a previous call")
 
     def _raise_on_failure(self, where):
         self._unchecked = None
@@ -312,8 +318,7 @@ class Solver(ABC):
     # ------------------------------------------------------------------ step / skip
     def _advance(self, n_steps, bound, emit):
         torch = _torch()
-        if self._unchecked:
-            self._raise_on_failure(self._unchecked)
+        self._oldest_host = None
         B, n, dev = self.B, self.n, self._device
         t_out = y_out = None
         if emit:
@@ -404,7 +409,12 @@ class Solver(ABC):
                 self._handle, C.byref(self._state), grid.data_ptr(), m, float(bound),
                 y_out.data_ptr(), m * n, n, 1, 0, self._stream(),
             ))
-        self._raise_on_failure("run")
+        self._oldest_host = None
+        if self._torch_out and self._out_device.type == "cuda" and self._batched:
+            self._unchecked = "run"  # results stay on the device: failed trajectories (sticky status,
+            # NaN outputs) are reported by the next synchronising call or raise_for_status()
+        else:
+            self._raise_on_failure("run")
         return y_out
 
     def run(self, t):
@@ -415,12 +425,10 @@ class Solver(ABC):
         if not is_sorted:
             ndx = np.argsort(t)
             t = t[ndx]
-        torch = _torch()
-        pre = torch.stack([self._ts[0].max(), (self._status >= _lib.TRAJ_NONFINITE).sum().to(torch.float64)]).tolist()
-        oldest = pre[0]
-        if pre[1]:
-            self._raise_on_failure(self._unchecked or "a previous call")
-        self._unchecked = None
+        # oldest history time: known on the host for a solver that has not advanced yet, otherwise
+        # one small device reduction (failed trajectories keep their status inside the kernels, so
+        # no failure pre-check is needed here)
+        oldest = self._oldest_host if self._oldest_host is not None else float(self._ts[0].max().item())
         if t[0] < oldest:
             raise ValueError(
                 f"Cannot interpolate at t={t[0]} as it is smaller than the current smallest value in history ({oldest})"
