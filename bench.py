@@ -249,13 +249,11 @@ def main():
     clocks = sampler.finish()
     ms_total = ev[0].elapsed_time(ev[1])
     ms_run = sum(a.elapsed_time(b) for a, b in run_ev)
-    tm = torch.tensor([ms_total, ms_run], dtype=torch.float64, device=dev)
-    cnt = torch.stack([steps_acc, attempts]).to(torch.float64)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, ms_run = float(tm[0]), float(tm[1])
-    total_steps, total_attempts = float(cnt[0]), float(cnt[1])
+    from nbkode_b200 import distributed as nd
+
+    # device-timed, max over ranks; work summed over ranks (the driver computes efficiency itself)
+    (ms_total, ms_run), (total_steps, total_attempts) = nd.reduce_max_sum(
+        [ms_total, ms_run], [float(steps_acc.item()), float(attempts.item())], device=dev)
     value = total_steps / (ms_total * 1e-3)
 
     # ------------------------------------------------------------ e2e arm (pinned host buffers in and out)
@@ -271,12 +269,8 @@ def main():
         e2e_steps += int(nacc.sum())
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    e2e_n = torch.tensor([float(e2e_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
-    e2e_value = float(e2e_n[0]) / float(e2e_t[0])
+    (e2e_s,), (e2e_total,) = nd.reduce_max_sum([e2e_s], [float(e2e_steps)], device=dev)
+    e2e_value = e2e_total / e2e_s
     h2d = y0_host.numel() * 8 + p_host.numel() * 8
     d2h = y.numel() * 8 + nacc.numel() * 8
 
@@ -288,7 +282,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": {**workload_config(world), "trajectories_per_gpu": B},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,

@@ -30,6 +30,27 @@ from .util import CaseInsensitiveDict
 
 _INT_MAX = 2**31 - 1
 
+# device copies of recently used output grids: uploading a grid from pageable host memory makes the
+# driver synchronise the stream, which would serialise back-to-back passes on the same grid
+_GRID_CACHE: dict = {}
+_GRID_CACHE_MAX = 32
+
+
+def _device_grid(grid_host: np.ndarray, device):
+    torch = _torch()
+    key = (str(device), grid_host.tobytes())
+    hit = _GRID_CACHE.get(key)
+    if hit is not None:
+        return hit
+    pinned = torch.from_numpy(np.ascontiguousarray(grid_host)).pin_memory()
+    dev = pinned.to(device, non_blocking=True)
+    if len(_GRID_CACHE) >= _GRID_CACHE_MAX:
+        _GRID_CACHE.pop(next(iter(_GRID_CACHE)))
+    if grid_host.nbytes <= 1 << 20:
+        _GRID_CACHE[key] = dev
+    dev._nbk_pinned_src = pinned  # keep the staging buffer alive until the copy has run
+    return dev
+
 
 def _torch():
     import torch
@@ -401,7 +422,7 @@ class Solver(ABC):
     def _run_grid(self, grid_host: np.ndarray, bound: float):
         torch = _torch()
         B, n, dev, m = self.B, self.n, self._device, int(grid_host.size)
-        grid = torch.from_numpy(np.ascontiguousarray(grid_host)).to(dev, non_blocking=True)
+        grid = _device_grid(grid_host, dev)
         fill = torch.empty if math.isinf(bound) else (lambda *a, **k: torch.full(*a, math.nan, **k))
         y_out = fill((B, m, n), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
