@@ -69,10 +69,13 @@ typedef struct {
     int n_params;         /* parameters per trajectory (0 allowed) */
     int params_shared;    /* 1: one parameter vector for the whole ensemble */
     long long batch;      /* B */
-    const char *rhs;      /* built-in right-hand side: "lorenz", "vdp", "decay"; or NULL */
-    const char *rhs_src;  /* CUDA C source defining
+    const char *rhs;      /* built-in right-hand side: "lorenz", "vdp", "decay" (per-thread regime),
+                             "rd1d", "linear" (CTA regime); or NULL */
+    const char *rhs_src;  /* CUDA C source compiled by NVRTC into the integrator kernels; or NULL.  Defines
                                NBK_RHS nbk_rhs(double t, const double* y, const double* p, double* dy)
-                             compiled by NVRTC into the integrator kernels; or NULL.
+                             (per-thread regime, y/dy in registers) or, for large systems,
+                               NBK_RHS_I nbk_rhs_i(double t, const double* y, const double* p, int i, int n)
+                             (CTA regime: returns component i, y is the whole vector in shared memory).
                              Replaces numba.njit(rhs) of nbkode/core.py:125-132. */
     /* VariableStepOptions, nbkode/core.py:661-679 (min_step/max_step are never enforced by
        the reference and therefore absent) */
@@ -103,6 +106,12 @@ void nbk_destroy(nbk_solver *s);
 int nbk_layout(const nbk_solver *s, int *len_history, int *stage_rows);
 /* 1 if the kernels came from NVRTC, 0 if from the ahead-of-time catalogue. */
 int nbk_is_jit(const nbk_solver *s);
+/* Execution regime, which also fixes the layout of nbk_state:
+     0  one trajectory per thread (n <= 64):   ts [L][B], ys/fs [L][n][B], K [S+1][n][B], params [np][B]
+     1  one CTA per trajectory (large n; chosen by the right-hand side: built-ins "rd1d", "linear" or
+        user source defining nbk_rhs_i): ts [B][2], ys/fs [B][2][n], K [B][S+1][n], params [B][np]
+        (a trajectory's n values are contiguous).  h, counters and status are [B] in both. */
+int nbk_regime(const nbk_solver *s);
 
 /* Replaces Solver.__init__ / VariableStep.__init__ / Multistep.__init__
    (nbkode/core.py:106-141, :687-706, nbkode/multistep/core.py:37-65): f0 = rhs(t0, y0), history

@@ -1,0 +1,415 @@
+// nbk_cta.cuh -- CTA-per-trajectory regime (K3) for large systems (method-of-lines grids,
+// n up to a few thousand): one thread block integrates one trajectory.
+//
+//  * every thread owns E consecutive state components: its slice of y, of the stage derivatives
+//    K0..K_S and of y_new live in registers (all loops over E are unrolled);
+//  * the stage ARGUMENT vector y + h*sum(a_sj K_j) is staged in shared memory (two buffers used
+//    alternately: one __syncthreads per stage) so that the right-hand side can read neighbours /
+//    the whole vector;
+//  * the scaled error norm is a warp-shuffle reduction followed by one shared-memory hop; every
+//    thread then computes the same accept/reject decision and step-size factor, so a CTA never
+//    diverges -- only CTAs differ in their number of steps, and they pull trajectories from the
+//    same global queue as the per-thread kernels;
+//  * state layout is trajectory-major (a trajectory's n values are contiguous, so the CTA's loads
+//    and stores are coalesced): ts [B][2], ys/fs [B][2][n], K [B][S+1][n], h [B],
+//    params [B][np] or shared [np].
+//
+// Reference rows restated: the same as nbk_device.cuh (FSAL stage loop explicit.py:60-79, error
+// norm / controller runge_kutta/core.py:73-99, accept loop explicit.py:81-99, t_bound guard
+// core.py:176-184, RkInterpolator explicit.py:354-403, select_initial_step core.py:695-705,
+// drivers core.py:483-537, 598-619).
+#ifndef NBK_CTA_CUH
+#define NBK_CTA_CUH
+
+#include "nbk_device.cuh"
+
+namespace nbk {
+
+// Sum over the block; every thread returns the same value (same summation order everywhere).
+// The caller guarantees a __syncthreads between two uses of `red` (the stage barriers do).
+NBK_DEV double block_sum(double v, double *red, int nwarps) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < nwarps; ++w) tot += red[w];
+    return tot;
+}
+
+// =====================================================================================
+// Right-hand sides of the CTA regime:
+//   template <int E> static void eval(t, yown[E], ysm (whole vector, shared memory), p, i0, n, dy[E])
+// `yown` is the thread's slice of the vector that is also in `ysm`.
+// =====================================================================================
+
+struct rhs_rd1d_cta {  // periodic 1-D reaction-diffusion: d (y[i+1] - 2 y[i] + y[i-1]) + r y (1 - y)
+    static constexpr int NP = 2;
+    template <int E>
+    static NBK_DEV void eval(double, const double (&yown)[E], const double *ysm, const double *p, int i0, int n,
+                             double (&dy)[E]) {
+        const double d = __ldg(p), r = __ldg(p + 1);
+        if (i0 >= n) return;
+        // only the two halo values come from shared memory, the interior from registers
+        double left = ysm[i0 == 0 ? n - 1 : i0 - 1];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            if (i < n) {
+                const double right = (e + 1 < E && i + 1 < n) ? yown[e + 1 < E ? e + 1 : e] : ysm[i + 1 == n ? 0 : i + 1];
+                dy[e] = d * (right - 2 * yown[e] + left) + r * yown[e] * (1 - yown[e]);
+                left = yown[e];
+            }
+        }
+    }
+};
+
+struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANSPOSED ([j][i]) so that
+                         // consecutive threads read consecutive addresses; y[j] is a broadcast smem read
+    static constexpr int NP = -1;  // n*n, run-time
+    template <int E>
+    static NBK_DEV void eval(double, const double (&)[E], const double *ysm, const double *At, int i0, int n,
+                             double (&dy)[E]) {
+        double acc[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double yj = ysm[j];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (i0 + e < n) acc[e] = fma(__ldg(At + (long long)j * n + i0 + e), yj, acc[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) dy[e] = acc[e];
+    }
+};
+
+#ifdef NBK_USER_RHS_CTA
+// User right-hand side of the CTA regime, compiled by NVRTC: component-wise
+//   __device__ double nbk_rhs_i(double t, const double* y, const double* p, int i, int n)
+// where y is the whole stage-argument vector (shared memory).
+struct rhs_user_cta {
+    static constexpr int NP = -1;
+    template <int E>
+    static NBK_DEV void eval(double t, const double (&)[E], const double *ysm, const double *p, int i0, int n,
+                             double (&dy)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (i0 + e < n) dy[e] = nbk_rhs_i(t, ysm, p, i0 + e, n);
+    }
+};
+#endif
+
+// =====================================================================================
+// One FSAL attempt of the whole CTA.  K[0] holds this thread's slice of f(t, y).
+// =====================================================================================
+template <class Tab, class Rhs, int E>
+NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[Tab::S + 1][E], const double *p, int i0,
+                         int n, double *buf0, double *buf1, double *red, int nwarps, double (&ynew)[E], double &err2,
+                         double rtol, double atol) {
+    constexpr int S = Tab::S;
+#pragma unroll
+    for (int s = 1; s <= S; ++s) {
+        double ys[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                const bool nz = s < S ? Tab::a(s < S ? s : 0, j) != 0.0 : Tab::b(j) != 0.0;
+                if (nz) {
+                    const double c = s < S ? Tab::cb().a[s < S ? s : 0][j] : Tab::cb().b[j];
+                    acc = first ? c * K[j][e] : fma(c, K[j][e], acc);
+                    first = false;
+                }
+            }
+            ys[e] = fma(h, acc, y[e]);
+        }
+        double *buf = (s & 1) ? buf1 : buf0;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (i0 + e < n) buf[i0 + e] = ys[e];
+        __syncthreads();
+        Rhs::template eval<E>(s < S ? fma(h, Tab::cb().c[s < S ? s : 0], t) : t + h, ys, buf, p, i0, n, K[s]);
+        if (s == S) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) ynew[e] = ys[e];
+        }
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        double ee = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j <= S; ++j) {
+            if (Tab::e(j) != 0.0) {
+                ee = first ? Tab::cb().e[j] * K[j][e] : fma(Tab::cb().e[j], K[j][e], ee);
+                first = false;
+            }
+        }
+        if (i0 + e < n) {
+            const double sc = fma(rtol, abs_max(ynew[e], y[e]), atol);
+            const double r = ee * fast_rcp(sc);
+            part = fma(r, r, part);
+        }
+    }
+    err2 = block_sum(part, red, nwarps) * (h * h / (double)n);
+}
+
+// rms(x / scale) over the whole vector (cold path)
+template <int E>
+NBK_DEV double cta_rms_scaled(const double (&x)[E], const double (&sc)[E], int i0, int n, double *red, int nwarps) {
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (i0 + e < n) {
+            const double v = x[e] / sc[e];
+            part = fma(v, v, part);
+        }
+    const double tot = block_sum(part, red, nwarps);
+    __syncthreads();  // `red` is reused by the next norm
+    return sqrt(tot) / sqrt((double)n);
+}
+
+// =====================================================================================
+// Construction: f0, history, initial step (select_initial_step with block-wide norms)
+// =====================================================================================
+template <class Tab, class Rhs, int E>
+NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
+    constexpr int S = Tab::S;
+    const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
+    double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
+    for (long long idx = blockIdx.x; idx < a.B; idx += gridDim.x) {
+        __syncthreads();
+        // per-trajectory parameters: copy the user's row into the state's [B][np] array
+        if (!a.params_shared) {
+            for (int c = tid; c < a.n_params; c += blockDim.x)
+                a.params[idx * a.n_params + c] = a.p0[idx * a.p0_sb + c * a.p0_sc];
+            __syncthreads();  // made visible to the block before the first right-hand side call
+        }
+        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        double y[E], f[E], sc[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            y[e] = i0 + e < n ? a.y0[idx * a.y0_sb + (long long)(i0 + e) * a.y0_sc] : 0.0;
+            f[e] = 0.0;
+            if (i0 + e < n) buf0[i0 + e] = y[e];
+        }
+        __syncthreads();
+        Rhs::template eval<E>(a.t0, y, buf0, p, i0, n, f);
+        double h = a.h0 ? a.h0[idx] : a.h_init;
+        if (!(h == h)) {
+            // scipy select_initial_step (direction +1, unbounded), SURVEY.md row a4
+#pragma unroll
+            for (int e = 0; e < E; ++e) sc[e] = a.atol + fabs(y[e]) * a.rtol;
+            const double d0 = cta_rms_scaled<E>(y, sc, i0, n, red, nwarps);
+            const double d1 = cta_rms_scaled<E>(f, sc, i0, n, red, nwarps);
+            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            double y1[E], f1[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                y1[e] = y[e] + h0 * f[e];
+                f1[e] = 0.0;
+                if (i0 + e < n) buf1[i0 + e] = y1[e];
+            }
+            __syncthreads();
+            Rhs::template eval<E>(a.t0 + h0, y1, buf1, p, i0, n, f1);
+#pragma unroll
+            for (int e = 0; e < E; ++e) f1[e] -= f[e];
+            const double d2 = cta_rms_scaled<E>(f1, sc, i0, n, red, nwarps) / h0;
+            double h1;
+            if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+            else h1 = pow(0.01 / fmax(d1, d2), 1.0 / (Tab::Q + 1));
+            h = fmin(100 * h0, h1);
+        }
+        const long long nn = n;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            if (i < n) {
+                a.ys[(idx * 2 + 0) * nn + i] = y[e];
+                a.ys[(idx * 2 + 1) * nn + i] = y[e];
+                a.fs[(idx * 2 + 0) * nn + i] = f[e];
+                a.fs[(idx * 2 + 1) * nn + i] = f[e];
+#pragma unroll
+                for (int s = 0; s <= S; ++s) a.K[(idx * (S + 1) + s) * nn + i] = 0.0;
+            }
+        }
+        if (tid == 0) {
+            a.ts[idx * 2] = a.t0;
+            a.ts[idx * 2 + 1] = a.t0;
+            a.h[idx] = h;
+            a.n_acc[idx] = 0;
+            a.n_rej[idx] = 0;
+            a.status[idx] = NBK_TRAJ_OK;
+        }
+    }
+}
+
+// =====================================================================================
+// Advance: persistent CTAs pulling trajectories from the global queue.
+// =====================================================================================
+template <class Tab, class Rhs, int E, int MODE>
+NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
+    constexpr int S = Tab::S;
+    const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
+    const long long nn = n;
+    double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
+    long long *s_idx = (long long *)(red + 32);
+    const double rtol = a.rtol, atol = a.atol, bound = a.bound;
+    const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
+
+    for (;;) {
+        __syncthreads();  // the previous trajectory's last readers of s_idx / the buffers are done
+        if (tid == 0) *s_idx = (long long)atomicAdd(a.work_counter, 1ULL);
+        __syncthreads();
+        const long long idx = *s_idx;
+        if (idx >= a.B) break;
+
+        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        double t = a.ts[idx * 2 + 1], h = a.h[idx];
+        double y[E], K[S + 1][E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            y[e] = i < n ? a.ys[(idx * 2 + 1) * nn + i] : 0.0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) K[s][e] = 0.0;
+            K[S][e] = i < n ? a.fs[(idx * 2 + 1) * nn + i] : 0.0;  // f(t, y): K[0] of the first attempt
+        }
+        int status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
+        int nacc = 0, natt = 0, kout = 0;
+        double te_next = d_inf();
+        bool running = status == NBK_TRAJ_OK;
+        if (running && MODE == NBK_MODE_RUN) {
+            if (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                // grid points inside the stored last step: answered from history (core.py:401-408)
+                const double t_old = a.ts[idx * 2];
+                double y_old[E], Kh[S + 1][E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = i0 + e;
+                    y_old[e] = i < n ? a.ys[(idx * 2) * nn + i] : 0.0;
+#pragma unroll
+                    for (int s = 0; s <= S; ++s) Kh[s][e] = (i < n && !a.pristine) ? a.K[(idx * (S + 1) + s) * nn + i] : 0.0;
+                }
+                while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                    double out[E];
+                    rk_dense<Tab, E>(__ldg(a.tgrid + kout), t_old, t, y_old, y, Kh, out);
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                    ++kout;
+                }
+            }
+            running = kout < a.m;
+            if (running) te_next = __ldg(a.tgrid + kout);
+        } else if (running) {
+            running = a.n_steps > 0;
+        }
+        if (status >= NBK_TRAJ_NONFINITE && MODE == NBK_MODE_RUN) {
+            for (int k = 0; k < a.m; ++k)
+                for (int e = 0; e < E; ++e)
+                    if (i0 + e < n) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)(i0 + e) * a.o_sc] = d_nan();
+        }
+        if (running && (t + h > bound)) {  // guard of the first step (core.py:176-184)
+            status = NBK_TRAJ_BOUND;
+            running = false;
+        }
+        bool fresh = true;
+        while (running) {  // every quantity steering this loop is identical in all threads of the CTA
+            if (fresh) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) K[0][e] = K[S][e];
+            }
+            double ynew[E], err2;
+            cta_attempt<Tab, Rhs, E>(t, h, y, K, p, i0, n, buf0, buf1, red, nwarps, ynew, err2, rtol, atol);
+            const bool accept = (unsigned)__double2hiint(err2) < 0x3ff00000u;
+            const double t_new = t + h;
+            h *= step_factor<Tab>(err2, a.safety, a.min_factor, a.max_factor, a.x_lo, a.x_hi);
+            ++natt;
+            bool done = false;
+            if (accept) {
+                if (MODE == NBK_MODE_RUN) {
+                    while (t_new >= te_next) {
+                        double out[E];
+                        rk_dense<Tab, E>(te_next, t, t_new, y, ynew, K, out);
+#pragma unroll
+                        for (int e = 0; e < E; ++e)
+                            if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                        ++kout;
+                        te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                    }
+                    done = kout >= a.m;
+                } else {
+                    if (a.emit) {
+                        if (tid == 0) a.t_out[idx * a.to_sb + nacc] = t_new;
+#pragma unroll
+                        for (int e = 0; e < E; ++e)
+                            if (i0 + e < n) a.y_out[idx * a.o_sb + nacc * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
+                    }
+                    done = nacc + 1 >= a.n_steps;
+                }
+            }
+            if (d_nonfinite(err2) || d_collapsed(h)) {
+                status = NBK_TRAJ_NONFINITE;
+                done = true;
+            } else if (!done && natt >= max_att) {
+                status = NBK_TRAJ_MAXATTEMPTS;
+                done = true;
+            }
+            if (accept && !done && (t_new + h > bound)) {  // guard of the next step
+                status = NBK_TRAJ_BOUND;
+                done = true;
+            }
+            if (done) {
+                // history slot 0 = start of the last accepted step (see advance_adaptive)
+                if (tid == 0) a.ts[idx * 2] = t;
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (i0 + e < n) a.ys[(idx * 2) * nn + i0 + e] = y[e];
+                running = false;
+            }
+            if (accept) {
+                t = t_new;
+#pragma unroll
+                for (int e = 0; e < E; ++e) y[e] = ynew[e];
+                ++nacc;
+            }
+            fresh = accept;
+        }
+        // ---- retire
+        if (nacc > 0) {
+            const bool clean = status == NBK_TRAJ_OK || status == NBK_TRAJ_BOUND;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = i0 + e;
+                if (i < n) {
+                    a.ys[(idx * 2 + 1) * nn + i] = y[e];
+                    a.fs[(idx * 2) * nn + i] = K[0][e];
+                    a.fs[(idx * 2 + 1) * nn + i] = clean ? K[S][e] : K[0][e];
+#pragma unroll
+                    for (int s = 0; s <= S; ++s) a.K[(idx * (S + 1) + s) * nn + i] = K[s][e];
+                }
+            }
+        }
+        if (tid == 0) {
+            if (nacc > 0) a.ts[idx * 2 + 1] = t;
+            a.h[idx] = h;
+            if (a.pristine) {
+                a.n_acc[idx] = nacc;
+                a.n_rej[idx] = natt - nacc;
+            } else {
+                a.n_acc[idx] += nacc;
+                a.n_rej[idx] += natt - nacc;
+            }
+            a.status[idx] = status;
+            a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nacc;
+        }
+    }
+}
+
+}  // namespace nbk
+#endif

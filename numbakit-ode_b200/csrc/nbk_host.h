@@ -4,7 +4,8 @@
 
 struct nbk_static_program {
     int method;            // 23, 45, 1..5
-    int n, n_params;
+    int n, n_params;       // n == -1: any (run-time) size, CTA regime
+    int cta_elems;         // 0: one trajectory per thread; E > 0: one CTA per trajectory, E components per thread
     const void *k_init;    // host stubs of the __global__ kernels (cudaLaunchKernel)
     const void *k_run;
     const void *k_step;

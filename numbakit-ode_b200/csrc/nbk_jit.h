@@ -9,7 +9,9 @@ struct nbk_jit_request {
     int method;             // 23, 45, 1..5
     int n, n_params;
     std::string rhs_type;   // C++ type name of a built-in rhs (e.g. "nbk::rhs_decay<2,2>") or empty
-    std::string user_src;   // user source defining nbk_rhs(...) (used when rhs_type is empty)
+    std::string user_src;   // user source defining nbk_rhs(...) / nbk_rhs_i(...) (used when rhs_type is empty)
+    int cta_elems = 0;      // > 0: CTA-per-trajectory regime (nbk_program_cta.cu) with E components per thread
+    int cta_maxt = 0;       // block-size cap the CTA kernels are compiled for
 };
 
 struct nbk_jit_module {
@@ -28,7 +30,11 @@ bool nbk_jit_load(const std::vector<char> &cubin, nbk_jit_module &mod, std::stri
 void nbk_jit_unload(nbk_jit_module &mod);
 
 // cuLaunchKernel with a single by-value argument block.
-bool nbk_jit_launch(void *func, unsigned grid, unsigned block, void *arg_block, void *stream, std::string &err);
+bool nbk_jit_launch(void *func, unsigned grid, unsigned block, size_t smem, void *arg_block, void *stream,
+                    std::string &err);
+// opt in to more than 48 KB of dynamic shared memory / occupancy with dynamic shared memory
+bool nbk_jit_set_smem(void *func, size_t smem, std::string &err);
+bool nbk_jit_occupancy_smem(void *func, int block, size_t smem, int *blocks_per_sm, int *regs, std::string &err);
 // cuOccupancyMaxActiveBlocksPerMultiprocessor / register count of a CUfunction.
 bool nbk_jit_occupancy(void *func, int block, int *blocks_per_sm, int *regs, std::string &err);
 // block size the kernel was compiled for (__launch_bounds__ -> CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK)

@@ -30,6 +30,8 @@ struct nbk_kargs {
     int first_stepper;    // multistep start-up: 0 none, 23/45 adaptive RK, 1..5 Adams-Bashforth-k
     int pristine;         // the state is exactly what the init kernel wrote (no step taken yet):
                           // the advance kernel then skips loading the K rows / old history slot
+    int n, n_params;      // run-time sizes (CTA-per-trajectory regime; the per-thread regime has them
+                          // as template parameters)
     // ---- init inputs (user layout: element (b, c) at base[b*sb + c*sc])
     const double *y0;
     long long y0_sb, y0_sc;

@@ -1,0 +1,50 @@
+// nbk_program_cta.cu -- init / run / step kernels of one (method, RHS) pair in the
+// CTA-per-trajectory regime (nbk_cta.cuh).  Macros: NBK_METHOD (23 | 45), NBK_RHS_T (a CTA
+// right-hand side type), NBK_E (state components per thread), NBK_TAG.  The block size is chosen at
+// launch: ceil(n / NBK_E) rounded up to a warp; dynamic shared memory = (2*T*E + 34) doubles.
+#include "nbk_cta.cuh"
+
+#define NBK_CAT2(a, b) a##b
+#define NBK_CAT(a, b) NBK_CAT2(a, b)
+#define NBK_KERNEL(stem) NBK_CAT(NBK_CAT(nbk_, stem), NBK_CAT(_, NBK_TAG))
+
+typedef NBK_RHS_T nbk_rhs_t;
+#if NBK_METHOD == 45
+typedef nbk::tab_rk45 nbk_tab_t;
+#elif NBK_METHOD == 23
+typedef nbk::tab_rk23 nbk_tab_t;
+#else
+#error "the CTA regime implements the adaptive Runge-Kutta methods (NBK_METHOD 23 or 45)"
+#endif
+#ifndef NBK_E
+#define NBK_E 4
+#endif
+#ifndef NBK_CTA_MAXT
+#define NBK_CTA_MAXT 512  // largest block the kernels are compiled for: n <= NBK_E * NBK_CTA_MAXT
+#endif
+
+extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
+    extern __shared__ double nbk_smem[];
+    nbk::cta_init_adaptive<nbk_tab_t, nbk_rhs_t, NBK_E>(a, nbk_smem);
+}
+extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
+    extern __shared__ double nbk_smem[];
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
+}
+extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
+    extern __shared__ double nbk_smem[];
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
+}
+
+#ifndef __CUDACC_RTC__
+#include "nbk_host.h"
+extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
+    out->method = NBK_METHOD;
+    out->n = -1;  // any n: run-time
+    out->n_params = nbk_rhs_t::NP;
+    out->cta_elems = NBK_E;
+    out->k_init = (const void *)&NBK_KERNEL(init);
+    out->k_run = (const void *)&NBK_KERNEL(run);
+    out->k_step = (const void *)&NBK_KERNEL(step);
+}
+#endif

@@ -75,19 +75,23 @@ class _Cache:
         self._s = solver
 
     @property
-    def ts(self):
+    def ts(self):  # (L,) or (L, B)
         s = self._s
-        return s._out(s._ts[:, 0] if not s._batched else s._ts)
+        full = s._ts if s._regime == 0 else s._ts.t()
+        return s._out(full[:, 0] if not s._batched else full)
+
+    def _window(self, arr):  # (L, n) or (B, L, n)
+        s = self._s
+        full = arr.permute(2, 0, 1) if s._regime == 0 else arr
+        return s._out(full[0] if not s._batched else full)
 
     @property
     def ys(self):
-        s = self._s
-        return s._out(s._ys[:, :, 0] if not s._batched else s._ys.permute(2, 0, 1))
+        return self._window(self._s._ys)
 
     @property
     def fs(self):
-        s = self._s
-        return s._out(s._fs[:, :, 0] if not s._batched else s._fs.permute(2, 0, 1))
+        return self._window(self._s._fs)
 
     t = property(lambda self: self._s.t)
     y = property(lambda self: self._s.y)
@@ -170,6 +174,11 @@ class Solver(ABC):
         self._params_shared = shared
 
         # ---- right-hand side -> built-in name or CUDA C
+        if callable(rhs) and self.n > _rhs.MAX_TRACED_N:
+            raise TypeError(
+                f"a Python right-hand side is traced component by component, which is limited to n <= "
+                f"{_rhs.MAX_TRACED_N}; for n = {self.n} pass a CTA built-in ('rd1d', 'linear') or CUDA C source defining "
+                "nbk_rhs_i(t, y, p, i, n)")
         name, src = _rhs.resolve(rhs, self.n, p_shape if p_shape else (self.n_params,), params is not None)
         if name == "decay" and self.n_params not in (1, self.n):
             raise ValueError("built-in 'decay' needs 1 or n parameters")
@@ -189,19 +198,27 @@ class Solver(ABC):
         L, SR = C.c_int(0), C.c_int(0)
         _lib.check(_lib.lib().nbk_layout(handle, C.byref(L), C.byref(SR)))
         assert L.value == self.LEN_HISTORY and SR.value == self.STAGE_ROWS
+        # 0: one trajectory per thread (trajectory index fastest); 1: one CTA per trajectory (a trajectory's
+        # n values contiguous) -- see nbk_regime() in include/nbkode_b200.h
+        self._regime = int(_lib.lib().nbk_regime(handle))
 
-        # ---- ensemble state in HBM (SoA, trajectory index fastest)
+        # ---- ensemble state in HBM
         B, n, dev = self.B, self.n, self._device
         f64 = torch.float64
-        self._ts = torch.empty((L.value, B), dtype=f64, device=dev)
-        self._ys = torch.empty((L.value, n, B), dtype=f64, device=dev)
-        self._fs = torch.empty((L.value, n, B), dtype=f64, device=dev)
-        self._K = torch.empty((SR.value, n, B), dtype=f64, device=dev) if SR.value else None
-        self._h = torch.empty((B,), dtype=f64, device=dev)
-        if self.n_params:
-            self._p = torch.empty((self.n_params,) if shared else (self.n_params, B), dtype=f64, device=dev)
+        if self._regime == 0:
+            self._ts = torch.empty((L.value, B), dtype=f64, device=dev)
+            self._ys = torch.empty((L.value, n, B), dtype=f64, device=dev)
+            self._fs = torch.empty((L.value, n, B), dtype=f64, device=dev)
+            self._K = torch.empty((SR.value, n, B), dtype=f64, device=dev) if SR.value else None
+            p_shape_dev = (self.n_params,) if shared else (self.n_params, B)
         else:
-            self._p = None
+            self._ts = torch.empty((B, L.value), dtype=f64, device=dev)
+            self._ys = torch.empty((B, L.value, n), dtype=f64, device=dev)
+            self._fs = torch.empty((B, L.value, n), dtype=f64, device=dev)
+            self._K = torch.empty((B, SR.value, n), dtype=f64, device=dev) if SR.value else None
+            p_shape_dev = (self.n_params,) if shared else (B, self.n_params)
+        self._h = torch.empty((B,), dtype=f64, device=dev)
+        self._p = torch.empty(p_shape_dev, dtype=f64, device=dev) if self.n_params else None
         self._nacc = torch.empty((B,), dtype=torch.int64, device=dev)
         self._nrej = torch.empty((B,), dtype=torch.int64, device=dev)
         self._status = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -300,20 +317,26 @@ class Solver(ABC):
         # alive until the cyclic garbage collector runs
         return _Cache(self)
 
+    def _slot_t(self, slot):  # (B,) history times of one slot (0 oldest, -1 newest)
+        return self._ts[slot] if self._regime == 0 else self._ts[:, slot]
+
+    def _slot(self, arr, slot):  # (B, n)
+        return arr[slot].t() if self._regime == 0 else arr[:, slot]
+
     @property
     def t(self):
-        cur = self._ts[-1]
+        cur = self._slot_t(-1)
         return float(cur[0].item()) if not self._batched else self._out(cur)
 
     @property
     def y(self):
-        cur = self._ys[-1]
-        return self._out(cur[:, 0].reshape(self._y0_shape)) if not self._batched else self._out(cur.t())
+        cur = self._slot(self._ys, -1)
+        return self._out(cur[0].reshape(self._y0_shape)) if not self._batched else self._out(cur)
 
     @property
     def f(self):
-        cur = self._fs[-1]
-        return self._out(cur[:, 0].reshape(self._y0_shape)) if not self._batched else self._out(cur.t())
+        cur = self._slot(self._fs, -1)
+        return self._out(cur[0].reshape(self._y0_shape)) if not self._batched else self._out(cur)
 
     @property
     def n_accepted(self):
@@ -449,7 +472,7 @@ class Solver(ABC):
         # oldest history time: known on the host for a solver that has not advanced yet, otherwise
         # one small device reduction (failed trajectories keep their status inside the kernels, so
         # no failure pre-check is needed here)
-        oldest = self._oldest_host if self._oldest_host is not None else float(self._ts[0].max().item())
+        oldest = self._oldest_host if self._oldest_host is not None else float(self._slot_t(0).max().item())
         if t[0] < oldest:
             raise ValueError(
                 f"Cannot interpolate at t={t[0]} as it is smaller than the current smallest value in history ({oldest})"
@@ -479,7 +502,7 @@ class Solver(ABC):
         """Dense output inside the recorded history (nbkode/core.py:449-472)."""
         if self._unchecked:
             self._raise_on_failure(self._unchecked)
-        lo, hi = float(self._ts[0].max().item()), float(self._ts[-1].min().item())
+        lo, hi = float(self._slot_t(0).max().item()), float(self._slot_t(-1).min().item())
         if not (lo <= t <= hi):
             raise ValueError(f"Time {t} to interpolate outside range ([{lo}, {hi}])")
         y_out = self._run_grid(np.array([float(t)]), math.inf)

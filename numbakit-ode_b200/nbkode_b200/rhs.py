@@ -27,8 +27,12 @@ BUILTINS = {
     # name -> (n or None for "from y0", n_params rule)
     "lorenz": (3, 3),
     "vdp": (2, 1),
-    "decay": (None, None),  # n from y0; n_params 1 or n
+    "decay": (None, None),   # n from y0; n_params 1 or n
+    # CTA-per-trajectory regime (large systems, csrc/nbk_cta.cuh)
+    "rd1d": (None, 2),       # periodic 1-D reaction-diffusion, params (d, r)
+    "linear": (None, None),  # y' = A y, params = the shared n x n matrix
 }
+MAX_TRACED_N = 64
 
 
 class CudaRHS:
@@ -36,7 +40,7 @@ class CudaRHS:
 
     def __init__(self, source: str, name: str = "user"):
         if "nbk_rhs" not in source:
-            raise ValueError("CUDA right-hand side source must define nbk_rhs(t, y, p, dy)")
+            raise ValueError("CUDA right-hand side source must define nbk_rhs(t, y, p, dy) or nbk_rhs_i(t, y, p, i, n)")
         self.source = source
         self.name = name
 

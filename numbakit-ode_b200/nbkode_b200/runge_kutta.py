@@ -43,7 +43,8 @@ class RungeKutta(Solver, abstract=True):
     @property
     def K(self):
         """Stage derivatives of the last accepted step, (S+1, n) or (B, S+1, n)."""
-        return self._out(self._K[:, :, 0] if not self._batched else self._K.permute(2, 0, 1))
+        full = self._K.permute(2, 0, 1) if self._regime == 0 else self._K
+        return self._out(full[0] if not self._batched else full)
 
 
 class AdaptiveRungeKutta(RungeKutta, abstract=True):

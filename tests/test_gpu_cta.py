@@ -1,0 +1,112 @@
+"""GPU parity tests of the CTA-per-trajectory regime (K3, csrc/nbk_cta.cuh): large systems
+(BASELINE.json configs[3] linear n=128 with a shared matrix, configs[4] 1-D reaction-diffusion
+method of lines n=2048) against the C oracle and the reference's golden vectors."""
+
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import nbkode_b200 as nbk  # noqa: E402
+from oracle import nbk_oracle_c as oc  # noqa: E402
+from oracle import nbk_oracle_np as onp  # noqa: E402
+
+
+def within(y, ref, rtol, atol, slack=1.0):
+    return np.abs(np.asarray(y) - np.asarray(ref)) <= slack * (rtol * np.abs(ref) + atol)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b))) / max(1.0, float(np.max(np.abs(b))))
+
+
+@pytest.mark.parametrize("cls,n,B", [("RungeKutta45", 2048, 48), ("RungeKutta23", 2048, 8), ("RungeKutta45", 100, 40),
+                                     ("RungeKutta45", 700, 12), ("RungeKutta45", 3000, 6)])
+def test_rd1d_vs_oracle(cls, n, B):
+    """C5 generator (kappa, r, phase sweep); n = 100 / 700 / 3000 exercise other CTA shapes
+    (1, 2 and 12 components per thread, the latter two compiled by NVRTC)."""
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+    ts = [0.25, 0.5]
+    ref = oc.run_ensemble(cls, "rd1d", y0, p, ts, rtol=1e-6, atol=1e-9, nthreads=8)
+    s = getattr(nbk, cls)("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    assert s._regime == 1
+    assert rel(s.h, ref["h0"]) < 1e-12
+    t, y = s.run(ts)
+    assert y.shape == (B, 2, n)
+    assert np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
+    assert within(y, ref["ys"], 1e-6, 1e-9).all()
+    assert rel(y, ref["ys"]) < 1e-9 and rel(s.y, ref["y_end"]) < 1e-7 and rel(s.t, ref["t_end"]) < 1e-7
+    assert (s.status == 0).all() and s.K.shape == (B, s.STAGE_ROWS, n) and s.cache.ys.shape == (B, 2, n)
+
+
+def test_linear_shared_matrix_vs_oracle():
+    """C4: y' = A y, n = 128, one dense A shared by the whole ensemble."""
+    B, n = 300, 128
+    y0, A = onp.linear_ensemble(B, n=n, seed=2)
+    ref = oc.run_ensemble("RungeKutta45", "linear", y0, A, [1.0, 10.0], rtol=1e-6, atol=1e-9, params_shared=True, nthreads=8)
+    s = nbk.RungeKutta45("linear", 0.0, y0, A, rtol=1e-6, atol=1e-9)
+    assert s._regime == 1 and not s.is_jit
+    t, y = s.run([1.0, 10.0])
+    assert np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
+    assert within(y, ref["ys"], 1e-6, 1e-9).all() and rel(y, ref["ys"]) < 1e-9
+
+
+def test_golden_large_n_cases_through_cta_kernels():
+    for c in load_golden("adaptive_single.json"):
+        if c["rhs"] not in ("rd1d", "linear"):
+            continue
+        kw = dict(c["kw"])
+        s = getattr(nbk, c["cls"])(c["rhs"], 0.0, np.array(c["y0"]), np.array(c["p"]), **kw)
+        assert s._regime == 1
+        assert rel(float(s.h), c["h0"]) < 1e-12 and rel(s.f, c["f0"]) < 1e-13
+        t, y = s.run(c["ts"])
+        assert s.n_accepted == c["n_accepted"]
+        assert rel(y, c["ys"]) < 1e-9 and rel(s.K, c["K_end"]) < 1e-6
+        assert isinstance(s.t, float) and s.y.shape == (len(c["y0"]),)
+
+
+USER_RD1D = """
+NBK_RHS_I nbk_rhs_i(double t, const double* y, const double* p, int i, int n) {
+    const double yl = y[i == 0 ? n - 1 : i - 1], yr = y[i + 1 == n ? 0 : i + 1];
+    return p[0] * (yr - 2 * y[i] + yl) + p[1] * y[i] * (1 - y[i]);
+}
+"""
+
+
+def test_user_cuda_rhs_and_api_in_cta_regime():
+    B, n = 10, 600
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=5)
+    a = nbk.RungeKutta45("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    b = nbk.RungeKutta45(nbk.CudaRHS(USER_RD1D), 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    assert b.is_jit and b._regime == 1
+    ta, ya = a.run([0.2, 0.4])
+    tb, yb = b.run([0.2, 0.4])
+    assert np.array_equal(a.n_accepted, b.n_accepted) and rel(ya, yb) < 1e-12
+    # step / skip / resumed run / interpolate / t_bound in the CTA regime
+    c = nbk.RungeKutta45("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    t1, y1 = c.step(n=5)
+    assert t1.shape == (B, 5) and y1.shape == (B, 5, n)
+    c.skip(n=3)
+    o = onp.AdaptiveRK("RungeKutta45", onp.rhs_rd1d, 0.0, y0[0], p[0], rtol=1e-6, atol=1e-9)
+    tr, yr = onp.steps(o, n=8)
+    assert rel(t1[0], tr[:5]) < 1e-10 and rel(y1[0], yr[:5]) < 1e-9 and rel(c.t[0], tr[-1]) < 1e-10
+    tc, yc = c.run([0.4])
+    assert within(yc, ya[:, 1:], 1e-6, 1e-9, slack=1).all()
+    lo, hi = c.cache.ts
+    mid = c.interpolate(float(max(lo.max(), hi.min() - 1e-4)))
+    assert mid.shape == (B, n) and np.isfinite(mid).all()
+    d = nbk.RungeKutta45("rd1d", 0.0, y0[0], p[0], rtol=1e-6, atol=1e-9, t_bound=0.1)
+    with pytest.raises(ValueError):
+        d.run([0.2])
+    td, yd = d.step(upto_t=0.1)
+    assert len(td) > 0 and td[-1] <= 0.1 and d.status == 1
