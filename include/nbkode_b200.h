@@ -74,8 +74,9 @@ typedef struct {
     const char *rhs_src;  /* CUDA C source compiled by NVRTC into the integrator kernels; or NULL.  Defines
                                NBK_RHS nbk_rhs(double t, const double* y, const double* p, double* dy)
                              (per-thread regime, y/dy in registers) or, for large systems,
-                               NBK_RHS_I nbk_rhs_i(double t, const double* y, const double* p, int i, int n)
-                             (CTA regime: returns component i, y is the whole vector in shared memory).
+                               NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n)
+                             (CTA regime: returns component i; y[j] reads component j of the whole vector, which lives in
+                             shared memory).
                              Replaces numba.njit(rhs) of nbkode/core.py:125-132. */
     /* VariableStepOptions, nbkode/core.py:661-679 (min_step/max_step are never enforced by
        the reference and therefore absent) */

@@ -30,12 +30,28 @@ namespace nbk {
 NBK_DEV double block_sum(double v, double *red, int nwarps) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    double tot = 0.0;
-    for (int w = 0; w < nwarps; ++w) tot += red[w];
+    // every warp reduces the (<= 32) warp partials with the same butterfly: identical total everywhere
+    double tot = lane < nwarps ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     return tot;
 }
+
+// The stage-argument vector in shared memory.  Thread `tid` owns the E consecutive components
+// i = tid*E + e, but they are stored TRANSPOSED, component (tid, e) at base[e*T + tid]: for a fixed e
+// the 32 lanes of a warp touch 32 consecutive doubles, so neither the stores of the owners nor the
+// halo reads of a stencil have bank conflicts (the natural order would be a 4-way conflict for E = 4;
+// measured 65 % of all shared wavefronts were replays).  operator[] takes the natural index.
+template <int E>
+struct smem_vec {
+    const double *base;
+    int T;
+    NBK_DEV double operator[](int i) const { return base[(i % E) * T + i / E]; }
+    NBK_DEV double at(int tid, int e) const { return base[e * T + tid]; }
+};
 
 // =====================================================================================
 // Right-hand sides of the CTA regime:
@@ -46,17 +62,19 @@ NBK_DEV double block_sum(double v, double *red, int nwarps) {
 struct rhs_rd1d_cta {  // periodic 1-D reaction-diffusion: d (y[i+1] - 2 y[i] + y[i-1]) + r y (1 - y)
     static constexpr int NP = 2;
     template <int E>
-    static NBK_DEV void eval(double, const double (&yown)[E], const double *ysm, const double *p, int i0, int n,
+    static NBK_DEV void eval(double, const double (&yown)[E], smem_vec<E> ysm, const double *p, int i0, int n,
                              double (&dy)[E]) {
         const double d = __ldg(p), r = __ldg(p + 1);
         if (i0 >= n) return;
         // only the two halo values come from shared memory, the interior from registers
         double left = ysm[i0 == 0 ? n - 1 : i0 - 1];
+        const int ilast = i0 + E - 1 < n ? i0 + E - 1 : n - 1;
+        const double halo_right = ysm[ilast + 1 == n ? 0 : ilast + 1];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int i = i0 + e;
             if (i < n) {
-                const double right = (e + 1 < E && i + 1 < n) ? yown[e + 1 < E ? e + 1 : e] : ysm[i + 1 == n ? 0 : i + 1];
+                const double right = (i == ilast) ? halo_right : yown[e + 1 < E ? e + 1 : e];
                 dy[e] = d * (right - 2 * yown[e] + left) + r * yown[e] * (1 - yown[e]);
                 left = yown[e];
             }
@@ -68,7 +86,7 @@ struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANS
                          // consecutive threads read consecutive addresses; y[j] is a broadcast smem read
     static constexpr int NP = -1;  // n*n, run-time
     template <int E>
-    static NBK_DEV void eval(double, const double (&)[E], const double *ysm, const double *At, int i0, int n,
+    static NBK_DEV void eval(double, const double (&)[E], smem_vec<E> ysm, const double *At, int i0, int n,
                              double (&dy)[E]) {
         double acc[E];
 #pragma unroll
@@ -86,12 +104,12 @@ struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANS
 
 #ifdef NBK_USER_RHS_CTA
 // User right-hand side of the CTA regime, compiled by NVRTC: component-wise
-//   __device__ double nbk_rhs_i(double t, const double* y, const double* p, int i, int n)
-// where y is the whole stage-argument vector (shared memory).
+//   NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n)
+// where y[j] reads component j of the whole stage-argument vector (shared memory).
 struct rhs_user_cta {
     static constexpr int NP = -1;
     template <int E>
-    static NBK_DEV void eval(double t, const double (&)[E], const double *ysm, const double *p, int i0, int n,
+    static NBK_DEV void eval(double t, const double (&)[E], smem_vec<E> ysm, const double *p, int i0, int n,
                              double (&dy)[E]) {
 #pragma unroll
         for (int e = 0; e < E; ++e)
@@ -127,11 +145,12 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
             ys[e] = fma(h, acc, y[e]);
         }
         double *buf = (s & 1) ? buf1 : buf0;
+        const int T = blockDim.x;
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-            if (i0 + e < n) buf[i0 + e] = ys[e];
+        for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = ys[e];  // transposed, conflict-free (see smem_vec)
         __syncthreads();
-        Rhs::template eval<E>(s < S ? fma(h, Tab::cb().c[s < S ? s : 0], t) : t + h, ys, buf, p, i0, n, K[s]);
+        Rhs::template eval<E>(s < S ? fma(h, Tab::cb().c[s < S ? s : 0], t) : t + h, ys, smem_vec<E>{buf, T}, p, i0, n,
+                              K[s]);
         if (s == S) {
 #pragma unroll
             for (int e = 0; e < E; ++e) ynew[e] = ys[e];
@@ -195,10 +214,10 @@ NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
         for (int e = 0; e < E; ++e) {
             y[e] = i0 + e < n ? a.y0[idx * a.y0_sb + (long long)(i0 + e) * a.y0_sc] : 0.0;
             f[e] = 0.0;
-            if (i0 + e < n) buf0[i0 + e] = y[e];
+            buf0[e * blockDim.x + tid] = y[e];
         }
         __syncthreads();
-        Rhs::template eval<E>(a.t0, y, buf0, p, i0, n, f);
+        Rhs::template eval<E>(a.t0, y, smem_vec<E>{buf0, (int)blockDim.x}, p, i0, n, f);
         double h = a.h0 ? a.h0[idx] : a.h_init;
         if (!(h == h)) {
             // scipy select_initial_step (direction +1, unbounded), SURVEY.md row a4
@@ -212,10 +231,10 @@ NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
             for (int e = 0; e < E; ++e) {
                 y1[e] = y[e] + h0 * f[e];
                 f1[e] = 0.0;
-                if (i0 + e < n) buf1[i0 + e] = y1[e];
+                buf1[e * blockDim.x + tid] = y1[e];
             }
             __syncthreads();
-            Rhs::template eval<E>(a.t0 + h0, y1, buf1, p, i0, n, f1);
+            Rhs::template eval<E>(a.t0 + h0, y1, smem_vec<E>{buf1, (int)blockDim.x}, p, i0, n, f1);
 #pragma unroll
             for (int e = 0; e < E; ++e) f1[e] -= f[e];
             const double d2 = cta_rms_scaled<E>(f1, sc, i0, n, red, nwarps) / h0;

@@ -83,7 +83,7 @@ def test_golden_large_n_cases_through_cta_kernels():
 
 
 USER_RD1D = """
-NBK_RHS_I nbk_rhs_i(double t, const double* y, const double* p, int i, int n) {
+NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n) {
     const double yl = y[i == 0 ? n - 1 : i - 1], yr = y[i + 1 == n ? 0 : i + 1];
     return p[0] * (yr - 2 * y[i] + yl) + p[1] * y[i] * (1 - y[i]);
 }

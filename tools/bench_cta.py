@@ -1,0 +1,37 @@
+"""Secondary benchmark (GPU box): BASELINE.json configs[4] -- 1-D reaction-diffusion method of lines,
+n = 2048 per trajectory, RungeKutta45 rtol=1e-6 atol=1e-9, t in [0, 1], one CTA per trajectory (K3) --
+and configs[3] -- linear y' = A y, n = 128, shared dense A (generic K3 path; the DMMA kernel K4 is not built yet).
+Reports attempted steps/s and the FP64 roofline fraction (6R + 66n + 18 FLOP per attempt)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "numbakit-ode_b200")]
+import numpy as np, torch
+import nbkode_b200 as nbk
+from oracle import nbk_oracle_np as onp
+
+which = sys.argv[1] if len(sys.argv) > 1 else "rd1d"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else (16384 if which == "rd1d" else 65536)
+peak, _ = nbk.fp64_peak(0, 20000)
+if which == "rd1d":
+    n, T = 2048, 1.0
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+    flop = 6 * 8 * n + 66 * n + 18
+    mk = lambda: nbk.RungeKutta45("rd1d", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
+else:
+    n, T = 128, 10.0
+    y0, p = onp.linear_ensemble(B, n=n, seed=2)
+    flop = 6 * 2 * n * n + 66 * n + 18
+    mk = lambda: nbk.RungeKutta45("linear", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
+y0d, pd = torch.from_numpy(y0).cuda(), torch.from_numpy(p).cuda()
+times = []
+for it in range(4):
+    s = mk()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); s.run([T]); e1.record(); torch.cuda.synchronize()
+    times.append(e0.elapsed_time(e1))
+s.raise_for_status()
+att = int((s._nacc.sum() + s._nrej.sum()).item()); acc = int(s._nacc.sum().item())
+ms = min(times[1:])
+print(json.dumps({"config": which, "B": B, "n": n, "ms": ms, "times": times, "accepted_steps": acc, "attempts": att,
+                  "accepted_steps_per_s": acc / ms * 1e3, "flop_per_attempt": flop, "tflops": att * flop / ms * 1e3 / 1e12,
+                  "peak_tflops": peak, "frac": att * flop / ms * 1e3 / 1e12 / peak, "launch": s.last_launch()}))
