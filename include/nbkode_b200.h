@@ -153,6 +153,8 @@ int nbk_jit_compile_only(const nbk_config *cfg, long long *cubin_bytes);
 /* FP64 vector-pipe roofline denominator: runs a register-resident DFMA chain kernel for
    `iters` iterations and returns the achieved TFLOP/s (2 FLOP per DFMA) and its duration. */
 int nbk_fp64_peak(int device, int iters, double *tflops, double *millis);
+/* The same for the FP64 tensor pipe (mma.sync m8n8k4 f64): denominator for shared-matrix linear systems. */
+int nbk_fp64_mma_peak(int device, int iters, double *tflops, double *millis);
 
 #ifdef __cplusplus
 }

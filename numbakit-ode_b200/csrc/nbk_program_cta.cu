@@ -43,6 +43,8 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->n = -1;  // any n: run-time
     out->n_params = nbk_rhs_t::NP;
     out->cta_elems = NBK_E;
+    out->mma_tile = 0;
+    out->mma_smem = 0;
     out->k_init = (const void *)&NBK_KERNEL(init);
     out->k_run = (const void *)&NBK_KERNEL(run);
     out->k_step = (const void *)&NBK_KERNEL(step);

@@ -44,7 +44,7 @@ _lib = None
 
 EXPORTS = (
     "nbk_version", "nbk_last_error", "nbk_create", "nbk_destroy", "nbk_layout", "nbk_is_jit", "nbk_regime", "nbk_init",
-    "nbk_run", "nbk_step", "nbk_last_launch", "nbk_jit_compile_only", "nbk_fp64_peak",
+    "nbk_run", "nbk_step", "nbk_last_launch", "nbk_jit_compile_only", "nbk_fp64_peak", "nbk_fp64_mma_peak",
 )
 
 
@@ -74,6 +74,7 @@ def lib():
     L.nbk_last_launch.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.nbk_jit_compile_only.argtypes = [C.POINTER(NbkConfig), C.POINTER(ll)]
     L.nbk_fp64_peak.argtypes = [i, i, C.POINTER(dbl), C.POINTER(dbl)]
+    L.nbk_fp64_mma_peak.argtypes = [i, i, C.POINTER(dbl), C.POINTER(dbl)]
     _lib = L
     return L
 
@@ -95,4 +96,11 @@ def fp64_peak(device=0, iters=20000):
     """Measured FP64 DFMA throughput of the device: (TFLOP/s, milliseconds)."""
     tf, ms = C.c_double(0), C.c_double(0)
     check(lib().nbk_fp64_peak(device, iters, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+def fp64_mma_peak(device=0, iters=4000):
+    """Measured FP64 tensor-pipe (DMMA m8n8k4) throughput: (TFLOP/s, milliseconds)."""
+    tf, ms = C.c_double(0), C.c_double(0)
+    check(lib().nbk_fp64_mma_peak(device, iters, C.byref(tf), C.byref(ms)))
     return tf.value, ms.value

@@ -120,3 +120,46 @@ def test_user_cuda_rhs_and_api_in_cta_regime():
         d.run([0.2])
     td, yd = d.step(upto_t=0.1)
     assert len(td) > 0 and td[-1] <= 0.1 and d.status == 1
+
+
+def test_linear_dmma_kernel_k4():
+    """K4 (csrc/nbk_mma.cuh): right-hand side of a 16-trajectory tile as an FP64 DMMA GEMM.  Checked
+    against the C oracle and against the generic CTA kernel (NBK_NO_MMA=1) on the same ensemble,
+    including a partial last tile, n < 128 (zero-padded rows), dense output and step()."""
+    import os
+
+    for n, B in ((128, 300), (96, 37), (8, 5)):
+        y0, A = onp.linear_ensemble(B, n=n, seed=2)
+        ts = [0.5, 1.0, 4.0, 10.0]
+        ref = oc.run_ensemble("RungeKutta45", "linear", y0, A, ts, rtol=1e-6, atol=1e-9, params_shared=True, nthreads=8)
+        s = nbk.RungeKutta45("linear", 0.0, y0, A, rtol=1e-6, atol=1e-9)
+        assert s._regime == 1 and s.last_launch()["block"] == 0  # nothing launched yet by run/step
+        t, y = s.run(ts)
+        assert s.last_launch()["block"] == 256  # the DMMA program
+        assert np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
+        assert within(y, ref["ys"], 1e-6, 1e-9).all() and rel(y, ref["ys"]) < 1e-9
+        assert rel(s.t, ref["t_end"]) < 1e-7 and rel(s.y, ref["y_end"]) < 1e-7 and rel(s.h, ref["h_end"]) < 1e-6
+        os.environ["NBK_NO_MMA"] = "1"
+        try:
+            g = nbk.RungeKutta45("linear", 0.0, y0, A, rtol=1e-6, atol=1e-9)
+        finally:
+            del os.environ["NBK_NO_MMA"]
+        tg, yg = g.run(ts)
+        assert g.last_launch()["block"] != 256
+        assert np.array_equal(g.n_accepted, s.n_accepted) and rel(y, yg) < 1e-11 and rel(s.K, g.K) < 1e-9
+        # resumed run and step() through K4
+        r = nbk.RungeKutta45("linear", 0.0, y0, A, rtol=1e-6, atol=1e-9)
+        _, y1 = r.run(ts[:2])
+        _, y2 = r.run(ts[2:])
+        assert np.array_equal(np.concatenate([y1, y2], 1), y)
+        mid = 0.5 * (r.cache.ts[0].max() + r.cache.ts[1].min())
+        if r.cache.ts[0].max() <= mid <= r.cache.ts[1].min():
+            assert rel(r.interpolate(float(mid)), g.interpolate(float(mid))) < 1e-10
+        q = nbk.RungeKutta45("linear", 0.0, y0, A, rtol=1e-6, atol=1e-9)
+        tq, yq = q.step(n=4)
+        o = onp.AdaptiveRK("RungeKutta45", onp.rhs_linear, 0.0, y0[0], A, rtol=1e-6, atol=1e-9)
+        tr, yr = onp.steps(o, n=4)
+        assert rel(tq[0], tr) < 1e-10 and rel(yq[0], yr) < 1e-9
+    s23 = nbk.RungeKutta23("linear", 0.0, y0, A, rtol=1e-5, atol=1e-8)
+    ref = oc.run_ensemble("RungeKutta23", "linear", y0, A, [2.0], rtol=1e-5, atol=1e-8, params_shared=True)
+    assert within(s23.run([2.0])[1], ref["ys"], 1e-5, 1e-8).all() and np.abs(s23.n_accepted - ref["n_accepted"]).max() <= 1
