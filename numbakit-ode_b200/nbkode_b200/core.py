@@ -111,6 +111,7 @@ class Solver(ABC):
     LEN_HISTORY: int = 2
     METHOD_ID: int = 0
     STAGE_ROWS: int = 0
+    OUT_LAYOUT: str = "bmn"  # device layout of run()'s dense output: "bmn" = (B, m, n) as returned
 
     def __init_subclass__(cls, abstract=False, **kwargs):
         super().__init_subclass__(**kwargs)
@@ -447,11 +448,19 @@ class Solver(ABC):
         B, n, dev, m = self.B, self.n, self._device, int(grid_host.size)
         grid = _device_grid(grid_host, dev)
         fill = torch.empty if math.isinf(bound) else (lambda *a, **k: torch.full(*a, math.nan, **k))
-        y_out = fill((B, m, n), dtype=torch.float64, device=dev)
+        layout = os.environ.get("NBK_OUT_LAYOUT") or self.OUT_LAYOUT
+        if layout == "mnb" and self._regime == 0 and B > 1:
+            # device layout [m][n][B]: a warp's 32 trajectories write 32 consecutive doubles per output
+            # point and component (fixed-step kernels advance in lock-step); returned as a (B, m, n) view
+            store = fill((m, n, B), dtype=torch.float64, device=dev)
+            y_out, strides = store.permute(2, 0, 1), (1, n * B, B)
+        else:
+            y_out = fill((B, m, n), dtype=torch.float64, device=dev)
+            strides = (m * n, n, 1)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().nbk_run(
                 self._handle, C.byref(self._state), grid.data_ptr(), m, float(bound),
-                y_out.data_ptr(), m * n, n, 1, 0, self._stream(),
+                y_out.data_ptr(), strides[0], strides[1], strides[2], 0, self._stream(),
             ))
         self._oldest_host = None
         if self._torch_out and self._out_device.type == "cuda" and self._batched:
