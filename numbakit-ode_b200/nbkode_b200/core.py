@@ -48,7 +48,8 @@ def _device_grid(grid_host: np.ndarray, device):
         _GRID_CACHE.pop(next(iter(_GRID_CACHE)))
     if grid_host.nbytes <= 1 << 20:
         _GRID_CACHE[key] = dev
-    dev._nbk_pinned_src = pinned  # keep the staging buffer alive until the copy has run
+    # a cached grid may be used from other streams later: make sure the upload has landed
+    torch.cuda.current_stream(device).synchronize()
     return dev
 
 
@@ -268,7 +269,8 @@ class Solver(ABC):
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
-        return _torch().cuda.current_stream(self._device).cuda_stream
+        self._last_stream = _torch().cuda.current_stream(self._device)
+        return self._last_stream.cuda_stream
 
     def _to_device(self, x):
         torch = _torch()
@@ -277,18 +279,33 @@ class Solver(ABC):
         arr = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
         return torch.from_numpy(arr).to(self._device, non_blocking=True)
 
-    def _out(self, x):
+    def _out(self, x, wait=True):
         """Device tensor -> the caller's array type (NumPy, or a torch tensor on the device the
-        inputs came from; host tensors are returned in pinned memory)."""
+        inputs came from; host tensors are returned in pinned memory).  With ``wait=False`` the copy
+        to pinned memory is only queued: call :meth:`synchronize` before reading it."""
         if self._torch_out:
             if self._out_device.type == "cuda":
                 return x
             torch = _torch()
             host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
             host.copy_(x, non_blocking=True)
-            torch.cuda.current_stream(self._device).synchronize()
+            if wait:
+                torch.cuda.current_stream(self._device).synchronize()
             return host
         return x.detach().cpu().numpy()
+
+    def synchronize(self):
+        """Wait for everything queued by this solver on the current stream and raise if a trajectory
+        failed.  Needed after ``run(..., wait=False)`` / ``counts(wait=False)`` before the returned
+        pinned host tensors are read."""
+        stream = getattr(self, "_last_stream", None) or _torch().cuda.current_stream(self._device)
+        stream.synchronize()
+        with _torch().cuda.stream(stream):
+            self._raise_on_failure(self._unchecked or "a previous call")
+
+    def counts(self, wait=True):
+        """(n_accepted, n_rejected) per trajectory in the caller's array type."""
+        return self._out(self._nacc, wait), self._out(self._nrej, wait)
 
     def _host(self, x):
         return x.detach().cpu().numpy()
@@ -443,7 +460,7 @@ class Solver(ABC):
             self._advance(int(n), upto_t, False)
 
     # ------------------------------------------------------------------ run / interpolate
-    def _run_grid(self, grid_host: np.ndarray, bound: float):
+    def _run_grid(self, grid_host: np.ndarray, bound: float, wait: bool = True):
         torch = _torch()
         B, n, dev, m = self.B, self.n, self._device, int(grid_host.size)
         grid = _device_grid(grid_host, dev)
@@ -463,16 +480,18 @@ class Solver(ABC):
                 y_out.data_ptr(), strides[0], strides[1], strides[2], 0, self._stream(),
             ))
         self._oldest_host = None
-        if self._torch_out and self._out_device.type == "cuda" and self._batched:
-            self._unchecked = "run"  # results stay on the device: failed trajectories (sticky status,
-            # NaN outputs) are reported by the next synchronising call or raise_for_status()
+        if (self._torch_out and self._out_device.type == "cuda" and self._batched) or not wait:
+            self._unchecked = "run"  # results stay on the device (or the caller asked not to wait): failed
+            # trajectories (sticky status, NaN outputs) are reported by the next synchronising call
         else:
             self._raise_on_failure("run")
         return y_out
 
-    def run(self, t):
+    def run(self, t, wait: bool = True):
         """Integrate, interpolating at each time of ``t`` (nbkode/core.py:315-332, 385-447).
-        Steps are never clipped to the output times."""
+        Steps are never clipped to the output times.  ``wait=False`` (batched solvers with host
+        torch tensors) only queues the work and the copy of the result to pinned memory, so that
+        several ensembles can be pipelined on different CUDA streams; see :meth:`synchronize`."""
         t = np.atleast_1d(np.asarray(t.detach().cpu() if hasattr(t, "detach") else t)).astype(np.float64)
         is_sorted = t.size == 1 or bool(np.all(t[:-1] <= t[1:]))
         if not is_sorted:
@@ -487,7 +506,7 @@ class Solver(ABC):
                 f"Cannot interpolate at t={t[0]} as it is smaller than the current smallest value in history ({oldest})"
             )
         self._check_time(np.max(t))
-        y_out = self._run_grid(t, self.t_bound)
+        y_out = self._run_grid(t, self.t_bound, wait or not self._batched)
         if not self._batched:
             k = int(self._nout[0].item())  # < m only if the t_bound guard fired (prefix, core.py:611-617)
             ts, ys = t[:k], self._out(y_out[0, :k].reshape((k,) + self._y0_shape))
@@ -500,7 +519,7 @@ class Solver(ABC):
             ondx = np.argsort(ndx)
             ys = ys[:, _torch().from_numpy(ondx).to(self._device)]
             t = t[ondx]
-        return t, self._out(ys)
+        return t, self._out(ys, wait)
 
     def run_events(self, t, events):
         if events:
