@@ -54,6 +54,12 @@ extern "C" {
 #define NBK_AB3 3
 #define NBK_AB4 4
 #define NBK_AB5 5
+/* fixed-step explicit Runge-Kutta classes, nbkode/runge_kutta/explicit.py:102-129 */
+#define NBK_RUNGE2 202
+#define NBK_RUNGE3 203
+#define NBK_HEUN3 213
+#define NBK_RK4 204
+#define NBK_RK38 238
 
 /* per-trajectory status */
 #define NBK_TRAJ_OK 0
@@ -64,7 +70,7 @@ extern "C" {
 typedef struct nbk_solver nbk_solver;
 
 typedef struct {
-    int method;           /* NBK_RK23, NBK_RK45, NBK_AB1..5 */
+    int method;           /* NBK_RK23, NBK_RK45, NBK_AB1..5, NBK_RUNGE2 ... NBK_RK38 */
     int n;                /* state size */
     int n_params;         /* parameters per trajectory (0 allowed) */
     int params_shared;    /* 1: one parameter vector for the whole ensemble */

@@ -197,6 +197,38 @@ struct tab_ab {
     }
 };
 
+// Fixed-step explicit Runge-Kutta classes of the reference (nbkode/runge_kutta/explicit.py:102-129):
+// Runge2 (202), Runge3 (203, four stages as the reference lists it), Heun3 (213), RungeKutta4 (204),
+// RungeKutta3_8 (238).
+template <int ID>
+struct tab_erk {
+    static constexpr int S = ID == 202 ? 2 : (ID == 213 ? 3 : 4);
+    static NBK_HD double a(int i, int j) {
+        constexpr double A202[4][4] = {{0}, {1.0 / 2}};
+        constexpr double A203[4][4] = {{0}, {1.0 / 2}, {0, 1}, {0, 0, 1}};
+        constexpr double A213[4][4] = {{0}, {1.0 / 3}, {0, 2.0 / 3}};
+        constexpr double A204[4][4] = {{0}, {1.0 / 2}, {0, 1.0 / 2}, {0, 0, 1}};
+        constexpr double A238[4][4] = {{0}, {1.0 / 3}, {-1.0 / 3, 1}, {1, -1, 1}};
+        return ID == 202 ? A202[i][j] : ID == 203 ? A203[i][j] : ID == 213 ? A213[i][j] : ID == 204 ? A204[i][j] : A238[i][j];
+    }
+    static NBK_HD double b(int j) {
+        constexpr double B202[4] = {0, 1.0};
+        constexpr double B203[4] = {1.0 / 6, 4.0 / 6, 0, 1.0 / 6};
+        constexpr double B213[4] = {1.0 / 4, 0, 3.0 / 4};
+        constexpr double B204[4] = {1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6};
+        constexpr double B238[4] = {1.0 / 8, 3.0 / 8, 3.0 / 8, 1.0 / 8};
+        return ID == 202 ? B202[j] : ID == 203 ? B203[j] : ID == 213 ? B213[j] : ID == 204 ? B204[j] : B238[j];
+    }
+    static NBK_HD double c(int j) {
+        constexpr double C202[4] = {0, 1.0 / 2};
+        constexpr double C203[4] = {0, 1.0 / 2, 1, 1};
+        constexpr double C213[4] = {0, 1.0 / 3, 2.0 / 3};
+        constexpr double C204[4] = {0, 1.0 / 2, 1.0 / 2, 1};
+        constexpr double C238[4] = {0, 1.0 / 3, 2.0 / 3, 1};
+        return ID == 202 ? C202[j] : ID == 203 ? C203[j] : ID == 213 ? C213[j] : ID == 204 ? C204[j] : C238[j];
+    }
+};
+
 // runtime-order copy for the (cold) multistep start-up with an Adams-Bashforth first stepper
 NBK_DEV double ab_weight(int order, int j) {
     const double Bv[6][5] = {
@@ -1013,6 +1045,179 @@ NBK_DEV void init_ab(const nbk_kargs &a) {
     a.n_acc[idx] = 0;
     a.n_rej[idx] = 0;
     a.status[idx] = status;
+}
+
+// =====================================================================================
+// Fixed-step explicit Runge-Kutta (Runge2, Runge3, Heun3, RungeKutta4, RungeKutta3_8):
+// stage loop nbkode/runge_kutta/explicit.py:28-46, step runge_kutta/core.py:33-42, dense output
+// = Hermite over the last step (core.py:577-596 with LEN_HISTORY = 2).  Static mapping like the
+// Adams-Bashforth kernels: all trajectories take the same number of steps.
+// =====================================================================================
+template <int ID, class Rhs>
+NBK_DEV void init_erk(const nbk_kargs &a) {
+    constexpr int N = Rhs::N, NPX = Rhs::NP > 0 ? Rhs::NP : 1, S = tab_erk<ID>::S;
+    const long long B = a.B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B) return;
+    double y[N], f[N], p[NPX];
+    load_initial<Rhs>(a, idx, y, p);
+    Rhs::eval(a.t0, y, p, f);
+    a.ts[idx] = a.t0;
+    a.ts[B + idx] = a.t0;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        a.ys[(long long)c * B + idx] = y[c];
+        a.ys[(long long)(N + c) * B + idx] = y[c];
+        a.fs[(long long)c * B + idx] = f[c];
+        a.fs[(long long)(N + c) * B + idx] = f[c];
+#pragma unroll
+        for (int s = 0; s < S; ++s) a.K[((long long)s * N + c) * B + idx] = 0.0;
+    }
+    a.h[idx] = a.h0 ? a.h0[idx] : a.h_init;
+    a.n_acc[idx] = 0;
+    a.n_rej[idx] = 0;
+    a.status[idx] = NBK_TRAJ_OK;
+}
+
+template <int ID, class Rhs, int MODE>
+NBK_DEV void advance_erk(const nbk_kargs &a) {
+    using Tab = tab_erk<ID>;
+    constexpr int N = Rhs::N, NP = Rhs::NP, NPX = NP > 0 ? NP : 1, S = Tab::S;
+    const long long B = a.B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B) return;
+    double ts[2], ys[2][N], fs[2][N], K[S][N], p[NPX];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        ts[l] = a.ts[(long long)l * B + idx];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            ys[l][c] = a.ys[((long long)l * N + c) * B + idx];
+            fs[l][c] = a.fs[((long long)l * N + c) * B + idx];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int c = 0; c < N; ++c) K[s][c] = 0.0;
+    const double h = a.h[idx];
+    load_params<NP>(a, idx, p);
+    int kout = 0, status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
+    long long nsteps = 0;
+    double te_next = d_inf();
+    bool running;
+    if (status != NBK_TRAJ_OK) {
+        running = false;
+        if (MODE == NBK_MODE_RUN)
+            for (int k = 0; k < a.m; ++k)
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + k * a.o_sk + c * a.o_sc] = d_nan();
+    } else if (MODE == NBK_MODE_RUN) {
+        while (kout < a.m && __ldg(a.tgrid + kout) <= ts[1]) {
+            double out[N];
+            hermite_window<2, N>(__ldg(a.tgrid + kout), ts, ys, fs, out);
+#pragma unroll
+            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+            ++kout;
+        }
+        running = kout < a.m;
+        if (running) te_next = __ldg(a.tgrid + kout);
+    } else {
+        running = a.n_steps > 0;
+    }
+    while (running) {
+        if (ts[1] + h > a.bound) {
+            status = NBK_TRAJ_BOUND;
+            break;
+        }
+        const double t = ts[1];
+#pragma unroll
+        for (int c = 0; c < N; ++c) K[0][c] = fs[1][c];
+#pragma unroll
+        for (int s = 1; s < S; ++s) {
+            double ystage[N];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                double acc = 0.0;
+                bool first = true;
+#pragma unroll
+                for (int j = 0; j < s; ++j) {
+                    if (Tab::a(s, j) != 0.0) {
+                        acc = first ? Tab::a(s, j) * K[j][c] : fma(Tab::a(s, j), K[j][c], acc);
+                        first = false;
+                    }
+                }
+                ystage[c] = fma(h, acc, ys[1][c]);
+            }
+            Rhs::eval(fma(h, Tab::c(s), t), ystage, p, K[s]);
+        }
+        const double t_new = t + h;
+        double ynew[N], fnew[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            // y + (h*B) . K with the vector h*B formed first, as the reference does
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                if (Tab::b(j) != 0.0) {
+                    acc = first ? (h * Tab::b(j)) * K[j][c] : fma(h * Tab::b(j), K[j][c], acc);
+                    first = false;
+                }
+            }
+            ynew[c] = ys[1][c] + acc;
+        }
+        Rhs::eval(t_new, ynew, p, fnew);
+        ts[0] = ts[1];
+        ts[1] = t_new;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            ys[0][c] = ys[1][c];
+            fs[0][c] = fs[1][c];
+            ys[1][c] = ynew[c];
+            fs[1][c] = fnew[c];
+        }
+        ++nsteps;
+        if (MODE == NBK_MODE_RUN) {
+            while (t_new >= te_next) {
+                double out[N];
+                hermite_window<2, N>(te_next, ts, ys, fs, out);
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                ++kout;
+                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+            }
+            running = kout < a.m;
+        } else {
+            if (a.emit) {
+                a.t_out[idx * a.to_sb + (nsteps - 1)] = t_new;
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + (nsteps - 1) * a.o_sk + c * a.o_sc] = ynew[c];
+            }
+            running = nsteps < a.n_steps;
+        }
+        if (running && nsteps >= a.max_attempts) {
+            status = NBK_TRAJ_MAXATTEMPTS;
+            break;
+        }
+    }
+    if (nsteps > 0) {
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            a.ts[(long long)l * B + idx] = ts[l];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                a.ys[((long long)l * N + c) * B + idx] = ys[l][c];
+                a.fs[((long long)l * N + c) * B + idx] = fs[l][c];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int c = 0; c < N; ++c) a.K[((long long)s * N + c) * B + idx] = K[s][c];
+        a.n_acc[idx] += nsteps;
+    }
+    a.status[idx] = status;
+    a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
 }
 
 }  // namespace nbk

@@ -4,7 +4,8 @@
 // -DNBK_TAG=..) and at run time by NVRTC for user right-hand sides (nbk_jit.cpp passes the
 // same macros plus -DNBK_USER_RHS and prepends the user's nbk_rhs definition).
 //
-// NBK_METHOD: 23 / 45 = RungeKutta23 / RungeKutta45; 1..5 = AdamsBashforth-k (1 == ForwardEuler).
+// NBK_METHOD: 23 / 45 = RungeKutta23 / RungeKutta45; 1..5 = AdamsBashforth-k (1 == ForwardEuler);
+// 202 / 203 / 213 / 204 / 238 = Runge2 / Runge3 / Heun3 / RungeKutta4 / RungeKutta3_8 (fixed step).
 #include "nbk_device.cuh"
 
 #define NBK_CAT2(a, b) a##b
@@ -21,8 +22,14 @@ typedef nbk::tab_rk23 nbk_tab_t;
 #define NBK_ADAPTIVE 1
 #elif NBK_METHOD >= 1 && NBK_METHOD <= 5
 #define NBK_ADAPTIVE 0
+#elif NBK_METHOD == 202 || NBK_METHOD == 203 || NBK_METHOD == 213 || NBK_METHOD == 204 || NBK_METHOD == 238
+#define NBK_ADAPTIVE 0
+#define NBK_FIXED_RK 1
 #else
-#error "NBK_METHOD must be 23, 45 or 1..5"
+#error "NBK_METHOD must be 23, 45, 1..5 or a fixed-step Runge-Kutta id (202, 203, 213, 204, 238)"
+#endif
+#ifndef NBK_FIXED_RK
+#define NBK_FIXED_RK 0
 #endif
 
 #ifndef NBK_MIN_BLOCKS
@@ -32,6 +39,8 @@ typedef nbk::tab_rk23 nbk_tab_t;
 extern "C" __global__ void __launch_bounds__(NBK_BLOCK) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
 #if NBK_ADAPTIVE
     nbk::init_adaptive<nbk_tab_t, nbk_rhs_t>(a);
+#elif NBK_FIXED_RK
+    nbk::init_erk<NBK_METHOD, nbk_rhs_t>(a);
 #else
     nbk::init_ab<NBK_METHOD, nbk_rhs_t>(a);
 #endif
@@ -40,6 +49,8 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK) NBK_KERNEL(init)(const _
 extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
 #if NBK_ADAPTIVE
     nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_RUN>(a);
+#elif NBK_FIXED_RK
+    nbk::advance_erk<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN>(a);
 #else
     nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN>(a);
 #endif
@@ -48,6 +59,8 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERN
 extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
 #if NBK_ADAPTIVE
     nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_STEP>(a);
+#elif NBK_FIXED_RK
+    nbk::advance_erk<NBK_METHOD, nbk_rhs_t, NBK_MODE_STEP>(a);
 #else
     nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_STEP>(a);
 #endif

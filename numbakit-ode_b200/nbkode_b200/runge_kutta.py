@@ -47,6 +47,54 @@ class RungeKutta(Solver, abstract=True):
         return self._out(full[0] if not self._batched else full)
 
 
+class ERK(RungeKutta, abstract=True):
+    """Fixed-step explicit Runge-Kutta (nbkode/runge_kutta/explicit.py:9-46, 102-129): default h = 1,
+    dense output by the Hermite cubic over the last step."""
+
+    @classproperty
+    def stages(cls):
+        return len(cls.A)
+
+    @classproperty
+    def STAGE_ROWS(cls):
+        return len(cls.A)
+
+
+class Runge2(ERK):
+    METHOD_ID = 202
+    A = np.array([[0, 0], [1 / 2, 0]])
+    B = np.array([0, 1.0])
+    C = np.array([0, 1 / 2])
+
+
+class Runge3(ERK):
+    METHOD_ID = 203
+    A = np.array([[0, 0, 0, 0], [1 / 2, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]])
+    B = np.array([1, 4, 0, 1]) / 6
+    C = np.array([0, 1 / 2, 1, 1])
+
+
+class Heun3(ERK):
+    METHOD_ID = 213
+    A = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0]]) / 3
+    B = np.array([1, 0, 3]) / 4
+    C = np.array([0, 1, 2]) / 3
+
+
+class RungeKutta4(ERK):
+    METHOD_ID = 204
+    A = np.array([[0, 0, 0, 0], [1 / 2, 0, 0, 0], [0, 1 / 2, 0, 0], [0, 0, 1, 0]])
+    B = np.array([1, 2, 2, 1]) / 6
+    C = np.array([0, 1, 1, 2]) / 2
+
+
+class RungeKutta3_8(ERK):
+    METHOD_ID = 238
+    A = np.array([[0, 0, 0, 0], [1 / 3, 0, 0, 0], [-1 / 3, 1, 0, 0], [1, -1, 1, 0]])
+    B = np.array([1, 3, 3, 1]) / 8
+    C = np.array([0, 1, 2, 3]) / 3
+
+
 class AdaptiveRungeKutta(RungeKutta, abstract=True):
     """FSAL embedded pairs with the reference's I-controller
     (nbkode/runge_kutta/core.py:56-128, explicit.py:49-99)."""

@@ -138,11 +138,26 @@ static const double AB_B[6][5] = {
     {55.0 / 24, -59.0 / 24, 37.0 / 24, -9.0 / 24},
     {1901.0 / 720, -2774.0 / 720, 2616.0 / 720, -1274.0 / 720, 251.0 / 720}};
 
+/* Fixed-step explicit RK tableaux (explicit.py:102-129): Runge2 202, Runge3 203, Heun3 213,
+   RungeKutta4 204, RungeKutta3_8 238 */
+typedef struct { int id, S; double A[4][4], B[4], C[4]; } erk_tab;
+static const erk_tab ERK_TABS[5] = {
+    {202, 2, {{0}, {1.0 / 2}}, {0, 1.0}, {0, 1.0 / 2}},
+    {203, 4, {{0}, {1.0 / 2}, {0, 1}, {0, 0, 1}}, {1.0 / 6, 4.0 / 6, 0, 1.0 / 6}, {0, 1.0 / 2, 1, 1}},
+    {213, 3, {{0}, {1.0 / 3}, {0, 2.0 / 3}}, {1.0 / 4, 0, 3.0 / 4}, {0, 1.0 / 3, 2.0 / 3}},
+    {204, 4, {{0}, {1.0 / 2}, {0, 1.0 / 2}, {0, 0, 1}}, {1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6}, {0, 1.0 / 2, 1.0 / 2, 1}},
+    {238, 4, {{0}, {1.0 / 3}, {-1.0 / 3, 1}, {1, -1, 1}}, {1.0 / 8, 3.0 / 8, 3.0 / 8, 1.0 / 8}, {0, 1.0 / 3, 2.0 / 3, 1}}};
+static const erk_tab *erk_lookup(int id) {
+    for (int i = 0; i < 5; ++i) if (ERK_TABS[i].id == id) return &ERK_TABS[i];
+    return 0;
+}
+
 /* ------------------------------------------------------------------ single-trajectory solver */
 
 typedef struct {
     const orc_config *cfg;
-    const tableau *tab;  /* NULL for Adams-Bashforth */
+    const tableau *tab;  /* NULL for Adams-Bashforth / fixed-step RK */
+    const erk_tab *erk;  /* fixed-step explicit RK, else NULL */
     rhs_fn rhs;
     const double *p;
     int n, L, order;
@@ -337,7 +352,38 @@ static void hermite_interp(const solver *s, double te, double *out) {
     }
 }
 
-static int any_step(solver *s, double bound) { return s->tab ? rk_step(s, bound) : ab_step(s, bound); }
+/* fixed-step explicit RK: explicit.py:28-46 + runge_kutta/core.py:33-42 */
+static int erk_step(solver *s, double bound) {
+    const erk_tab *T = s->erk;
+    const int n = s->n, S = T->S;
+    if (CUR_T(s) + s->h > bound) return 0;
+    const double t = CUR_T(s), h = s->h;
+    const double *y = CUR_Y(s);
+    double *K = s->K;
+    memcpy(K, CUR_F(s), sizeof(double) * n);
+    for (int st = 1; st < S; ++st) {
+        for (int i = 0; i < n; ++i) {
+            double dy = T->A[st][0] * K[i];
+            for (int j = 1; j < st; ++j) dy += T->A[st][j] * K[(size_t)j * n + i];
+            s->ytmp[i] = y[i] + h * dy;
+        }
+        s->rhs(t + h * T->C[st], s->ytmp, s->p, K + (size_t)st * n, n, s->cfg->np);
+    }
+    const double t_new = t + h;
+    for (int i = 0; i < n; ++i) {
+        double acc = (h * T->B[0]) * K[i];
+        for (int j = 1; j < S; ++j) acc += (h * T->B[j]) * K[(size_t)j * n + i];
+        s->ynew[i] = y[i] + acc;
+    }
+    s->rhs(t_new, s->ynew, s->p, s->ytmp, n, s->cfg->np);
+    push(s, t_new, s->ynew, s->ytmp);
+    s->n_acc++;
+    return 1;
+}
+
+static int any_step(solver *s, double bound) {
+    return s->tab ? rk_step(s, bound) : (s->erk ? erk_step(s, bound) : ab_step(s, bound));
+}
 static void any_interp(const solver *s, double te, double *out) {
     if (s->tab) rk_interp(s, te, out); else hermite_interp(s, te, out);
 }
@@ -405,11 +451,15 @@ static void run_one(const job *J, long i) {
     const int adaptive = c->method == 23 || c->method == 45;
     const tableau *T = c->method == 45 ? &DP45 : (c->method == 23 ? &BS23 : NULL);
     solver s;
-    solver_alloc(&s, c, T, adaptive ? 0 : c->method, c->rtol, c->atol, p);
+    const erk_tab *erk = erk_lookup(c->method);
+    solver_alloc(&s, c, T, (adaptive || erk) ? 0 : c->method, c->rtol, c->atol, p);
+    s.erk = erk;
     solver_start(&s, c->t0, J->y0 + (size_t)i * n);
     int status = 0;
     if (adaptive) {
         s.h = isnan(c->first_step) ? initial_step(&s, T->q) : c->first_step;
+    } else if (erk) {
+        s.h = c->h;
     } else {
         s.h = c->h;
         if (ab_startup(&s, c->first_stepper) != 0) status = 2;
@@ -460,7 +510,8 @@ static void *worker(void *arg) {
 int orc_run_ensemble(const orc_config *cfg, long B, const double *y0, const double *params,
                      const double *ts, int m, const orc_result *res, int nthreads) {
     if (!cfg || cfg->rhs < 0 || cfg->rhs > 4 || cfg->n < 1) return -1;
-    if (!(cfg->method == 23 || cfg->method == 45 || (cfg->method >= 1 && cfg->method <= 5))) return -1;
+    if (!(cfg->method == 23 || cfg->method == 45 || (cfg->method >= 1 && cfg->method <= 5) || erk_lookup(cfg->method)))
+        return -1;
     pthread_once(&tab_once, init_tableaux);
     job J;
     J.cfg = cfg; J.B = B; J.y0 = y0; J.params = params; J.ts = ts; J.m = m; J.res = *res;

@@ -310,6 +310,56 @@ class AdamsBashforth:
         return y0 + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * f0 + T * f1))
 
 
+# Fixed-step explicit Runge-Kutta tableaux (nbkode/runge_kutta/explicit.py:102-129)
+ERK_TABLEAUX = {
+    "Runge2": (np.array([[0, 0], [1 / 2, 0]]), np.array([0, 1.0]), np.array([0, 1 / 2])),
+    "Runge3": (np.array([[0, 0, 0, 0], [1 / 2, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]]), np.array([1, 4, 0, 1]) / 6,
+               np.array([0, 1 / 2, 1, 1])),
+    "Heun3": (np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0]]) / 3, np.array([1, 0, 3]) / 4, np.array([0, 1, 2]) / 3),
+    "RungeKutta4": (np.array([[0, 0, 0, 0], [1 / 2, 0, 0, 0], [0, 1 / 2, 0, 0], [0, 0, 1, 0]]),
+                    np.array([1, 2, 2, 1]) / 6, np.array([0, 1, 1, 2]) / 2),
+    "RungeKutta3_8": (np.array([[0, 0, 0, 0], [1 / 3, 0, 0, 0], [-1 / 3, 1, 0, 0], [1, -1, 1, 0]]),
+                      np.array([1, 3, 3, 1]) / 8, np.array([0, 1, 2, 3]) / 3),
+}
+
+
+class FixedRK:
+    """Fixed-step explicit Runge-Kutta classes of the reference (Runge2, Runge3, Heun3, RungeKutta4,
+    RungeKutta3_8): stage loop nbkode/runge_kutta/explicit.py:28-46, step runge_kutta/core.py:33-42,
+    dense output = window Hermite over the last step (nbkode/core.py:577-596)."""
+
+    def __init__(self, name, rhs, t0, y0, params=None, *, h=None, t_bound=np.inf):
+        self.A, self.B, self.C = ERK_TABLEAUX[name]
+        self.rhs = _bind(rhs, params)
+        self.t_bound = t_bound
+        self.h = np.array(h, dtype=float) if h is not None else 1
+        t0 = float(t0)
+        y0 = np.array(y0, dtype=float, ndmin=1)
+        self.cache = History(2, t0, y0, self.rhs(t0, y0))
+        self.K = np.zeros((len(self.A), y0.size))
+
+    t = property(lambda self: self.cache.t)
+    y = property(lambda self: self.cache.y)
+    f = property(lambda self: self.cache.f)
+
+    def step(self, bound=None):
+        bound = self.t_bound if bound is None else bound
+        c, K, h = self.cache, self.K, self.h
+        if c.t + h > bound:
+            return False
+        t, y = c.t, c.y
+        K[0] = c.f
+        for s in range(1, len(self.A)):
+            dy = self.A[s, :s] @ K[:s]
+            K[s] = self.rhs(t + h * self.C[s], y + h * dy)
+        t = t + h
+        y = y + h * self.B @ K
+        c.push(t, y, self.rhs(t, y))
+        return True
+
+    interpolate = AdamsBashforth.interpolate
+
+
 def run(solver, ts):
     """nbkode/core.py:598-619 (_run_eval) for points ahead of solver.t, preceded by the
     past-point branch of run_events (core.py:401-408).  ``ts`` must be sorted."""

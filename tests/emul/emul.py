@@ -56,7 +56,9 @@ RHS_TYPES = {"lorenz": ("nbk::rhs_lorenz", 3, 3), "vdp": ("nbk::rhs_vdp", 2, 1)}
 METHOD_IDS = {
     "RungeKutta23": 23, "RungeKutta45": 45, "ForwardEuler": 1, "AdamsBashforth1": 1, "AdamsBashforth2": 2,
     "AdamsBashforth3": 3, "AdamsBashforth4": 4, "AdamsBashforth5": 5,
+    "Runge2": 202, "Runge3": 203, "Heun3": 213, "RungeKutta4": 204, "RungeKutta3_8": 238,
 }
+ERK_STAGES = {202: 2, 203: 4, 213: 3, 204: 4, 238: 4}
 _libs = {}
 
 
@@ -101,8 +103,8 @@ class EmulEnsemble:
         self.np_ = params.shape[1]
         self.fn = _program(self.mid, rhs, self.n, self.np_)
         adaptive = self.mid in (23, 45)
-        self.L = 2 if adaptive else max(self.mid, 2)
-        self.SR = {23: 4, 45: 7}.get(self.mid, 0)
+        self.L = 2 if (adaptive or self.mid in ERK_STAGES) else max(self.mid, 2)
+        self.SR = {23: 4, 45: 7, **ERK_STAGES}.get(self.mid, 0)
         B, n = self.B, self.n
         self.ts = np.zeros((self.L, B)); self.ys = np.zeros((self.L, n, B)); self.fs = np.zeros((self.L, n, B))
         self.K = np.zeros((max(self.SR, 1), n, B)); self.h = np.zeros(B)

@@ -158,6 +158,18 @@ def main():
     fixed.append(fixed_case("AdamsBashforth2", "decay", [1.0, 2.0], [0.01, 0.05], [1.0, 10.0], 0.01))
     dump("fixed_single.json", fixed)
 
+    # ---------------------------------------------------------------- fixed-step explicit RK
+    erk = []
+    for cls in ("Runge2", "Runge3", "Heun3", "RungeKutta4", "RungeKutta3_8"):
+        erk.append(fixed_case(cls, "vdp", *vdp, [5.0, 10.0, 20.0], 0.01))
+        erk.append(fixed_case(cls, "vdp", [1.0, -0.5], [3.0], np.linspace(0, 4, 41), 0.0125))
+        erk.append(fixed_case(cls, "lorenz", *lor, np.linspace(0, 2, 21), 0.001))
+        erk.append(fixed_case(cls, "decay", [1.0, 2.0], [0.01, 0.05], [1.0, 10.0], 0.25))
+        s_ = getattr(nbkode, cls)(onp.rhs_vdp, 0.0, np.array([2.0, 0.0]), params=np.array([1.0]), h=0.05)
+        ts_, ys_ = s_.step(n=10)
+        erk[-1]["step10_t"], erk[-1]["step10_y"], erk[-1]["step10_K"] = L(ts_), L(ys_), L(s_.K)
+    dump("erk_fixed.json", erk)
+
     # ---------------------------------------------------------------- ensembles
     y0, p = onp.lorenz_ensemble(1_000_000, seed=0)
     ens = {"B_total": 1_000_000, "seed": 0, "rows": [], "rtol": 1e-6, "atol": 1e-9, "T": 10.0}

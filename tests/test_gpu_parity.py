@@ -103,6 +103,33 @@ def test_fixed_single(c):
     assert rel(s.y, c["y_end"]) <= tol and rel(s.f, c["f_end"]) <= tol
 
 
+@pytest.mark.parametrize("c", load_golden("erk_fixed.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_fixed_rk_single(c):
+    """Fixed-step explicit Runge-Kutta classes (SURVEY.md 8(f) #1): 1e-12 bar."""
+    s = getattr(nbk, c["cls"])(c["rhs"], 0.0, np.array(c["y0"]), np.array(c["p"]), h=c["h"])
+    tol = 1e-9 if c["rhs"] == "lorenz" else FIXED_TOL
+    t, y = s.run(c["ts"])
+    assert rel(y, c["ys"]) <= tol and s.t == c["t_end"]
+    assert rel(s.y, c["y_end"]) <= tol and rel(s.f, c["f_end"]) <= tol
+    if "step10_t" in c:
+        s = getattr(nbk, c["cls"])("vdp", 0.0, [2.0, 0.0], [1.0], h=0.05)
+        tt, yy = s.step(n=10)
+        assert rel(tt, c["step10_t"]) < 1e-15 and rel(yy, c["step10_y"]) <= FIXED_TOL and rel(s.K, c["step10_K"]) <= FIXED_TOL
+
+
+def test_fixed_rk_ensemble_vs_oracle():
+    B = 2048
+    y0, p = onp.vdp_ensemble(B, seed=1)
+    ts = np.linspace(0, 10, 101)
+    for cls in ("RungeKutta4", "Heun3", "Runge2", "Runge3", "RungeKutta3_8"):
+        ref = oc.run_ensemble(cls, "vdp", y0, p, ts, h=0.01, nthreads=8)
+        s = getattr(nbk, cls)("vdp", 0.0, y0, p, h=0.01)
+        t, y = s.run(ts)
+        per_traj = np.max(np.abs(y - ref["ys"]), axis=(1, 2)) / np.maximum(1.0, np.max(np.abs(ref["ys"]), axis=(1, 2)))
+        assert per_traj.max() <= FIXED_TOL, (cls, per_traj.max())
+        assert np.array_equal(s.t, ref["t_end"])
+
+
 # ------------------------------------------------------------------ C2: Lorenz ensemble
 def test_lorenz_golden_rows():
     g = load_golden("lorenz_ensemble_rk45.json")

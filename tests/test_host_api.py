@@ -15,7 +15,7 @@ from nbkode_b200.util import CaseInsensitiveDict
 
 from conftest import ROOT
 
-N_SOLVERS = 8  # ForwardEuler, AdamsBashforth1..5, RungeKutta23, RungeKutta45 (the explicit hot path)
+N_SOLVERS = 13  # ForwardEuler, AdamsBashforth1..5, RungeKutta23/45 (hot path) + the 5 fixed-step explicit RKs
 
 
 # ------------------------------------------------------------------ registry
@@ -27,7 +27,7 @@ def test_get_solvers_groups():
     assert len(nbkode.get_solvers("Euler")) == 1  # BackwardEuler is implicit: out of scope
     assert len(nbkode.get_solvers("euler")) == 1
     assert len(nbkode.get_solvers("adams-bashforth")) == 5
-    assert len(nbkode.get_solvers("Runge-Kutta")) == 2
+    assert len(nbkode.get_solvers("Runge-Kutta")) == 7
     assert nbkode.get_groups() == ("Adams-Bashforth", "Euler", "Runge-Kutta")
     with pytest.raises(KeyError):
         nbkode.get_solvers("not-a-group")
@@ -42,7 +42,8 @@ def test_get_solvers_filters():
     for solver in nbkode.get_solvers(fixed_step=False):
         assert solver.FIXED_STEP is False
     assert set(nbkode.get_solvers(fixed_step=False) + nbkode.get_solvers(fixed_step=True)) == set(nbkode.get_solvers())
-    assert set(nbkode.get_solvers(runge_kutta=True)) == {nbkode.RungeKutta23, nbkode.RungeKutta45}
+    assert {nbkode.RungeKutta23, nbkode.RungeKutta45, nbkode.RungeKutta4} <= set(nbkode.get_solvers(runge_kutta=True))
+    assert set(nbkode.get_solvers(runge_kutta=True, fixed_step=False)) == {nbkode.RungeKutta23, nbkode.RungeKutta45}
     assert len(nbkode.get_solvers(multistep=True)) == 6
     # README.rst:63 -- with the corrected IMPLICIT flag the explicit fixed-step solvers are listed
     assert nbkode.ForwardEuler in nbkode.get_solvers(implicit=False, fixed_step=True)
@@ -79,6 +80,10 @@ def test_class_attributes_match_reference_tableaux():
         assert np.array_equal(cls.B, onp.AB_B[k]) and cls.ORDER == k and cls.LEN_HISTORY == max(k, 2)
         assert cls.A[-1] == -1 and np.count_nonzero(cls.A) == 1
     assert nbkode.ForwardEuler.GROUP == "Euler" and nbkode.ForwardEuler.ALIASES == ("Euler",)
+    for name, (A, B, C) in onp.ERK_TABLEAUX.items():
+        cls = getattr(nbkode, name)
+        assert np.array_equal(cls.A, A) and np.array_equal(cls.B, B) and np.array_equal(cls.C, C)
+        assert cls.FIXED_STEP is True and cls.stages == len(A) and cls.LEN_HISTORY == 2
 
 
 # ------------------------------------------------------------------ CaseInsensitiveDict (test_util.py)

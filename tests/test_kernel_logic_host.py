@@ -65,6 +65,20 @@ def test_fixed_single_vs_reference(c):
     assert rel(e.y[0], c["y_end"]) < tol0 and rel(e.ts[:, 0], c["end_ts"]) < 1e-15
 
 
+@pytest.mark.parametrize("c", load_golden("erk_fixed.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_fixed_rk_vs_reference(c):
+    """Runge2 / Runge3 / Heun3 / RungeKutta4 / RungeKutta3_8 (SURVEY.md 8(f) #1): 1e-12 bar."""
+    e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], h=c["h"])
+    tol = 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    ys = e.run(c["ts"])
+    assert rel(ys[0], c["ys"]) < tol and e.t[0] == c["t_end"] and rel(e.y[0], c["y_end"]) < tol
+    if "step10_t" in c:
+        e = EmulEnsemble(c["cls"], "vdp", [[2.0, 0.0]], [[1.0]], h=0.05)
+        t_out, y_out, cnt = e.step(10)
+        assert cnt[0] == 10 and rel(t_out[0], c["step10_t"]) < 1e-15 and rel(y_out[0], c["step10_y"]) < 1e-12
+        assert rel(e.K[:, :, 0], c["step10_K"]) < 1e-12
+
+
 def test_lorenz_ensemble_queue():
     g = load_golden("lorenz_ensemble_rk45.json")
     rows = g["rows"]

@@ -96,3 +96,12 @@ def test_t_bound_prefix():
     r = oc.run_ensemble("AdamsBashforth2", "decay", [[1.0]], [0.1], [0.5, 1.0, 1.5, 2.0], h=0.1, t_bound=1.25, first_stepper=None)
     assert r["status"][0] == 1 and r["n_out"][0] == 2
     assert np.isnan(r["ys"][0, 2:]).all() and np.isfinite(r["ys"][0, :2]).all()
+
+
+@pytest.mark.parametrize("c", load_golden("erk_fixed.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_fixed_rk(c):
+    r = oc.run_ensemble(c["cls"], c["rhs"], [c["y0"]], c["p"], c["ts"], h=c["h"])
+    tol = 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    _close(r["ys"][0], c["ys"], tol, "ys")
+    assert r["t_end"][0] == c["t_end"]
+    _close(r["y_end"][0], c["y_end"], tol)

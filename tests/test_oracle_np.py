@@ -133,3 +133,19 @@ def test_api_semantics(c):
     _eq(t, c["seq"][2][1])
     t, y = onp.steps(s, n=5, upto_t=ts[7])
     _eq(t, c["seq"][3][1])
+
+
+@pytest.mark.parametrize("c", load_golden("erk_fixed.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_fixed_rk_bitexact(c):
+    """Fixed-step explicit Runge-Kutta classes (SURVEY.md 8(f) #1)."""
+    s = onp.FixedRK(c["cls"], onp.RHS[c["rhs"]], 0.0, np.array(c["y0"]), np.array(c["p"]), h=c["h"])
+    _eq(s.cache.ys, c["init_ys"])
+    t, y = onp.run(s, c["ts"])
+    _eq(y, c["ys"], "run(ts)")
+    assert s.t == c["t_end"]
+    _eq(s.y, c["y_end"])
+    _eq(s.f, c["f_end"])
+    if "step10_t" in c:
+        s = onp.FixedRK(c["cls"], onp.rhs_vdp, 0.0, np.array([2.0, 0.0]), np.array([1.0]), h=0.05)
+        tt, yy = onp.steps(s, n=10)
+        _eq(tt, c["step10_t"]); _eq(yy, c["step10_y"]); _eq(s.K, c["step10_K"])
