@@ -42,6 +42,22 @@ METRIC = "accepted RK45 steps/s, 1M-traj Lorenz FP64"
 UNIT = "accepted steps/s"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the integrator kernel, per launch, from the committed
+    `ncu --set full` capture of this same command (profiles/); None if no capture is present."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full_K1_nbk_run_rk45_lorenz.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+            return float(rd[0]) * unit[rd[1]] + float(wr[0]) * unit[wr[1]]
+        except Exception:  # noqa: BLE001
+            continue
+    return None
+
+
 def workload_config(n_gpus):
     return {
         "workload": "Lorenz-63 ensemble, RungeKutta45 rtol=1e-6 atol=1e-9, t in [0,10], run([10.0])",
@@ -311,7 +327,7 @@ def main():
             "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None,
+                "traffic": ncu_traffic_bytes(), "traffic_unit": "bytes of DRAM traffic per launch (ncu); algorithmic: ~100 B in + ~330 B out per trajectory",
                 "note": "FP64 vector (DFMA) pipe; achieved = attempted steps x 264 algorithmic FLOP / persistent-kernel time "
                         "(CUDA events); peak = nbk_fp64_peak DFMA chain measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "kernel": "nbk_run_rk45_lorenz", "kernel_ms_per_step": ms_run / args.steps,

@@ -49,6 +49,7 @@ extern "C" {
 /* methods: nbkode class names -> ids */
 #define NBK_RK23 23 /* RungeKutta23   nbkode/runge_kutta/explicit.py:132-164 */
 #define NBK_RK45 45 /* RungeKutta45   nbkode/runge_kutta/explicit.py:167-253 */
+#define NBK_DOP853 853 /* DOP853      nbkode/runge_kutta/explicit.py:282-351 (per-thread regime) */
 #define NBK_AB1 1   /* AdamsBashforth1 / ForwardEuler  multistep/adams_bashforth.py:17-20, euler.py:19-27 */
 #define NBK_AB2 2   /* AdamsBashforth2..5              multistep/adams_bashforth.py:23-61 */
 #define NBK_AB3 3

@@ -27,6 +27,7 @@
 #define NBK_DEVICE_CUH
 
 #include "nbk_kargs.h"
+#include "nbk_dop853_coeffs.h"
 
 #define NBK_DEV __device__ __forceinline__
 #define NBK_HD __host__ __device__ constexpr
@@ -86,6 +87,7 @@ struct cbank_rk23;
 struct cbank_rk45;
 struct tab_rk23 {  // Bogacki-Shampine 3(2), nbkode/runge_kutta/explicit.py:146-151
     static constexpr int S = 3, Q = 2, M = 3, ROOT = 6, ID = 23;
+    static constexpr bool DOP = false;
     static __device__ __forceinline__ const cbank_rk23 &cb();
     static NBK_HD double a(int i, int j) {
         constexpr double A[3][3] = {{0, 0, 0}, {1.0 / 2, 0, 0}, {0, 3.0 / 4, 0}};
@@ -111,6 +113,7 @@ struct tab_rk23 {  // Bogacki-Shampine 3(2), nbkode/runge_kutta/explicit.py:146-
 
 struct tab_rk45 {  // Dormand-Prince 5(4), nbkode/runge_kutta/explicit.py:185-239
     static constexpr int S = 6, Q = 4, M = 4, ROOT = 10, ID = 45;
+    static constexpr bool DOP = false;
     static __device__ __forceinline__ const cbank_rk45 &cb();
     static NBK_HD double a(int i, int j) {
         constexpr double A[6][6] = {
@@ -176,6 +179,43 @@ static __constant__ cbank_rk45 nbk_c45 = {
      {0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
      {0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
      {0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}}};
+
+// DOP853 (nbkode/runge_kutta/explicit.py:282-351): 12 stages + FSAL, error estimate from the E5 and E3
+// rows, 7th-order dense output from three extra stages (rows 13..15 of A/C) and D.  Coefficients:
+// nbk_dop853_coeffs.h (generated from SciPy; identical to nbkode/runge_kutta/dop853_coefficients.py).
+struct cbank_dop853 { double a[16][16], b[12], c[16], e3[13], e5[13], d[4][16]; };
+static __constant__ cbank_dop853 nbk_c853 = {NBK_DOP853_A_INIT, NBK_DOP853_B_INIT, NBK_DOP853_C_INIT,
+                                            NBK_DOP853_E3_INIT, NBK_DOP853_E5_INIT, NBK_DOP853_D_INIT};
+struct tab_dop853 {
+    static constexpr int S = 12, Q = 7, M = 7, ROOT = 16, ID = 853;
+    static constexpr bool DOP = true;
+    static NBK_HD double a(int i, int j) {
+        constexpr double A[16][16] = NBK_DOP853_A_INIT;
+        return A[i][j];
+    }
+    static NBK_HD double b(int j) {
+        constexpr double Bv[12] = NBK_DOP853_B_INIT;
+        return Bv[j];
+    }
+    static NBK_HD double c(int j) {
+        constexpr double Cv[16] = NBK_DOP853_C_INIT;
+        return Cv[j];
+    }
+    static NBK_HD double e(int j) { return e5(j); }
+    static NBK_HD double e5(int j) {
+        constexpr double Ev[13] = NBK_DOP853_E5_INIT;
+        return Ev[j];
+    }
+    static NBK_HD double e3(int j) {
+        constexpr double Ev[13] = NBK_DOP853_E3_INIT;
+        return Ev[j];
+    }
+    static NBK_HD double d(int i, int j) {
+        constexpr double Dv[4][16] = NBK_DOP853_D_INIT;
+        return Dv[i][j];
+    }
+    static __device__ __forceinline__ const cbank_dop853 &cb() { return nbk_c853; }
+};
 
 __device__ __forceinline__ const cbank_rk23 &tab_rk23::cb() { return nbk_c23; }
 __device__ __forceinline__ const cbank_rk45 &tab_rk45::cb() { return nbk_c45; }
@@ -329,6 +369,9 @@ NBK_DEV double inv_root(double x) {
     } else if (R == 6) {
         const double y4 = y2 * y2;
         yr = y4 * y2;
+    } else if (R == 16) {
+        const double y4 = y2 * y2, y8 = y4 * y4;
+        yr = y8 * y8;
     } else {
         yr = 1.0;
 #pragma unroll
@@ -395,23 +438,54 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
         ynew[i] = fma(h, acc, y[i]);
     }
     Rhs::eval(t + h, ynew, p, K[S]);
-    double acc2 = 0.0;
+    if constexpr (Tab::DOP) {
+        // err5 = h E5.K, err3 = h E3.K; norm = err5n / sqrt(1 + (err3n / (10 err5n))^2)  (explicit.py:325-336)
+        // in squared terms with a = err5n^2, b = err3n^2:  norm^2 = a^2 / (a + b/100)
+        double a5 = 0.0, a3 = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        double e = 0.0;
-        bool first = true;
+        for (int i = 0; i < N; ++i) {
+            double e5 = 0.0, e3 = 0.0;
+            bool f5 = true, f3 = true;
 #pragma unroll
-        for (int j = 0; j <= S; ++j) {
-            if (Tab::e(j) != 0.0) {
-                e = first ? Tab::cb().e[j] * K[j][i] : fma(Tab::cb().e[j], K[j][i], e);
-                first = false;
+            for (int j = 0; j <= S; ++j) {
+                if (Tab::e5(j) != 0.0) {
+                    e5 = f5 ? Tab::cb().e5[j] * K[j][i] : fma(Tab::cb().e5[j], K[j][i], e5);
+                    f5 = false;
+                }
+                if (Tab::e3(j) != 0.0) {
+                    e3 = f3 ? Tab::cb().e3[j] * K[j][i] : fma(Tab::cb().e3[j], K[j][i], e3);
+                    f3 = false;
+                }
             }
+            const double rs = fast_rcp(fma(rtol, abs_max(ynew[i], y[i]), atol));
+            const double r5 = e5 * rs, r3 = e3 * rs;
+            a5 = fma(r5, r5, a5);
+            a3 = fma(r3, r3, a3);
         }
-        const double sc = fma(rtol, abs_max(ynew[i], y[i]), atol);
-        const double r = e * fast_rcp(sc);
-        acc2 = fma(r, r, acc2);
+        const double hh = h * h * (1.0 / N);
+        a5 *= hh;
+        a3 *= hh;
+        const double den = fma(0.01, a3, a5);
+        err2 = den > 0.0 ? a5 * a5 / den : a5;  // a5 == a3 == 0: exact step (the reference divides 0/0 here)
+    } else {
+        double acc2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double e = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j <= S; ++j) {
+                if (Tab::e(j) != 0.0) {
+                    e = first ? Tab::cb().e[j] * K[j][i] : fma(Tab::cb().e[j], K[j][i], e);
+                    first = false;
+                }
+            }
+            const double sc = fma(rtol, abs_max(ynew[i], y[i]), atol);
+            const double r = e * fast_rcp(sc);
+            acc2 = fma(r, r, acc2);
+        }
+        err2 = acc2 * (h * h * (1.0 / N));  // h factored out of the N components
     }
-    err2 = acc2 * (h * h * (1.0 / N));  // h factored out of the N components
 }
 
 // I-controller of the reference: h *= clip(safety * norm^(-1/(q+1)), min_factor, max_factor)
@@ -456,6 +530,72 @@ NBK_DEV void rk_dense(double te, double t_old, double t_new, const double (&y_ol
             pw *= x;
         }
         out[i] = fma(H, acc, y_old[i]);
+    }
+}
+
+// DOP853 dense output (DOP853Interpolator, explicit.py:406-481): three extra stages (rows 13..15) built
+// on the accepted step [t_old, t], then F[0..6]; evaluated by the alternating x / (1-x) Horner scheme.
+template <class Rhs>
+NBK_DEV void dop853_prepare(double t_old, double t, const double (&y_old)[Rhs::N], const double (&y)[Rhs::N],
+                            const double (&K)[13][Rhs::N], const double (&p)[Rhs::NP > 0 ? Rhs::NP : 1],
+                            double (&F)[7][Rhs::N]) {
+    using Tab = tab_dop853;
+    constexpr int N = Rhs::N;
+    const double h = t - t_old;
+    double Ke[3][N];
+#pragma unroll
+    for (int s = 13; s < 16; ++s) {
+        double ys[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < s; ++j)
+                if (Tab::a(s, j) != 0.0) acc = fma(Tab::cb().a[s][j], j < 13 ? K[j < 13 ? j : 0][i] : Ke[j >= 13 ? j - 13 : 0][i], acc);
+            ys[i] = fma(acc, h, y_old[i]);
+        }
+        Rhs::eval(fma(Tab::cb().c[s], h, t_old), ys, p, Ke[s - 13]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double dy = y[i] - y_old[i];
+        F[0][i] = dy;
+        F[1][i] = h * K[0][i] - dy;
+        F[2][i] = 2 * dy - h * (K[12][i] + K[0][i]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (Tab::d(r, j) != 0.0) acc = fma(Tab::cb().d[r][j], j < 13 ? K[j < 13 ? j : 0][i] : Ke[j >= 13 ? j - 13 : 0][i], acc);
+            F[3 + r][i] = h * acc;
+        }
+    }
+}
+
+template <int N>
+NBK_DEV void dop853_eval(double te, double t_old, double t, const double (&y_old)[N], const double (&y)[N],
+                         const double (&F)[7][N], double (&out)[N]) {
+    if (te == t) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = y[i];
+        return;
+    }
+    if (te == t_old) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = y_old[i];
+        return;
+    }
+    const double x = (te - t_old) / (t - t_old);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            acc += F[6 - k][i];
+            acc *= (k % 2 == 0) ? x : (1 - x);
+        }
+        out[i] = acc + y_old[i];
     }
 }
 
@@ -605,12 +745,30 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     } else if (MODE == NBK_MODE_RUN) {
                         // grid points inside the stored last step are answered from history
                         // without stepping (core.py:401-408)
-                        while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
-                            double out[N];
-                            rk_dense<Tab, N>(__ldg(a.tgrid + kout), t_old, t, y_old, y, K, out);
+                        if constexpr (Tab::DOP) {
+                            if (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                                double F[7][N];
 #pragma unroll
-                            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
-                            ++kout;
+                                for (int k = 0; k < 7; ++k)
+#pragma unroll
+                                    for (int c = 0; c < N; ++c) F[k][c] = 0.0;
+                                if (t_old < t) dop853_prepare<Rhs>(t_old, t, y_old, y, K, p, F);
+                                while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                                    double out[N];
+                                    dop853_eval<N>(__ldg(a.tgrid + kout), t_old, t, y_old, y, F, out);
+#pragma unroll
+                                    for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                                    ++kout;
+                                }
+                            }
+                        } else {
+                            while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                                double out[N];
+                                rk_dense<Tab, N>(__ldg(a.tgrid + kout), t_old, t, y_old, y, K, out);
+#pragma unroll
+                                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                                ++kout;
+                            }
                         }
                         running = kout < a.m;
                         te_next = running ? __ldg(a.tgrid + kout) : d_inf();
@@ -656,9 +814,12 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 if (accept) {
                     if (MODE == NBK_MODE_RUN) {
                         if (t_new >= te_next) {
+                            double F[Tab::DOP ? 7 : 1][N];
+                            if constexpr (Tab::DOP) dop853_prepare<Rhs>(t, t_new, y, ynew, K, p, F);
                             do {
                                 double out[N];
-                                rk_dense<Tab, N>(te_next, t, t_new, y, ynew, K, out);
+                                if constexpr (Tab::DOP) dop853_eval<N>(te_next, t, t_new, y, ynew, F, out);
+                                else rk_dense<Tab, N>(te_next, t, t_new, y, ynew, K, out);
 #pragma unroll
                                 for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
                                 ++kout;

@@ -4,7 +4,7 @@
 // -DNBK_TAG=..) and at run time by NVRTC for user right-hand sides (nbk_jit.cpp passes the
 // same macros plus -DNBK_USER_RHS and prepends the user's nbk_rhs definition).
 //
-// NBK_METHOD: 23 / 45 = RungeKutta23 / RungeKutta45; 1..5 = AdamsBashforth-k (1 == ForwardEuler);
+// NBK_METHOD: 23 / 45 / 853 = RungeKutta23 / RungeKutta45 / DOP853; 1..5 = AdamsBashforth-k (1 == ForwardEuler);
 // 202 / 203 / 213 / 204 / 238 = Runge2 / Runge3 / Heun3 / RungeKutta4 / RungeKutta3_8 (fixed step).
 #include "nbk_device.cuh"
 
@@ -19,6 +19,9 @@ typedef nbk::tab_rk45 nbk_tab_t;
 #define NBK_ADAPTIVE 1
 #elif NBK_METHOD == 23
 typedef nbk::tab_rk23 nbk_tab_t;
+#define NBK_ADAPTIVE 1
+#elif NBK_METHOD == 853
+typedef nbk::tab_dop853 nbk_tab_t;
 #define NBK_ADAPTIVE 1
 #elif NBK_METHOD >= 1 && NBK_METHOD <= 5
 #define NBK_ADAPTIVE 0
