@@ -1,4 +1,4 @@
-"""Adaptive explicit Runge-Kutta solvers: RungeKutta23, RungeKutta45.
+"""Explicit Runge-Kutta solvers: fixed-step Runge2..RungeKutta3_8, adaptive RungeKutta23, RungeKutta45, DOP853.
 
 Class attributes mirror nbkode/runge_kutta/explicit.py:132-253 (tableaux ``A, B, C, E, P``,
 ``error_estimator_order``, ``stages``); the arithmetic runs in the CUDA kernels of
@@ -171,3 +171,25 @@ class RungeKutta45(AdaptiveRungeKutta):
         ]
     )
     error_estimator_order = 4
+
+
+class DOP853(AdaptiveRungeKutta):
+    """Hairer's explicit 8(5,3) pair (nbkode/runge_kutta/explicit.py:282-351): 12 stages + FSAL,
+    error norm ``err5 / sqrt(1 + (err3 / (10 err5))**2)``, 7th-order dense output that costs three
+    extra right-hand-side evaluations per interpolated step (``DOP853Interpolator``, :406-481)."""
+
+    from . import dop853_tableau as _tab
+
+    METHOD_ID = 853
+    STAGE_ROWS = 13
+    n_stages = _tab.N_STAGES
+    order = 8
+    error_estimator_order = 7
+    A = _tab.A[:12, :12].copy()
+    B = _tab.B
+    C = _tab.C[:12]
+    E3 = _tab.E3
+    E5 = _tab.E5
+    D = _tab.D
+    A_EXTRA = _tab.A[13:]
+    C_EXTRA = _tab.C[13:]

@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libnbk_oracle.so")
 
 RHS_ID = {"decay": 0, "lorenz": 1, "vdp": 2, "linear": 3, "rd1d": 4}
 METHOD_ID = {
-    "RungeKutta23": 23, "RungeKutta45": 45, "ForwardEuler": 1, "AdamsBashforth1": 1,
+    "RungeKutta23": 23, "RungeKutta45": 45, "DOP853": 853, "ForwardEuler": 1, "AdamsBashforth1": 1,
     "AdamsBashforth2": 2, "AdamsBashforth3": 3, "AdamsBashforth4": 4, "AdamsBashforth5": 5,
     "Runge2": 202, "Runge3": 203, "Heun3": 213, "RungeKutta4": 204, "RungeKutta3_8": 238,
 }

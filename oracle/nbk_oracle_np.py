@@ -2,7 +2,7 @@
 
 This module is an *oracle*: a single-trajectory CPU restatement of the algorithms the
 reference (hgrecco/numbakit-ode, ``/root/reference``) runs for ForwardEuler,
-AdamsBashforth1..5, RungeKutta23 and RungeKutta45.  Only ``tests/``,
+AdamsBashforth1..5, RungeKutta23, RungeKutta45, DOP853 and the fixed-step explicit Runge-Kutta classes.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import it; the
 product package ``nbkode_b200`` never does.
 
@@ -68,7 +68,36 @@ class DP45:
     )
 
 
-RK_METHODS = {"RungeKutta23": BS23, "RungeKutta45": DP45}
+class DOP853Tab:
+    """DOP853 (nbkode/runge_kutta/explicit.py:282-303).  The reference's
+    nbkode/runge_kutta/dop853_coefficients.py is a copy of SciPy's module of the same name (Hairer's
+    published 8(5,3) tableau); the oracle reads the numbers from the installed SciPy, and
+    tests/golden/make_golden.py asserts they equal the reference's arrays."""
+
+    name = "DOP853"
+    q = 7
+
+    def __init__(self):
+        from scipy.integrate._ivp import dop853_coefficients as dc
+
+        self.n_stages = dc.N_STAGES  # 12
+        self.A = dc.A[:12, :12].copy()
+        self.B = dc.B
+        self.C = dc.C[:12]
+        self.E3, self.E5, self.D = dc.E3, dc.E5, dc.D
+        self.A_FULL, self.C_FULL = dc.A, dc.C
+        self.A_EXTRA, self.C_EXTRA = dc.A[13:], dc.C[13:]
+
+
+class _LazyMethods(dict):
+    def __missing__(self, key):
+        if key == "DOP853":
+            self[key] = DOP853Tab()
+            return self[key]
+        raise KeyError(key)
+
+
+RK_METHODS = _LazyMethods({"RungeKutta23": BS23, "RungeKutta45": DP45})
 
 # Adams-Bashforth weights exactly as listed by the reference classes
 # (nbkode/multistep/adams_bashforth.py:20,31,44,57,61).  NB the reference applies B[0]
@@ -215,9 +244,16 @@ class AdaptiveRK:
             return False
         while True:
             t_new, y_new = self._attempt()
-            err = self.h * (self.M.E @ self.K)
             scale = self.atol + self.rtol * np.maximum(np.abs(y_new), np.abs(c.y))
-            norm = np.sqrt(np.mean((err / scale) ** 2))
+            if self.M.name == "DOP853":
+                # explicit.py:325-336: two estimates combined; 0/0 -> nan when the step is exact
+                err5 = np.sqrt(np.mean(((self.h * (self.M.E5 @ self.K)) / scale) ** 2))
+                err3 = np.sqrt(np.mean(((self.h * (self.M.E3 @ self.K)) / scale) ** 2))
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    norm = err5 / np.sqrt(1 + ((err3 / (10 * err5)) ** 2))
+            else:
+                err = self.h * (self.M.E @ self.K)
+                norm = np.sqrt(np.mean((err / scale) ** 2))
             if norm == 0:
                 self.h *= self.max_factor
                 ok = True
@@ -237,12 +273,48 @@ class AdaptiveRK:
             return c.ys[-1].copy()
         if t_eval == c.ts[-2]:
             return c.ys[-2].copy()
+        if self.M.name == "DOP853":
+            return self._interpolate_dop853(t_eval)
         Q = self.K.T.dot(self.M.P)
         t_old, y_old = c.ts[-2], c.ys[-2]
         H = c.ts[-1] - t_old
         x = (t_eval - t_old) / H
         p = np.cumprod(np.repeat(x, Q.shape[1]))
         return H * np.dot(Q, p) + y_old
+
+
+def _interpolate_dop853(self, t_eval):
+    """DOP853Interpolator.update + evaluate (nbkode/runge_kutta/explicit.py:406-481): three extra
+    stages on the last accepted step, F[0..6], alternating x / (1 - x) Horner scheme."""
+    M, c = self.M, self.cache
+    K = np.empty((16, c.y.size))
+    K[:13] = self.K
+    t_old, y_old, t, y = c.ts[-2], c.ys[-2], c.ts[-1], c.ys[-1]
+    h = t - t_old
+    f = c.f
+    for s, (a, cc) in enumerate(zip(M.A_EXTRA, M.C_EXTRA), 13):
+        dy = np.dot(K[:s].T, a[:s]) * h
+        K[s] = self.rhs(t_old + cc * h, y_old + dy)
+    F = np.empty((7, c.y.size))
+    f_old = K[0]
+    delta_y = y - y_old
+    F[0] = delta_y
+    F[1] = h * f_old - delta_y
+    F[2] = 2 * delta_y - h * (f + f_old)
+    F[3:] = h * np.dot(M.D, K)
+    x = (t_eval - t_old) / h
+    out = np.zeros_like(y_old)
+    for i, fr in enumerate(F[::-1]):
+        out += fr
+        if i % 2 == 0:
+            out *= x
+        else:
+            out *= 1 - x
+    out += y_old
+    return out
+
+
+AdaptiveRK._interpolate_dop853 = _interpolate_dop853
 
 
 class AdamsBashforth:

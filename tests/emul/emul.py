@@ -54,7 +54,7 @@ KArgs = _kargs_struct()
 
 RHS_TYPES = {"lorenz": ("nbk::rhs_lorenz", 3, 3), "vdp": ("nbk::rhs_vdp", 2, 1)}
 METHOD_IDS = {
-    "RungeKutta23": 23, "RungeKutta45": 45, "ForwardEuler": 1, "AdamsBashforth1": 1, "AdamsBashforth2": 2,
+    "RungeKutta23": 23, "RungeKutta45": 45, "DOP853": 853, "ForwardEuler": 1, "AdamsBashforth1": 1, "AdamsBashforth2": 2,
     "AdamsBashforth3": 3, "AdamsBashforth4": 4, "AdamsBashforth5": 5,
     "Runge2": 202, "Runge3": 203, "Heun3": 213, "RungeKutta4": 204, "RungeKutta3_8": 238,
 }
@@ -72,7 +72,7 @@ def _program(method, rhs, n, npar):
         return _libs[tag]
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, f"libemul_{tag}.so")
-    deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_kargs.h", "nbk_program.cu")]
+    deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_kargs.h", "nbk_program.cu", "nbk_dop853_coeffs.h")]
     deps += [os.path.join(HERE, f) for f in ("nbk_emul.cpp", "cuda_host_shim.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         pre = os.path.join(BUILD, f"pre_{tag}.h")
@@ -102,9 +102,9 @@ class EmulEnsemble:
         params = params.reshape(1, -1) if params_shared else params.reshape(self.B, -1)
         self.np_ = params.shape[1]
         self.fn = _program(self.mid, rhs, self.n, self.np_)
-        adaptive = self.mid in (23, 45)
+        adaptive = self.mid in (23, 45, 853)
         self.L = 2 if (adaptive or self.mid in ERK_STAGES) else max(self.mid, 2)
-        self.SR = {23: 4, 45: 7, **ERK_STAGES}.get(self.mid, 0)
+        self.SR = {23: 4, 45: 7, 853: 13, **ERK_STAGES}.get(self.mid, 0)
         B, n = self.B, self.n
         self.ts = np.zeros((self.L, B)); self.ys = np.zeros((self.L, n, B)); self.fs = np.zeros((self.L, n, B))
         self.K = np.zeros((max(self.SR, 1), n, B)); self.h = np.zeros(B)
@@ -114,7 +114,7 @@ class EmulEnsemble:
         self.nacc = np.zeros(B, np.int64); self.nrej = np.zeros(B, np.int64)
         self.status = np.zeros(B, np.int32); self.nout = np.zeros(B, np.int32)
         self.counter = np.zeros(1, np.uint64)
-        root = 10 if self.mid == 45 else 6
+        root = {45: 10, 853: 16}.get(self.mid, 6)
         self.base = dict(
             B=B, ts=self.ts.ctypes.data, ys=self.ys.ctypes.data, fs=self.fs.ctypes.data, K=self.K.ctypes.data,
             h=self.h.ctypes.data, params=self.p.ctypes.data, n_acc=self.nacc.ctypes.data, n_rej=self.nrej.ctypes.data,

@@ -96,7 +96,93 @@ def fixed_case(cls, rhs, y0, p, ts, h, **kw):
     return out
 
 
+def api_record(cls, kw):
+    """Value flow of nbkode/testsuite/test_solver.py::test_f1_public_api for one class."""
+    mk = lambda **extra: getattr(nbkode, cls)(onp.rhs_decay, 0.0, np.array([1.0]), params=np.array([0.01]), **kw, **extra)  # noqa: E731
+    s = mk()
+    ts, ys = s.step(n=20)
+    rec = {"cls": cls, "ts20": L(ts), "ys20": L(ys)}
+    s = mk()
+    seq = []
+    t, y = s.step()
+    seq.append(["step", L(t), L(y)])
+    t, y = s.step(n=2)
+    seq.append(["step_n2", L(t), L(y)])
+    t, y = s.step(upto_t=ts[5])
+    seq.append(["step_upto5", L(t), L(y)])
+    t, y = s.step(n=5, upto_t=ts[7])
+    seq.append(["step_n5_upto7", L(t), L(y)])
+    t, y = s.step(n=1, upto_t=ts[-1])
+    seq.append(["step_n1_uptolast", L(t), L(y)])
+    s.skip()
+    seq.append(["skip", float(s.t)])
+    s.skip(n=2)
+    seq.append(["skip_n2", float(s.t)])
+    s.skip(upto_t=0.5 * (ts[13] + ts[14]))
+    seq.append(["skip_upto", float(s.t)])
+    s.skip(n=5, upto_t=0.5 * (ts[15] + ts[16]))
+    seq.append(["skip_n5_upto", float(s.t)])
+    s.skip(n=1, upto_t=ts[-1])
+    seq.append(["skip_n1_upto", float(s.t)])
+    rec["seq"] = seq
+    s = mk(t_bound=10_000_000)
+    trev = np.linspace(0, 10, 20)[::-1]
+    t, y = s.run(trev)
+    rec["run_rev_t"] = L(t)
+    rec["run_rev_y"] = L(y)
+    # resumed run: two calls give the same numbers as one
+    s = mk()
+    ta, ya = s.run(np.linspace(0, 4, 9))
+    past = 0.5 * (float(s.cache.ts[0]) + float(s.t))  # lies inside the history window
+    tb, yb = s.run(np.concatenate(([past], np.linspace(4.5, 8, 8))))
+    rec["resume_a"] = L(ya)
+    rec["resume_b_t"] = L(tb)
+    rec["resume_b"] = L(yb)
+    return rec
+
+
+def dop853_section():
+    """DOP853 (SURVEY.md 8(f) #2): single trajectories, rows of the C2 Lorenz ensemble, API value flow."""
+    from scipy.integrate._ivp import dop853_coefficients as sdc
+
+    from nbkode.runge_kutta import dop853_coefficients as rdc
+
+    # the oracle and the CUDA tableau header read SciPy's copy of Hairer's coefficients: identical arrays
+    for name in ("A", "B", "C", "E3", "E5", "D"):
+        assert np.array_equal(getattr(sdc, name), getattr(rdc, name)), name
+    lor = ([1.0, 1.0, 1.0], [10.0, 28.0, 8 / 3])
+    cls = "DOP853"
+    single = [
+        adaptive_case(cls, "lorenz", *lor, [2.5, 5.0, 10.0], rtol=1e-6, atol=1e-9),
+        adaptive_case(cls, "lorenz", *lor, np.linspace(0, 3, 31), rtol=1e-3, atol=1e-6),
+        adaptive_case(cls, "lorenz", *lor, np.linspace(0, 5, 501), rtol=1e-9, atol=1e-12),
+        adaptive_case(cls, "vdp", [2.0, 0.0], [1.0], [5.0, 10.0, 20.0], rtol=1e-6, atol=1e-9),
+        adaptive_case(cls, "vdp", [2.0, 0.0], [5.0], np.linspace(0, 20, 41), rtol=1e-6, atol=1e-9),
+        adaptive_case(cls, "decay", [1.0, 2.0], [0.01, 0.05], np.linspace(0, 300, 16)),
+        adaptive_case(cls, "decay", [1.0], [0.01], [30.0], first_step=0.5),
+        adaptive_case(cls, "vdp", [2.0, 0.0], [2.0], [10.0], rtol=1e-5, atol=1e-8, min_factor=0.3, max_factor=4.0,
+                      safety_factor=0.8),
+    ]
+    rng = np.random.default_rng(11)
+    A8 = rng.standard_normal((8, 8)) / np.sqrt(8) - np.eye(8)
+    single.append(adaptive_case(cls, "linear", rng.standard_normal(8), A8, [1.0, 10.0], rtol=1e-6, atol=1e-9))
+    y0, p = onp.lorenz_ensemble(1_000_000, seed=0)
+    rows = []
+    for i in list(range(16)) + list(range(999_992, 1_000_000)):
+        r = adaptive_case(cls, "lorenz", y0[i], p[i], [10.0], rtol=1e-6, atol=1e-9)
+        r["row"] = i
+        for k in ("cls", "rhs", "kw", "ts", "K_end", "f0", "f_end", "t_old", "y_old"):
+            r.pop(k)
+        rows.append(r)
+    dump("dop853.json", {"single": single, "ensemble": {"B_total": 1_000_000, "seed": 0, "rtol": 1e-6, "atol": 1e-9,
+                                                        "T": 10.0, "rows": rows},
+                         "api": api_record(cls, {"h": 0.1})})
+
+
 def main():
+    if sys.argv[1:] == ["dop853"]:
+        return dop853_section()
+    dop853_section()
     # ---------------------------------------------------------------- C1: README example
     c1 = []
     for cls, kw in [
@@ -208,46 +294,7 @@ def main():
         kw = {"h": 0.1}
         if "Runge" not in cls:
             kw["first_stepper_cls"] = None
-        mk = lambda **extra: getattr(nbkode, cls)(onp.rhs_decay, 0.0, np.array([1.0]), params=np.array([0.01]), **kw, **extra)  # noqa: E731
-        s = mk()
-        ts, ys = s.step(n=20)
-        rec = {"cls": cls, "ts20": L(ts), "ys20": L(ys)}
-        s = mk()
-        seq = []
-        t, y = s.step()
-        seq.append(["step", L(t), L(y)])
-        t, y = s.step(n=2)
-        seq.append(["step_n2", L(t), L(y)])
-        t, y = s.step(upto_t=ts[5])
-        seq.append(["step_upto5", L(t), L(y)])
-        t, y = s.step(n=5, upto_t=ts[7])
-        seq.append(["step_n5_upto7", L(t), L(y)])
-        t, y = s.step(n=1, upto_t=ts[-1])
-        seq.append(["step_n1_uptolast", L(t), L(y)])
-        s.skip()
-        seq.append(["skip", float(s.t)])
-        s.skip(n=2)
-        seq.append(["skip_n2", float(s.t)])
-        s.skip(upto_t=0.5 * (ts[13] + ts[14]))
-        seq.append(["skip_upto", float(s.t)])
-        s.skip(n=5, upto_t=0.5 * (ts[15] + ts[16]))
-        seq.append(["skip_n5_upto", float(s.t)])
-        s.skip(n=1, upto_t=ts[-1])
-        seq.append(["skip_n1_upto", float(s.t)])
-        rec["seq"] = seq
-        s = mk(t_bound=10_000_000)
-        trev = np.linspace(0, 10, 20)[::-1]
-        t, y = s.run(trev)
-        rec["run_rev_t"] = L(t)
-        rec["run_rev_y"] = L(y)
-        # resumed run: two calls give the same numbers as one
-        s = mk()
-        ta, ya = s.run(np.linspace(0, 4, 9))
-        past = 0.5 * (float(s.cache.ts[0]) + float(s.t))  # lies inside the history window
-        tb, yb = s.run(np.concatenate(([past], np.linspace(4.5, 8, 8))))
-        rec["resume_a"] = L(ya)
-        rec["resume_b_t"] = L(tb)
-        rec["resume_b"] = L(yb)
+        rec = api_record(cls, kw)
         api.append(rec)
     dump("api_semantics.json", api)
 

@@ -282,3 +282,68 @@ def test_shared_matrix_params_traced_linear():
     t, y = s.run([1.0, 5.0])
     ref = oc.run_ensemble("RungeKutta45", "linear", y0, A, [1.0, 5.0], rtol=1e-6, atol=1e-9, params_shared=True)
     assert within(y, ref["ys"], 1e-6, 1e-9).all() and np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
+
+
+# ------------------------------------------------------------------ DOP853
+_DOP = load_golden("dop853.json")
+
+
+@pytest.mark.parametrize("c", _DOP["single"], ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_dop853_single(c):
+    kw = dict(c["kw"])
+    rtol, atol = kw.get("rtol", 1e-3), kw.get("atol", 1e-6)
+    s = nbk.DOP853(_rhs_for(c), 0.0, np.array(c["y0"]), np.array(c["p"]), **kw)
+    assert rel(float(s.h), c["h0"]) < 1e-13
+    t, y = s.run(c["ts"])
+    assert y.shape == (len(c["ts"]), len(c["y0"]))
+    assert abs(s.n_accepted - c["n_accepted"]) <= 1
+    assert within(y, c["ys"], rtol, atol).all()
+    assert within(s.y, c["y_end"], rtol, atol, slack=2).all()
+    if s.n_accepted == c["n_accepted"]:
+        assert rel(y, c["ys"]) < 1e-7
+        assert rel(s.K, c["K_end"]) < 1e-5 and rel(s.cache.ts, [c["t_old"], c["t_end"]]) < 1e-7
+
+
+def test_dop853_golden_rows_and_oracle_ensemble():
+    g = _DOP["ensemble"]
+    rows = g["rows"]
+    y0 = np.array([r["y0"] for r in rows])
+    p = np.array([r["p"] for r in rows])
+    s = nbk.DOP853("lorenz", 0.0, y0, p, rtol=g["rtol"], atol=g["atol"])
+    assert not s.is_jit
+    assert rel(s.h, [r["h0"] for r in rows]) < 1e-13
+    t, y = s.run([g["T"]])
+    assert np.abs(s.n_accepted - np.array([r["n_accepted"] for r in rows])).max() <= 1
+    assert within(y, np.array([r["ys"] for r in rows]), g["rtol"], g["atol"]).all()
+    # 20k trajectories against the C oracle, dense output on a grid
+    B = 20000
+    y0, p = onp.lorenz_ensemble(B, seed=321)
+    ts = np.linspace(0.5, 10, 20)
+    ref = oc.run_ensemble("DOP853", "lorenz", y0, p, ts, rtol=1e-6, atol=1e-9, nthreads=8)
+    s = nbk.DOP853("lorenz", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    t, y = s.run(ts)
+    dn = np.abs(s.n_accepted - ref["n_accepted"])
+    assert within(y, ref["ys"], 1e-6, 1e-9).all(axis=(1, 2)).mean() >= 0.999
+    assert (dn <= 1).mean() >= 0.999 and (dn == 0).mean() > 0.99
+    assert (s.status == 0).all()
+
+
+def test_dop853_api_flow():
+    c = _DOP["api"]
+    mk = lambda: nbk.DOP853("decay", 0.0, np.array([1.0]), np.array([0.01]))  # noqa: E731
+    s = mk()
+    ts, ys = s.step(n=20)
+    assert rel(ts, c["ts20"]) < 1e-9 and rel(ys, c["ys20"]) < 1e-10
+    s = mk()
+    t, y = s.run(np.linspace(0, 4, 9))
+    assert rel(y, c["resume_a"]) < 1e-11
+    t, y = s.run(c["resume_b_t"])  # first point lies inside the stored last step
+    assert rel(y, c["resume_b"]) < 1e-11
+    s = mk()
+    t, y = s.run(np.array(c["run_rev_t"]))
+    assert rel(y, c["run_rev_y"]) < 1e-11
+    # a traced Python right-hand side goes through NVRTC with the same kernels
+    sj = nbk.DOP853(lambda t, y, k: -k * y, 0.0, np.array([1.0]), np.array([0.01]))
+    assert sj.is_jit
+    tj, yj = sj.run(np.linspace(0, 4, 9))
+    assert rel(yj, c["resume_a"]) < 1e-11

@@ -15,7 +15,7 @@ from nbkode_b200.util import CaseInsensitiveDict
 
 from conftest import ROOT
 
-N_SOLVERS = 13  # ForwardEuler, AdamsBashforth1..5, RungeKutta23/45 (hot path) + the 5 fixed-step explicit RKs
+N_SOLVERS = 14  # ForwardEuler, AdamsBashforth1..5, RungeKutta23/45 (hot path) + the 5 fixed-step explicit RKs + DOP853
 
 
 # ------------------------------------------------------------------ registry
@@ -27,7 +27,7 @@ def test_get_solvers_groups():
     assert len(nbkode.get_solvers("Euler")) == 1  # BackwardEuler is implicit: out of scope
     assert len(nbkode.get_solvers("euler")) == 1
     assert len(nbkode.get_solvers("adams-bashforth")) == 5
-    assert len(nbkode.get_solvers("Runge-Kutta")) == 7
+    assert len(nbkode.get_solvers("Runge-Kutta")) == 8
     assert nbkode.get_groups() == ("Adams-Bashforth", "Euler", "Runge-Kutta")
     with pytest.raises(KeyError):
         nbkode.get_solvers("not-a-group")
@@ -43,7 +43,7 @@ def test_get_solvers_filters():
         assert solver.FIXED_STEP is False
     assert set(nbkode.get_solvers(fixed_step=False) + nbkode.get_solvers(fixed_step=True)) == set(nbkode.get_solvers())
     assert {nbkode.RungeKutta23, nbkode.RungeKutta45, nbkode.RungeKutta4} <= set(nbkode.get_solvers(runge_kutta=True))
-    assert set(nbkode.get_solvers(runge_kutta=True, fixed_step=False)) == {nbkode.RungeKutta23, nbkode.RungeKutta45}
+    assert set(nbkode.get_solvers(runge_kutta=True, fixed_step=False)) == {nbkode.RungeKutta23, nbkode.RungeKutta45, nbkode.DOP853}
     assert len(nbkode.get_solvers(multistep=True)) == 6
     # README.rst:63 -- with the corrected IMPLICIT flag the explicit fixed-step solvers are listed
     assert nbkode.ForwardEuler in nbkode.get_solvers(implicit=False, fixed_step=True)
@@ -170,7 +170,7 @@ def test_nvrtc_compiles_user_and_builtin_programs_for_sm100a():
         return np.array([y[1], p[0] * (1 - y[0] ** 2) * y[1] - y[0]])
 
     src = rhs.trace(f, 2, (1,), True).source.encode()
-    for method in (45, 23, 4, 1):
+    for method in (45, 23, 853, 4, 1, 204):
         _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(method, 2, 1, src=src)), C.byref(sz)))
         assert sz.value > 10_000
     _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 5, 5, rhs_name=b"decay")), C.byref(sz)))

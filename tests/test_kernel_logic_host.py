@@ -167,3 +167,35 @@ def test_nonfinite_guard_terminates():
     e = EmulEnsemble("RungeKutta45", "decay", [[1.0]], [[-1e308]], first_step=1.0)
     e.run([10.0])
     assert e.status[0] == 2
+
+
+# ---------------------------------------------------------------- DOP853
+_DOP = load_golden("dop853.json")
+DOP_SINGLE = [c for c in _DOP["single"] if c["rhs"] in ("lorenz", "vdp", "decay")]
+
+
+@pytest.mark.parametrize("c", DOP_SINGLE, ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_dop853_single_vs_reference(c):
+    e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], **c["kw"])
+    assert rel(e.h[0], c["h0"]) < 1e-14
+    ys = e.run(c["ts"])
+    assert e.nacc[0] == c["n_accepted"]
+    assert rel(ys[0], c["ys"]) < (1e-8 if c["rhs"] == "lorenz" else 1e-10)
+    assert rel(e.t[0], c["t_end"]) < 1e-8 and rel(e.y[0], c["y_end"]) < 1e-7 and rel(e.h[0], c["h_end"]) < 1e-6
+    assert rel(e.K[:, :, 0], c["K_end"]) < 1e-6
+    assert rel(e.ts[0, 0], c["t_old"]) < 1e-8 and rel(e.ys[0, :, 0], c["y_old"]) < 1e-7
+    assert e.status[0] == 0 and e.nout[0] == len(c["ts"])
+
+
+def test_dop853_resume_and_past_points():
+    """Two run() calls equal one; a grid point inside the stored last step is answered from history
+    (needs the three extra dense-output stages rebuilt from the stored K)."""
+    c = _DOP["api"]
+    e = EmulEnsemble("DOP853", "decay", [[1.0]], [[0.01]])
+    ya = e.run(np.linspace(0, 4, 9))
+    assert rel(ya[0], c["resume_a"]) < 1e-12
+    yb = e.run(c["resume_b_t"])
+    assert rel(yb[0], c["resume_b"]) < 1e-12
+    e = EmulEnsemble("DOP853", "decay", [[1.0]], [[0.01]])
+    tt, yy, cnt = e.step(20)
+    assert cnt[0] == 20 and rel(tt[0], c["ts20"]) < 1e-9 and rel(yy[0], c["ys20"]) < 1e-10

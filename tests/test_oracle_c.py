@@ -105,3 +105,34 @@ def test_fixed_rk(c):
     _close(r["ys"][0], c["ys"], tol, "ys")
     assert r["t_end"][0] == c["t_end"]
     _close(r["y_end"][0], c["y_end"], tol)
+
+
+# ---------------------------------------------------------------- DOP853
+_DOP = load_golden("dop853.json")
+
+
+@pytest.mark.parametrize("c", _DOP["single"], ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_dop853_single(c):
+    # the 8(5,3) tableau has coefficients up to ~43 that cancel, so summation-order differences between
+    # BLAS and the C loops are ~20x those of RK45: 1e-10 (non-chaotic) / 1e-8 (Lorenz) on the dense output
+    kw = dict(c["kw"])
+    r = oc.run_ensemble(c["cls"], c["rhs"], [c["y0"]], c["p"], c["ts"], params_shared=c["rhs"] == "linear", **kw)
+    _close(r["h0"][0], c["h0"], 1e-14, "h0")
+    assert r["n_accepted"][0] == c["n_accepted"]
+    _close(r["ys"][0], c["ys"], 1e-8 if c["rhs"] == "lorenz" else 1e-10, "ys")
+    _close(r["t_end"][0], c["t_end"], 1e-8, "t_end")
+    _close(r["y_end"][0], c["y_end"], 1e-7, "y_end")
+    _close(r["h_end"][0], c["h_end"], 1e-6, "h_end")  # E5.K cancels ~8 digits at rtol 1e-5..1e-6
+    assert r["status"][0] == 0 and r["n_out"][0] == len(c["ts"])
+
+
+def test_dop853_ensemble_rows():
+    g = _DOP["ensemble"]
+    rows = g["rows"]
+    y0 = np.array([r["y0"] for r in rows])
+    p = np.array([r["p"] for r in rows])
+    r = oc.run_ensemble("DOP853", "lorenz", y0, p, [g["T"]], rtol=g["rtol"], atol=g["atol"], nthreads=4)
+    assert np.array_equal(r["n_accepted"], [q["n_accepted"] for q in rows])
+    _close(r["ys"][:, 0], [q["ys"][0] for q in rows], 1e-8)
+    _close(r["t_end"], [q["t_end"] for q in rows], 1e-8)
+    _close(r["h0"], [q["h0"] for q in rows], 1e-14)

@@ -149,3 +149,40 @@ def test_fixed_rk_bitexact(c):
         s = onp.FixedRK(c["cls"], onp.rhs_vdp, 0.0, np.array([2.0, 0.0]), np.array([1.0]), h=0.05)
         tt, yy = onp.steps(s, n=10)
         _eq(tt, c["step10_t"]); _eq(yy, c["step10_y"]); _eq(s.K, c["step10_K"])
+
+
+# ---------------------------------------------------------------- DOP853
+_DOP = load_golden("dop853.json")
+
+
+@pytest.mark.parametrize("c", _DOP["single"], ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_dop853_single_bitexact(c):
+    test_adaptive_single_bitexact(c)
+
+
+def test_dop853_ensemble_rows():
+    g = _DOP["ensemble"]
+    y0, p = onp.lorenz_ensemble(g["B_total"], g["seed"])
+    for r in g["rows"]:
+        i = r["row"]
+        _eq(y0[i], r["y0"])
+        s = onp.AdaptiveRK("DOP853", onp.rhs_lorenz, 0.0, y0[i], p[i], rtol=g["rtol"], atol=g["atol"])
+        assert float(s.h) == r["h0"]
+        t, y = onp.run(s, [g["T"]])
+        _eq(y, r["ys"])
+        assert s.t == r["t_end"] and s.n_accepted == r["n_accepted"] and float(s.h) == r["h_end"]
+        _eq(s.y, r["y_end"])
+
+
+def test_dop853_api_semantics():
+    c = _DOP["api"]
+    mk = lambda: onp.AdaptiveRK("DOP853", onp.rhs_decay, 0.0, [1.0], np.array([0.01]))  # noqa: E731
+    s = mk()
+    ts, ys = onp.steps(s, n=20)
+    _eq(ts, c["ts20"])
+    _eq(ys, c["ys20"])
+    s = mk()
+    t, y = onp.run(s, np.linspace(0, 4, 9))
+    _eq(y, c["resume_a"])
+    t, y = onp.run(s, c["resume_b_t"])
+    _eq(y, c["resume_b"])
