@@ -67,6 +67,10 @@ extern "C" {
 #define NBK_TRAJ_BOUND 1       /* stopped by the t_bound / upto_t guard, nbkode/core.py:176-184 */
 #define NBK_TRAJ_NONFINITE 2   /* non-finite error norm or collapsed step (the reference spins forever) */
 #define NBK_TRAJ_MAXATTEMPTS 3 /* attempt budget of the call exhausted */
+#define NBK_TRAJ_EVBRACKET 4   /* nbk_run_events: an event function does not change sign on the step's interpolant
+                                  (the reference's bisect raises ValueError, nbkode/nbcompat/zeros.py:516-520) */
+#define NBK_TRAJ_EVENT (-1)    /* nbk_run_events: stopped by a terminal event (clean stop) */
+#define NBK_MAX_EVENTS 8
 
 typedef struct nbk_solver nbk_solver;
 
@@ -150,12 +154,37 @@ int nbk_step(nbk_solver *s, const nbk_state *st, long long n_steps, double bound
              double *t_out, long long to_sb, double *y_out, long long o_sb, long long o_sk,
              long long o_sc, long long max_attempts, void *stream);
 
+/* Events, replacing event_handler.build_handler + Solver._run_eval_events (nbkode/event_handler.py,
+   nbkode/core.py:334-447, :621-647).  nbk_set_events compiles (NVRTC) a variant of the run kernel with the
+   n_events event functions inlined; event_src is CUDA C defining
+       NBK_EVENT nbk_event(int k, double t, const double* y, const double* p)     (returns g_k(t, y))
+   Per-thread regime only.  nbk_run_events is nbk_run plus, after every accepted step, sign-change detection per
+   event (direction[k] in {-1, 0, +1}), bisection of the root on the step's dense output (|g| <= 1.48e-8, <= 50
+   halvings: nbkode/nbcompat/zeros.py:508-533) and recording of (t, y(t)); a terminal event (terminal[k] != 0) stops
+   its trajectory: output row n_out-1 holds the event state, t_terminal[b] its time, status NBK_TRAJ_EVENT. */
+typedef struct {
+    int n_events;          /* must equal the value given to nbk_set_events */
+    int capacity;          /* events stored per (trajectory, event function) */
+    const int *direction;  /* host, [n_events] */
+    const int *terminal;   /* host, [n_events] */
+    double *t_events;      /* device, [B][n_events][capacity] */
+    double *y_events;      /* device, [B][n_events][capacity][n] */
+    int *counts;           /* device, [B][n_events]: events detected (> capacity: the excess was not stored) */
+    double *t_terminal;    /* device, [B] */
+} nbk_events;
+int nbk_set_events(nbk_solver *s, int n_events, const char *event_src);
+int nbk_run_events(nbk_solver *s, const nbk_state *st, const double *ts, int m, double t_bound, double *y_out,
+                   long long o_sb, long long o_sk, long long o_sc, const nbk_events *ev, long long max_attempts,
+                   void *stream);
+
 /* Launch geometry of the most recent nbk_run / nbk_step (for reporting). */
 int nbk_last_launch(const nbk_solver *s, int *grid, int *block, int *regs_per_thread);
 
 /* NVRTC front half only (no device needed): compiles the kernels of cfg for sm_100a and returns
    the cubin size; used by the CPU test-suite and to pre-warm the program cache. */
 int nbk_jit_compile_only(const nbk_config *cfg, long long *cubin_bytes);
+/* The same for the event variant of the program (see nbk_set_events). */
+int nbk_jit_compile_events_only(const nbk_config *cfg, int n_events, const char *event_src, long long *cubin_bytes);
 
 /* FP64 vector-pipe roofline denominator: runs a register-resident DFMA chain kernel for
    `iters` iterations and returns the achieved TFLOP/s (2 FLOP per DFMA) and its duration. */

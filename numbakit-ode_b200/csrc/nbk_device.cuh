@@ -636,13 +636,128 @@ NBK_DEV void load_params(const nbk_kargs &a, long long idx, double (&p)[NP > 0 ?
 
 
 // =====================================================================================
+// Events (run_events, nbkode/core.py:334-447 + nbkode/event_handler.py).  Compiled only into
+// programs built with -DNBK_NEVENTS=k: the user (or the Python tracer) supplies
+//   NBK_EVENT nbk_event(int k, double t, const double* y, const double* p)
+// After every accepted step each event function is evaluated at the new point; a sign change
+// against its previous value (filtered by the event's direction) is located by bisection on the
+// step's dense output -- tolerance |g| <= 1.48e-8, at most 50 halvings (nbcompat/zeros.py:508-533)
+// -- and recorded with the interpolated state; a terminal event stops the trajectory and its
+// (t, y) replaces the output row the trajectory was integrating towards (core.py:641-644).
+// =====================================================================================
+#ifdef NBK_NEVENTS
+template <int N, int NPX>
+NBK_DEV void events_start(const nbk_kargs &a, long long idx, double t, const double (&y)[N], const double (&p)[NPX],
+                          double (&ev_last)[NBK_NEVENTS]) {
+    // build_handler(events, self.t, self.y): last_value = func(t, y), empty lists (event_handler.py:127-135)
+#pragma unroll
+    for (int k = 0; k < NBK_NEVENTS; ++k) {
+        ev_last[k] = nbk_event(k, t, y, p);
+        a.ev_count[idx * NBK_NEVENTS + k] = 0;
+    }
+}
+
+// Dense: functor (double te, double (&out)[N]) over the step [t_old, t_new] that was just accepted.
+// Returns true if a terminal event fired; t_term then holds that event's time.
+template <int N, int NPX, class Dense>
+NBK_DEV bool events_after_step(const nbk_kargs &a, long long idx, double t_old, double t_new, const double (&y_new)[N],
+                               const double (&p)[NPX], double (&ev_last)[NBK_NEVENTS], Dense &dense, double &t_term,
+                               int &status) {
+    bool terminate = false;
+#pragma unroll
+    for (int k = 0; k < NBK_NEVENTS; ++k) {
+        const double value = nbk_event(k, t_new, y_new, p);
+        const double last = ev_last[k];
+        const bool up = last <= 0.0 && value >= 0.0, down = last >= 0.0 && value <= 0.0;
+        const int dir = a.ev_dir[k];
+        const bool trigger = (up && dir > 0) || (down && dir < 0) || ((up || down) && dir == 0);
+        ev_last[k] = value;
+        if (!trigger) continue;
+        double root = t_new, out[N];
+        if (value != 0.0) {
+            double left = t_old, right = t_new;
+            dense(left, out);
+            double yl = nbk_event(k, left, out, p);
+            if (yl == 0.0) {
+                root = left;
+            } else if (!(yl * value < 0.0)) {
+                status = NBK_TRAJ_EVBRACKET;
+                return true;
+            } else {
+                double mid = left;
+                for (int it = 0; it < 50; ++it) {
+                    mid = (left + right) / 2;
+                    dense(mid, out);
+                    const double ym = nbk_event(k, mid, out, p);
+                    if (fabs(ym) <= 1.48e-8) break;
+                    if ((ym > 0.0) == (yl > 0.0)) {
+                        left = mid;
+                        yl = ym;
+                    } else {
+                        right = mid;
+                    }
+                }
+                root = mid;
+            }
+        }
+        const long long slot = idx * NBK_NEVENTS + k;
+        const int cnt = a.ev_count[slot];
+        // "This is required to avoid duplicates" (event_handler.py:158-160)
+        const bool dup = cnt > 0 && cnt <= a.ev_cap && a.ev_t[slot * a.ev_cap + cnt - 1] == root;
+        if (!dup) {
+            if (cnt < a.ev_cap) {
+                a.ev_t[slot * a.ev_cap + cnt] = root;
+                dense(root, out);
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.ev_y[(slot * a.ev_cap + cnt) * N + c] = out[c];
+            }
+            a.ev_count[slot] = cnt + 1;
+        }
+        if ((a.ev_terminal >> k) & 1) {
+            // EventHandler.evaluate: min_t is never raised, so the LAST terminal event of the list wins
+            terminate = true;
+            t_term = root;
+        }
+    }
+    return terminate;
+}
+
+// dense output of one accepted adaptive step (RkInterpolator / DOP853Interpolator), prepared lazily
+template <class Tab, class Rhs>
+struct step_dense {
+    static constexpr int N = Rhs::N, NPX = Rhs::NP > 0 ? Rhs::NP : 1;
+    double t_old, t_new;
+    const double (&y_old)[N];
+    const double (&y_new)[N];
+    const double (&K)[Tab::S + 1][N];
+    const double (&p)[NPX];
+    double F[Tab::DOP ? 7 : 1][N];
+    bool prepared;
+    NBK_DEV step_dense(double t0, double t1, const double (&y0)[N], const double (&y1)[N], const double (&K_)[Tab::S + 1][N],
+                       const double (&p_)[NPX])
+        : t_old(t0), t_new(t1), y_old(y0), y_new(y1), K(K_), p(p_), prepared(false) {}
+    NBK_DEV void operator()(double te, double (&out)[N]) {
+        if constexpr (Tab::DOP) {
+            if (!prepared) {
+                dop853_prepare<Rhs>(t_old, t_new, y_old, y_new, K, p, F);
+                prepared = true;
+            }
+            dop853_eval<N>(te, t_old, t_new, y_old, y_new, F, out);
+        } else {
+            rk_dense<Tab, N>(te, t_old, t_new, y_old, y_new, K, out);
+        }
+    }
+};
+#endif  // NBK_NEVENTS
+
+// =====================================================================================
 // Adaptive advance kernel body (RungeKutta23 / RungeKutta45), persistent with lane refill.
 // MODE RUN : for ti in tgrid: while t < ti: step; emit dense(ti)      (core.py:598-619)
 // MODE STEP: up to n_steps accepted steps, each emitted as (t, y)      (core.py:483-537)
 // Every loop iteration is one ATTEMPT for every running lane; accept/reject is resolved with
 // selects, so lanes of a warp only diverge when a trajectory is loaded, emits or retires.
 // =====================================================================================
-template <class Tab, class Rhs, int MODE>
+template <class Tab, class Rhs, int MODE, bool EV = false>
 NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     constexpr int N = Rhs::N, NP = Rhs::NP, NPX = NP > 0 ? NP : 1, S = Tab::S;
     const unsigned FULL = NBK_FULL_MASK;
@@ -664,12 +779,15 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     int kout = 0;            // RUN: next grid index
     bool fresh = true;       // the next attempt opens a new step (K[S] holds f(t, y))
     int status = NBK_TRAJ_OK;
+#ifdef NBK_NEVENTS
+    double ev_last[NBK_NEVENTS];  // EV: value of every event function at the last accepted point
+#endif
 
     for (;;) {
         // ---------------------------------------------------------------- (1) retire
         if (finishing) {
             if (nacc > 0) {
-                const bool clean = status == NBK_TRAJ_OK || status == NBK_TRAJ_BOUND;
+                const bool clean = status != NBK_TRAJ_NONFINITE && status != NBK_TRAJ_MAXATTEMPTS;
                 a.ts[B + idx] = t;
 #pragma unroll
                 for (int c = 0; c < N; ++c) {
@@ -772,6 +890,9 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                         }
                         running = kout < a.m;
                         te_next = running ? __ldg(a.tgrid + kout) : d_inf();
+#ifdef NBK_NEVENTS
+                        if constexpr (EV) events_start<N, NPX>(a, idx, t, y, p, ev_last);
+#endif
                     } else {
                         running = a.n_steps > 0;
                     }
@@ -812,7 +933,35 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 ++natt;
                 bool done = false;
                 if (accept) {
-                    if (MODE == NBK_MODE_RUN) {
+                    if (MODE == NBK_MODE_RUN && EV) {
+#ifdef NBK_NEVENTS
+                        // events first, then the grid points inside the step (core.py:638-645)
+                        step_dense<Tab, Rhs> dense(t, t_new, y, ynew, K, p);
+                        double t_term = 0.0;
+                        if (events_after_step<N, NPX>(a, idx, t, t_new, ynew, p, ev_last, dense, t_term, status)) {
+                            if (status != NBK_TRAJ_EVBRACKET) {
+                                double out[N];
+                                dense(t_term, out);
+#pragma unroll
+                                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                                a.ev_tterm[idx] = t_term;
+                                ++kout;
+                                status = NBK_TRAJ_EVENT;
+                            }
+                            done = true;
+                        } else if (t_new >= te_next) {
+                            do {
+                                double out[N];
+                                dense(te_next, out);
+#pragma unroll
+                                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                                ++kout;
+                                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                            } while (t_new >= te_next);
+                            done = kout >= a.m;
+                        }
+#endif
+                    } else if (MODE == NBK_MODE_RUN) {
                         if (t_new >= te_next) {
                             double F[Tab::DOP ? 7 : 1][N];
                             if constexpr (Tab::DOP) dop853_prepare<Rhs>(t, t_new, y, ynew, K, p, F);
@@ -894,7 +1043,19 @@ NBK_DEV void hermite_window(double te, const double (&ts)[L], const double (&ys)
     }
 }
 
-template <int ORDER, class Rhs, int MODE>
+#ifdef NBK_NEVENTS
+// dense output of the fixed-step solvers (window Hermite) as the functor events_after_step takes
+template <int L, int N>
+struct window_dense {
+    const double (&ts)[L];
+    const double (&ys)[L][N];
+    const double (&fs)[L][N];
+    NBK_DEV window_dense(const double (&t_)[L], const double (&y_)[L][N], const double (&f_)[L][N]) : ts(t_), ys(y_), fs(f_) {}
+    NBK_DEV void operator()(double te, double (&out)[N]) { hermite_window<L, N>(te, ts, ys, fs, out); }
+};
+#endif
+
+template <int ORDER, class Rhs, int MODE, bool EV = false>
 NBK_DEV void advance_ab(const nbk_kargs &a) {
     constexpr int N = Rhs::N, NP = Rhs::NP, NPX = NP > 0 ? NP : 1, L = tab_ab<ORDER>::LEN;
     const long long B = a.B;
@@ -920,6 +1081,9 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
     long long nsteps = 0;
     double te_next = d_inf();
     bool running;
+#ifdef NBK_NEVENTS
+    double ev_last[NBK_NEVENTS];
+#endif
     if (status != NBK_TRAJ_OK) {
         // failed earlier (start-up): stays failed, outputs are NaN
         running = false;
@@ -936,6 +1100,9 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
         }
         running = kout < a.m;
         if (running) te_next = __ldg(a.tgrid + kout);
+#ifdef NBK_NEVENTS
+        if constexpr (EV) events_start<N, NPX>(a, idx, ts[L - 1], ys[L - 1], p, ev_last);
+#endif
     } else {
         running = a.n_steps > 0;
     }
@@ -971,6 +1138,26 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
             fs[L - 1][c] = fnew[c];
         }
         ++nsteps;
+#ifdef NBK_NEVENTS
+        if constexpr (EV && MODE == NBK_MODE_RUN) {
+            // the bisection brackets the previous point ts[L-2] and the new one; for L > 2 the window Hermite
+            // does not pass through ts[L-2], which is where the reference's bisect raises ValueError
+            window_dense<L, N> dense(ts, ys, fs);
+            double t_term = 0.0;
+            if (events_after_step<N, NPX>(a, idx, ts[L - 2], t_new, ynew, p, ev_last, dense, t_term, status)) {
+                if (status != NBK_TRAJ_EVBRACKET) {
+                    double out[N];
+                    dense(t_term, out);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                    a.ev_tterm[idx] = t_term;
+                    ++kout;
+                    status = NBK_TRAJ_EVENT;
+                }
+                break;
+            }
+        }
+#endif
         if (MODE == NBK_MODE_RUN) {
             while (t_new >= te_next) {
                 double out[N];
@@ -1240,7 +1427,7 @@ NBK_DEV void init_erk(const nbk_kargs &a) {
     a.status[idx] = NBK_TRAJ_OK;
 }
 
-template <int ID, class Rhs, int MODE>
+template <int ID, class Rhs, int MODE, bool EV = false>
 NBK_DEV void advance_erk(const nbk_kargs &a) {
     using Tab = tab_erk<ID>;
     constexpr int N = Rhs::N, NP = Rhs::NP, NPX = NP > 0 ? NP : 1, S = Tab::S;
@@ -1267,6 +1454,9 @@ NBK_DEV void advance_erk(const nbk_kargs &a) {
     long long nsteps = 0;
     double te_next = d_inf();
     bool running;
+#ifdef NBK_NEVENTS
+    double ev_last[NBK_NEVENTS];
+#endif
     if (status != NBK_TRAJ_OK) {
         running = false;
         if (MODE == NBK_MODE_RUN)
@@ -1282,6 +1472,9 @@ NBK_DEV void advance_erk(const nbk_kargs &a) {
         }
         running = kout < a.m;
         if (running) te_next = __ldg(a.tgrid + kout);
+#ifdef NBK_NEVENTS
+        if constexpr (EV) events_start<N, NPX>(a, idx, ts[1], ys[1], p, ev_last);
+#endif
     } else {
         running = a.n_steps > 0;
     }
@@ -1338,6 +1531,24 @@ NBK_DEV void advance_erk(const nbk_kargs &a) {
             fs[1][c] = fnew[c];
         }
         ++nsteps;
+#ifdef NBK_NEVENTS
+        if constexpr (EV && MODE == NBK_MODE_RUN) {
+            window_dense<2, N> dense(ts, ys, fs);
+            double t_term = 0.0;
+            if (events_after_step<N, NPX>(a, idx, ts[0], t_new, ynew, p, ev_last, dense, t_term, status)) {
+                if (status != NBK_TRAJ_EVBRACKET) {
+                    double out[N];
+                    dense(t_term, out);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                    a.ev_tterm[idx] = t_term;
+                    ++kout;
+                    status = NBK_TRAJ_EVENT;
+                }
+                break;
+            }
+        }
+#endif
         if (MODE == NBK_MODE_RUN) {
             while (t_new >= te_next) {
                 double out[N];

@@ -9,6 +9,10 @@
 #define NBK_TRAJ_BOUND 1       // stopped by the t_bound / upto_t guard (nbkode/core.py:176-184)
 #define NBK_TRAJ_NONFINITE 2   // non-finite error norm or step size collapsed to 0
 #define NBK_TRAJ_MAXATTEMPTS 3 // attempt budget of this call exhausted
+#define NBK_TRAJ_EVBRACKET 4   // run_events: the event function has the same sign at both ends of the step on the
+                               // interpolant (the reference's bisect raises ValueError, nbcompat/zeros.py:516-520)
+#define NBK_TRAJ_EVENT (-1)    // run_events: stopped by a terminal event (clean stop, not sticky)
+#define NBK_MAX_EVENTS 8
 
 // advance modes
 #define NBK_MODE_RUN 0   // run(ts): emit dense output at the shared grid tgrid[0..m)
@@ -56,6 +60,15 @@ struct nbk_kargs {
     int *n_out;           // [B] grid points emitted (RUN) / steps taken (STEP) in this call
     long long max_attempts;
     unsigned long long *work_counter;  // persistent-kernel trajectory queue head
+    // ---- run_events (nbkode/core.py:334-447, event_handler.py); read only by programs compiled with NBK_NEVENTS
+    int ev_cap;           // capacity per (trajectory, event) of ev_t / ev_y
+    int ev_terminal;      // bit k set: event k is terminal
+    int ev_dir[8];        // direction of event k: -1, 0, +1 (sign of event.direction)
+    double *ev_t;         // [B][NE][cap]    event times in order of detection
+    double *ev_y;         // [B][NE][cap][n] interpolated states at the event times
+    int *ev_count;        // [B][NE] events detected in this call (only the first ev_cap are stored)
+    double *ev_tterm;     // [B] time of the terminal event that stopped the trajectory: replaces the time of
+                          //     output row n_out-1 (core.py:641-644); untouched otherwise
 };
 
 #endif

@@ -69,6 +69,19 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERN
 #endif
 }
 
+#ifdef NBK_NEVENTS
+// run_events: the run kernel with the event functions compiled in (NVRTC only)
+extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
+#if NBK_ADAPTIVE
+    nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_RUN, true>(a);
+#elif NBK_FIXED_RK
+    nbk::advance_erk<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN, true>(a);
+#else
+    nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN, true>(a);
+#endif
+}
+#endif
+
 #ifndef __CUDACC_RTC__
 #include "nbk_host.h"
 // registration record picked up by nbk_api.cu (static catalogue)

@@ -9,7 +9,7 @@ a ctypes C-ABI; there is no CPU fallback.
 
 from . import multistep, runge_kutta  # noqa: F401  (importing registers the solver classes)
 from .core import Solver, get_groups, get_solver, get_solvers, list_solvers
-from .rhs import CudaRHS
+from .rhs import CudaEvents, CudaRHS
 from ._lib import CompileError, NbkError, fp64_peak
 
 __version__ = "0.1.0"

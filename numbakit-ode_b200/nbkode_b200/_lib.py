@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NBK_LIB_PATH") or os.path.join(HERE, "libnbkode_b200.so")
 
 NBK_OK, NBK_EINVAL, NBK_ECUDA, NBK_ECOMPILE, NBK_ENOTFOUND = 0, -1, -2, -3, -4
-TRAJ_OK, TRAJ_BOUND, TRAJ_NONFINITE, TRAJ_MAXATTEMPTS = 0, 1, 2, 3
+TRAJ_OK, TRAJ_BOUND, TRAJ_NONFINITE, TRAJ_MAXATTEMPTS, TRAJ_EVBRACKET, TRAJ_EVENT = 0, 1, 2, 3, 4, -1
+MAX_EVENTS = 8
 
 
 class NbkConfig(C.Structure):
@@ -32,6 +33,12 @@ class NbkState(C.Structure):
                 ("ts", "ys", "fs", "K", "h", "params", "n_accepted", "n_rejected", "status", "n_out", "work_counter")]
 
 
+class NbkEvents(C.Structure):
+    _fields_ = [("n_events", C.c_int), ("capacity", C.c_int), ("direction", C.POINTER(C.c_int)),
+                ("terminal", C.POINTER(C.c_int)), ("t_events", C.c_void_p), ("y_events", C.c_void_p),
+                ("counts", C.c_void_p), ("t_terminal", C.c_void_p)]
+
+
 class NbkError(RuntimeError):
     pass
 
@@ -45,6 +52,7 @@ _lib = None
 EXPORTS = (
     "nbk_version", "nbk_last_error", "nbk_create", "nbk_destroy", "nbk_layout", "nbk_is_jit", "nbk_regime", "nbk_init",
     "nbk_run", "nbk_step", "nbk_last_launch", "nbk_jit_compile_only", "nbk_fp64_peak", "nbk_fp64_mma_peak",
+    "nbk_set_events", "nbk_run_events", "nbk_jit_compile_events_only",
 )
 
 
@@ -75,6 +83,9 @@ def lib():
     L.nbk_jit_compile_only.argtypes = [C.POINTER(NbkConfig), C.POINTER(ll)]
     L.nbk_fp64_peak.argtypes = [i, i, C.POINTER(dbl), C.POINTER(dbl)]
     L.nbk_fp64_mma_peak.argtypes = [i, i, C.POINTER(dbl), C.POINTER(dbl)]
+    L.nbk_set_events.argtypes = [vp, i, C.c_char_p]
+    L.nbk_run_events.argtypes = [vp, C.POINTER(NbkState), vp, i, dbl, vp, ll, ll, ll, C.POINTER(NbkEvents), ll, vp]
+    L.nbk_jit_compile_events_only.argtypes = [C.POINTER(NbkConfig), i, C.c_char_p, C.POINTER(ll)]
     _lib = L
     return L
 

@@ -174,6 +174,8 @@ class Solver(ABC):
                 shared = 1
         self.n_params = 0 if p_t is None else int(p_t.shape[1])
         self._params_shared = shared
+        self._p_shape = p_shape if p_shape else (self.n_params,)
+        self._events_key = None
 
         # ---- right-hand side -> built-in name or CUDA C
         if callable(rhs) and self.n > _rhs.MAX_TRACED_N:
@@ -521,10 +523,109 @@ class Solver(ABC):
             t = t[ondx]
         return t, self._out(ys, wait)
 
-    def run_events(self, t, events):
-        if events:
-            raise NotImplementedError("events are outside the explicit hot path of nbkode_b200 (SURVEY.md 8(f) #3)")
-        return self.run(t) + ([], [])
+    def run_events(self, t, events, max_events: int = 64):
+        """:meth:`run` with event detection (nbkode/core.py:334-447, nbkode/event_handler.py).
+
+        ``events``: a callable ``event(t, y)`` (or ``event(t, y, p)``), an iterable of them -- traced to CUDA C
+        like a Python right-hand side, with the optional ``terminal`` / ``direction`` attributes of the SciPy
+        convention -- or a :class:`nbkode_b200.CudaEvents`.  After every accepted step a sign change of an
+        event function is located by bisection on the step's dense output (tolerance 1.48e-8 on the event
+        value, at most 50 halvings) and recorded; a terminal event stops its trajectory and its ``(t, y)``
+        replaces the output row the trajectory was integrating towards.
+
+        Unbatched solvers return the reference's ``(t, y, t_events, y_events)`` (lists per event).  Batched
+        solvers return ``t`` of shape ``(m,)`` -- or ``(B, m)`` when a terminal event stopped any trajectory,
+        NaN after the stop --, ``y (B, m, n)`` (NaN after the stop), and per event the NaN-padded arrays
+        ``t_events[k] (B, K_k)``, ``y_events[k] (B, K_k, n)``; ``solver.event_counts`` is ``(B, n_events)``.
+        ``max_events`` bounds the events stored per trajectory and event function."""
+        if not events:
+            return self.run(t) + ([], [])
+        torch = _torch()
+        if self._regime != 0:
+            raise NotImplementedError("events are implemented for the one-trajectory-per-thread regime (n <= 64)")
+        ev = _rhs.trace_events(events, self.n, self._p_shape, self.params is not None)
+        if not (1 <= ev.n_events <= _lib.MAX_EVENTS):
+            raise ValueError(f"between 1 and {_lib.MAX_EVENTS} event functions are supported")
+        if self._events_key != (ev.n_events, ev.source):
+            _lib.check(_lib.lib().nbk_set_events(self._handle, ev.n_events, ev.source.encode()))
+            self._events_key = (ev.n_events, ev.source)
+        t = np.atleast_1d(np.asarray(t.detach().cpu() if hasattr(t, "detach") else t)).astype(np.float64)
+        is_sorted = t.size == 1 or bool(np.all(t[:-1] <= t[1:]))
+        if not is_sorted:
+            ndx = np.argsort(t)
+            t = t[ndx]
+        oldest = self._oldest_host if self._oldest_host is not None else float(self._slot_t(0).max().item())
+        if t[0] < oldest:
+            raise ValueError(
+                f"Cannot interpolate at t={t[0]} as it is smaller than the current smallest value in history ({oldest})"
+            )
+        self._check_time(np.max(t))
+        if t[0] <= float(self._slot_t(-1).max().item()):
+            import warnings
+
+            # the reference calls the non-existent warnings.warning here (core.py:441)
+            warnings.warn("Events for past events are not implemented yet.", stacklevel=2)
+        B, n, dev, m, NE, cap = self.B, self.n, self._device, int(t.size), ev.n_events, int(max_events)
+        grid = _device_grid(t, dev)
+        y_out = torch.full((B, m, n), math.nan, dtype=torch.float64, device=dev)
+        ev_t = torch.full((B, NE, cap), math.nan, dtype=torch.float64, device=dev)
+        ev_y = torch.full((B, NE, cap, n), math.nan, dtype=torch.float64, device=dev)
+        ev_c = torch.zeros((B, NE), dtype=torch.int32, device=dev)
+        t_term = torch.full((B,), math.nan, dtype=torch.float64, device=dev)
+        direction = (C.c_int * NE)(*ev.direction)
+        terminal = (C.c_int * NE)(*[int(x) for x in ev.terminal])
+        block = _lib.NbkEvents(NE, cap, direction, terminal, ev_t.data_ptr(), ev_y.data_ptr(), ev_c.data_ptr(),
+                               t_term.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nbk_run_events(
+                self._handle, C.byref(self._state), grid.data_ptr(), m, float(self.t_bound),
+                y_out.data_ptr(), m * n, n, 1, C.byref(block), 0, self._stream(),
+            ))
+        self._oldest_host = None
+        status = self._status
+        if bool((status == _lib.TRAJ_EVBRACKET).any().item()):
+            self._unchecked = None
+            raise ValueError("In bisect, 'fun(left, *args)' must have and opposite sign to 'fun(right, *args)'.")
+        self._raise_on_failure("run_events")
+        counts = ev_c.cpu().numpy()
+        if counts.size and int(counts.max()) > cap:
+            raise RuntimeError(f"a trajectory produced {int(counts.max())} events of one kind but max_events={cap}; "
+                               "call run_events with a larger max_events")
+        self.event_counts = counts[0] if not self._batched else counts
+        stopped = status == _lib.TRAJ_EVENT
+        if not self._batched:
+            k = int(self._nout[0].item())
+            ts, ys = t[:k].copy(), self._out(y_out[0, :k].reshape((k,) + self._y0_shape))
+            if bool(stopped[0].item()):
+                ts[k - 1] = float(t_term[0].item())
+            et, ey = ev_t[0].cpu().numpy(), ev_y[0].cpu().numpy()
+            t_events = [[float(v) for v in et[j, :counts[0, j]]] for j in range(NE)]
+            y_events = [[ey[j, i].reshape(self._y0_shape).copy() for i in range(counts[0, j])] for j in range(NE)]
+            if not is_sorted and k == t.size:
+                ondx = np.argsort(ndx)
+                return ts[ondx], ys[ondx], t_events, y_events
+            return ts, ys, t_events, y_events
+        ys = y_out
+        if bool(stopped.any().item()):
+            nout = self._nout.to(torch.int64)
+            cols = torch.arange(m, device=dev)
+            tt = torch.from_numpy(t).to(dev).repeat(B, 1)
+            tt = torch.where(cols[None, :] < nout[:, None], tt, torch.full_like(tt, math.nan))
+            rows = torch.nonzero(stopped).ravel()
+            tt[rows, nout[rows] - 1] = t_term[rows]
+            t_ret = self._out(tt)
+        else:
+            t_ret = t
+        if not is_sorted and not bool(stopped.any().item()):
+            ondx = np.argsort(ndx)
+            ys = ys[:, torch.from_numpy(ondx).to(dev)]
+            t_ret = t[ondx]
+        t_events, y_events = [], []
+        for j in range(NE):
+            kj = int(counts[:, j].max()) if counts.size else 0
+            t_events.append(self._out(ev_t[:, j, :kj]))
+            y_events.append(self._out(ev_y[:, j, :kj]))
+        return t_ret, self._out(ys), t_events, y_events
 
     def interpolate(self, t: float):
         """Dense output inside the recorded history (nbkode/core.py:449-472)."""

@@ -188,6 +188,73 @@ def trace(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     return CudaRHS("\n".join(lines) + "\n", name=getattr(func, "__name__", "traced"))
 
 
+class CudaEvents:
+    """CUDA C source of ``n_events`` event functions for :meth:`Solver.run_events`::
+
+        NBK_EVENT nbk_event(int k, double t, const double* y, const double* p) { ... return g_k; }
+
+    ``terminal`` / ``direction`` follow the SciPy convention the reference uses (nbkode/core.py:343-366)."""
+
+    def __init__(self, source: str, n_events: int, terminal=None, direction=None):
+        if "nbk_event" not in source:
+            raise ValueError("CUDA event source must define nbk_event(k, t, y, p)")
+        self.source, self.n_events = source, int(n_events)
+        self.terminal = [bool(x) for x in (terminal if terminal is not None else [False] * self.n_events)]
+        self.direction = [int(np.sign(x)) for x in (direction if direction is not None else [0] * self.n_events)]
+        if len(self.terminal) != self.n_events or len(self.direction) != self.n_events:
+            raise ValueError("terminal / direction must have one entry per event")
+
+
+def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
+    """Standardise ``events`` (a callable, an iterable of callables ``event(t, y)`` -- or ``event(t, y, p)`` --
+    with optional ``terminal`` / ``direction`` attributes, or a :class:`CudaEvents`) the way
+    ``event_handler.build_handler`` does (nbkode/event_handler.py:236-262) and emit ``nbk_event``."""
+    import inspect
+
+    if isinstance(events, CudaEvents):
+        return events
+    if callable(events):
+        events = (events,)
+    events = list(events)
+    lines = ["NBK_EVENT nbk_event(int k, double t, const double* y, const double* p) {"]
+    terminal, direction = [], []
+    for k, ev in enumerate(events):
+        terminal.append(bool(getattr(ev, "terminal", False)))
+        direction.append(int(np.sign(getattr(ev, "direction", 0))))
+        tr = _Trace()
+        t = Expr(tr, "t")
+        y = np.empty(n, dtype=object)
+        for i in range(n):
+            y[i] = Expr(tr, f"y[{i}]")
+        try:
+            nargs = len(inspect.signature(ev).parameters)
+        except (TypeError, ValueError):
+            nargs = 2
+        try:
+            if nargs >= 3 and has_params:
+                p = np.empty(int(np.prod(params_shape, dtype=int)), dtype=object)
+                for i in range(p.size):
+                    p[i] = Expr(tr, f"p[{i}]")
+                out = ev(t, y, p.reshape(params_shape))
+            else:
+                out = ev(t, y)
+        except TraceError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            raise TraceError(f"could not trace event {getattr(ev, '__name__', ev)!r} into CUDA C "
+                             f"({type(exc).__name__}: {exc}); pass nbkode_b200.CudaEvents instead") from exc
+        out = np.asarray(out, dtype=object).ravel()
+        if out.size != 1:
+            raise TraceError("an event function must return one float")
+        lines.append(f"  if (k == {k}) {{")
+        lines += tr.stmts
+        lines.append(f"    return {Expr._c(out[0])};")
+        lines.append("  }")
+    lines.append("  return 0.0;")
+    lines.append("}")
+    return CudaEvents("\n".join(lines) + "\n", len(events), terminal, direction)
+
+
 def resolve(rhs, n: int, params_shape, has_params: bool):
     """-> (builtin_name or None, cuda_source or None)."""
     if isinstance(rhs, CudaRHS):

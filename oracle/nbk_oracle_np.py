@@ -446,6 +446,90 @@ def run(solver, ts):
     return ts, np.array(out).reshape(len(ts), -1)
 
 
+def _bisect(fun, left, right, tol=1.48e-8, maxiter=50):
+    """nbkode/nbcompat/zeros.py:508-533 (rtol = 0)."""
+    if not left < right:
+        raise ValueError("In bisect, 'left' must be smaller than 'rigth'.")
+    yl = fun(left)
+    if yl == 0:
+        return left
+    yr = fun(right)
+    if yr == 0:
+        return right
+    if not yl * yr < 0:
+        raise ValueError("In bisect, 'fun(left, *args)' must have and opposite sign to 'fun(right, *args)'.")
+    for _ in range(maxiter):
+        mid = (left + right) / 2
+        ym = fun(mid)
+        if np.abs(ym - 0) <= tol:
+            break
+        if np.sign(ym) == np.sign(yl):
+            left, yl = mid, ym
+        else:
+            right, yr = mid, ym
+    return mid
+
+
+class _Event:
+    """nbkode/event_handler.py:96-177."""
+
+    def __init__(self, func, is_terminal, direction, init_t, init_y):
+        self.func, self.is_terminal, self.direction = func, is_terminal, direction
+        self.last_t = init_t
+        self.last_value = func(init_t, init_y)
+        self.t, self.y = [], []
+
+    def evaluate(self, solver):
+        t, y = solver.t, solver.y
+        value = self.func(t, y)
+        up = (self.last_value <= 0.0) & (value >= 0.0)
+        down = (self.last_value >= 0.0) & (value <= 0.0)
+        either = up | down
+        trigger = up & (self.direction > 0) | down & (self.direction < 0) | either & (self.direction == 0)
+        if trigger:
+            if value == 0:
+                root = t
+            else:
+                root = _bisect(lambda tt: self.func(tt, solver.interpolate(tt)), self.last_t, t)
+            if not (self.t and self.t[-1] == root):
+                self.t.append(root)
+                self.y.append(solver.interpolate(root))
+        self.last_t = t
+        self.last_value = value
+        return trigger and self.is_terminal
+
+
+def run_events(solver, ts, events):
+    """nbkode/core.py:385-447 + :621-647 (_run_eval_events) + event_handler.build_handler/EventHandler.evaluate.
+    Returns (t, y, t_events, y_events); ``ts`` sorted and ahead of solver.t."""
+    ts = np.atleast_1d(ts).astype(np.float64).copy()
+    if callable(events):
+        events = (events,)
+    evs = [_Event(e, bool(getattr(e, "terminal", False)), int(np.sign(getattr(e, "direction", 0))), solver.t, solver.y.copy())
+           for e in events]
+    out = np.empty((ts.size, solver.y.size))
+    n_rows = ts.size
+    done = False
+    for ndx, ti in enumerate(ts):
+        while solver.t < ti:
+            if not solver.step():
+                n_rows, done = ndx, True
+                break
+            terminate, last_event = False, None
+            for e in evs:
+                if e.evaluate(solver):
+                    terminate = True
+                    last_event = (e.t[-1], e.y[-1]) if e.t else (np.nan, np.empty(0) * np.nan)
+            if terminate:
+                ts[ndx], out[ndx] = last_event
+                n_rows, done = ndx + 1, True
+                break
+        if done:
+            break
+        out[ndx] = solver.interpolate(ti)
+    return ts[:n_rows], out[:n_rows], [list(e.t) for e in evs], [list(e.y) for e in evs]
+
+
 def steps(solver, n=None, upto_t=None):
     """nbkode/core.py:214-267 step(n=, upto_t=) -> (t[k], y[k, n])."""
     tt, yy = [], []
@@ -484,6 +568,47 @@ def rhs_rd1d(t, y, p):
     d, r = p[0], p[1]
     return d * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + r * y * (1 - y)
 
+
+# event functions shared by the golden-vector generator and the tests (SciPy convention: optional
+# ``terminal`` / ``direction`` attributes, nbkode/core.py:343-366)
+def ev_y0(t, y):
+    return y[0]
+
+
+def ev_y1_down(t, y):
+    return y[1]
+
+
+ev_y1_down.direction = -1
+
+
+def ev_z25_up(t, y):
+    return y[2] - 25.0
+
+
+ev_z25_up.direction = 1
+
+
+def ev_x_m8_terminal(t, y):
+    return y[0] + 8.0
+
+
+ev_x_m8_terminal.terminal = True
+ev_x_m8_terminal.direction = -1
+
+
+def ev_time(t, y):
+    return t - 2.5 + 0.0 * y[0]
+
+
+def ev_y0_up_terminal(t, y):
+    return y[0]
+
+
+ev_y0_up_terminal.terminal = True
+ev_y0_up_terminal.direction = 1
+
+EVENTS = {"y0_up_terminal": ev_y0_up_terminal, "y0": ev_y0, "y1_down": ev_y1_down, "z25_up": ev_z25_up, "x_m8_terminal": ev_x_m8_terminal, "time": ev_time}
 
 RHS = {"decay": rhs_decay, "lorenz": rhs_lorenz, "vdp": rhs_vdp, "linear": rhs_linear, "rd1d": rhs_rd1d}
 

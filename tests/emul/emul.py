@@ -43,8 +43,11 @@ def _kargs_struct():
         base = m.group(2)
         for name in m.group(3).split(","):
             name = name.strip()
+            arr = re.match(r"(\w+)\[(\d+)\]$", name)
             if name.startswith("*"):
                 fields.append((name.lstrip("* "), C.c_void_p))
+            elif arr:
+                fields.append((arr.group(1), _CTYPES[base] * int(arr.group(2))))
             else:
                 fields.append((name, _CTYPES[base]))
     return type("KArgs", (C.Structure,), {"_fields_": fields})
@@ -62,12 +65,17 @@ ERK_STAGES = {202: 2, 203: 4, 213: 3, 204: 4, 238: 4}
 _libs = {}
 
 
-def _program(method, rhs, n, npar):
+def _program(method, rhs, n, npar, events=None):
+    """events: (n_events, CUDA C source defining nbk_event) -> also builds the run_events kernel (kernel 3)"""
     if rhs == "decay":
         # typedef through a forced include: a -D value cannot carry the template comma portably
         rtype, tag = f"nbk::rhs_decay<{n},{npar}>", f"m{method}_decay_{n}_{npar}"
     else:
         rtype, tag = RHS_TYPES[rhs][0], f"m{method}_{rhs}"
+    if events:
+        import hashlib
+
+        tag += "_ev" + hashlib.sha1(events[1].encode()).hexdigest()[:10]
     if tag in _libs:
         return _libs[tag]
     os.makedirs(BUILD, exist_ok=True)
@@ -78,6 +86,8 @@ def _program(method, rhs, n, npar):
         pre = os.path.join(BUILD, f"pre_{tag}.h")
         with open(pre, "w") as fh:
             fh.write(f"#define NBK_METHOD {method}\n#define NBK_RHS_T {rtype}\n#define NBK_TAG {tag}\n")
+            if events:
+                fh.write(f"#define NBK_NEVENTS {events[0]}\n#define NBK_EVENT static inline double\n{events[1]}\n")
         subprocess.check_call([
             "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
             "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", "-include", pre,
@@ -101,6 +111,7 @@ class EmulEnsemble:
         params = np.ascontiguousarray(np.asarray(params, float))
         params = params.reshape(1, -1) if params_shared else params.reshape(self.B, -1)
         self.np_ = params.shape[1]
+        self._rhs_name = rhs
         self.fn = _program(self.mid, rhs, self.n, self.np_)
         adaptive = self.mid in (23, 45, 853)
         self.L = 2 if (adaptive or self.mid in ERK_STAGES) else max(self.mid, 2)
@@ -144,6 +155,26 @@ class EmulEnsemble:
         self.counter[0] = 0
         self.fn(1, C.byref(a), self.B)
         return out
+
+    def run_events(self, ts, events, cap=64, t_bound=math.inf):
+        """events: nbkode_b200.rhs.CudaEvents (e.g. from rhs.trace_events).  Mirrors Solver.run_events' buffers."""
+        fn = _program(self.mid, self._rhs_name, self.n, self.np_, (events.n_events, events.source))
+        ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
+        m, NE = ts.size, events.n_events
+        out = np.full((self.B, m, self.n), np.nan)
+        ev_t = np.full((self.B, NE, cap), np.nan); ev_y = np.full((self.B, NE, cap, self.n), np.nan)
+        ev_c = np.zeros((self.B, NE), np.int32); t_term = np.full(self.B, np.nan)
+        a = KArgs(**self.base)
+        a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
+        a.pristine, self._pristine = int(self._pristine), False
+        a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
+        a.ev_cap, a.ev_terminal = cap, sum(1 << k for k, x in enumerate(events.terminal) if x)
+        for k, d in enumerate(events.direction):
+            a.ev_dir[k] = d
+        a.ev_t, a.ev_y, a.ev_count, a.ev_tterm = ev_t.ctypes.data, ev_y.ctypes.data, ev_c.ctypes.data, t_term.ctypes.data
+        self.counter[0] = 0
+        fn(3, C.byref(a), self.B)
+        return out, ev_t, ev_y, ev_c, t_term
 
     def step(self, n_steps, bound=math.inf, emit=True):
         t_out = np.full((self.B, max(n_steps, 1)), np.nan)

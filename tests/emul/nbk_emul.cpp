@@ -14,6 +14,9 @@ extern "C" int EMUL_NAME(int kernel, const nbk_kargs *a, long long n_threads) {
         if (kernel == 0) NBK_KERNEL(init)(*a);
         else if (kernel == 1) NBK_KERNEL(run)(*a);
         else if (kernel == 2) NBK_KERNEL(step)(*a);
+#ifdef NBK_NEVENTS
+        else if (kernel == 3) NBK_KERNEL(runev)(*a);
+#endif
         else return -1;
     }
     return 0;

@@ -179,9 +179,43 @@ def dop853_section():
                          "api": api_record(cls, {"h": 0.1})})
 
 
+def events_section():
+    """run_events (SURVEY.md 8(f) #3): the reference's own event handling on its dense outputs."""
+    lor = ([1.0, 1.0, 1.0], [10.0, 28.0, 8 / 3])
+    cases = []
+    for cls in ("RungeKutta45", "RungeKutta23", "DOP853", "RungeKutta4", "Heun3", "ForwardEuler", "AdamsBashforth2",
+                "AdamsBashforth3"):
+        adaptive = cls in ("RungeKutta45", "RungeKutta23", "DOP853")
+        for rhs, y0, p, ts, evs, kw in (
+            ("lorenz", *lor, [1.0, 2.0, 3.0, 4.0], ["y0", "z25_up"], dict(rtol=1e-6, atol=1e-9) if adaptive else dict(h=0.002)),
+            ("lorenz", *lor, [1.0, 2.0, 3.0, 4.0], ["y0", "x_m8_terminal", "time"], dict(rtol=1e-6, atol=1e-9) if adaptive else dict(h=0.002)),
+            ("vdp", [2.0, 0.0], [1.0], np.linspace(0.5, 20, 40), ["y0", "y1_down"], dict(rtol=1e-6, atol=1e-9) if adaptive else dict(h=0.01)),
+            ("vdp", [2.0, 0.0], [1.0], np.linspace(0.5, 20, 40), ["y1_down", "y0_up_terminal"], dict(rtol=1e-6, atol=1e-9) if adaptive else dict(h=0.01)),
+        ):
+            s = getattr(nbkode, cls)(onp.RHS[rhs], 0.0, np.array(y0, float), params=np.array(p, float), **kw)
+            rec = {"cls": cls, "rhs": rhs, "y0": L(y0), "p": L(p), "kw": kw, "ts": L(ts), "events": evs}
+            try:
+                t, y, te, ye = s.run_events(np.array(ts, float), [onp.EVENTS[e] for e in evs])
+            except ValueError as exc:
+                rec["raises"] = str(exc)
+                cases.append(rec)
+                continue
+            # the reference appends interpolate(root) without copying: when the root is a step end point that is
+            # a VIEW of the history buffer and later steps overwrite it (aliasing bug, event_handler.py:160 +
+            # explicit.py:372-375).  Such entries are flagged and excluded from the parity checks.
+            alias = [[bool(getattr(x, "base", None) is not None) for x in lst] for lst in ye]
+            rec.update(t=L(t), y=L(y), t_events=[L(x) for x in te], y_events=[L(x) for x in ye], y_events_aliased=alias,
+                       t_end=float(s.t))
+            cases.append(rec)
+    dump("events.json", cases)
+
+
 def main():
     if sys.argv[1:] == ["dop853"]:
         return dop853_section()
+    if sys.argv[1:] == ["events"]:
+        return events_section()
+    events_section()
     dop853_section()
     # ---------------------------------------------------------------- C1: README example
     c1 = []

@@ -208,3 +208,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "build.py", os.path.join(dirpath, f)
+
+
+def test_nvrtc_compiles_event_programs_and_traces_events():
+    from oracle import nbk_oracle_np as onp
+
+    lib = _lib.lib()
+    sz = C.c_longlong(0)
+    ev = rhs.trace_events([onp.ev_y0, onp.ev_z25_up, onp.ev_x_m8_terminal], 3, (3,), True)
+    assert ev.n_events == 3 and ev.terminal == [False, False, True] and ev.direction == [0, 1, -1]
+    assert "nbk_event" in ev.source
+    for method in (45, 853, 2, 204):
+        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(method, 3, 3, rhs_name=b"lorenz")), 3, ev.source.encode(), C.byref(sz)))
+        assert sz.value > 10_000
+    with pytest.raises(ValueError):
+        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(45, 3, 3, rhs_name=b"lorenz")), 9, ev.source.encode(), C.byref(sz)))
+    with pytest.raises(ValueError):  # CTA regime: not implemented
+        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(45, 2048, 2, rhs_name=b"rd1d")), 1, ev.source.encode(), C.byref(sz)))
+    with pytest.raises(rhs.TraceError):
+        rhs.trace_events(lambda t, y: 1.0 if y[0] > 0 else -1.0, 3, (3,), True)

@@ -199,3 +199,40 @@ def test_dop853_resume_and_past_points():
     e = EmulEnsemble("DOP853", "decay", [[1.0]], [[0.01]])
     tt, yy, cnt = e.step(20)
     assert cnt[0] == 20 and rel(tt[0], c["ts20"]) < 1e-9 and rel(yy[0], c["ys20"]) < 1e-10
+
+
+# ---------------------------------------------------------------- events
+EVENT_CASES = [c for c in load_golden("events.json")]
+
+
+@pytest.mark.parametrize("c", EVENT_CASES, ids=lambda c: f"{c['cls']}-{c['rhs']}-{'+'.join(c['events'])}")
+def test_events_vs_reference(c):
+    """The run_events kernel (host build) against the live reference's run_events: same events in the same
+    order, event times to the bisection's resolution, truncated outputs for terminal events."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "numbakit-ode_b200"))
+    from nbkode_b200 import rhs as nrhs
+
+    ev = nrhs.trace_events([onp.EVENTS[e] for e in c["events"]], len(c["y0"]), (len(c["p"]),), True)
+    kw = dict(c["kw"])
+    e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], first_stepper=45, **kw)
+    out, ev_t, ev_y, ev_c, t_term = e.run_events(c["ts"], ev)
+    k = int(e.nout[0])
+    assert k == len(c["t"])
+    t_ref = np.array(c["t"])
+    tol_y = 2e-6 if c["rhs"] == "lorenz" else 1e-7  # adaptive step sequences differ at the 1e-9 level
+    if e.status[0] == -1:  # terminal event: its time replaces the last row's
+        assert rel(t_term[0], t_ref[-1]) < 1e-7
+        assert rel(out[0, :k - 1], np.array(c["y"])[:k - 1]) < tol_y if k > 1 else True
+        assert rel(out[0, k - 1], c["y"][-1]) < 1e-6
+    else:
+        assert e.status[0] == 0 and np.array_equal(t_ref, c["ts"][:k])
+        assert rel(out[0, :k], c["y"]) < tol_y
+    assert np.isnan(out[0, k:]).all()
+    for j, (te, ye, al) in enumerate(zip(c["t_events"], c["y_events"], c["y_events_aliased"])):
+        assert ev_c[0, j] == len(te)
+        if te:
+            # the root is located to |g| <= 1.48e-8 on the interpolant: times agree to ~1e-8 / |g'|
+            assert rel(ev_t[0, j, :len(te)], te) < 1e-6
+            for i, (v, aliased) in enumerate(zip(ye, al)):
+                if not aliased:
+                    assert rel(ev_y[0, j, i], v) < 1e-5
