@@ -27,7 +27,7 @@
  *                                            (nbkode/runge_kutta/core.py:25-27), RK only
  *    h  [B]                                  next step size (nbkode/core.py:706)
  *    params [np][B] or [np]                  nbkode/core.py:118-119
- *    n_accepted, n_rejected [B], status [B], n_out [B], work_counter [1]   (no reference counterpart)
+ *    n_accepted, n_rejected [B], status [B], n_out [B], work_counter [2]   (no reference counterpart)
  *  L and S+1 come from nbk_layout().
  */
 #ifndef NBKODE_B200_H
@@ -101,8 +101,10 @@ typedef struct {          /* all device pointers, see the layout above */
     double *ts, *ys, *fs, *K, *h, *params;
     long long *n_accepted, *n_rejected;
     int *status, *n_out;
-    unsigned long long *work_counter; /* 8 bytes of scratch: head of the trajectory queue of the
-                                         persistent adaptive kernels (reset by every call) */
+    unsigned long long *work_counter; /* 16 bytes, reset by every call: [0] head of the trajectory queue of the
+                                         persistent adaptive kernels, [1] number of trajectories that ended the
+                                         call with a failure status (>= NBK_TRAJ_NONFINITE): one 8-byte copy tells
+                                         the host whether anything failed */
 } nbk_state;
 
 int nbk_version(void);

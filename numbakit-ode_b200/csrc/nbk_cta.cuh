@@ -169,7 +169,7 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
             }
         }
         if (i0 + e < n) {
-            const double sc = fma(rtol, abs_max(ynew[e], y[e]), atol);
+            const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
             const double r = ee * fast_rcp(sc);
             part = fma(r, r, part);
         }
@@ -425,6 +425,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
                 a.n_rej[idx] += natt - nacc;
             }
             a.status[idx] = status;
+            if (status >= NBK_TRAJ_NONFINITE) atomicAdd(a.work_counter + 1, 1ULL);
             a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nacc;
         }
     }

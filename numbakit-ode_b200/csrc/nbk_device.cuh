@@ -88,6 +88,7 @@ struct cbank_rk45;
 struct tab_rk23 {  // Bogacki-Shampine 3(2), nbkode/runge_kutta/explicit.py:146-151
     static constexpr int S = 3, Q = 2, M = 3, ROOT = 6, ID = 23;
     static constexpr bool DOP = false;
+    typedef cbank_rk23 bank;
     static __device__ __forceinline__ const cbank_rk23 &cb();
     static NBK_HD double a(int i, int j) {
         constexpr double A[3][3] = {{0, 0, 0}, {1.0 / 2, 0, 0}, {0, 3.0 / 4, 0}};
@@ -114,6 +115,7 @@ struct tab_rk23 {  // Bogacki-Shampine 3(2), nbkode/runge_kutta/explicit.py:146-
 struct tab_rk45 {  // Dormand-Prince 5(4), nbkode/runge_kutta/explicit.py:185-239
     static constexpr int S = 6, Q = 4, M = 4, ROOT = 10, ID = 45;
     static constexpr bool DOP = false;
+    typedef cbank_rk45 bank;
     static __device__ __forceinline__ const cbank_rk45 &cb();
     static NBK_HD double a(int i, int j) {
         constexpr double A[6][6] = {
@@ -214,14 +216,13 @@ struct tab_dop853 {
         constexpr double Dv[4][16] = NBK_DOP853_D_INIT;
         return Dv[i][j];
     }
+    typedef cbank_dop853 bank;
     static __device__ __forceinline__ const cbank_dop853 &cb() { return nbk_c853; }
 };
 
 __device__ __forceinline__ const cbank_rk23 &tab_rk23::cb() { return nbk_c23; }
 __device__ __forceinline__ const cbank_rk45 &tab_rk45::cb() { return nbk_c45; }
 
-// Adams-Bashforth weights exactly as the reference lists them; index 0 multiplies the OLDEST
-// derivative of the window (nbkode/multistep/core.py:101,109).
 template <int ORDER>
 struct tab_ab {
     static constexpr int ID = ORDER, LEN = ORDER > 2 ? ORDER : 2;
@@ -332,10 +333,11 @@ struct rhs_user {
 // Arithmetic helpers
 // =====================================================================================
 
-// 1/x for positive normal x: MUFU.RCP64H seed (relative error e <= 2^-23) and ONE third-order
-// step r (1 + e + e^2), whose truncation error e^3 <= 2^-69 is below double rounding: three
-// dependent DFMA instead of the ~12 instruction IEEE division sequence (result within ~1 ulp,
-// not correctly rounded).
+// 1/x for positive normal x: MUFU.RCP64H seed (relative error e <= 2^-23) and ONE Newton step
+// r (1 + e): two dependent DFMA instead of the ~12 instruction IEEE division sequence.  Truncation
+// error e^2 <= 2^-46 (7e-15): it only scales the error estimate, whose own cancellation noise
+// (E.K loses ~5 digits) is three orders of magnitude larger.  (A third-order step, 2^-69, costs one
+// more DFMA per component: measured +0.6 % kernel time.)
 NBK_DEV double fast_rcp(double x) {
     double r;
 #ifdef NBK_HOST_EMUL
@@ -344,8 +346,7 @@ NBK_DEV double fast_rcp(double x) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
     const double e = fma(-x, r, 1.0);
-    const double q = fma(e, e, e);
-    return fma(r, q, r);
+    return fma(r, e, r);
 }
 
 // x^(-1/R) for a positive normal x inside float range ([1e-30, 1e30], guaranteed by the clamp in
@@ -404,6 +405,7 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
                         const double (&p)[Rhs::NP > 0 ? Rhs::NP : 1], double (&ynew)[Rhs::N], double &err2,
                         double rtol, double atol) {
     constexpr int N = Rhs::N, S = Tab::S;
+    const typename Tab::bank &cb = Tab::cb();
 #pragma unroll
     for (int s = 1; s < S; ++s) {
         double ys[N];
@@ -414,13 +416,13 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 #pragma unroll
             for (int j = 0; j < s; ++j) {
                 if (Tab::a(s, j) != 0.0) {
-                    acc = first ? Tab::cb().a[s][j] * K[j][i] : fma(Tab::cb().a[s][j], K[j][i], acc);
+                    acc = first ? cb.a[s][j] * K[j][i] : fma(cb.a[s][j], K[j][i], acc);
                     first = false;
                 }
             }
             ys[i] = fma(h, acc, y[i]);
         }
-        Rhs::eval(fma(h, Tab::cb().c[s], t), ys, p, K[s]);
+        Rhs::eval(fma(h, cb.c[s], t), ys, p, K[s]);
     }
     // y_new = y + h (B . K[:S]).  (The reference forms the vector h*B first; the difference is one
     // rounding, far inside the parity bars, and saves the S scalar multiplies.)
@@ -431,7 +433,7 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 #pragma unroll
         for (int j = 0; j < S; ++j) {
             if (Tab::b(j) != 0.0) {
-                acc = first ? Tab::cb().b[j] * K[j][i] : fma(Tab::cb().b[j], K[j][i], acc);
+                acc = first ? cb.b[j] * K[j][i] : fma(cb.b[j], K[j][i], acc);
                 first = false;
             }
         }
@@ -449,15 +451,15 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 #pragma unroll
             for (int j = 0; j <= S; ++j) {
                 if (Tab::e5(j) != 0.0) {
-                    e5 = f5 ? Tab::cb().e5[j] * K[j][i] : fma(Tab::cb().e5[j], K[j][i], e5);
+                    e5 = f5 ? cb.e5[j] * K[j][i] : fma(cb.e5[j], K[j][i], e5);
                     f5 = false;
                 }
                 if (Tab::e3(j) != 0.0) {
-                    e3 = f3 ? Tab::cb().e3[j] * K[j][i] : fma(Tab::cb().e3[j], K[j][i], e3);
+                    e3 = f3 ? cb.e3[j] * K[j][i] : fma(cb.e3[j], K[j][i], e3);
                     f3 = false;
                 }
             }
-            const double rs = fast_rcp(fma(rtol, abs_max(ynew[i], y[i]), atol));
+            const double rs = fast_rcp(pos_max(fma(rtol, fabs(ynew[i]), atol), fma(rtol, fabs(y[i]), atol)));
             const double r5 = e5 * rs, r3 = e3 * rs;
             a5 = fma(r5, r5, a5);
             a3 = fma(r3, r3, a3);
@@ -476,11 +478,13 @@ NBK_DEV void rk_attempt(double t, double h, const double (&y)[Rhs::N], double (&
 #pragma unroll
             for (int j = 0; j <= S; ++j) {
                 if (Tab::e(j) != 0.0) {
-                    e = first ? Tab::cb().e[j] * K[j][i] : fma(Tab::cb().e[j], K[j][i], e);
+                    e = first ? cb.e[j] * K[j][i] : fma(cb.e[j], K[j][i], e);
                     first = false;
                 }
             }
-            const double sc = fma(rtol, abs_max(ynew[i], y[i]), atol);
+            // atol + rtol max(|a|, |b|) == max(atol + rtol |a|, atol + rtol |b|) bit for bit (monotone); the |.| are
+            // free operand modifiers of DFMA, the max of two positive doubles runs on the integer pipe
+            const double sc = pos_max(fma(rtol, fabs(ynew[i]), atol), fma(rtol, fabs(y[i]), atol));
             const double r = e * fast_rcp(sc);
             acc2 = fma(r, r, acc2);
         }
@@ -619,6 +623,14 @@ NBK_DEV double initial_step(double t0, const double (&y0)[Rhs::N], const double 
     if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
     else h1 = pow(0.01 / fmax(d1, d2), 1.0 / (q + 1));
     return fmin(100 * h0, h1);
+}
+
+// Final status of a trajectory for this call.  Failures are also counted in work_counter[1], so that the host
+// learns "did anything fail" from one 8-byte copy instead of a reduction kernel (which could not start while a
+// persistent kernel of another stream fills the GPU).
+NBK_DEV void store_status(const nbk_kargs &a, long long idx, int status) {
+    a.status[idx] = status;
+    if (status >= NBK_TRAJ_NONFINITE) atomicAdd(a.work_counter + 1, 1ULL);
 }
 
 // -------------------------------------------------------------------------------------
@@ -808,7 +820,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 a.n_acc[idx] += nacc;
                 a.n_rej[idx] += natt - nacc;
             }
-            a.status[idx] = status;
+            store_status(a, idx, status);
             a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nacc;
             finishing = false;
             idx = -1;
@@ -1009,11 +1021,13 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     running = false;
                     finishing = true;
                 }
-                // commit (selects, no divergence)
-                t = accept ? t_new : t;
+                // commit (predicated moves, no divergence)
+                if (accept) {
+                    t = t_new;
 #pragma unroll
-                for (int c = 0; c < N; ++c) y[c] = accept ? ynew[c] : y[c];
-                nacc += accept ? 1 : 0;
+                    for (int c = 0; c < N; ++c) y[c] = ynew[c];
+                    ++nacc;
+                }
                 fresh = accept;
             }
         }
@@ -1193,7 +1207,7 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
         }
         a.n_acc[idx] += nsteps;
     }
-    a.status[idx] = status;
+    store_status(a, idx, status);
     a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
 }
 
@@ -1392,7 +1406,7 @@ NBK_DEV void init_ab(const nbk_kargs &a) {
     a.h[idx] = h;
     a.n_acc[idx] = 0;
     a.n_rej[idx] = 0;
-    a.status[idx] = status;
+    store_status(a, idx, status);
 }
 
 // =====================================================================================
@@ -1588,7 +1602,7 @@ NBK_DEV void advance_erk(const nbk_kargs &a) {
             for (int c = 0; c < N; ++c) a.K[((long long)s * N + c) * B + idx] = K[s][c];
         a.n_acc[idx] += nsteps;
     }
-    a.status[idx] = status;
+    store_status(a, idx, status);
     a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
 }
 

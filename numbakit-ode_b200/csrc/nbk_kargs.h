@@ -59,7 +59,8 @@ struct nbk_kargs {
     long long to_sb;
     int *n_out;           // [B] grid points emitted (RUN) / steps taken (STEP) in this call
     long long max_attempts;
-    unsigned long long *work_counter;  // persistent-kernel trajectory queue head
+    unsigned long long *work_counter;  // [2]: [0] persistent-kernel trajectory queue head, [1] trajectories that
+                                       // ended this call with a failure status (>= NBK_TRAJ_NONFINITE)
     // ---- run_events (nbkode/core.py:334-447, event_handler.py); read only by programs compiled with NBK_NEVENTS
     int ev_cap;           // capacity per (trajectory, event) of ev_t / ev_y
     int ev_terminal;      // bit k set: event k is terminal

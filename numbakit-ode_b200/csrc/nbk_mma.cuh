@@ -230,7 +230,7 @@ _Pragma("unroll")
                     }
                 }
                 if (row < n) {
-                    const double sc = fma(rtol, abs_max(ynew[mt][nt][q], y[mt][nt][q]), atol);
+                    const double sc = pos_max(fma(rtol, fabs(ynew[mt][nt][q]), atol), fma(rtol, fabs(y[mt][nt][q]), atol));
                     const double r = ee * fast_rcp(sc);
                     part[nt][q] = fma(r, r, part[nt][q]);
                 }
@@ -372,6 +372,7 @@ _Pragma("unroll")
                 a.n_rej[idx] += cs->natt[c] - cs->nacc[c];
             }
             a.status[idx] = cs->status[c];
+            if (cs->status[c] >= NBK_TRAJ_NONFINITE) atomicAdd(a.work_counter + 1, 1ULL);
             a.n_out[idx] = MODE == NBK_MODE_RUN ? cs->kout[c] : cs->nacc[c];
         }
     }

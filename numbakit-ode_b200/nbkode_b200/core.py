@@ -227,7 +227,7 @@ class Solver(ABC):
         self._nrej = torch.empty((B,), dtype=torch.int64, device=dev)
         self._status = torch.empty((B,), dtype=torch.int32, device=dev)
         self._nout = torch.zeros((B,), dtype=torch.int32, device=dev)
-        self._queue = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self._queue = torch.zeros((2,), dtype=torch.int64, device=dev)  # [queue head, failures of the last call]
         ptr = lambda x: x.data_ptr() if x is not None else None  # noqa: E731
         self._state = _lib.NbkState(
             ptr(self._ts), ptr(self._ys), ptr(self._fs), ptr(self._K), ptr(self._h), ptr(self._p),
@@ -319,7 +319,9 @@ class Solver(ABC):
 
     def _raise_on_failure(self, where):
         self._unchecked = None
-        bad = int((self._status >= _lib.TRAJ_NONFINITE).sum().item())
+        # one 8-byte copy (no kernel: a reduction could not start while a persistent kernel of another stream
+        # fills the GPU, which would serialise pipelined ensembles)
+        bad = int(self._queue[1].item())
         if bad:
             raise RuntimeError(
                 f"{bad} of {self.B} trajectories failed in {where}: non-finite error norm, collapsed step size or "

@@ -124,7 +124,7 @@ class EmulEnsemble:
             self.p[:] = params[0]
         self.nacc = np.zeros(B, np.int64); self.nrej = np.zeros(B, np.int64)
         self.status = np.zeros(B, np.int32); self.nout = np.zeros(B, np.int32)
-        self.counter = np.zeros(1, np.uint64)
+        self.counter = np.zeros(2, np.uint64)
         root = {45: 10, 853: 16}.get(self.mid, 6)
         self.base = dict(
             B=B, ts=self.ts.ctypes.data, ys=self.ys.ctypes.data, fs=self.fs.ctypes.data, K=self.K.ctypes.data,
@@ -152,7 +152,7 @@ class EmulEnsemble:
         a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
         a.pristine, self._pristine = int(self._pristine), False
         a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
-        self.counter[0] = 0
+        self.counter[:] = 0
         self.fn(1, C.byref(a), self.B)
         return out
 
@@ -172,7 +172,7 @@ class EmulEnsemble:
         for k, d in enumerate(events.direction):
             a.ev_dir[k] = d
         a.ev_t, a.ev_y, a.ev_count, a.ev_tterm = ev_t.ctypes.data, ev_y.ctypes.data, ev_c.ctypes.data, t_term.ctypes.data
-        self.counter[0] = 0
+        self.counter[:] = 0
         fn(3, C.byref(a), self.B)
         return out, ev_t, ev_y, ev_c, t_term
 
@@ -184,7 +184,7 @@ class EmulEnsemble:
         a.pristine, self._pristine = int(self._pristine), False
         a.t_out, a.to_sb = t_out.ctypes.data, max(n_steps, 1)
         a.y_out, a.o_sb, a.o_sk, a.o_sc = y_out.ctypes.data, max(n_steps, 1) * self.n, self.n, 1
-        self.counter[0] = 0
+        self.counter[:] = 0
         self.fn(2, C.byref(a), self.B)
         return t_out, y_out, self.nout.copy()
 
