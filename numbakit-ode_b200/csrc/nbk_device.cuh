@@ -505,10 +505,26 @@ NBK_DEV double step_factor(double err2, double safety, double min_factor, double
     return pos_min(max_factor, pos_max(min_factor, f));
 }
 
-// Dense output inside the last accepted step [t_old, t_new] (RkInterpolator.evaluate).
+// Dense output inside the last accepted step [t_old, t_new] (RkInterpolator, explicit.py:354-403):
+// Q = K^T P once per step (RkInterpolator.update), then y(te) = y_old + H (Q . [x, x^2, ...]), x = (te - t_old) / H.
 template <class Tab, int N>
-NBK_DEV void rk_dense(double te, double t_old, double t_new, const double (&y_old)[N], const double (&y_new)[N],
-                      const double (&K)[Tab::S + 1][N], double (&out)[N]) {
+NBK_DEV void rk_dense_coeffs(const double (&K)[Tab::S + 1][N], double (&Q)[N][Tab::M]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < Tab::M; ++k) {
+            double q = 0.0;
+#pragma unroll
+            for (int j = 0; j <= Tab::S; ++j)
+                if (Tab::p(j, k) != 0.0) q = fma(K[j][i], Tab::cb().p[j][k], q);
+            Q[i][k] = q;
+        }
+    }
+}
+
+template <class Tab, int N, bool RCP = false>
+NBK_DEV void rk_dense_eval(double te, double t_old, double t_new, const double (&y_old)[N], const double (&y_new)[N],
+                           const double (&Q)[N][Tab::M], double (&out)[N], double inv_H = 0.0) {
     if (te == t_new) {
 #pragma unroll
         for (int i = 0; i < N; ++i) out[i] = y_new[i];
@@ -520,21 +536,26 @@ NBK_DEV void rk_dense(double te, double t_old, double t_new, const double (&y_ol
         return;
     }
     const double H = t_new - t_old;
-    const double x = (te - t_old) / H;
+    // RCP: the caller divided 1 / H once for all grid points of the step (x within 1 ulp of the quotient)
+    const double x = RCP ? (te - t_old) * inv_H : (te - t_old) / H;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double acc = 0.0, pw = x;
 #pragma unroll
         for (int k = 0; k < Tab::M; ++k) {
-            double q = 0.0;
-#pragma unroll
-            for (int j = 0; j <= Tab::S; ++j)
-                if (Tab::p(j, k) != 0.0) q = fma(K[j][i], Tab::cb().p[j][k], q);
-            acc = fma(q, pw, acc);
+            acc = fma(Q[i][k], pw, acc);
             pw *= x;
         }
         out[i] = fma(H, acc, y_old[i]);
     }
+}
+
+template <class Tab, int N>
+NBK_DEV void rk_dense(double te, double t_old, double t_new, const double (&y_old)[N], const double (&y_new)[N],
+                      const double (&K)[Tab::S + 1][N], double (&out)[N]) {
+    double Q[N][Tab::M];
+    rk_dense_coeffs<Tab, N>(K, Q);
+    rk_dense_eval<Tab, N>(te, t_old, t_new, y_old, y_new, Q, out);
 }
 
 // DOP853 dense output (DOP853Interpolator, explicit.py:406-481): three extra stages (rows 13..15) built
@@ -975,14 +996,19 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
 #endif
                     } else if (MODE == NBK_MODE_RUN) {
                         if (t_new >= te_next) {
-                            double F[Tab::DOP ? 7 : 1][N];
+                            // interpolant of this step, built once and evaluated at every grid point inside it
+                            double F[Tab::DOP ? 7 : N][Tab::DOP ? N : Tab::M];
                             if constexpr (Tab::DOP) dop853_prepare<Rhs>(t, t_new, y, ynew, K, p, F);
+                            else rk_dense_coeffs<Tab, N>(K, F);
+                            const double inv_H = 1.0 / (t_new - t);
+                            double *dst = a.y_out + (idx * a.o_sb + kout * a.o_sk);
                             do {
                                 double out[N];
                                 if constexpr (Tab::DOP) dop853_eval<N>(te_next, t, t_new, y, ynew, F, out);
-                                else rk_dense<Tab, N>(te_next, t, t_new, y, ynew, K, out);
+                                else rk_dense_eval<Tab, N, true>(te_next, t, t_new, y, ynew, F, out, inv_H);
 #pragma unroll
-                                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                                for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
+                                dst += a.o_sk;
                                 ++kout;
                                 te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
                             } while (t_new >= te_next);

@@ -103,7 +103,7 @@ def test_events_cuda_source_params_and_errors():
     # no events -> plain run
     s4 = nbk.RungeKutta23("vdp", 0.0, y0, p, rtol=1e-6, atol=1e-9)
     out = s4.run_events([5.0, 10.0], None)
-    assert out[2] == [] and out[3] == [] and np.array_equal(out[1], y)
+    assert out[2] == [] and out[3] == [] and rel(out[1], y) < 1e-13  # (the plain run divides 1 / H once per step)
     # resumed: a second run_events call continues from the state the first one left
     t5, y5, te5, ye5 = s.run_events([12.0], ev)
     assert y5.shape == (256, 1, 2) and np.isfinite(y5).all()
