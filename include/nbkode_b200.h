@@ -55,6 +55,13 @@ extern "C" {
 #define NBK_AB3 3
 #define NBK_AB4 4
 #define NBK_AB5 5
+/* implicit linear multistep (per-thread regime, n <= 8, kernels compiled by NVRTC):
+   AdamsMoulton1..5 = 11..15 (BackwardEuler == AdamsMoulton1), nbkode/multistep/adams_moulton.py:31-61, euler.py:30-36;
+   BDF1..6 = 31..36, nbkode/multistep/bdf.py:16-44; implicit step nbkode/multistep/core.py:115-170 */
+#define NBK_AM1 11
+#define NBK_AM5 15
+#define NBK_BDF1 31
+#define NBK_BDF6 36
 /* fixed-step explicit Runge-Kutta classes, nbkode/runge_kutta/explicit.py:102-129 */
 #define NBK_RUNGE2 202
 #define NBK_RUNGE3 203
@@ -69,6 +76,8 @@ extern "C" {
 #define NBK_TRAJ_MAXATTEMPTS 3 /* attempt budget of the call exhausted */
 #define NBK_TRAJ_EVBRACKET 4   /* nbk_run_events: an event function does not change sign on the step's interpolant
                                   (the reference's bisect raises ValueError, nbkode/nbcompat/zeros.py:516-520) */
+#define NBK_TRAJ_NEWTON 5      /* implicit multistep: Newton / secant iteration did not converge (the reference raises
+                                  RuntimeError, nbkode/nbcompat/zeros.py:432-434, :503-505) */
 #define NBK_TRAJ_EVENT (-1)    /* nbk_run_events: stopped by a terminal event (clean stop) */
 #define NBK_MAX_EVENTS 8
 

@@ -238,6 +238,44 @@ struct tab_ab {
     }
 };
 
+// Implicit linear multistep classes of the reference: AdamsMoulton1..5 (ids 11..15; BackwardEuler is
+// AdamsMoulton1) and BDF1..6 (ids 31..36), nbkode/multistep/adams_moulton.py:31-61, bdf.py:16-44.
+// y_new solves  y - h Bn f(t_new, y) - (h B . fs[-K:] - A . ys[-K:]) = 0  (multistep/core.py:115-170); like the
+// Adams-Bashforth classes, index 0 of A / B multiplies the OLDEST history entry.  K = A.size is the reference's
+// ORDER (AdamsMoulton2 therefore has K = 1), LEN = max(K, 2) its LEN_HISTORY.
+template <int ID>
+struct tab_im {
+    static constexpr bool BDF = ID >= 31;
+    static constexpr int K = BDF ? ID - 30 : (ID <= 12 ? 1 : ID - 11);
+    static constexpr int LEN = K > 2 ? K : 2;
+    static NBK_HD double a(int j) {
+        constexpr double Abdf[7][6] = {
+            {0},
+            {-1.0},
+            {1.0 / 3, -4.0 / 3},
+            {-2.0 / 11, 9.0 / 11, -18.0 / 11},
+            {3.0 / 25, -16.0 / 25, 36.0 / 25, -48.0 / 25},
+            {-12.0 / 137, 75.0 / 137, -200.0 / 137, 300.0 / 137, -300.0 / 137},
+            {10.0 / 147, -72.0 / 147, 225.0 / 147, -400.0 / 147, 450.0 / 147, -360.0 / 147}};
+        return BDF ? Abdf[K][j] : (j == K - 1 ? -1.0 : 0.0);
+    }
+    static NBK_HD double b(int j) {
+        constexpr double Bam[6][4] = {
+            {0},
+            {0.0},
+            {1.0 / 2},
+            {-1.0 / 12, 2.0 / 3},
+            {19.0 / 24, -5.0 / 24, 1.0 / 24},
+            {646.0 / 720, -264.0 / 720, 106.0 / 720, -19.0 / 720}};
+        return BDF ? 0.0 : Bam[ID - 10][j];
+    }
+    static NBK_HD double bn() {
+        constexpr double BNam[6] = {0, 1.0, 1.0 / 2, 5.0 / 12, 9.0 / 24, 251.0 / 720};
+        constexpr double BNbdf[7] = {0, 1.0, 2.0 / 3, 6.0 / 11, 12.0 / 25, 60.0 / 137, 60.0 / 147};
+        return BDF ? BNbdf[K] : BNam[ID - 10];
+    }
+};
+
 // Fixed-step explicit Runge-Kutta classes of the reference (nbkode/runge_kutta/explicit.py:102-129):
 // Runge2 (202), Runge3 (203, four stages as the reference lists it), Heun3 (213), RungeKutta4 (204),
 // RungeKutta3_8 (238).
@@ -1238,6 +1276,289 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
 }
 
 // =====================================================================================
+// Implicit linear multistep (AdamsMoulton1..5 / BackwardEuler, BDF1..6): the advance_ab driver with the
+// implicit step of nbkode/multistep/core.py:115-170.  The root of  g(y) = y - h Bn f(t_new, y) - Kc  is found
+// exactly as the reference does it (nbkode/nbcompat/zeros.py): for n > 1 Newton's method with a central
+// finite-difference Jacobian (eps = 1e-10) and an LU solve with partial pivoting, started from the current
+// y, stopped when ||g||_2 <= 1.48e-8, at most 50 iterations (newton_hd, :460-505); for n == 1 the secant
+// method of scipy's `newton` (:350-392) started from y and y (1 + 1e-4) +- 1e-4, stopped when the iterate
+// moves by <= 1.48e-8.  A step that does not converge fails the trajectory (the reference raises RuntimeError).
+// =====================================================================================
+template <int N>
+NBK_DEV bool lu_solve(double (&J)[N][N], double (&r)[N]) {  // J x = r, result in r (np.linalg.solve == LAPACK dgesv)
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int piv = k;
+        double best = fabs(J[k][k]);
+#pragma unroll
+        for (int q = k + 1; q < N; ++q) {
+            const double v = fabs(J[q][k]);
+            if (v > best) {
+                best = v;
+                piv = q;
+            }
+        }
+        ok = ok && best > 0.0;
+#pragma unroll
+        for (int q = k + 1; q < N; ++q) {  // row interchange k <-> piv with selects (all indices stay static)
+            const bool sw = piv == q;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                const double up = J[k][c], lo = J[q][c];
+                J[k][c] = sw ? lo : up;
+                J[q][c] = sw ? up : lo;
+            }
+            const double up = r[k], lo = r[q];
+            r[k] = sw ? lo : up;
+            r[q] = sw ? up : lo;
+        }
+        const double inv = 1.0 / J[k][k];
+#pragma unroll
+        for (int q = k + 1; q < N; ++q) {
+            const double m = J[q][k] * inv;
+#pragma unroll
+            for (int c = k + 1; c < N; ++c) J[q][c] = fma(-m, J[k][c], J[q][c]);
+            r[q] = fma(-m, r[k], r[q]);
+        }
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+        double acc = r[k];
+#pragma unroll
+        for (int c = k + 1; c < N; ++c) acc = fma(-J[k][c], r[c], acc);
+        r[k] = acc / J[k][k];
+    }
+    return ok;
+}
+
+template <class Rhs>
+NBK_DEV void implicit_root(double t, double hBn, const double (&x)[Rhs::N], const double (&Kc)[Rhs::N],
+                           const double (&p)[Rhs::NP > 0 ? Rhs::NP : 1], double (&g)[Rhs::N]) {
+    double f[Rhs::N];
+    Rhs::eval(t, x, p, f);
+#pragma unroll
+    for (int i = 0; i < Rhs::N; ++i) g[i] = x[i] - hBn * f[i] - Kc[i];  // y - h_Bn * rhs(t, y) - K  (core.py:121-122)
+}
+
+// returns false if the iteration does not converge (or meets a singular Jacobian / non-finite values)
+template <class Rhs>
+NBK_DEV bool implicit_solve(double t, double hBn, const double (&Kc)[Rhs::N], const double (&p)[Rhs::NP > 0 ? Rhs::NP : 1],
+                            double (&y)[Rhs::N]) {
+    constexpr int N = Rhs::N;
+    const double tol = 1.48e-8;
+    if constexpr (N == 1) {
+        // secant method (zeros.py:350-392 with fprime = None, x1 = None)
+        double p0[1] = {1.0 * y[0]}, p1[1], q0[1], q1[1];
+        const double eps = 1e-4;
+        p1[0] = y[0] * (1 + eps);
+        p1[0] += p1[0] >= 0 ? eps : -eps;
+        implicit_root<Rhs>(t, hBn, p0, Kc, p, q0);
+        implicit_root<Rhs>(t, hBn, p1, Kc, p, q1);
+        if (fabs(q1[0]) < fabs(q0[0])) {
+            double tmp = p0[0]; p0[0] = p1[0]; p1[0] = tmp;
+            tmp = q0[0]; q0[0] = q1[0]; q1[0] = tmp;
+        }
+        for (int it = 0; it < 50; ++it) {
+            double pn;
+            if (q1[0] == q0[0]) {
+                if (p1[0] != p0[0]) return false;  // "tolerance reached": j_newton raises RuntimeError
+                y[0] = (p1[0] + p0[0]) / 2.0;
+                return true;
+            }
+            if (fabs(q1[0]) > fabs(q0[0])) pn = (-q0[0] / q1[0] * p1[0] + p0[0]) / (1 - q0[0] / q1[0]);
+            else pn = (-q1[0] / q0[0] * p0[0] + p1[0]) / (1 - q1[0] / q0[0]);
+            if (fabs(pn - p1[0]) <= tol) {
+                y[0] = pn;
+                return true;
+            }
+            p0[0] = p1[0];
+            q0[0] = q1[0];
+            p1[0] = pn;
+            implicit_root<Rhs>(t, hBn, p1, Kc, p, q1);
+        }
+        return false;
+    } else {
+        double val[N];
+        implicit_root<Rhs>(t, hBn, y, Kc, p, val);
+        int it = 0;
+        for (;;) {
+            double d2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) d2 = fma(val[i], val[i], d2);
+            if (sqrt(d2) <= tol) return true;  // isclose(distance, 0, rtol=0, atol=1.48e-8); NaN never passes
+            const double eps = 1e-10;
+            double J[N][N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double x1[N], x2[N], f1[N], f2[N];
+#pragma unroll
+                for (int c = 0; c < N; ++c) x1[c] = x2[c] = y[c];
+                x1[i] += eps;
+                x2[i] -= eps;
+                implicit_root<Rhs>(t, hBn, x1, Kc, p, f1);
+                implicit_root<Rhs>(t, hBn, x2, Kc, p, f2);
+#pragma unroll
+                for (int c = 0; c < N; ++c) J[c][i] = (f1[c] - f2[c]) / (2 * eps);
+            }
+            double delta[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) delta[i] = -val[i];
+            if (!lu_solve<N>(J, delta)) return false;
+#pragma unroll
+            for (int i = 0; i < N; ++i) y[i] = y[i] + delta[i];
+            implicit_root<Rhs>(t, hBn, y, Kc, p, val);
+            if (++it > 50) return false;  // iteration_counter > maxiter (zeros.py:487-488), checked after the update
+        }
+    }
+}
+
+template <int ID, class Rhs, int MODE, bool EV = false>
+NBK_DEV void advance_im(const nbk_kargs &a) {
+    using Tab = tab_im<ID>;
+    constexpr int N = Rhs::N, NP = Rhs::NP, NPX = NP > 0 ? NP : 1, L = Tab::LEN, KK = Tab::K;
+    const long long B = a.B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B) return;
+    double ts[L], ys[L][N], fs[L][N], p[NPX];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        ts[l] = a.ts[(long long)l * B + idx];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            ys[l][c] = a.ys[((long long)l * N + c) * B + idx];
+            fs[l][c] = a.fs[((long long)l * N + c) * B + idx];
+        }
+    }
+    const double h = a.h[idx];
+    load_params<NP>(a, idx, p);
+    const double hBn = h * Tab::bn();
+    int kout = 0, status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
+    long long nsteps = 0;
+    double te_next = d_inf();
+    bool running;
+#ifdef NBK_NEVENTS
+    double ev_last[NBK_NEVENTS];
+#endif
+    if (status != NBK_TRAJ_OK) {
+        running = false;
+        if (MODE == NBK_MODE_RUN)
+            for (int k = 0; k < a.m; ++k)
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + k * a.o_sk + c * a.o_sc] = d_nan();
+    } else if (MODE == NBK_MODE_RUN) {
+        while (kout < a.m && __ldg(a.tgrid + kout) <= ts[L - 1]) {
+            double out[N];
+            hermite_window<L, N>(__ldg(a.tgrid + kout), ts, ys, fs, out);
+#pragma unroll
+            for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+            ++kout;
+        }
+        running = kout < a.m;
+        if (running) te_next = __ldg(a.tgrid + kout);
+#ifdef NBK_NEVENTS
+        if constexpr (EV) events_start<N, NPX>(a, idx, ts[L - 1], ys[L - 1], p, ev_last);
+#endif
+    } else {
+        running = a.n_steps > 0;
+    }
+    while (running) {
+        if (ts[L - 1] + h > a.bound) {
+            status = NBK_TRAJ_BOUND;
+            break;
+        }
+        const double t_new = ts[L - 1] + h;
+        double Kc[N], ynew[N], fnew[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            // K = h*B @ fs[-K:] - A @ ys[-K:]   (core.py:133, :150)
+            double hb = 0.0, ay = 0.0;
+#pragma unroll
+            for (int j = 0; j < KK; ++j) {
+                if (Tab::b(j) != 0.0) hb = fma(h * Tab::b(j), fs[L - KK + j][c], hb);
+                if (Tab::a(j) != 0.0) ay = fma(Tab::a(j), ys[L - KK + j][c], ay);
+            }
+            Kc[c] = hb - ay;
+            ynew[c] = ys[L - 1][c];  // Newton / secant start from the current state
+        }
+        if (!implicit_solve<Rhs>(t_new, hBn, Kc, p, ynew)) {
+            status = NBK_TRAJ_NEWTON;
+            break;
+        }
+        Rhs::eval(t_new, ynew, p, fnew);
+#pragma unroll
+        for (int l = 0; l < L - 1; ++l) {
+            ts[l] = ts[l + 1];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                ys[l][c] = ys[l + 1][c];
+                fs[l][c] = fs[l + 1][c];
+            }
+        }
+        ts[L - 1] = t_new;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            ys[L - 1][c] = ynew[c];
+            fs[L - 1][c] = fnew[c];
+        }
+        ++nsteps;
+#ifdef NBK_NEVENTS
+        if constexpr (EV && MODE == NBK_MODE_RUN) {
+            window_dense<L, N> dense(ts, ys, fs);
+            double t_term = 0.0;
+            if (events_after_step<N, NPX>(a, idx, ts[L - 2], t_new, ynew, p, ev_last, dense, t_term, status)) {
+                if (status != NBK_TRAJ_EVBRACKET) {
+                    double out[N];
+                    dense(t_term, out);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                    a.ev_tterm[idx] = t_term;
+                    ++kout;
+                    status = NBK_TRAJ_EVENT;
+                }
+                break;
+            }
+        }
+#endif
+        if (MODE == NBK_MODE_RUN) {
+            while (t_new >= te_next) {
+                double out[N];
+                hermite_window<L, N>(te_next, ts, ys, fs, out);
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
+                ++kout;
+                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+            }
+            running = kout < a.m;
+        } else {
+            if (a.emit) {
+                a.t_out[idx * a.to_sb + (nsteps - 1)] = t_new;
+#pragma unroll
+                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + (nsteps - 1) * a.o_sk + c * a.o_sc] = ynew[c];
+            }
+            running = nsteps < a.n_steps;
+        }
+        if (running && nsteps >= a.max_attempts) {
+            status = NBK_TRAJ_MAXATTEMPTS;
+            break;
+        }
+    }
+    if (nsteps > 0) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            a.ts[(long long)l * B + idx] = ts[l];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                a.ys[((long long)l * N + c) * B + idx] = ys[l][c];
+                a.fs[((long long)l * N + c) * B + idx] = fs[l][c];
+            }
+        }
+        a.n_acc[idx] += nsteps;
+    }
+    store_status(a, idx, status);
+    a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
+}
+
+// =====================================================================================
 // Construction kernels (one thread per trajectory; cold path: IEEE division / sqrt / pow)
 // =====================================================================================
 template <class Rhs>
@@ -1352,7 +1673,7 @@ NBK_DEV void init_ab(const nbk_kargs &a) {
     Rhs::eval(a.t0, y, p, f);
     const double h = a.h0 ? a.h0[idx] : a.h_init;
     // history: L copies of (t0, y0, f0) (buffer.py:14-19), then ORDER-1 start-up points pushed
-    double pt[4], py[4][N], pf[4][N];
+    double pt[5], py[5][N], pf[5][N];
     int npush = 0, status = NBK_TRAJ_OK;
     const int fsr = a.first_stepper;
     if (ORDER > 1 && fsr != 0) {

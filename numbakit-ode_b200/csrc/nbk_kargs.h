@@ -11,6 +11,7 @@
 #define NBK_TRAJ_MAXATTEMPTS 3 // attempt budget of this call exhausted
 #define NBK_TRAJ_EVBRACKET 4   // run_events: the event function has the same sign at both ends of the step on the
                                // interpolant (the reference's bisect raises ValueError, nbcompat/zeros.py:516-520)
+#define NBK_TRAJ_NEWTON 5      // implicit step: Newton / secant iteration did not converge (the reference raises RuntimeError)
 #define NBK_TRAJ_EVENT (-1)    // run_events: stopped by a terminal event (clean stop, not sticky)
 #define NBK_MAX_EVENTS 8
 

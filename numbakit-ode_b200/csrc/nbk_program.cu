@@ -5,7 +5,8 @@
 // same macros plus -DNBK_USER_RHS and prepends the user's nbk_rhs definition).
 //
 // NBK_METHOD: 23 / 45 / 853 = RungeKutta23 / RungeKutta45 / DOP853; 1..5 = AdamsBashforth-k (1 == ForwardEuler);
-// 202 / 203 / 213 / 204 / 238 = Runge2 / Runge3 / Heun3 / RungeKutta4 / RungeKutta3_8 (fixed step).
+// 202 / 203 / 213 / 204 / 238 = Runge2 / Runge3 / Heun3 / RungeKutta4 / RungeKutta3_8 (fixed step);
+// 11..15 = AdamsMoulton1..5 (BackwardEuler == 11), 31..36 = BDF1..6 (implicit multistep).
 #include "nbk_device.cuh"
 
 #define NBK_CAT2(a, b) a##b
@@ -25,6 +26,9 @@ typedef nbk::tab_dop853 nbk_tab_t;
 #define NBK_ADAPTIVE 1
 #elif NBK_METHOD >= 1 && NBK_METHOD <= 5
 #define NBK_ADAPTIVE 0
+#elif (NBK_METHOD >= 11 && NBK_METHOD <= 15) || (NBK_METHOD >= 31 && NBK_METHOD <= 36)
+#define NBK_ADAPTIVE 0
+#define NBK_IMPLICIT 1
 #elif NBK_METHOD == 202 || NBK_METHOD == 203 || NBK_METHOD == 213 || NBK_METHOD == 204 || NBK_METHOD == 238
 #define NBK_ADAPTIVE 0
 #define NBK_FIXED_RK 1
@@ -33,6 +37,9 @@ typedef nbk::tab_dop853 nbk_tab_t;
 #endif
 #ifndef NBK_FIXED_RK
 #define NBK_FIXED_RK 0
+#endif
+#ifndef NBK_IMPLICIT
+#define NBK_IMPLICIT 0
 #endif
 
 #ifndef NBK_MIN_BLOCKS
@@ -44,6 +51,8 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK) NBK_KERNEL(init)(const _
     nbk::init_adaptive<nbk_tab_t, nbk_rhs_t>(a);
 #elif NBK_FIXED_RK
     nbk::init_erk<NBK_METHOD, nbk_rhs_t>(a);
+#elif NBK_IMPLICIT
+    nbk::init_ab<nbk::tab_im<NBK_METHOD>::K, nbk_rhs_t>(a);  // same history window and start-up as Adams-Bashforth-K
 #else
     nbk::init_ab<NBK_METHOD, nbk_rhs_t>(a);
 #endif
@@ -54,6 +63,8 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERN
     nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_RUN>(a);
 #elif NBK_FIXED_RK
     nbk::advance_erk<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN>(a);
+#elif NBK_IMPLICIT
+    nbk::advance_im<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN>(a);
 #else
     nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN>(a);
 #endif
@@ -64,6 +75,8 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERN
     nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_STEP>(a);
 #elif NBK_FIXED_RK
     nbk::advance_erk<NBK_METHOD, nbk_rhs_t, NBK_MODE_STEP>(a);
+#elif NBK_IMPLICIT
+    nbk::advance_im<NBK_METHOD, nbk_rhs_t, NBK_MODE_STEP>(a);
 #else
     nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_STEP>(a);
 #endif
@@ -76,6 +89,8 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERN
     nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_RUN, true>(a);
 #elif NBK_FIXED_RK
     nbk::advance_erk<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN, true>(a);
+#elif NBK_IMPLICIT
+    nbk::advance_im<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN, true>(a);
 #else
     nbk::advance_ab<NBK_METHOD, nbk_rhs_t, NBK_MODE_RUN, true>(a);
 #endif

@@ -1,4 +1,5 @@
-"""Fixed-step explicit multistep solvers: AdamsBashforth1..5 and ForwardEuler.
+"""Fixed-step multistep solvers: AdamsBashforth1..5 / ForwardEuler (explicit) and AdamsMoulton1..5 /
+BackwardEuler / BDF1..6 (implicit).
 
 Mirrors nbkode/multistep/core.py:12-112, nbkode/multistep/adams_bashforth.py and
 nbkode/euler.py:19-27, including the behaviours SURVEY.md section 0 lists:
@@ -38,7 +39,7 @@ class Multistep(Solver, abstract=True):
 
     @classproperty
     def ORDER(cls):
-        return cls.B.size
+        return cls.A.size
 
     def __init__(self, rhs, t0, y0, params=None, *, first_stepper_cls="auto", **kwargs):
         fs_id = 0
@@ -103,3 +104,69 @@ class ForwardEuler(AdamsBashforth1):
 
     ALIASES = ("Euler",)
     GROUP = "Euler"
+
+
+class ImplicitMultistep(Multistep, abstract=True):
+    """Implicit linear multistep methods (nbkode/multistep/core.py:115-170): every step solves
+    ``y - h Bn f(t_new, y) - (h B . fs - A . ys) = 0`` on the device the way the reference does -- Newton with a
+    finite-difference Jacobian for n > 1, the secant method for n == 1 (nbkode/nbcompat/zeros.py).  Per-thread
+    regime, n <= 8; the kernels are compiled by NVRTC on first use.  ``IMPLICIT`` is ``True`` (the reference's
+    flag is inverted, see the module docstring)."""
+
+    IMPLICIT = True
+
+    @classproperty
+    def LEN_HISTORY(cls):
+        return max(cls.A.size, 2)
+
+
+class AdamsMoulton(ImplicitMultistep, abstract=True):
+    GROUP = "Adams-Moulton"
+
+    @classproperty
+    def A(cls):
+        A = np.zeros_like(cls.B)
+        A[-1] = -1
+        return A
+
+
+class BDF(ImplicitMultistep, abstract=True):
+    GROUP = "BDF"
+
+    @classproperty
+    def B(cls):
+        return np.zeros_like(cls.A)
+
+
+def _implicit(base, name, method_id, doc, **attrs):
+    arr = {k: (np.asarray(v, dtype=float) if k in ("A", "B") else v) for k, v in attrs.items()}
+    size = (arr.get("A") if "A" in arr else arr["B"]).size
+    return type(name, (base,), {**arr, "LEN_HISTORY": max(size, 2), "METHOD_ID": method_id, "__doc__": doc,
+                                "__module__": __name__})
+
+
+AdamsMoulton1 = _implicit(AdamsMoulton, "AdamsMoulton1", 11, "Adams-Moulton, one step (implicit Euler).", B=[0.0], Bn=1.0)
+AdamsMoulton2 = _implicit(AdamsMoulton, "AdamsMoulton2", 12, "Adams-Moulton (trapezoidal rule).", B=[1 / 2], Bn=1 / 2)
+AdamsMoulton3 = _implicit(AdamsMoulton, "AdamsMoulton3", 13, "Adams-Moulton, two steps.", B=[-1 / 12, 2 / 3], Bn=5 / 12)
+AdamsMoulton4 = _implicit(AdamsMoulton, "AdamsMoulton4", 14, "Adams-Moulton, three steps.", B=np.array([19, -5, 1]) / 24,
+                          Bn=9 / 24)
+AdamsMoulton5 = _implicit(AdamsMoulton, "AdamsMoulton5", 15, "Adams-Moulton, four steps.",
+                          B=np.array([646, -264, 106, -19]) / 720, Bn=251 / 720)
+
+
+class BackwardEuler(AdamsMoulton1):
+    """y[n+1] = y[n] + h f(t[n+1], y[n+1])  (nbkode/euler.py:30-36)."""
+
+    GROUP = "Euler"
+
+
+BDF1 = _implicit(BDF, "BDF1", 31, "Backward differentiation formula, order 1.", A=[-1.0], Bn=1.0)
+BDF2 = _implicit(BDF, "BDF2", 32, "Backward differentiation formula, order 2.", A=np.array([1, -4]) / 3, Bn=2 / 3)
+BDF3 = _implicit(BDF, "BDF3", 33, "Backward differentiation formula, order 3.", A=np.array([-2, 9, -18]) / 11,
+                 Bn=6 / 11)
+BDF4 = _implicit(BDF, "BDF4", 34, "Backward differentiation formula, order 4.", A=np.array([3, -16, 36, -48]) / 25,
+                 Bn=12 / 25)
+BDF5 = _implicit(BDF, "BDF5", 35, "Backward differentiation formula, order 5.",
+                 A=np.array([-12, 75, -200, 300, -300]) / 137, Bn=60 / 137)
+BDF6 = _implicit(BDF, "BDF6", 36, "Backward differentiation formula, order 6.",
+                 A=np.array([10, -72, 225, -400, 450, -360]) / 147, Bn=60 / 147)

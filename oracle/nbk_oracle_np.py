@@ -382,6 +382,147 @@ class AdamsBashforth:
         return y0 + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * f0 + T * f1))
 
 
+# Implicit linear multistep classes (nbkode/multistep/adams_moulton.py:31-61, bdf.py:16-44, euler.py:30-36):
+# name -> (A, B, Bn).  Adams-Moulton: A = [0, ..., 0, -1] of B's size; BDF: B = zeros of A's size.
+def _am(B, Bn):
+    B = np.array(B, dtype=float)
+    A = np.zeros_like(B)
+    A[-1] = -1
+    return A, B, Bn
+
+
+def _bdf(A, Bn):
+    A = np.array(A, dtype=float)
+    return A, np.zeros_like(A), Bn
+
+
+IMPLICIT_TABLEAUX = {
+    "AdamsMoulton1": _am([0.0], 1.0),
+    "BackwardEuler": _am([0.0], 1.0),
+    "AdamsMoulton2": _am([1 / 2], 1 / 2),
+    "AdamsMoulton3": _am([-1 / 12, 2 / 3], 5 / 12),
+    "AdamsMoulton4": _am(np.array([19, -5, 1]) / 24, 9 / 24),
+    "AdamsMoulton5": _am(np.array([646, -264, 106, -19]) / 720, 251 / 720),
+    "BDF1": _bdf([-1.0], 1.0),
+    "BDF2": _bdf(np.array([1, -4]) / 3, 2 / 3),
+    "BDF3": _bdf(np.array([-2, 9, -18]) / 11, 6 / 11),
+    "BDF4": _bdf(np.array([3, -16, 36, -48]) / 25, 12 / 25),
+    "BDF5": _bdf(np.array([-12, 75, -200, 300, -300]) / 137, 60 / 137),
+    "BDF6": _bdf(np.array([10, -72, 225, -400, 450, -360]) / 147, 60 / 147),
+}
+
+
+def _secant(func, x0, tol=1.48e-8, maxiter=50):
+    """scipy's `newton` without derivative as vendored in nbkode/nbcompat/zeros.py:350-392 (j_newton: any
+    flag other than OK raises RuntimeError, :432-434)."""
+    p0 = 1.0 * x0
+    eps = 1e-4
+    p1 = x0 * (1 + eps)
+    p1 += eps if p1 >= 0 else -eps
+    q0 = func(p0)
+    q1 = func(p1)
+    if np.abs(q1) < np.abs(q0):
+        p0, p1, q0, q1 = p1, p0, q1, q0
+    for _ in range(maxiter):
+        if q1 == q0:
+            if p1 != p0:
+                raise RuntimeError
+            return (p1 + p0) / 2.0
+        if np.abs(q1) > np.abs(q0):
+            p = (-q0 / q1 * p1 + p0) / (1 - q0 / q1)
+        else:
+            p = (-q1 / q0 * p0 + p1) / (1 - q1 / q0)
+        if np.abs(p - p1) <= tol:
+            return p
+        p0, q0 = p1, q1
+        p1 = p
+        q1 = func(p1)
+    raise RuntimeError
+
+
+def _newton_hd(func, y, atol=1.48e-8, maxiter=50):
+    """nbkode/nbcompat/zeros.py:440-505: Newton with a central finite-difference Jacobian (eps = 1e-10)."""
+    def jacobian(x):
+        eps = 1e-10
+        J = np.zeros((len(x), len(x)), dtype=np.float64)
+        for i in range(len(x)):
+            x1 = x.copy()
+            x2 = x.copy()
+            x1[i] += eps
+            x2[i] -= eps
+            J[:, i] = (func(x1) - func(x2)) / (2 * eps)
+        return J
+
+    value = func(y)
+    distance = np.linalg.norm(value, ord=2)
+    it = 0
+    while not np.abs(distance - 0) <= atol:
+        delta = np.linalg.solve(jacobian(y), -value)
+        y = y + delta
+        value = func(y)
+        distance = np.linalg.norm(value, ord=2)
+        it += 1
+        if it > maxiter:
+            raise RuntimeError
+    return y
+
+
+class ImplicitMultistep:
+    """AdamsMoulton1..5 / BackwardEuler / BDF1..6: ctor and start-up nbkode/multistep/core.py:37-65 (the same as the
+    Adams-Bashforth classes), implicit step :115-170, dense output = window Hermite (nbkode/core.py:577-596)."""
+
+    def __init__(self, name, rhs, t0, y0, params=None, *, h=None, t_bound=np.inf, first_stepper="auto"):
+        self.A, self.B, self.Bn = IMPLICIT_TABLEAUX[name]
+        self.order = self.A.size
+        self.L = max(self.order, 2)
+        self.rhs = _bind(rhs, params)
+        self.t_bound = t_bound
+        self.h = np.array(h, dtype=float) if h is not None else 1
+        t0 = float(t0)
+        y0 = np.array(y0, dtype=float, ndmin=1)
+        self.cache = History(self.L, t0, y0, self.rhs(t0, y0))
+        c = self.cache
+        if first_stepper is None or self.order == 1:
+            return
+        if first_stepper == "auto":
+            first_stepper = "RungeKutta45"
+        if isinstance(first_stepper, int):
+            sub = AdamsBashforth(first_stepper, self.rhs, c.t, c.y, h=self.h)
+            for _ in range(self.order - 1):
+                sub.step()
+                c.push(sub.t, sub.y, sub.f)
+        else:
+            sub = AdaptiveRK(first_stepper, self.rhs, c.t, c.y)
+            for ti in np.arange(1, self.order) * self.h:
+                while sub.t < ti:
+                    sub.step()
+                yi = sub.interpolate(ti)
+                c.push(ti, yi, self.rhs(ti, yi))
+
+    t = property(lambda self: self.cache.t)
+    y = property(lambda self: self.cache.y)
+    f = property(lambda self: self.cache.f)
+
+    def step(self, bound=None):
+        bound = self.t_bound if bound is None else bound
+        c, h = self.cache, self.h
+        if c.t + h > bound:
+            return False
+        dA, dB = self.L - self.A.size, self.L - self.B.size
+        t_new = c.t + h
+        K = h * self.B @ c.fs[dB:] - self.A @ c.ys[dA:]
+        h_Bn = h * self.Bn
+        root = lambda y: y - h_Bn * self.rhs(t_new, y) - K  # noqa: E731
+        if c.y.size == 1:
+            y_new = _secant(root, c.y.copy())
+        else:
+            y_new = _newton_hd(root, c.y.copy())
+        c.push(t_new, y_new, self.rhs(t_new, y_new))
+        return True
+
+    interpolate = AdamsBashforth.interpolate
+
+
 # Fixed-step explicit Runge-Kutta tableaux (nbkode/runge_kutta/explicit.py:102-129)
 ERK_TABLEAUX = {
     "Runge2": (np.array([[0, 0], [1 / 2, 0]]), np.array([0, 1.0]), np.array([0, 1 / 2])),

@@ -61,7 +61,16 @@ METHOD_IDS = {
     "AdamsBashforth3": 3, "AdamsBashforth4": 4, "AdamsBashforth5": 5,
     "Runge2": 202, "Runge3": 203, "Heun3": 213, "RungeKutta4": 204, "RungeKutta3_8": 238,
 }
+METHOD_IDS.update({"BackwardEuler": 11, **{f"AdamsMoulton{k}": 10 + k for k in range(1, 6)}, **{f"BDF{k}": 30 + k for k in range(1, 7)}})
 ERK_STAGES = {202: 2, 203: 4, 213: 3, 204: 4, 238: 4}
+
+
+def implicit_order(mid):  # size of A for AdamsMoulton1..5 (11..15) / BDF1..6 (31..36), else 0
+    if 11 <= mid <= 15:
+        return 1 if mid <= 12 else mid - 11
+    if 31 <= mid <= 36:
+        return mid - 30
+    return 0
 _libs = {}
 
 
@@ -114,7 +123,7 @@ class EmulEnsemble:
         self._rhs_name = rhs
         self.fn = _program(self.mid, rhs, self.n, self.np_)
         adaptive = self.mid in (23, 45, 853)
-        self.L = 2 if (adaptive or self.mid in ERK_STAGES) else max(self.mid, 2)
+        self.L = 2 if (adaptive or self.mid in ERK_STAGES) else max(implicit_order(self.mid) or self.mid, 2)
         self.SR = {23: 4, 45: 7, 853: 13, **ERK_STAGES}.get(self.mid, 0)
         B, n = self.B, self.n
         self.ts = np.zeros((self.L, B)); self.ys = np.zeros((self.L, n, B)); self.fs = np.zeros((self.L, n, B))

@@ -210,7 +210,26 @@ def events_section():
     dump("events.json", cases)
 
 
+def implicit_section():
+    """Implicit multistep families (SURVEY.md 8(f) #4): BackwardEuler, AdamsMoulton1..5, BDF1..6."""
+    lor = ([1.0, 1.0, 1.0], [10.0, 28.0, 8 / 3])
+    cases = []
+    for cls in ("BackwardEuler", "AdamsMoulton1", "AdamsMoulton2", "AdamsMoulton3", "AdamsMoulton4", "AdamsMoulton5",
+                "BDF1", "BDF2", "BDF3", "BDF4", "BDF5", "BDF6"):
+        cases.append(fixed_case(cls, "vdp", [2.0, 0.0], [1.0], [1.0, 2.0, 5.0], 0.01))
+        cases.append(fixed_case(cls, "vdp", [1.0, -0.5], [5.0], np.linspace(0, 2, 21), 0.0125))   # mildly stiff
+        cases.append(fixed_case(cls, "lorenz", *lor, np.linspace(0, 1, 11), 0.001))
+        cases.append(fixed_case(cls, "decay", [1.0], [0.1], [1.0, 2.0, 10.0], 0.1))               # n = 1: secant method
+        cases.append(fixed_case(cls, "decay", [1.0, 2.0], [0.01, 0.05], [1.0, 10.0], 0.25))
+    cases.append(fixed_case("BDF3", "vdp", [2.0, 0.0], [1.0], [1.0, 2.0], 0.01, first_stepper_cls=None))
+    cases.append(fixed_case("AdamsMoulton5", "vdp", [2.0, 0.0], [1.0], [1.0, 2.0], 0.01, first_stepper_cls="AdamsBashforth2"))
+    dump("implicit_fixed.json", cases)
+
+
 def main():
+    if sys.argv[1:] == ["implicit"]:
+        return implicit_section()
+    implicit_section()
     if sys.argv[1:] == ["dop853"]:
         return dop853_section()
     if sys.argv[1:] == ["events"]:

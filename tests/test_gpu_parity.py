@@ -353,3 +353,50 @@ def test_dop853_api_flow():
     assert sj.is_jit
     tj, yj = sj.run(np.linspace(0, 4, 9))
     assert rel(yj, c["resume_a"]) < 1e-11
+
+
+# ------------------------------------------------------------------ implicit multistep
+@pytest.mark.parametrize("c", load_golden("implicit_fixed.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}-{c['kw']}")
+def test_implicit_multistep_single(c):
+    """BackwardEuler / AdamsMoulton1..5 / BDF1..6 against the live reference.  Bar 5e-7 relative: the reference's own
+    results move by up to 1.4e-7 under a one-ulp change of y0 (Newton stopped at 1.48e-8 with a finite-difference
+    Jacobian), see tests/test_kernel_logic_host.py::test_implicit_multistep_vs_reference."""
+    kw = {k: (None if v == "None" else v) for k, v in c["kw"].items()}
+    s = getattr(nbk, c["cls"])(c["rhs"], 0.0, np.array(c["y0"]), np.array(c["p"]), h=c["h"], **kw)
+    assert s.is_jit and s.IMPLICIT
+    assert rel(s.cache.ts, c["init_ts"]) < 1e-15
+    t, y = s.run(c["ts"])
+    assert rel(y, c["ys"]) < 5e-7
+    assert s.t == c["t_end"]
+    assert rel(s.y, c["y_end"]) < 5e-7 and rel(s.f, c["f_end"]) < 5e-6
+    assert rel(s.cache.ts, c["end_ts"]) < 1e-15
+
+
+def test_implicit_multistep_ensemble_api_and_failure():
+    B = 64
+    y0, p = onp.vdp_ensemble(B, seed=1)
+    ts = np.linspace(0, 2, 9)
+    for cls in ("BDF2", "AdamsMoulton4", "BackwardEuler"):
+        s = getattr(nbk, cls)("vdp", 0.0, y0, p, h=0.01)
+        t, y = s.run(ts)
+        assert y.shape == (B, 9, 2) and (s.status == 0).all()
+        for i in (0, 31, 63):
+            o = onp.ImplicitMultistep(cls, onp.rhs_vdp, 0.0, y0[i], p[i], h=0.01)
+            _, yo = onp.run(o, ts)
+            assert rel(y[i], yo) < 5e-7 and s.t[i] == o.t
+    # step / skip / traced Python right-hand side (same value flow as the explicit fixed-step solvers)
+    s = nbk.BDF3(lambda t, y, k: -k * y, 0.0, np.array([1.0, 2.0]), np.array([0.01, 0.05]), h=0.25, first_stepper_cls=None)
+    tt, yy = s.step(n=4)
+    o = onp.ImplicitMultistep("BDF3", onp.rhs_decay, 0.0, [1.0, 2.0], np.array([0.01, 0.05]), h=0.25, first_stepper=None)
+    to, yo = onp.steps(o, n=4)
+    assert rel(tt, to) < 1e-15 and rel(yy, yo) < 5e-7
+    s.skip(n=2)
+    assert abs(s.t - 1.5) < 1e-14
+    # a step whose Newton iteration cannot converge fails the trajectory (the reference raises RuntimeError)
+    bad = nbk.BackwardEuler("decay", 0.0, np.array([[1.0, 1.0], [1.0, 1.0]]), np.array([[-1e308, 0.1], [0.1, 0.1]]), h=1.0)
+    with pytest.raises(RuntimeError):
+        bad.run([3.0])
+    assert list(bad.status) == [5, 0]
+    # n > 8 is rejected with a clear message
+    with pytest.raises(ValueError, match="n <= 8"):
+        nbk.BDF2("decay", 0.0, np.ones(9), np.array([0.1]), h=0.1)

@@ -15,7 +15,7 @@ from nbkode_b200.util import CaseInsensitiveDict
 
 from conftest import ROOT
 
-N_SOLVERS = 14  # ForwardEuler, AdamsBashforth1..5, RungeKutta23/45 (hot path) + the 5 fixed-step explicit RKs + DOP853
+N_SOLVERS = 26  # every solver class of the reference (nbkode/testsuite/test_introspection.py:18)
 
 
 # ------------------------------------------------------------------ registry
@@ -24,11 +24,12 @@ def test_get_solvers():
 
 
 def test_get_solvers_groups():
-    assert len(nbkode.get_solvers("Euler")) == 1  # BackwardEuler is implicit: out of scope
-    assert len(nbkode.get_solvers("euler")) == 1
+    assert len(nbkode.get_solvers("Euler")) == 2
+    assert len(nbkode.get_solvers("euler")) == 2
+    assert len(nbkode.get_solvers("Adams-Moulton")) == 5 and len(nbkode.get_solvers("BDF")) == 6
     assert len(nbkode.get_solvers("adams-bashforth")) == 5
     assert len(nbkode.get_solvers("Runge-Kutta")) == 8
-    assert nbkode.get_groups() == ("Adams-Bashforth", "Euler", "Runge-Kutta")
+    assert nbkode.get_groups() == ("Adams-Bashforth", "Adams-Moulton", "BDF", "Euler", "Runge-Kutta")
     with pytest.raises(KeyError):
         nbkode.get_solvers("not-a-group")
 
@@ -36,7 +37,9 @@ def test_get_solvers_groups():
 def test_get_solvers_filters():
     for solver in nbkode.get_solvers(implicit=False):
         assert solver.IMPLICIT is False
-    assert nbkode.get_solvers(implicit=True) == ()
+    assert len(nbkode.get_solvers(implicit=True)) == 12
+    for solver in nbkode.get_solvers(implicit=True):
+        assert solver.IMPLICIT is True and solver.FIXED_STEP is True
     for solver in nbkode.get_solvers(fixed_step=True):
         assert solver.FIXED_STEP is True
     for solver in nbkode.get_solvers(fixed_step=False):
@@ -44,7 +47,7 @@ def test_get_solvers_filters():
     assert set(nbkode.get_solvers(fixed_step=False) + nbkode.get_solvers(fixed_step=True)) == set(nbkode.get_solvers())
     assert {nbkode.RungeKutta23, nbkode.RungeKutta45, nbkode.RungeKutta4} <= set(nbkode.get_solvers(runge_kutta=True))
     assert set(nbkode.get_solvers(runge_kutta=True, fixed_step=False)) == {nbkode.RungeKutta23, nbkode.RungeKutta45, nbkode.DOP853}
-    assert len(nbkode.get_solvers(multistep=True)) == 6
+    assert len(nbkode.get_solvers(multistep=True)) == 18
     # README.rst:63 -- with the corrected IMPLICIT flag the explicit fixed-step solvers are listed
     assert nbkode.ForwardEuler in nbkode.get_solvers(implicit=False, fixed_step=True)
 
@@ -79,6 +82,10 @@ def test_class_attributes_match_reference_tableaux():
         cls = getattr(nbkode, f"AdamsBashforth{k}")
         assert np.array_equal(cls.B, onp.AB_B[k]) and cls.ORDER == k and cls.LEN_HISTORY == max(k, 2)
         assert cls.A[-1] == -1 and np.count_nonzero(cls.A) == 1
+    for name, (A, B, Bn) in onp.IMPLICIT_TABLEAUX.items():
+        cls = getattr(nbkode, name)
+        assert np.array_equal(cls.A, A) and np.array_equal(cls.B, B) and cls.Bn == Bn, name
+        assert cls.ORDER == A.size and cls.LEN_HISTORY == max(A.size, 2) and cls.IMPLICIT is True
     assert nbkode.ForwardEuler.GROUP == "Euler" and nbkode.ForwardEuler.ALIASES == ("Euler",)
     for name, (A, B, C) in onp.ERK_TABLEAUX.items():
         cls = getattr(nbkode, name)
@@ -170,7 +177,7 @@ def test_nvrtc_compiles_user_and_builtin_programs_for_sm100a():
         return np.array([y[1], p[0] * (1 - y[0] ** 2) * y[1] - y[0]])
 
     src = rhs.trace(f, 2, (1,), True).source.encode()
-    for method in (45, 23, 853, 4, 1, 204):
+    for method in (45, 23, 853, 4, 1, 204, 11, 15, 31, 36):
         _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(method, 2, 1, src=src)), C.byref(sz)))
         assert sz.value > 10_000
     _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 5, 5, rhs_name=b"decay")), C.byref(sz)))

@@ -211,3 +211,18 @@ def test_events_bitexact(c):
             if not aliased:  # see make_golden.py: the reference's own aliasing bug
                 _eq(u, v, "y_events")
     assert s.t == c["t_end"]
+
+
+# ---------------------------------------------------------------- implicit multistep
+@pytest.mark.parametrize("c", load_golden("implicit_fixed.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}-{c['kw']}")
+def test_implicit_multistep_bitexact(c):
+    s = onp.ImplicitMultistep(c["cls"], onp.RHS[c["rhs"]], 0.0, np.array(c["y0"]), np.array(c["p"]), h=c["h"],
+                              first_stepper=_first_stepper(c["kw"]))
+    _eq(s.cache.ts, c["init_ts"], "start-up ts")
+    _eq(s.cache.ys, c["init_ys"], "start-up ys")
+    t, y = onp.run(s, c["ts"])
+    _eq(y, c["ys"], "run(ts)")
+    assert s.t == c["t_end"]
+    _eq(s.y, c["y_end"])
+    _eq(s.f, c["f_end"])
+    _eq(s.cache.ts, c["end_ts"])
