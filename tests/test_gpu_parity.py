@@ -393,7 +393,7 @@ def test_implicit_multistep_ensemble_api_and_failure():
     s.skip(n=2)
     assert abs(s.t - 1.5) < 1e-14
     # a step whose Newton iteration cannot converge fails the trajectory (the reference raises RuntimeError)
-    bad = nbk.BackwardEuler("decay", 0.0, np.array([[1.0, 1.0], [1.0, 1.0]]), np.array([[-1e308, 0.1], [0.1, 0.1]]), h=1.0)
+    bad = nbk.BackwardEuler("decay", 0.0, np.array([[1.0, 1.0], [1.0, 1.0]]), np.array([[np.nan, 0.1], [0.1, 0.1]]), h=1.0)
     with pytest.raises(RuntimeError):
         bad.run([3.0])
     assert list(bad.status) == [5, 0]
