@@ -175,12 +175,12 @@ def exponential2(t, x):
     return np.asarray([-0.01, -0.05]) * x
 
 
-@pytest.mark.parametrize("name", ["RK23", "RK45"])
+@pytest.mark.parametrize("name", ["RK23", "RK45", "DOP853"])
 def test_against_scipy_lockstep(name):
     """nbkode/testsuite/test_against_scipy.py:64-83: lock-step step() against SciPy."""
     from scipy import integrate
 
-    nb_cls = nbkode.RungeKutta23 if name == "RK23" else nbkode.RungeKutta45
+    nb_cls = {"RK23": nbkode.RungeKutta23, "RK45": nbkode.RungeKutta45, "DOP853": nbkode.DOP853}[name]
     nb = nb_cls(exponential2, 0, y0_2)
     sp = getattr(integrate, name)(exponential2, 0, y0_2, t_bound=30)
     assert_allclose(nb.f, sp.f)
@@ -197,12 +197,16 @@ def test_against_scipy_lockstep(name):
         assert_allclose(nb.K, sp.K)
 
 
-def test_interpolate_against_scipy():
+@pytest.mark.parametrize("name", ["RK45", "DOP853"])
+def test_interpolate_against_scipy(name):
+    """nbkode/testsuite/test_against_scipy.py:84-97 (test_interpolate; the reference excludes RK23, whose dense
+    output does not match SciPy's -- we mirror the reference's)."""
     from scipy import integrate
 
+    nb_cls = {"RK23": nbkode.RungeKutta23, "RK45": nbkode.RungeKutta45, "DOP853": nbkode.DOP853}[name]
     t_eval = np.linspace(0, 300, 160)
-    nb_t, nb_y = nbkode.RungeKutta45(exponential2, 0, y0_2, t_bound=500).run(t_eval)
-    sp = integrate.solve_ivp(exponential2, [0, 500], y0_2, t_eval=t_eval, method="RK45")
+    nb_t, nb_y = nb_cls(exponential2, 0, y0_2, t_bound=500).run(t_eval)
+    sp = integrate.solve_ivp(exponential2, [0, 500], y0_2, t_eval=t_eval, method=name)
     assert_allclose(nb_t, sp.t)
     assert_allclose(nb_y, sp.y.T)
 

@@ -225,7 +225,7 @@ def test_nvrtc_compiles_event_programs_and_traces_events():
     ev = rhs.trace_events([onp.ev_y0, onp.ev_z25_up, onp.ev_x_m8_terminal], 3, (3,), True)
     assert ev.n_events == 3 and ev.terminal == [False, False, True] and ev.direction == [0, 1, -1]
     assert "nbk_event" in ev.source
-    for method in (45, 853, 2, 204):
+    for method in (45, 853, 2, 204, 13, 32):
         _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(method, 3, 3, rhs_name=b"lorenz")), 3, ev.source.encode(), C.byref(sz)))
         assert sz.value > 10_000
     with pytest.raises(ValueError):
