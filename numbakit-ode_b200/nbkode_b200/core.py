@@ -178,11 +178,6 @@ class Solver(ABC):
         self._events_key = None
 
         # ---- right-hand side -> built-in name or CUDA C
-        if callable(rhs) and self.n > _rhs.MAX_TRACED_N:
-            raise TypeError(
-                f"a Python right-hand side is traced component by component, which is limited to n <= "
-                f"{_rhs.MAX_TRACED_N}; for n = {self.n} pass a CTA built-in ('rd1d', 'linear') or CUDA C source defining "
-                "nbk_rhs_i(t, y, p, i, n)")
         name, src = _rhs.resolve(rhs, self.n, p_shape if p_shape else (self.n_params,), params is not None)
         if name == "decay" and self.n_params not in (1, self.n):
             raise ValueError("built-in 'decay' needs 1 or n parameters")

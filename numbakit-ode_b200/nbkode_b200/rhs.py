@@ -188,6 +188,349 @@ def trace(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     return CudaRHS("\n".join(lines) + "\n", name=getattr(func, "__name__", "traced"))
 
 
+# --------------------------------------------------------------------------------------
+# vector tracer: NumPy-style right-hand sides of large systems -> component-wise nbk_rhs_i
+# --------------------------------------------------------------------------------------
+# A method-of-lines right-hand side is written with whole-array NumPy expressions
+# (``d * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + r * y * (1 - y)``, slices, ``np.concatenate``, assignment into
+# ``np.zeros_like(y)``).  Running it once on a symbolic vector yields, for every output component i, one C expression
+# in i: exactly the form the CTA-per-trajectory kernels take (``nbk_rhs_i(t, y, p, i, n)``, csrc/nbk_cta.cuh).
+
+_HANDLED = {}
+
+
+def _implements(np_func):
+    def deco(f):
+        _HANDLED[np_func] = f
+        return f
+    return deco
+
+
+class Vec:
+    """A symbolic vector of ``length`` doubles: ``code(j)`` gives the C expression of element j (j: C int expression)."""
+
+    __array_priority__ = 1000.0
+
+    def __init__(self, length, code):
+        self.length, self.code = int(length), code
+
+    # ---- NumPy protocols
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs.get("out") is not None:
+            return NotImplemented
+        name = ufunc.__name__
+        binary = {"add": "+", "subtract": "-", "multiply": "*", "true_divide": "/", "divide": "/"}
+        if name in binary and len(inputs) == 2:
+            return _vec_binary(inputs[0], inputs[1], binary[name])
+        if name == "negative":
+            return _vec_unary(inputs[0], lambda a: f"(-{a})")
+        if name == "positive":
+            return inputs[0]
+        if name in ("power", "float_power"):
+            return _vec_pow(inputs[0], inputs[1])
+        if name == "square":
+            return _vec_pow(inputs[0], 2)
+        if name in _UNARY and len(inputs) == 1:
+            return _vec_unary(inputs[0], lambda a, f=_UNARY[name]: f"{f}({a})")
+        if name in ("maximum", "minimum") and len(inputs) == 2:
+            fn = "fmax" if name == "maximum" else "fmin"
+            return _vec_binary(inputs[0], inputs[1], None, lambda a, b: f"{fn}({a}, {b})")
+        raise TraceError(f"numpy.{name} cannot be traced into a component-wise right-hand side")
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func not in _HANDLED:
+            raise TraceError(f"numpy.{func.__name__} cannot be traced into a component-wise right-hand side; "
+                             "write the right-hand side as CUDA C defining nbk_rhs_i(t, y, p, i, n)")
+        return _HANDLED[func](*args, **kwargs)
+
+    # ---- Python operators
+    def __add__(self, o): return _vec_binary(self, o, "+")
+    def __radd__(self, o): return _vec_binary(o, self, "+")
+    def __sub__(self, o): return _vec_binary(self, o, "-")
+    def __rsub__(self, o): return _vec_binary(o, self, "-")
+    def __mul__(self, o): return _vec_binary(self, o, "*")
+    def __rmul__(self, o): return _vec_binary(o, self, "*")
+    def __truediv__(self, o): return _vec_binary(self, o, "/")
+    def __rtruediv__(self, o): return _vec_binary(o, self, "/")
+    def __neg__(self): return _vec_unary(self, lambda a: f"(-{a})")
+    def __pos__(self): return self
+    def __abs__(self): return _vec_unary(self, lambda a: f"fabs({a})")
+    def __pow__(self, e): return _vec_pow(self, e)
+    def __len__(self): return self.length
+
+    @property
+    def shape(self): return (self.length,)
+
+    @property
+    def size(self): return self.length
+
+    ndim = 1
+    dtype = np.dtype(np.float64)
+
+    def copy(self): return Vec(self.length, self.code)
+
+    def __bool__(self):
+        raise TraceError("data-dependent control flow cannot be traced; write the right-hand side as CUDA C")
+
+    def __getitem__(self, key):
+        if isinstance(key, (numbers.Integral, np.integer)):
+            k = int(key) + (self.length if key < 0 else 0)
+            if not 0 <= k < self.length:
+                raise IndexError(key)
+            return Sc(self.code(str(k)))
+        if isinstance(key, slice):
+            a, b, st = key.indices(self.length)
+            if st != 1:
+                raise TraceError("only unit-stride slices can be traced")
+            return Vec(max(b - a, 0), lambda j, a=a, c=self.code: c(f"({j} + {a})" if a else j))
+        raise TraceError("only integer and slice indices can be traced")
+
+    def __setitem__(self, key, value):
+        """In-place assembly ``out[a:b] = expr`` / ``out[k] = scalar`` (e.g. boundary rows of a stencil)."""
+        if isinstance(key, (numbers.Integral, np.integer)):
+            k = int(key) + (self.length if key < 0 else 0)
+            key = slice(k, k + 1)
+        if not isinstance(key, slice):
+            raise TraceError("only integer and slice assignments can be traced")
+        a, b, st = key.indices(self.length)
+        if st != 1:
+            raise TraceError("only unit-stride slice assignments can be traced")
+        val = _as_vec(value, b - a)
+        old = self.code
+        self.code = lambda j, a=a, b=b, old=old, v=val.code: (
+            f"(({j}) >= {a} && ({j}) < {b} ? {v(f'(({j}) - {a})' if a else j)} : {old(j)})")
+
+
+class Sc:
+    """A symbolic scalar (time, a parameter, one vector element, or arithmetic on them)."""
+
+    __array_priority__ = 1001.0
+
+    def __init__(self, code):
+        self.c = code
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if any(isinstance(x, Vec) or (isinstance(x, np.ndarray) and x.ndim == 1) for x in inputs):
+            return Vec.__array_ufunc__(None, ufunc, method, *inputs, **kwargs)  # vector (x) scalar
+        if method != "__call__":
+            return NotImplemented
+        name = ufunc.__name__
+        binary = {"add": "+", "subtract": "-", "multiply": "*", "true_divide": "/", "divide": "/"}
+        if name in binary and len(inputs) == 2:
+            return Sc(f"({_sc(inputs[0])} {binary[name]} {_sc(inputs[1])})")
+        if name == "negative":
+            return Sc(f"(-{_sc(inputs[0])})")
+        if name in _UNARY and len(inputs) == 1:
+            return Sc(f"{_UNARY[name]}({_sc(inputs[0])})")
+        if name in ("power", "float_power"):
+            return Sc(_pow_code(_sc(inputs[0]), inputs[1]))
+        raise TraceError(f"numpy.{name} cannot be traced")
+
+    def _b(self, o, op, swap=False):
+        if isinstance(o, Vec):
+            return NotImplemented
+        a, b = (_sc(o), self.c) if swap else (self.c, _sc(o))
+        return Sc(f"({a} {op} {b})")
+
+    def __add__(self, o): return self._b(o, "+")
+    def __radd__(self, o): return self._b(o, "+", True)
+    def __sub__(self, o): return self._b(o, "-")
+    def __rsub__(self, o): return self._b(o, "-", True)
+    def __mul__(self, o): return self._b(o, "*")
+    def __rmul__(self, o): return self._b(o, "*", True)
+    def __truediv__(self, o): return self._b(o, "/")
+    def __rtruediv__(self, o): return self._b(o, "/", True)
+    def __neg__(self): return Sc(f"(-{self.c})")
+    def __pos__(self): return self
+    def __abs__(self): return Sc(f"fabs({self.c})")
+    def __pow__(self, e): return Sc(_pow_code(self.c, e))
+
+    def __bool__(self):
+        raise TraceError("data-dependent control flow cannot be traced; write the right-hand side as CUDA C")
+
+    def __float__(self):
+        raise TraceError("a traced value cannot be converted to float")
+
+
+def _sc(x) -> str:
+    if isinstance(x, Sc):
+        return x.c
+    if isinstance(x, (numbers.Real, np.floating, np.integer, np.bool_)):
+        return _lit(x)
+    if isinstance(x, np.ndarray) and x.ndim == 0:
+        return _lit(x.item())
+    raise TraceError(f"cannot use {type(x).__name__} as a scalar inside a traced right-hand side")
+
+
+def _pow_code(a: str, e) -> str:
+    if isinstance(e, (numbers.Integral, np.integer)) or (isinstance(e, float) and e.is_integer() and abs(e) <= 8):
+        k = int(e)
+        if k == 0:
+            return "1.0"
+        body = " * ".join([f"({a})"] * abs(k))
+        return f"({body})" if k > 0 else f"(1.0 / ({body}))"
+    return f"pow({a}, {_sc(e)})"
+
+
+class _Tables:
+    """Constant NumPy vectors captured by the right-hand side (grids, coefficient profiles): emitted as device arrays."""
+
+    def __init__(self):
+        self.arrays = []
+
+    def add(self, arr) -> str:
+        self.arrays.append(np.ascontiguousarray(arr, dtype=np.float64))
+        return f"nbk_tab{len(self.arrays) - 1}"
+
+    def source(self) -> str:
+        out = []
+        for k, a in enumerate(self.arrays):
+            out.append(f"__device__ const double nbk_tab{k}[{a.size}] = {{" + ", ".join(_lit(v) for v in a) + "};")
+        return "\n".join(out)
+
+
+_TABLES: "_Tables | None" = None
+
+
+def _as_vec(x, length) -> Vec:
+    if isinstance(x, Vec):
+        if x.length != length:
+            raise TraceError(f"shape mismatch in a traced right-hand side: ({x.length},) vs ({length},)")
+        return x
+    if isinstance(x, np.ndarray) and x.ndim == 1:
+        if x.size != length:
+            raise TraceError(f"shape mismatch in a traced right-hand side: ({x.size},) vs ({length},)")
+        name = _TABLES.add(x)
+        return Vec(length, lambda j, name=name: f"{name}[{j}]")
+    code = _sc(x)
+    return Vec(length, lambda j, code=code: code)
+
+
+def _len_of(x):
+    if isinstance(x, Vec):
+        return x.length
+    if isinstance(x, np.ndarray) and x.ndim == 1:
+        return x.size
+    return None
+
+
+def _vec_binary(a, b, op, fn=None):
+    length = _len_of(a) if _len_of(a) is not None else _len_of(b)
+    va, vb = _as_vec(a, length), _as_vec(b, length)
+    if fn is None:
+        return Vec(length, lambda j, x=va.code, y=vb.code: f"({x(j)} {op} {y(j)})")
+    return Vec(length, lambda j, x=va.code, y=vb.code: fn(x(j), y(j)))
+
+
+def _vec_unary(a, fn):
+    a = _as_vec(a, _len_of(a))
+    return Vec(a.length, lambda j, x=a.code: fn(x(j)))
+
+
+def _vec_pow(a, e):
+    if isinstance(e, (Vec, np.ndarray)) and not (isinstance(e, np.ndarray) and e.ndim == 0):
+        return _vec_binary(a, e, None, lambda x, y: f"pow({x}, {y})")
+    if not isinstance(a, Vec):
+        return _vec_binary(a, e, None, lambda x, y: f"pow({x}, {y})")
+    return Vec(a.length, lambda j, x=a.code: _pow_code(x(j), e))
+
+
+@_implements(np.roll)
+def _np_roll(a, shift, axis=None):
+    n, k = a.length, int(shift) % a.length
+    if k == 0:
+        return a
+    return Vec(n, lambda j, c=a.code: c(f"((({j}) + {n - k}) % {n})"))
+
+
+@_implements(np.concatenate)
+def _np_concatenate(parts, axis=0):
+    vecs = []
+    for part in parts:
+        if isinstance(part, Vec):
+            vecs.append(part)
+        elif isinstance(part, np.ndarray) and part.ndim == 1:
+            vecs.append(_as_vec(part, part.size))
+        elif isinstance(part, (list, tuple)):
+            vecs.extend(Vec(1, lambda j, c=_sc(x): c) for x in part)
+        else:
+            vecs.append(Vec(1, lambda j, c=_sc(part): c))
+    total = sum(v.length for v in vecs)
+
+    def code(j, vecs=vecs):
+        expr, start = None, total
+        for v in reversed(vecs):
+            start -= v.length
+            piece = v.code(f"(({j}) - {start})" if start else j)
+            expr = piece if expr is None else f"(({j}) < {start + v.length} ? {piece} : {expr})"
+        return expr
+
+    return Vec(total, code)
+
+
+@_implements(np.zeros_like)
+def _np_zeros_like(a, **kw):
+    return Vec(a.length, lambda j: "0.0")
+
+
+@_implements(np.empty_like)
+def _np_empty_like(a, **kw):
+    return Vec(a.length, lambda j: "0.0")
+
+
+@_implements(np.ones_like)
+def _np_ones_like(a, **kw):
+    return Vec(a.length, lambda j: "1.0")
+
+
+@_implements(np.asarray)
+def _np_asarray(a, *args, **kw):
+    return a
+
+
+@_implements(np.copy)
+def _np_copy(a, *args, **kw):
+    return a.copy()
+
+
+@_implements(np.gradient)
+def _np_gradient(a, *args, **kw):
+    raise TraceError("np.gradient is not traceable; write the stencil with slices or np.roll")
+
+
+def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
+    """Trace a NumPy-style whole-vector right-hand side into the component-wise ``nbk_rhs_i`` of the CTA regime."""
+    global _TABLES
+    _TABLES = _Tables()
+    try:
+        y = Vec(n, lambda j: f"y[{j}]")
+        t = Sc("t")
+        try:
+            if has_params:
+                size = int(np.prod(params_shape, dtype=int))
+                p = np.empty(size, dtype=object)
+                for k in range(size):
+                    p[k] = Sc(f"p[{k}]")
+                out = func(t, y, p.reshape(params_shape))
+            else:
+                out = func(t, y)
+        except TraceError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            raise TraceError(
+                f"could not trace {getattr(func, '__name__', func)!r} into a component-wise CUDA right-hand side "
+                f"({type(exc).__name__}: {exc}); pass a CTA built-in ('rd1d', 'linear') or CUDA C source defining "
+                "nbk_rhs_i(t, y, p, i, n)") from exc
+        out = _as_vec(out, n)
+        body = out.code("i")
+        src = _TABLES.source()
+    finally:
+        _TABLES = None
+    src += ("\nNBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n) {\n"
+            f"    return {body};\n}}\n")
+    return CudaRHS(src, name=getattr(func, "__name__", "traced"))
+
+
 class CudaEvents:
     """CUDA C source of ``n_events`` event functions for :meth:`Solver.run_events`::
 
@@ -266,5 +609,8 @@ def resolve(rhs, n: int, params_shape, has_params: bool):
             return None, rhs
         raise ValueError(f"unknown built-in right-hand side {rhs!r}; known: {sorted(BUILTINS)}")
     if callable(rhs):
+        if n > MAX_TRACED_N:
+            # large systems run one CTA per trajectory: the right-hand side is traced as a whole-vector expression
+            return None, trace_cta(rhs, n, params_shape, has_params).source
         return None, trace(rhs, n, params_shape, has_params).source
     raise TypeError("rhs must be a built-in name, CUDA C source, a CudaRHS or a traceable Python callable")

@@ -163,3 +163,44 @@ def test_linear_dmma_kernel_k4():
     s23 = nbk.RungeKutta23("linear", 0.0, y0, A, rtol=1e-5, atol=1e-8)
     ref = oc.run_ensemble("RungeKutta23", "linear", y0, A, [2.0], rtol=1e-5, atol=1e-8, params_shared=True)
     assert within(s23.run([2.0])[1], ref["ys"], 1e-5, 1e-8).all() and np.abs(s23.n_accepted - ref["n_accepted"]).max() <= 1
+
+
+def test_python_vector_rhs_traced_into_cta_regime():
+    """A NumPy-style right-hand side of a large system (what a reference user writes) runs through K3 unmodified."""
+    n, B = 2048, 6
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+
+    def rd(t, y, p):
+        d, r = p
+        return d * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + r * y * (1 - y)
+
+    s = nbk.RungeKutta45(rd, 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    assert s.is_jit and s._regime == 1
+    t, y = s.run([0.05, 0.1])
+    b = nbk.RungeKutta45("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    tb, yb = b.run([0.05, 0.1])
+    assert np.abs(s.n_accepted - b.n_accepted).max() <= 1
+    tol = 1e-6 * np.abs(yb) + 1e-9
+    assert (np.abs(y - yb) <= 3 * tol).all()  # stability-limited grid: 3x bar as for the built-in (DESIGN.md section 5)
+
+    # non-periodic stencil assembled by slice assignment, captured grid, time-dependent source: against the NumPy oracle
+    m = 100
+    x = np.linspace(0, 1, m)
+
+    def heat(t, y, p):
+        dy = np.zeros_like(y)
+        dy[1:-1] = p[0] * (y[2:] - 2 * y[1:-1] + y[:-2]) + np.sin(x[1:-1]) * np.exp(-t)
+        dy[0] = -y[0]
+        dy[-1] = 0.0
+        return dy
+
+    rng = np.random.default_rng(8)
+    y0h = rng.uniform(0, 1, (3, m))
+    ph = np.array([[30.0], [60.0], [90.0]])
+    s = nbk.RungeKutta23(heat, 0.0, y0h, ph, rtol=1e-5, atol=1e-8)
+    t, y = s.run([0.02, 0.05])
+    for i in range(3):
+        o = onp.AdaptiveRK("RungeKutta23", heat, 0.0, y0h[i], ph[i], rtol=1e-5, atol=1e-8)
+        _, yo = onp.run(o, [0.02, 0.05])
+        assert abs(s.n_accepted[i] - o.n_accepted) <= 1
+        assert (np.abs(y[i] - yo) <= 3 * (1e-5 * np.abs(yo) + 1e-8)).all()

@@ -234,3 +234,40 @@ def test_nvrtc_compiles_event_programs_and_traces_events():
         _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(45, 2048, 2, rhs_name=b"rd1d")), 1, ev.source.encode(), C.byref(sz)))
     with pytest.raises(rhs.TraceError):
         rhs.trace_events(lambda t, y: 1.0 if y[0] > 0 else -1.0, 3, (3,), True)
+
+
+def test_vector_tracer_emits_componentwise_cuda_and_compiles():
+    """NumPy-style whole-vector right-hand sides of large systems -> nbk_rhs_i of the CTA regime."""
+    lib = _lib.lib()
+    sz = C.c_longlong(0)
+
+    def rd(t, y, p):
+        d, r = p
+        return d * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + r * y * (1 - y)
+
+    src = rhs.trace_cta(rd, 2048, (2,), True).source
+    assert "nbk_rhs_i" in src and "% 2048" in src
+    _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 2048, 2, src=src.encode())), C.byref(sz)))
+    assert sz.value > 10_000
+
+    x = np.linspace(0, 1, 100)
+
+    def heat(t, y, p):  # Dirichlet-type boundaries assembled by slice assignment, a captured grid, a time-dependent source
+        dy = np.zeros_like(y)
+        dy[1:-1] = p[0] * (y[2:] - 2 * y[1:-1] + y[:-2]) + np.sin(x[1:-1]) * np.exp(-t)
+        dy[0] = -y[0]
+        dy[-1] = 0.0
+        return dy
+
+    src = rhs.trace_cta(heat, 100, (1,), True).source
+    assert "nbk_tab0[98]" in src
+    _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(23, 100, 1, src=src.encode())), C.byref(sz)))
+    # resolve() picks the vector tracer for n > 64 and the scalar tracer below
+    name, s2 = rhs.resolve(rd, 2048, (2,), True)
+    assert name is None and "nbk_rhs_i" in s2
+    name, s3 = rhs.resolve(rd, 16, (2,), True)
+    assert "nbk_rhs(" in s3
+    with pytest.raises(rhs.TraceError):
+        rhs.trace_cta(lambda t, y: np.cumsum(y), 100, (), False)
+    with pytest.raises(rhs.TraceError):
+        rhs.trace_cta(lambda t, y: y[:50], 100, (), False)
