@@ -17,7 +17,8 @@ y0, p = onp.lorenz_ensemble(B, 0)
 y0d, pd = torch.from_numpy(y0).cuda(), torch.from_numpy(p).cuda()
 times, att = [], 0
 for it in range(reps + 3):
-    s = getattr(nbk, method)("lorenz", 0.0, y0d, pd, rtol=rtol, atol=atol)
+    # NBK_TUNE_JIT=1: the same right-hand side as a Python callable (traced -> CUDA C -> NVRTC) instead of the catalogue kernel
+    s = getattr(nbk, method)(onp.rhs_lorenz if os.environ.get("NBK_TUNE_JIT") else "lorenz", 0.0, y0d, pd, rtol=rtol, atol=atol)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); s.run([10.0]); e1.record(); torch.cuda.synchronize()
     if it >= 3: times.append(e0.elapsed_time(e1))
