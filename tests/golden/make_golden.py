@@ -224,6 +224,19 @@ def implicit_section():
     cases.append(fixed_case("BDF3", "vdp", [2.0, 0.0], [1.0], [1.0, 2.0], 0.01, first_stepper_cls=None))
     cases.append(fixed_case("AdamsMoulton5", "vdp", [2.0, 0.0], [1.0], [1.0, 2.0], 0.01, first_stepper_cls="AdamsBashforth2"))
     dump("implicit_fixed.json", cases)
+    # events and the step/skip value flow with implicit solvers
+    extra = {"events": [], "api": []}
+    for cls in ("BackwardEuler", "AdamsMoulton3", "BDF2"):
+        s = getattr(nbkode, cls)(onp.rhs_vdp, 0.0, np.array([2.0, 0.0]), params=np.array([1.0]), h=0.01)
+        ts = np.linspace(0.5, 8, 16)
+        evs = ["y0", "y1_down"]
+        t, y, te, ye = s.run_events(ts, [onp.EVENTS[e] for e in evs])
+        alias = [[bool(getattr(x, "base", None) is not None) for x in lst] for lst in ye]
+        extra["events"].append({"cls": cls, "rhs": "vdp", "y0": [2.0, 0.0], "p": [1.0], "kw": {"h": 0.01}, "ts": L(ts), "events": evs,
+                                "t": L(t), "y": L(y), "t_events": [L(x) for x in te], "y_events": [L(x) for x in ye],
+                                "y_events_aliased": alias, "t_end": float(s.t)})
+        extra["api"].append(api_record(cls, {"h": 0.1, "first_stepper_cls": None}))
+    dump("implicit_extra.json", extra)
 
 
 def main():

@@ -123,3 +123,13 @@ def test_events_docs_cannon_example():
     t, y, te, ye = s.run_events(100, events=hit_ground)
     assert len(te) == 1 and len(te[0]) == 1 and abs(te[0][0] - 40.0) < 1e-6
     assert len(t) == 1 and abs(t[0] - 40.0) < 1e-6 and abs(y[0, 0]) < 1e-7
+
+
+@pytest.mark.parametrize("c", load_golden("implicit_extra.json")["events"], ids=lambda c: c["cls"])
+def test_events_with_implicit_solvers(c):
+    s = getattr(nbk, c["cls"])(c["rhs"], 0.0, np.array(c["y0"]), np.array(c["p"]), **c["kw"])
+    t, y, te, ye = s.run_events(c["ts"], [onp.EVENTS[e] for e in c["events"]])
+    assert rel(t, c["t"]) < 1e-12 and rel(y, c["y"]) < 5e-7  # Newton-tolerance bar of the implicit families
+    assert [len(x) for x in te] == [len(x) for x in c["t_events"]]
+    for a, b in zip(te, c["t_events"]):
+        assert rel(a, b) < 1e-6

@@ -258,3 +258,33 @@ def test_implicit_multistep_vs_reference(c):
     assert e.t[0] == c["t_end"]
     assert rel(e.y[0], c["y_end"]) < 5e-7 and rel(e.f[0], c["f_end"]) < 5e-6
     assert rel(e.ts[:, 0], c["end_ts"]) < 1e-15
+
+
+_IMX = load_golden("implicit_extra.json")
+
+
+@pytest.mark.parametrize("c", _IMX["events"], ids=lambda c: c["cls"])
+def test_implicit_events_vs_reference(c):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "numbakit-ode_b200"))
+    from nbkode_b200 import rhs as nrhs
+
+    ev = nrhs.trace_events([onp.EVENTS[e] for e in c["events"]], len(c["y0"]), (len(c["p"]),), True)
+    e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], first_stepper=45, **c["kw"])
+    out, ev_t, ev_y, ev_c, t_term = e.run_events(c["ts"], ev)
+    assert int(e.nout[0]) == len(c["t"]) and e.status[0] == 0
+    assert rel(out[0], c["y"]) < 5e-7
+    for j, (te, ye, al) in enumerate(zip(c["t_events"], c["y_events"], c["y_events_aliased"])):
+        assert ev_c[0, j] == len(te)
+        if te:
+            assert rel(ev_t[0, j, :len(te)], te) < 1e-6
+
+
+@pytest.mark.parametrize("c", _IMX["api"], ids=lambda c: c["cls"])
+def test_implicit_step_flow_vs_reference(c):
+    e = EmulEnsemble(c["cls"], "decay", [[1.0]], [[0.01]], h=0.1, first_stepper=0)
+    tt, yy, cnt = e.step(20)
+    assert cnt[0] == 20 and rel(tt[0], c["ts20"]) < 1e-14 and rel(yy[0], c["ys20"]) < 5e-7
+    e = EmulEnsemble(c["cls"], "decay", [[1.0]], [[0.01]], h=0.1, first_stepper=0)
+    ya = e.run(np.linspace(0, 4, 9))
+    yb = e.run(c["resume_b_t"])
+    assert rel(ya[0], c["resume_a"]) < 5e-7 and rel(yb[0], c["resume_b"]) < 5e-7

@@ -226,3 +226,31 @@ def test_implicit_multistep_bitexact(c):
     _eq(s.y, c["y_end"])
     _eq(s.f, c["f_end"])
     _eq(s.cache.ts, c["end_ts"])
+
+
+_IMX = load_golden("implicit_extra.json")
+
+
+@pytest.mark.parametrize("c", _IMX["events"], ids=lambda c: c["cls"])
+def test_implicit_events_bitexact(c):
+    s = onp.ImplicitMultistep(c["cls"], onp.RHS[c["rhs"]], 0.0, np.array(c["y0"]), np.array(c["p"]), **c["kw"])
+    t, y, te, ye = onp.run_events(s, c["ts"], [onp.EVENTS[e] for e in c["events"]])
+    _eq(t, c["t"]); _eq(y, c["y"])
+    for a, b, ya, yb, al in zip(te, c["t_events"], ye, c["y_events"], c["y_events_aliased"]):
+        _eq(a, b, "t_events")
+        for u, v, aliased in zip(ya, yb, al):
+            if not aliased:
+                _eq(u, v, "y_events")
+
+
+@pytest.mark.parametrize("c", _IMX["api"], ids=lambda c: c["cls"])
+def test_implicit_api_semantics(c):
+    mk = lambda: onp.ImplicitMultistep(c["cls"], onp.rhs_decay, 0.0, [1.0], np.array([0.01]), h=0.1, first_stepper=None)  # noqa: E731
+    s = mk()
+    ts, ys = onp.steps(s, n=20)
+    _eq(ts, c["ts20"]); _eq(ys, c["ys20"])
+    s = mk()
+    t, y = onp.run(s, np.linspace(0, 4, 9))
+    _eq(y, c["resume_a"])
+    t, y = onp.run(s, c["resume_b_t"])
+    _eq(y, c["resume_b"])
