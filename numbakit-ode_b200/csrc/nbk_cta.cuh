@@ -431,5 +431,372 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
     }
 }
 
+// =====================================================================================
+// Fixed-step solvers in the CTA regime: Adams-Bashforth-k / ForwardEuler (multistep/core.py:90-112) and the
+// fixed-step explicit Runge-Kutta classes (explicit.py:28-46, 102-129) for large systems.  One trajectory per
+// CTA, the history window / stage vectors of a thread's E components in registers, one barrier per right-hand
+// side evaluation.  State layout: ts [B][L], ys/fs [B][L][n], K [B][S][n] (Runge-Kutta), h [B].
+// =====================================================================================
+
+// window Hermite on a thread's slice (nbkode/core.py:577-596)
+template <int L, int E>
+NBK_DEV void cta_hermite(double te, const double (&ts)[L], const double (&ys)[L][E], const double (&fs)[L][E], double (&out)[E]) {
+    const double t0 = ts[0];
+    if (te == t0) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) out[e] = ys[0][e];
+        return;
+    }
+    const double dt = ts[L - 1] - t0;
+    const double T = (te - t0) / dt;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const double dy = ys[L - 1][e] - ys[0][e];
+        out[e] = ys[0][e] + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * fs[0][e] + T * fs[L - 1][e]));
+    }
+}
+
+// f(t, y) of the whole CTA: stage the vector (transposed, see smem_vec), one barrier, evaluate the slice
+template <class Rhs, int E>
+NBK_DEV void cta_eval(double t, const double (&y)[E], const double *p, int i0, int n, double *buf, double (&f)[E]) {
+    const int T = blockDim.x;
+#pragma unroll
+    for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = y[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) f[e] = 0.0;
+    Rhs::template eval<E>(t, y, smem_vec<E>{buf, T}, p, i0, n, f);
+}
+
+// Start-up points of an adaptive first stepper with DEFAULT tolerances (rtol 1e-3, atol 1e-6): dense output at the
+// absolute times hfix, 2 hfix, ... pushed into the history window (multistep/core.py:60-65).  Returns false on failure.
+template <class Tab, class Rhs, int E, int L>
+NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)[E], const double *p, int i0, int n,
+                            double hfix, int npts, double *buf0, double *buf1, double *red, int nwarps, double (&ts)[L],
+                            double (&ys)[L][E], double (&fs)[L][E]) {
+    constexpr int S = Tab::S;
+    const double rtol = 1e-3, atol = 1e-6;
+    double t = t0, t_old = t0, y[E], y_old[E], K[S + 1][E], sc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        y[e] = y_old[e] = y0[e];
+#pragma unroll
+        for (int s = 0; s <= S; ++s) K[s][e] = 0.0;
+        K[S][e] = f0[e];
+        sc[e] = atol + fabs(y0[e]) * rtol;
+    }
+    // select_initial_step with the default tolerances (same code path as cta_init_adaptive)
+    const double d0 = cta_rms_scaled<E>(y0, sc, i0, n, red, nwarps);
+    const double d1 = cta_rms_scaled<E>(f0, sc, i0, n, red, nwarps);
+    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    double y1[E], f1[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) y1[e] = y0[e] + h0 * f0[e];
+    __syncthreads();
+    cta_eval<Rhs, E>(t0 + h0, y1, p, i0, n, buf1, f1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) f1[e] -= f0[e];
+    const double d2 = cta_rms_scaled<E>(f1, sc, i0, n, red, nwarps) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(d1, d2), 1.0 / (Tab::Q + 1));
+    double h = fmin(100 * h0, h1);
+    bool fresh = true;
+    int budget = 1000000;
+    for (int j = 1; j <= npts; ++j) {
+        const double ti = j * hfix;
+        while (t < ti) {
+            if (fresh) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) K[0][e] = K[S][e];
+            }
+            double ynew[E], err2;
+            __syncthreads();
+            cta_attempt<Tab, Rhs, E>(t, h, y, K, p, i0, n, buf0, buf1, red, nwarps, ynew, err2, rtol, atol);
+            const bool accept = pos_less(err2, 1.0);
+            const double t_new = t + h;
+            h *= step_factor<Tab>(err2, 0.9, 0.2, 10.0, 1e-13, 1e8);
+            if (accept) {
+                t_old = t;
+                t = t_new;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    y_old[e] = y[e];
+                    y[e] = ynew[e];
+                }
+            }
+            fresh = accept;
+            if (d_nonfinite(err2) || d_collapsed(h) || --budget < 0) return false;
+        }
+        double out[E], fo[E];
+        rk_dense<Tab, E>(ti, t_old, t, y_old, y, K, out);
+        __syncthreads();
+        cta_eval<Rhs, E>(ti, out, p, i0, n, (j & 1) ? buf0 : buf1, fo);
+        // push(ti, out, fo)
+#pragma unroll
+        for (int l = 0; l < L - 1; ++l) {
+            ts[l] = ts[l + 1];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                ys[l][e] = ys[l + 1][e];
+                fs[l][e] = fs[l + 1][e];
+            }
+        }
+        ts[L - 1] = ti;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            ys[L - 1][e] = out[e];
+            fs[L - 1][e] = fo[e];
+        }
+    }
+    return true;
+}
+
+// METHOD: 1..5 Adams-Bashforth-k, 202/203/213/204/238 fixed-step Runge-Kutta
+template <int METHOD>
+struct cta_fixed_traits {
+    static constexpr bool ERK = METHOD >= 200;
+    static constexpr int L = ERK ? 2 : (METHOD > 2 ? METHOD : 2);
+    static constexpr int S = ERK ? tab_erk<ERK ? METHOD : 204>::S : 0;
+};
+
+template <int METHOD, class Rhs, int E>
+NBK_DEV void cta_init_fixed(const nbk_kargs &a, double *sm) {
+    using TR = cta_fixed_traits<METHOD>;
+    constexpr int L = TR::L, S = TR::S;
+    const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
+    const long long nn = n;
+    double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
+    for (long long idx = blockIdx.x; idx < a.B; idx += gridDim.x) {
+        __syncthreads();
+        if (!a.params_shared) {
+            for (int c = tid; c < a.n_params; c += blockDim.x)
+                a.params[idx * a.n_params + c] = a.p0[idx * a.p0_sb + c * a.p0_sc];
+            __syncthreads();
+        }
+        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        double y[E], f[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) y[e] = i0 + e < n ? a.y0[idx * a.y0_sb + (long long)(i0 + e) * a.y0_sc] : 0.0;
+        cta_eval<Rhs, E>(a.t0, y, p, i0, n, buf0, f);
+        const double h = a.h0 ? a.h0[idx] : a.h_init;
+        double ts[L], ys[L][E], fs[L][E];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            ts[l] = a.t0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                ys[l][e] = y[e];
+                fs[l][e] = f[e];
+            }
+        }
+        int status = NBK_TRAJ_OK;
+        if (!TR::ERK && METHOD > 1 && a.first_stepper != 0) {
+            bool ok = true;
+            if (a.first_stepper == 45)
+                ok = cta_rk_startup<tab_rk45, Rhs, E, L>(a.t0, y, f, p, i0, n, h, METHOD - 1, buf0, buf1, red, nwarps, ts, ys, fs);
+            else
+                ok = cta_rk_startup<tab_rk23, Rhs, E, L>(a.t0, y, f, p, i0, n, h, METHOD - 1, buf0, buf1, red, nwarps, ts, ys, fs);
+            if (!ok) status = NBK_TRAJ_NONFINITE;
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            if (i < n) {
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    a.ys[(idx * L + l) * nn + i] = ys[l][e];
+                    a.fs[(idx * L + l) * nn + i] = fs[l][e];
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) a.K[(idx * S + s) * nn + i] = 0.0;
+            }
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) a.ts[idx * L + l] = ts[l];
+            a.h[idx] = h;
+            a.n_acc[idx] = 0;
+            a.n_rej[idx] = 0;
+            a.status[idx] = status;
+            if (status >= NBK_TRAJ_NONFINITE) atomicAdd(a.work_counter + 1, 1ULL);
+        }
+    }
+}
+
+template <int METHOD, class Rhs, int E, int MODE>
+NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
+    using TR = cta_fixed_traits<METHOD>;
+    constexpr int L = TR::L, S = TR::S;
+    constexpr int KS = S > 0 ? S : 1;
+    const int n = a.n, tid = threadIdx.x, i0 = tid * E, npad = blockDim.x * E;
+    const long long nn = n;
+    double *buf0 = sm, *buf1 = sm + npad;
+    for (long long idx = blockIdx.x; idx < a.B; idx += gridDim.x) {
+        __syncthreads();
+        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        double ts[L], ys[L][E], fs[L][E], K[KS][E];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            ts[l] = a.ts[idx * L + l];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = i0 + e;
+                ys[l][e] = i < n ? a.ys[(idx * L + l) * nn + i] : 0.0;
+                fs[l][e] = i < n ? a.fs[(idx * L + l) * nn + i] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int e = 0; e < E; ++e) K[s][e] = 0.0;
+        const double h = a.h[idx];
+        int kout = 0, status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
+        long long nsteps = 0;
+        double te_next = d_inf();
+        bool running;
+        if (status != NBK_TRAJ_OK) {
+            running = false;
+            if (MODE == NBK_MODE_RUN)
+                for (int k = 0; k < a.m; ++k)
+                    for (int e = 0; e < E; ++e)
+                        if (i0 + e < n) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)(i0 + e) * a.o_sc] = d_nan();
+        } else if (MODE == NBK_MODE_RUN) {
+            while (kout < a.m && __ldg(a.tgrid + kout) <= ts[L - 1]) {
+                double out[E];
+                cta_hermite<L, E>(__ldg(a.tgrid + kout), ts, ys, fs, out);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                ++kout;
+            }
+            running = kout < a.m;
+            if (running) te_next = __ldg(a.tgrid + kout);
+        } else {
+            running = a.n_steps > 0;
+        }
+        int flip = 0;
+        while (running) {  // identical control flow in every thread of the CTA
+            if (ts[L - 1] + h > a.bound) {
+                status = NBK_TRAJ_BOUND;
+                break;
+            }
+            const double t = ts[L - 1], t_new = t + h;
+            double ynew[E], fnew[E];
+            if constexpr (TR::ERK) {
+                using Tab = tab_erk<TR::ERK ? METHOD : 204>;
+#pragma unroll
+                for (int e = 0; e < E; ++e) K[0][e] = fs[L - 1][e];
+#pragma unroll
+                for (int s = 1; s < S; ++s) {
+                    double ystage[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        double acc = 0.0;
+                        bool first = true;
+#pragma unroll
+                        for (int j = 0; j < s; ++j) {
+                            if (Tab::a(s, j) != 0.0) {
+                                acc = first ? Tab::a(s, j) * K[j][e] : fma(Tab::a(s, j), K[j][e], acc);
+                                first = false;
+                            }
+                        }
+                        ystage[e] = fma(h, acc, ys[L - 1][e]);
+                    }
+                    cta_eval<Rhs, E>(fma(h, Tab::c(s), t), ystage, p, i0, n, (flip ^= 1) ? buf1 : buf0, K[s]);
+                }
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    double acc = 0.0;
+                    bool first = true;
+#pragma unroll
+                    for (int j = 0; j < S; ++j) {
+                        if (Tab::b(j) != 0.0) {
+                            acc = first ? (h * Tab::b(j)) * K[j][e] : fma(h * Tab::b(j), K[j][e], acc);
+                            first = false;
+                        }
+                    }
+                    ynew[e] = ys[L - 1][e] + acc;
+                }
+            } else {
+                constexpr int ORDER = TR::ERK ? 1 : METHOD;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    double acc = (h * tab_ab<ORDER>::b(0)) * fs[L - ORDER][e];
+#pragma unroll
+                    for (int j = 1; j < ORDER; ++j) acc = fma(h * tab_ab<ORDER>::b(j), fs[L - ORDER + j][e], acc);
+                    ynew[e] = acc + ys[L - 1][e];
+                }
+            }
+            cta_eval<Rhs, E>(t_new, ynew, p, i0, n, (flip ^= 1) ? buf1 : buf0, fnew);
+#pragma unroll
+            for (int l = 0; l < L - 1; ++l) {
+                ts[l] = ts[l + 1];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    ys[l][e] = ys[l + 1][e];
+                    fs[l][e] = fs[l + 1][e];
+                }
+            }
+            ts[L - 1] = t_new;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                ys[L - 1][e] = ynew[e];
+                fs[L - 1][e] = fnew[e];
+            }
+            ++nsteps;
+            if (MODE == NBK_MODE_RUN) {
+                while (t_new >= te_next) {
+                    double out[E];
+                    cta_hermite<L, E>(te_next, ts, ys, fs, out);
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                    ++kout;
+                    te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                }
+                running = kout < a.m;
+            } else {
+                if (a.emit) {
+                    if (tid == 0) a.t_out[idx * a.to_sb + (nsteps - 1)] = t_new;
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (i0 + e < n) a.y_out[idx * a.o_sb + (nsteps - 1) * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
+                }
+                running = nsteps < a.n_steps;
+            }
+            if (running && nsteps >= a.max_attempts) {
+                status = NBK_TRAJ_MAXATTEMPTS;
+                break;
+            }
+        }
+        if (nsteps > 0) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = i0 + e;
+                if (i < n) {
+#pragma unroll
+                    for (int l = 0; l < L; ++l) {
+                        a.ys[(idx * L + l) * nn + i] = ys[l][e];
+                        a.fs[(idx * L + l) * nn + i] = fs[l][e];
+                    }
+#pragma unroll
+                    for (int s = 0; s < S; ++s) a.K[(idx * S + s) * nn + i] = K[s][e];
+                }
+            }
+        }
+        if (tid == 0) {
+            if (nsteps > 0) {
+#pragma unroll
+                for (int l = 0; l < L; ++l) a.ts[idx * L + l] = ts[l];
+                a.n_acc[idx] += nsteps;
+            }
+            a.status[idx] = status;
+            if (status >= NBK_TRAJ_NONFINITE) atomicAdd(a.work_counter + 1, 1ULL);
+            a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
+        }
+    }
+}
+
 }  // namespace nbk
 #endif

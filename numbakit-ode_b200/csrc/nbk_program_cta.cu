@@ -11,10 +11,14 @@
 typedef NBK_RHS_T nbk_rhs_t;
 #if NBK_METHOD == 45
 typedef nbk::tab_rk45 nbk_tab_t;
+#define NBK_CTA_ADAPTIVE 1
 #elif NBK_METHOD == 23
 typedef nbk::tab_rk23 nbk_tab_t;
+#define NBK_CTA_ADAPTIVE 1
+#elif (NBK_METHOD >= 1 && NBK_METHOD <= 5) || NBK_METHOD == 202 || NBK_METHOD == 203 || NBK_METHOD == 213 || NBK_METHOD == 204 || NBK_METHOD == 238
+#define NBK_CTA_ADAPTIVE 0  // fixed step: Adams-Bashforth-k / ForwardEuler and the fixed-step Runge-Kutta classes
 #else
-#error "the CTA regime implements the adaptive Runge-Kutta methods (NBK_METHOD 23 or 45)"
+#error "the CTA regime implements RungeKutta23/45, AdamsBashforth1..5 and the fixed-step Runge-Kutta classes"
 #endif
 #ifndef NBK_E
 #define NBK_E 4
@@ -25,15 +29,27 @@ typedef nbk::tab_rk23 nbk_tab_t;
 
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
+#if NBK_CTA_ADAPTIVE
     nbk::cta_init_adaptive<nbk_tab_t, nbk_rhs_t, NBK_E>(a, nbk_smem);
+#else
+    nbk::cta_init_fixed<NBK_METHOD, nbk_rhs_t, NBK_E>(a, nbk_smem);
+#endif
 }
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
+#if NBK_CTA_ADAPTIVE
     nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
+#else
+    nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
+#endif
 }
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
+#if NBK_CTA_ADAPTIVE
     nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
+#else
+    nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
+#endif
 }
 
 #ifndef __CUDACC_RTC__

@@ -204,3 +204,61 @@ def test_python_vector_rhs_traced_into_cta_regime():
         _, yo = onp.run(o, [0.02, 0.05])
         assert abs(s.n_accepted[i] - o.n_accepted) <= 1
         assert (np.abs(y[i] - yo) <= 3 * (1e-5 * np.abs(yo) + 1e-8)).all()
+
+
+FIXED_CTA = [("ForwardEuler", {}), ("AdamsBashforth2", {}), ("AdamsBashforth4", {}), ("AdamsBashforth5", {"first_stepper_cls": "RungeKutta23"}),
+             ("AdamsBashforth3", {"first_stepper_cls": None}), ("RungeKutta4", {}), ("Heun3", {}), ("Runge2", {}), ("Runge3", {}),
+             ("RungeKutta3_8", {})]
+
+
+@pytest.mark.parametrize("cls,kw", FIXED_CTA, ids=lambda x: x if isinstance(x, str) else "-".join(f"{v}" for v in x.values()) or "default")
+def test_fixed_step_solvers_in_cta_regime(cls, kw):
+    """Adams-Bashforth / ForwardEuler / fixed-step Runge-Kutta for large systems (one CTA per trajectory) against the
+    C oracle: the fixed-step bar of 1e-12 relative (1e-10 where an adaptive start-up with default tolerances feeds
+    the history: its accept decisions see rounding differences)."""
+    fs = kw.get("first_stepper_cls", "auto")
+    adaptive_startup = cls.startswith("AdamsBashforth") and int(cls[-1]) > 1 and fs is not None
+    tol = 1e-10 if adaptive_startup else 1e-12
+    for n, B, h, T in ((2048, 3, 2e-4, 0.01), (100, 5, 1e-3, 0.05)):
+        y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+        if n != 2048:
+            p = p * (n / 2048.0) ** 2  # keep h d < stability limit of the explicit methods on the coarser grid
+        ts = np.linspace(0, T, 6)
+        ref = oc.run_ensemble(cls, "rd1d", y0, p, ts, h=h, first_stepper=fs, nthreads=4)
+        s = getattr(nbk, cls)("rd1d", 0.0, y0, p, h=h, **kw)
+        assert s._regime == 1 and s.is_jit
+        t, y = s.run(ts)
+        err = np.max(np.abs(y - ref["ys"]), axis=(1, 2)) / np.maximum(1.0, np.max(np.abs(ref["ys"]), axis=(1, 2)))
+        assert err.max() <= tol, (cls, n, err.max())
+        assert np.array_equal(s.t, ref["t_end"]) and (s.status == 0).all()
+        assert rel(s.y, ref["y_end"]) <= tol and rel(s.f, ref["f_end"]) <= 1e3 * tol
+
+
+def test_fixed_step_cta_api_linear_and_traced_python():
+    rng = np.random.default_rng(5)
+    n, B = 70, 6
+    A = rng.standard_normal((n, n)) / math.sqrt(n) - np.eye(n)
+    y0 = rng.standard_normal((B, n))
+    ref = oc.run_ensemble("RungeKutta4", "linear", y0, A, [0.5, 1.0], h=0.01, params_shared=True)
+    s = nbk.RungeKutta4("linear", 0.0, y0, A, h=0.01)
+    t, y = s.run([0.5, 1.0])
+    assert rel(y, ref["ys"]) <= 1e-12
+    # step / skip / upto_t with the reference's value flow
+    s = nbk.AdamsBashforth2("rd1d", 0.0, *onp.rd1d_ensemble(2, n=300, seed=1), h=1e-4, first_stepper_cls=None)
+    tt, yy = s.step(n=5)
+    assert tt.shape == (2, 5) and yy.shape == (2, 5, 300) and np.allclose(tt[0], 1e-4 * np.arange(1, 6), rtol=1e-12)
+    s.skip(upto_t=1.05e-3)
+    assert np.allclose(s.t, 1e-3, rtol=1e-9)
+    assert s.cache.ys.shape == (2, 2, 300)
+    # a NumPy-style Python right-hand side through the vector tracer, fixed step
+    def rd(t, y, p):
+        return p[0] * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + p[1] * y * (1 - y)
+
+    y0, p = onp.rd1d_ensemble(2, n=512, seed=2)
+    p = p / 16.0
+    a = nbk.RungeKutta4(rd, 0.0, y0, p, h=1e-3)
+    b = nbk.RungeKutta4("rd1d", 0.0, y0, p, h=1e-3)
+    assert rel(a.run([0.02])[1], b.run([0.02])[1]) <= 1e-11
+    # DOP853 / implicit families are per-thread only: clear errors
+    with pytest.raises(ValueError, match="CTA"):
+        nbk.DOP853("rd1d", 0.0, y0, p)
