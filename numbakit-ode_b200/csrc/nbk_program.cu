@@ -84,7 +84,8 @@ extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERN
 
 #ifdef NBK_NEVENTS
 // run_events: the run kernel with the event functions compiled in (NVRTC only)
-extern "C" __global__ void __launch_bounds__(NBK_BLOCK, NBK_MIN_BLOCKS) NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
+// (no occupancy bound: the event state and the bisection need registers the plain run kernel does not)
+extern "C" __global__ void __launch_bounds__(NBK_BLOCK) NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
 #if NBK_ADAPTIVE
     nbk::advance_adaptive<nbk_tab_t, nbk_rhs_t, NBK_MODE_RUN, true>(a);
 #elif NBK_FIXED_RK
