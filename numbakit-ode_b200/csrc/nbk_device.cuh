@@ -387,6 +387,14 @@ NBK_DEV double fast_rcp(double x) {
     return fma(r, e, r);
 }
 
+// a / b for positive normal b: reciprocal seed + Newton step, then one residual correction of the quotient
+// (result within ~1 ulp; 6 instructions instead of the ~14 + slow path of the IEEE sequence).
+NBK_DEV double fast_div(double a, double b) {
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
 // x^(-1/R) for a positive normal x inside float range ([1e-30, 1e30], guaranteed by the clamp in
 // step_factor).  Seed: the top bits of x reinterpreted as a float (integer ops, no F2F), then
 // lg2/ex2 MUFU: relative error eps ~ 2e-7.  Polish: ONE third-order step on g(y) = y^-R - x,
@@ -1121,6 +1129,40 @@ NBK_DEV void hermite_window(double te, const double (&ts)[L], const double (&ys)
     }
 }
 
+// The same with the two end points of the window given explicitly (the ring-buffered advance loops below keep the
+// window rotated in registers) and the quotient by fast_div (T within ~1 ulp of the reference's division).
+template <int N>
+NBK_DEV void hermite_ends(double te, double t0, const double (&y0)[N], const double (&f0)[N], double t1, const double (&y1)[N],
+                          const double (&f1)[N], double (&out)[N]) {
+    if (te == t0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = y0[i];
+        return;
+    }
+    const double dt = t1 - t0;
+    const double T = fast_div(te - t0, dt);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double dy = y1[i] - y0[i];
+        out[i] = y0[i] + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * f0[i] + T * f1[i]));
+    }
+}
+
+// history window -> HBM, logical slot l living in physical slot (l + ROT) % L
+template <int L, int N, int ROT>
+NBK_DEV void store_window(const nbk_kargs &a, long long idx, const double (&ts)[L], const double (&ys)[L][N],
+                          const double (&fs)[L][N]) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        a.ts[(long long)l * a.B + idx] = ts[(l + ROT) % L];
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            a.ys[((long long)l * N + c) * a.B + idx] = ys[(l + ROT) % L][c];
+            a.fs[((long long)l * N + c) * a.B + idx] = fs[(l + ROT) % L][c];
+        }
+    }
+}
+
 #ifdef NBK_NEVENTS
 // dense output of the fixed-step solvers (window Hermite) as the functor events_after_step takes
 template <int L, int N>
@@ -1184,6 +1226,81 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
     } else {
         running = a.n_steps > 0;
     }
+    if constexpr (!EV) {
+        // Ring-buffered loop: L consecutive steps are unrolled with the window rotating through the same registers
+        // (logical slot l of rotation r is physical slot (l + r) % L), so a push overwrites the oldest slot instead
+        // of moving L - 1 slots (AdamsBashforth4 on n = 2: 30 register moves per step in the shifting version).
+        int rot = 0;
+        double *dst = MODE == NBK_MODE_RUN ? a.y_out + (idx * a.o_sb + kout * a.o_sk) : a.y_out + idx * a.o_sb;
+        while (running) {
+#pragma unroll
+            for (int r = 0; r < L; ++r) {
+                const int newest = (L - 1 + r) % L, oldest = r % L;
+                if (ts[newest] + h > a.bound) {
+                    status = NBK_TRAJ_BOUND;
+                    running = false;
+                    rot = r;
+                    break;
+                }
+                const double t_new = ts[newest] + h;
+                double ynew[N], fnew[N];
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    double acc = hB[0] * fs[(L - ORDER + r) % L][c];
+#pragma unroll
+                    for (int j = 1; j < ORDER; ++j) acc = fma(hB[j], fs[(L - ORDER + j + r) % L][c], acc);
+                    ynew[c] = acc + ys[newest][c];
+                }
+                Rhs::eval(t_new, ynew, p, fnew);
+                ts[oldest] = t_new;  // push: the oldest slot becomes the newest one of rotation r + 1
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    ys[oldest][c] = ynew[c];
+                    fs[oldest][c] = fnew[c];
+                }
+                ++nsteps;
+                rot = r + 1;
+                if (MODE == NBK_MODE_RUN) {
+                    while (t_new >= te_next) {
+                        double out[N];
+                        hermite_ends<N>(te_next, ts[(r + 1) % L], ys[(r + 1) % L], fs[(r + 1) % L], t_new, ynew, fnew, out);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
+                        dst += a.o_sk;
+                        ++kout;
+                        te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                    }
+                    running = kout < a.m;
+                } else {
+                    if (a.emit) {
+                        a.t_out[idx * a.to_sb + (nsteps - 1)] = t_new;
+#pragma unroll
+                        for (int c = 0; c < N; ++c) dst[c * a.o_sc] = ynew[c];
+                        dst += a.o_sk;
+                    }
+                    running = nsteps < a.n_steps;
+                }
+                if (running && nsteps >= a.max_attempts) {
+                    status = NBK_TRAJ_MAXATTEMPTS;
+                    running = false;
+                }
+                if (!running) break;
+            }
+        }
+        if (nsteps > 0) {
+            switch (rot % L) {
+                case 0: store_window<L, N, 0>(a, idx, ts, ys, fs); break;
+                case 1: store_window<L, N, 1 % L>(a, idx, ts, ys, fs); break;
+                case 2: store_window<L, N, 2 % L>(a, idx, ts, ys, fs); break;
+                case 3: store_window<L, N, 3 % L>(a, idx, ts, ys, fs); break;
+                default: store_window<L, N, 4 % L>(a, idx, ts, ys, fs); break;
+            }
+            a.n_acc[idx] += nsteps;
+        }
+        store_status(a, idx, status);
+        a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
+        return;
+    }
     while (running) {
         if (ts[L - 1] + h > a.bound) {
             status = NBK_TRAJ_BOUND;
@@ -1237,13 +1354,17 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
         }
 #endif
         if (MODE == NBK_MODE_RUN) {
-            while (t_new >= te_next) {
-                double out[N];
-                hermite_window<L, N>(te_next, ts, ys, fs, out);
+            if (t_new >= te_next) {
+                double *dst = a.y_out + (idx * a.o_sb + kout * a.o_sk);
+                do {
+                    double out[N];
+                    hermite_ends<N>(te_next, ts[0], ys[0], fs[0], ts[L - 1], ys[L - 1], fs[L - 1], out);
 #pragma unroll
-                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
-                ++kout;
-                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                    for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
+                    dst += a.o_sk;
+                    ++kout;
+                    te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                } while (t_new >= te_next);
             }
             running = kout < a.m;
         } else {
@@ -1520,13 +1641,17 @@ NBK_DEV void advance_im(const nbk_kargs &a) {
         }
 #endif
         if (MODE == NBK_MODE_RUN) {
-            while (t_new >= te_next) {
-                double out[N];
-                hermite_window<L, N>(te_next, ts, ys, fs, out);
+            if (t_new >= te_next) {
+                double *dst = a.y_out + (idx * a.o_sb + kout * a.o_sk);
+                do {
+                    double out[N];
+                    hermite_ends<N>(te_next, ts[0], ys[0], fs[0], ts[L - 1], ys[L - 1], fs[L - 1], out);
 #pragma unroll
-                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
-                ++kout;
-                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                    for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
+                    dst += a.o_sk;
+                    ++kout;
+                    te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                } while (t_new >= te_next);
             }
             running = kout < a.m;
         } else {
@@ -1911,13 +2036,17 @@ NBK_DEV void advance_erk(const nbk_kargs &a) {
         }
 #endif
         if (MODE == NBK_MODE_RUN) {
-            while (t_new >= te_next) {
-                double out[N];
-                hermite_window<2, N>(te_next, ts, ys, fs, out);
+            if (t_new >= te_next) {
+                double *dst = a.y_out + (idx * a.o_sb + kout * a.o_sk);
+                do {
+                    double out[N];
+                    hermite_ends<N>(te_next, ts[0], ys[0], fs[0], ts[1], ys[1], fs[1], out);
 #pragma unroll
-                for (int c = 0; c < N; ++c) a.y_out[idx * a.o_sb + kout * a.o_sk + c * a.o_sc] = out[c];
-                ++kout;
-                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                    for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
+                    dst += a.o_sk;
+                    ++kout;
+                    te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                } while (t_new >= te_next);
             }
             running = kout < a.m;
         } else {
