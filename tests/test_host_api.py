@@ -271,3 +271,46 @@ def test_vector_tracer_emits_componentwise_cuda_and_compiles():
         rhs.trace_cta(lambda t, y: np.cumsum(y), 100, (), False)
     with pytest.raises(rhs.TraceError):
         rhs.trace_cta(lambda t, y: y[:50], 100, (), False)
+
+
+def test_vector_tracer_values_match_numpy(tmp_path):
+    """The C expressions the vector tracer emits, compiled for the host, reproduce the NumPy right-hand side."""
+    import subprocess
+
+    x = np.linspace(0, 1, 100)
+
+    def heat(t, y, p):
+        dy = np.zeros_like(y)
+        dy[1:-1] = p[0] * (y[2:] - 2 * y[1:-1] + y[:-2]) + np.sin(x[1:-1]) * np.exp(-t)
+        dy[0] = -y[0]
+        dy[-1] = 0.0
+        return dy
+
+    def rd(t, y, p):
+        d, r = p
+        return d * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + r * y * (1 - y) ** 2 / (1 + np.abs(y))
+
+    def upwind(t, y, p):
+        flux = y * y * 0.5
+        return np.concatenate(([0.0], -(flux[1:] - flux[:-1]) * p[0])) + np.maximum(y, 0.25) * np.cos(t)
+
+    rng = np.random.default_rng(3)
+    for k, (fn, n, par) in enumerate(((heat, 100, [2.5]), (rd, 257, [0.7, 1.3]), (upwind, 90, [3.0]))):
+        src = rhs.trace_cta(fn, n, (len(par),), True).source
+        cfile = tmp_path / f"t{k}.cpp"
+        cfile.write_text(
+            "#include <cmath>\n#define __device__\n#define NBK_RHS_I static inline double\n"
+            "struct nbk_vec { const double* b; double operator[](int i) const { return b[i]; } };\n"
+            + src +
+            "\nextern \"C\" void eval_all(double t, const double* y, const double* p, int n, double* out) {\n"
+            "    for (int i = 0; i < n; ++i) out[i] = nbk_rhs_i(t, nbk_vec{y}, p, i, n);\n}\n")
+        so = tmp_path / f"t{k}.so"
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", str(cfile), "-o", str(so)])
+        lib = C.CDLL(str(so))
+        y = rng.uniform(-1, 1, n)
+        p = np.array(par)
+        out = np.empty(n)
+        dp = C.POINTER(C.c_double)
+        lib.eval_all(C.c_double(0.3), y.ctypes.data_as(dp), p.ctypes.data_as(dp), n, out.ctypes.data_as(dp))
+        ref = fn(0.3, y, p)
+        assert np.allclose(out, ref, rtol=1e-14, atol=1e-15), (fn.__name__, np.max(np.abs(out - ref)))
