@@ -314,3 +314,27 @@ def test_vector_tracer_values_match_numpy(tmp_path):
         lib.eval_all(C.c_double(0.3), y.ctypes.data_as(dp), p.ctypes.data_as(dp), n, out.ctypes.data_as(dp))
         ref = fn(0.3, y, p)
         assert np.allclose(out, ref, rtol=1e-14, atol=1e-15), (fn.__name__, np.max(np.abs(out - ref)))
+
+
+def test_cubin_disk_cache(tmp_path):
+    """User programs are compiled once per machine: a second process finds the cubin under NBK_CACHE_DIR."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, time, ctypes as C; sys.path[:0] = [%r, %r]\n"
+        "from nbkode_b200 import _lib\n"
+        "src = b'NBK_RHS nbk_rhs(double t, const double* y, const double* p, double* dy) { dy[0] = -p[0] * y[0] + 0.125; }'\n"
+        "cfg = _lib.NbkConfig(45, 1, 1, 0, 16, None, src, 1e-6, 1e-9, 0.2, 10.0, 0.9, 0, 0)\n"
+        "sz = C.c_longlong(0); t0 = time.perf_counter()\n"
+        "_lib.check(_lib.lib().nbk_jit_compile_only(C.byref(cfg), C.byref(sz)))\n"
+        "print(sz.value, time.perf_counter() - t0)\n" % (ROOT, os.path.join(ROOT, "numbakit-ode_b200")))
+    env = dict(os.environ, NBK_CACHE_DIR=str(tmp_path))
+    a = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    files = list(tmp_path.glob("*.cubin"))
+    assert len(files) == 1 and files[0].stat().st_size == int(a[0])
+    b = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert b[0] == a[0] and float(b[1]) < 0.5 * float(a[1])  # no NVRTC run the second time
+    off = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, NBK_CACHE_DIR=""), capture_output=True, text=True,
+                         check=True).stdout.split()
+    assert off[0] == a[0] and len(list(tmp_path.glob("*.cubin"))) == 1
