@@ -14,37 +14,25 @@ from ._lib import CompileError, NbkError, fp64_peak
 
 __version__ = "0.1.0"
 
-_SOLVERS_NAMES = None
-
-
-def test():  # pragma: no cover
-    """Run the repository test-suite (counterpart of nbkode.test())."""
-    import os
-
-    import pytest
-
-    return pytest.main([os.path.join(os.path.dirname(__file__), "..", "..", "tests"), "-q"])
+_FUNCTIONS = ("get_groups", "get_solver", "get_solvers", "test")
 
 
 def __dir__():
-    global _SOLVERS_NAMES
-    if not _SOLVERS_NAMES:
-        names = ["get_groups", "get_solvers", "get_solver", "test"]
-        names += list_solvers(include_alias=False)
-        _SOLVERS_NAMES = sorted(names)
-    return _SOLVERS_NAMES
+    # the four helpers + every registered solver class under its own name (aliases are not listed):
+    # what nbkode/__init__.py:51-61 exposes, recomputed on demand (the registry is small)
+    return sorted(_FUNCTIONS + tuple(list_solvers(include_alias=False)))
 
 
 def __getattr__(name):
-    try:
-        solver = get_solver(name)
-    except ValueError:
-        raise AttributeError(f"module {__name__} has no attribute {name}")
-    if solver.__name__ != name:
-        from warnings import warn
+    # solver classes are reachable as module attributes by name or alias (nbkode/__init__.py:64-75); an alias works
+    # but is reported, anything else is an ordinary AttributeError
+    import warnings
 
-        warn(
-            f"The name '{name}' is an alias and its use is discouraged. Use '{solver.__name__}' instead.",
-            stacklevel=2,
-        )
-    return solver
+    try:
+        cls = get_solver(name)
+    except ValueError:
+        raise AttributeError(f"module {__name__} has no attribute {name}") from None
+    if cls.__name__ != name:
+        warnings.warn(f"The name '{name}' is an alias and its use is discouraged. Use '{cls.__name__}' instead.",
+                      stacklevel=2)
+    return cls

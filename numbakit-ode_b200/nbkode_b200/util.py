@@ -1,8 +1,8 @@
-"""Small helpers of the registry (counterparts of nbkode/util.py:14-86)."""
+"""Small helpers of the registry (the roles of nbkode/util.py:14-86)."""
 
 from __future__ import annotations
 
-from collections.abc import MutableMapping
+from collections.abc import Mapping, MutableMapping
 
 
 class classproperty:
@@ -16,43 +16,54 @@ class classproperty:
 
 
 class CaseInsensitiveDict(MutableMapping):
-    """String-keyed mapping whose lookups ignore case while iteration yields the keys as
-    they were last written (the behaviour nbkode/util.py:22-86 relies on for
-    ``get_solver("forwardeuler")`` and ``get_solvers("euler")``)."""
+    """String-keyed mapping for the solver registry: ``get_solver("forwardeuler")`` and ``get_solvers("euler")``
+    must find ``ForwardEuler`` / the ``Euler`` group, while listing the registry shows the names as registered.
+    Two plain dicts share the case-folded key: one holds the values, one the spelling last used to store them."""
+
+    __slots__ = ("_values", "_spelling")
 
     def __init__(self, data=None, **kwargs):
-        self._items = {}  # folded key -> (original key, value)
-        self.update(data or {}, **kwargs)
-
-    @staticmethod
-    def _fold(key):
-        return key.lower()
+        self._values, self._spelling = {}, {}
+        if data is not None:
+            self.update(data)
+        if kwargs:
+            self.update(kwargs)
 
     def __setitem__(self, key, value):
-        self._items[self._fold(key)] = (key, value)
+        folded = key.casefold()
+        self._values[folded] = value
+        self._spelling[folded] = key
 
     def __getitem__(self, key):
-        return self._items[self._fold(key)][1]
+        return self._values[key.casefold()]
 
     def __delitem__(self, key):
-        del self._items[self._fold(key)]
+        folded = key.casefold()
+        del self._values[folded]
+        del self._spelling[folded]
+
+    def __contains__(self, key):
+        return isinstance(key, str) and key.casefold() in self._values
 
     def __iter__(self):
-        return (orig for orig, _ in self._items.values())
+        return iter(self._spelling.values())
 
     def __len__(self):
-        return len(self._items)
+        return len(self._values)
 
     def lower_items(self):
-        return ((k, v[1]) for k, v in self._items.items())
+        """(case-folded key, value) pairs."""
+        return self._values.items()
 
     def __eq__(self, other):
-        if not isinstance(other, MutableMapping) and not isinstance(other, dict):
+        if not isinstance(other, Mapping):
             return NotImplemented
-        return dict(self.lower_items()) == dict(CaseInsensitiveDict(other).lower_items())
+        if not isinstance(other, CaseInsensitiveDict):
+            other = CaseInsensitiveDict(other)
+        return self._values == other._values
 
     def copy(self):
-        return CaseInsensitiveDict(dict(self.items()))
+        return CaseInsensitiveDict(self)
 
     def __repr__(self):
-        return repr(dict(self.items()))
+        return "{" + ", ".join(f"{k!r}: {self[k]!r}" for k in self) + "}"

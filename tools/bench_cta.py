@@ -13,8 +13,9 @@ which = sys.argv[1] if len(sys.argv) > 1 else "rd1d"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else (16384 if which == "rd1d" else 65536)
 peak, _ = nbk.fp64_peak(0, 20000)
 if which == "rd1d":
-    n, T = 2048, 1.0
+    n, T = (int(sys.argv[3]) if len(sys.argv) > 3 else 2048), 1.0
     y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+    p[:, 0] *= (n / 2048.0) ** 2  # same h*d (stability-limited step count) on coarser grids
     flop = 6 * 8 * n + 66 * n + 18
     mk = lambda: nbk.RungeKutta45("rd1d", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
 else:
