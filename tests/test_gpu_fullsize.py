@@ -94,3 +94,32 @@ def test_c5_reaction_diffusion_65k_full_size():
     assert np.abs(s.n_accepted[sel].cpu().numpy() - ref["n_accepted"]).max() <= 1
     # conservation-type sanity of the logistic reaction term: the solution stays inside (0, 1]
     assert float(y.min()) > 0.0 and float(y.max()) <= 1.0 + 1e-9
+
+
+def test_state_arrays_beyond_2_to_31_elements():
+    """120 M Lorenz trajectories: the stage-row array K [7][3][B] has 2.5e9 elements, so every index expression has
+    to be 64-bit.  Inputs are generated on the device; trajectories at both ends and around every 2^31-element
+    boundary of K are checked against the C oracle."""
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs a 180 GB device")
+    B = 120_000_000
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    y0 = torch.empty((B, 3), dtype=torch.float64, device="cuda").uniform_(-10, 10, generator=gen)
+    y0[:, 2] += 25.0
+    p = torch.tensor([10.0, 28.0, 8 / 3], dtype=torch.float64, device="cuda")  # shared parameters
+    s = nbk.RungeKutta45("lorenz", 0.0, y0, p, rtol=1e-6, atol=1e-9, params_batched=False)
+    t, y = s.run([0.25])
+    s.raise_for_status()
+    assert y.shape == (B, 1, 3) and bool((s.status == 0).all())
+    cross = 2**31 - 17 * B  # (row 17 of K) * B + cross == 2^31: the first element a 32-bit offset cannot reach
+    assert 0 < cross < B
+    probe = [0, 1, cross - 1, cross, cross + 1, B // 2, B - 2, B - 1]
+    idx = torch.tensor(probe, device="cuda")
+    ref = oc.run_ensemble("RungeKutta45", "lorenz", y0[idx].cpu().numpy(), np.array([10.0, 28.0, 8 / 3]), [0.25],
+                          rtol=1e-6, atol=1e-9, params_shared=True)
+    assert within(y[idx].cpu().numpy(), ref["ys"], 1e-6, 1e-9).all()
+    assert np.array_equal(s.n_accepted[idx].cpu().numpy(), ref["n_accepted"])
+    k_last = s._K[6, 2, idx].cpu().numpy()  # last stage row, last component: the far end of the 2.5e9-element array
+    assert np.isfinite(k_last).all() and np.allclose(s.f[idx].cpu().numpy()[:, 2], k_last, rtol=1e-12)
+    del y, s, y0
+    torch.cuda.empty_cache()
