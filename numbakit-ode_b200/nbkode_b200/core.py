@@ -29,6 +29,8 @@ from . import rhs as _rhs
 from .util import CaseInsensitiveDict
 
 _INT_MAX = 2**31 - 1
+# method ids the CTA-per-trajectory kernels implement (include/nbkode_b200.h)
+_CTA_METHODS = frozenset({23, 45, 1, 2, 3, 4, 5, 202, 203, 213, 204, 238})
 
 # device copies of recently used output grids: uploading a grid from pageable host memory makes the
 # driver synchronise the stream, which would serialise back-to-back passes on the same grid
@@ -133,7 +135,8 @@ class Solver(ABC):
 
     # ------------------------------------------------------------------ construction
     def __init__(self, rhs, t0, y0, params=None, *, h=None, t_bound=np.inf, device=None,
-                 params_batched: Optional[bool] = None, _options=None, _first_step=None, _first_stepper=0):
+                 params_batched: Optional[bool] = None, regime: str = "auto", _options=None, _first_step=None,
+                 _first_stepper=0):
         torch = _torch()
         self.t_bound = t_bound
         self.user_rhs = rhs
@@ -178,7 +181,10 @@ class Solver(ABC):
         self._events_key = None
 
         # ---- right-hand side -> built-in name or CUDA C
-        name, src = _rhs.resolve(rhs, self.n, p_shape if p_shape else (self.n_params,), params is not None)
+        # Python callables are traced for the regime that suits the state size (``regime="thread"`` / ``"cta"`` force
+        # one, e.g. "thread" to use run_events or DOP853 on a mid-size system)
+        cta_ok = self.METHOD_ID in _CTA_METHODS and not (2 <= self.METHOD_ID <= 5 and 1 <= _first_stepper <= 5)
+        name, src = _rhs.resolve(rhs, self.n, p_shape if p_shape else (self.n_params,), params is not None, regime, cta_ok)
         if name == "decay" and self.n_params not in (1, self.n):
             raise ValueError("built-in 'decay' needs 1 or n parameters")
         self.rhs = name if name is not None else _rhs.CudaRHS(src)

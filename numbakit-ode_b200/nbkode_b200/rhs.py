@@ -235,6 +235,8 @@ class Vec:
         if name in ("maximum", "minimum") and len(inputs) == 2:
             fn = "fmax" if name == "maximum" else "fmin"
             return _vec_binary(inputs[0], inputs[1], None, lambda a, b: f"{fn}({a}, {b})")
+        if name == "matmul" and len(inputs) == 2:
+            return _vec_matmul(inputs[0], inputs[1])
         raise TraceError(f"numpy.{name} cannot be traced into a component-wise right-hand side")
 
     def __array_function__(self, func, types, args, kwargs):
@@ -256,6 +258,7 @@ class Vec:
     def __pos__(self): return self
     def __abs__(self): return _vec_unary(self, lambda a: f"fabs({a})")
     def __pow__(self, e): return _vec_pow(self, e)
+    def __rmatmul__(self, m): return _vec_matmul(m, self)
     def __len__(self): return self.length
 
     @property
@@ -377,6 +380,7 @@ class _Tables:
 
     def __init__(self):
         self.arrays = []
+        self.functions = []
 
     def add(self, arr) -> str:
         self.arrays.append(np.ascontiguousarray(arr, dtype=np.float64))
@@ -385,8 +389,16 @@ class _Tables:
     def source(self) -> str:
         out = []
         for k, a in enumerate(self.arrays):
-            out.append(f"__device__ const double nbk_tab{k}[{a.size}] = {{" + ", ".join(_lit(v) for v in a) + "};")
-        return "\n".join(out)
+            out.append(f"__device__ const double nbk_tab{k}[{a.size}] = {{" + ", ".join(_lit(v) for v in a.ravel()) + "};")
+        return "\n".join(out + self.functions)
+
+    def add_function(self, body_fmt) -> str:
+        """A helper device function (used for matrix-vector products: one row per component)."""
+        if not hasattr(self, "functions"):
+            self.functions = []
+        name = f"nbk_fn{len(self.functions)}"
+        self.functions.append(body_fmt.format(name=name))
+        return name
 
 
 _TABLES: "_Tables | None" = None
@@ -433,6 +445,32 @@ def _vec_pow(a, e):
     if not isinstance(a, Vec):
         return _vec_binary(a, e, None, lambda x, y: f"pow({x}, {y})")
     return Vec(a.length, lambda j, x=a.code: _pow_code(x(j), e))
+
+
+def _vec_matmul(m, v):
+    """``M @ v`` for a matrix that is constant (a captured 2-D NumPy array) or the parameter block itself (``p`` of
+    shape (r, n)): component i is the dot product of row i with the vector, emitted as one helper function with a
+    loop instead of r * n unrolled terms."""
+    if not isinstance(v, Vec):
+        raise TraceError("only matrix @ vector products can be traced")
+    n = v.length
+    if isinstance(m, np.ndarray) and m.ndim == 2 and m.shape[1] == n and m.dtype != object:
+        tab = _TABLES.add(m)
+        row = lambda i, tab=tab: f"{tab}[({i}) * {n} + j]"  # noqa: E731
+    elif isinstance(m, np.ndarray) and m.ndim == 2 and m.shape[1] == n and m.dtype == object:
+        first = m[0, 0]
+        if not (isinstance(first, Sc) and first.c.startswith("p[") and all(
+                isinstance(m[a, b], Sc) and m[a, b].c == f"p[{int(first.c[2:-1]) + a * n + b}]"
+                for a in (0, m.shape[0] - 1) for b in (0, n - 1))):
+            raise TraceError("matrix @ vector needs a NumPy matrix or a contiguous block of the parameters")
+        off = int(first.c[2:-1])
+        row = lambda i, off=off: f"p[{off} + ({i}) * {n} + j]"  # noqa: E731
+    else:
+        raise TraceError("matrix @ vector needs a 2-D matrix whose second dimension matches the vector")
+    fn = _TABLES.add_function(
+        "__device__ __forceinline__ double {name}(int i, double t, nbk_vec y, const double* p) {{\n"
+        f"    double s = 0.0;\n    for (int j = 0; j < {n}; ++j) s = fma({row('i')}, {v.code('j')}, s);\n    return s;\n}}}}")
+    return Vec(m.shape[0], lambda i, fn=fn: f"{fn}({i}, t, y, p)")
 
 
 @_implements(np.roll)
@@ -521,6 +559,8 @@ def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
                 f"could not trace {getattr(func, '__name__', func)!r} into a component-wise CUDA right-hand side "
                 f"({type(exc).__name__}: {exc}); pass a CTA built-in ('rd1d', 'linear') or CUDA C source defining "
                 "nbk_rhs_i(t, y, p, i, n)") from exc
+        if isinstance(out, (list, tuple)) or (isinstance(out, np.ndarray) and out.dtype == object):
+            out = _np_concatenate([[e] if not isinstance(e, Vec) else e for e in np.asarray(out, dtype=object).ravel()])
         out = _as_vec(out, n)
         body = out.code("i")
         src = _TABLES.source()
@@ -598,8 +638,16 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
     return CudaEvents("\n".join(lines) + "\n", len(events), terminal, direction)
 
 
-def resolve(rhs, n: int, params_shape, has_params: bool):
-    """-> (builtin_name or None, cuda_source or None)."""
+# Above this state size a traced right-hand side goes to the CTA regime when the solver has it: the per-thread
+# kernels keep 7 stage vectors of n doubles per thread and leave the register file around n = 12 (measured on B200,
+# RungeKutta45, 1 M decay trajectories: n = 16: 7.9 vs 11.4 ms, n = 24: 28 vs 11.8 ms, n = 32: 73 vs 11.8 ms,
+# n = 64: 202 vs 22.5 ms, per-thread vs CTA).
+CTA_AUTO_N = 16
+
+
+def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", cta_ok: bool = True):
+    """-> (builtin_name or None, cuda_source or None).  ``regime``: "auto" | "thread" | "cta" (Python callables only:
+    built-ins and CUDA C source fix their regime themselves)."""
     if isinstance(rhs, CudaRHS):
         return None, rhs.source
     if isinstance(rhs, str):
@@ -609,8 +657,19 @@ def resolve(rhs, n: int, params_shape, has_params: bool):
             return None, rhs
         raise ValueError(f"unknown built-in right-hand side {rhs!r}; known: {sorted(BUILTINS)}")
     if callable(rhs):
-        if n > MAX_TRACED_N:
-            # large systems run one CTA per trajectory: the right-hand side is traced as a whole-vector expression
+        if regime not in ("auto", "thread", "cta"):
+            raise ValueError("regime must be 'auto', 'thread' or 'cta'")
+        if regime == "thread" or (regime == "auto" and (n <= CTA_AUTO_N or not cta_ok)):
+            if n > MAX_TRACED_N:
+                raise ValueError(f"n = {n} needs the CTA regime, which this solver class does not have "
+                                 "(RungeKutta23/45, AdamsBashforth*, ForwardEuler and the fixed-step Runge-Kutta classes do)")
+            return None, trace(rhs, n, params_shape, has_params).source
+        # large (and mid-size) systems run one CTA per trajectory: the right-hand side is traced as a whole-vector
+        # expression; a function the vector tracer cannot handle falls back to the per-thread form while it can
+        try:
             return None, trace_cta(rhs, n, params_shape, has_params).source
-        return None, trace(rhs, n, params_shape, has_params).source
+        except TraceError:
+            if regime == "cta" or n > MAX_TRACED_N:
+                raise
+            return None, trace(rhs, n, params_shape, has_params).source
     raise TypeError("rhs must be a built-in name, CUDA C source, a CudaRHS or a traceable Python callable")

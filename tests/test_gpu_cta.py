@@ -264,3 +264,47 @@ def test_fixed_step_cta_api_linear_and_traced_python():
     # DOP853 / implicit families are per-thread only: clear errors
     with pytest.raises(ValueError, match="CTA"):
         nbk.DOP853("rd1d", 0.0, y0, p)
+
+
+def test_auto_regime_for_mid_size_traced_systems():
+    """A traced Python right-hand side with 16 < n <= 64 runs in the CTA regime by default (the per-thread kernels
+    leave the register file around n = 12); regime="thread" forces the per-thread form; both agree with the oracle."""
+    rng = np.random.default_rng(21)
+    n, B = 32, 200
+    A = rng.standard_normal((n, n)) / math.sqrt(n) - np.eye(n)
+    y0 = rng.standard_normal((B, n))
+
+    def lin(t, y):
+        return A @ y
+
+    auto = nbk.RungeKutta45(lin, 0.0, y0, rtol=1e-6, atol=1e-9)
+    thread = nbk.RungeKutta45(lin, 0.0, y0, rtol=1e-6, atol=1e-9, regime="thread")
+    assert auto._regime == 1 and thread._regime == 0
+    ts = [1.0, 5.0]
+    ya, yt = auto.run(ts)[1], thread.run(ts)[1]
+    ref = oc.run_ensemble("RungeKutta45", "linear", y0, A, ts, rtol=1e-6, atol=1e-9, params_shared=True, nthreads=4)
+    for y, s in ((ya, auto), (yt, thread)):
+        assert within(y, ref["ys"], 1e-6, 1e-9).all()
+        assert np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
+    # a small system written component by component, forced into the CTA regime, and the parameter block as a matrix
+    def lorenz(t, y, p):
+        x, yy, z = y
+        return np.array([p[0] * (yy - x), x * (p[1] - z) - yy, x * yy - p[2] * z])
+
+    y0l, pl = onp.lorenz_ensemble(64, seed=5)
+    a = nbk.RungeKutta45(lorenz, 0.0, y0l, pl, rtol=1e-6, atol=1e-9, regime="cta")
+    b = nbk.RungeKutta45("lorenz", 0.0, y0l, pl, rtol=1e-6, atol=1e-9)
+    assert a._regime == 1 and b._regime == 0
+    assert within(a.run([2.0])[1], b.run([2.0])[1], 1e-6, 1e-9, slack=50).all()  # chaos: 50x like smoke()
+    assert np.abs(a.n_accepted - b.n_accepted).max() <= 1
+
+    def linp(t, y, p):
+        return p @ y
+
+    c = nbk.RungeKutta23(linp, 0.0, y0, A, rtol=1e-5, atol=1e-8)  # shared (n, n) parameter block
+    assert c._regime == 1
+    refc = oc.run_ensemble("RungeKutta23", "linear", y0, A, [2.0], rtol=1e-5, atol=1e-8, params_shared=True, nthreads=4)
+    assert within(c.run([2.0])[1], refc["ys"], 1e-5, 1e-8).all()
+    # solver classes without a CTA regime stay per-thread (and keep events / DOP853 usable on mid-size systems)
+    d = nbk.DOP853(lin, 0.0, y0[:4], rtol=1e-6, atol=1e-9)
+    assert d._regime == 0

@@ -262,11 +262,18 @@ def test_vector_tracer_emits_componentwise_cuda_and_compiles():
     src = rhs.trace_cta(heat, 100, (1,), True).source
     assert "nbk_tab0[98]" in src
     _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(23, 100, 1, src=src.encode())), C.byref(sz)))
-    # resolve() picks the vector tracer for n > 64 and the scalar tracer below
+    # resolve(): the per-thread form up to n = 16, the component-wise (CTA) form above when the solver has that
+    # regime; "thread" / "cta" force one; a function the vector tracer cannot handle falls back while n <= 64
     name, s2 = rhs.resolve(rd, 2048, (2,), True)
     assert name is None and "nbk_rhs_i" in s2
-    name, s3 = rhs.resolve(rd, 16, (2,), True)
-    assert "nbk_rhs(" in s3
+    assert "nbk_rhs(" in rhs.resolve(rd, 16, (2,), True)[1]
+    assert "nbk_rhs_i" in rhs.resolve(rd, 17, (2,), True)[1]
+    assert "nbk_rhs(" in rhs.resolve(rd, 40, (2,), True, "auto", False)[1]      # solver without a CTA regime
+    assert "nbk_rhs(" in rhs.resolve(rd, 40, (2,), True, "thread")[1]
+    assert "nbk_rhs_i" in rhs.resolve(rd, 8, (2,), True, "cta")[1]
+    assert "nbk_rhs(" in rhs.resolve(lambda t, y: np.cumsum(y) * 0 + y, 30, (), False)[1]  # cumsum: scalar tracer only
+    with pytest.raises(ValueError):
+        rhs.resolve(rd, 100, (2,), True, "auto", False)
     with pytest.raises(rhs.TraceError):
         rhs.trace_cta(lambda t, y: np.cumsum(y), 100, (), False)
     with pytest.raises(rhs.TraceError):
@@ -295,11 +302,24 @@ def test_vector_tracer_values_match_numpy(tmp_path):
         return np.concatenate(([0.0], -(flux[1:] - flux[:-1]) * p[0])) + np.maximum(y, 0.25) * np.cos(t)
 
     rng = np.random.default_rng(3)
-    for k, (fn, n, par) in enumerate(((heat, 100, [2.5]), (rd, 257, [0.7, 1.3]), (upwind, 90, [3.0]))):
-        src = rhs.trace_cta(fn, n, (len(par),), True).source
+    A = rng.standard_normal((33, 33))
+
+    def lin_const(t, y, p):  # a captured matrix
+        return A @ y - p[0] * y
+
+    def lin_param(t, y, p):  # the parameter block as the matrix
+        return p.reshape(33, 33) @ y
+
+    def lorenz_scalar_style(t, y, p):  # written out component by component, as for a small system
+        x, yy, z = y
+        return np.array([p[0] * (yy - x), x * (p[1] - z) - yy, x * yy - p[2] * z])
+
+    for k, (fn, n, par) in enumerate(((heat, 100, [2.5]), (rd, 257, [0.7, 1.3]), (upwind, 90, [3.0]), (lin_const, 33, [0.3]),
+                                      (lin_param, 33, list(rng.standard_normal(33 * 33))), (lorenz_scalar_style, 3, [10.0, 28.0, 2.6]))):
+        src = rhs.trace_cta(fn, n, (33, 33) if fn is lin_param else (len(par),), True).source
         cfile = tmp_path / f"t{k}.cpp"
         cfile.write_text(
-            "#include <cmath>\n#define __device__\n#define NBK_RHS_I static inline double\n"
+            "#include <cmath>\n#define __device__\n#define __forceinline__ inline\n#define NBK_RHS_I static inline double\n"
             "struct nbk_vec { const double* b; double operator[](int i) const { return b[i]; } };\n"
             + src +
             "\nextern \"C\" void eval_all(double t, const double* y, const double* p, int n, double* out) {\n"
@@ -312,8 +332,8 @@ def test_vector_tracer_values_match_numpy(tmp_path):
         out = np.empty(n)
         dp = C.POINTER(C.c_double)
         lib.eval_all(C.c_double(0.3), y.ctypes.data_as(dp), p.ctypes.data_as(dp), n, out.ctypes.data_as(dp))
-        ref = fn(0.3, y, p)
-        assert np.allclose(out, ref, rtol=1e-14, atol=1e-15), (fn.__name__, np.max(np.abs(out - ref)))
+        ref = fn(0.3, y, p.reshape(33, 33) if fn is lin_param else p)
+        assert np.allclose(out, ref, rtol=1e-13, atol=1e-13), (fn.__name__, np.max(np.abs(out - ref)))
 
 
 def test_cubin_disk_cache(tmp_path):
