@@ -8,7 +8,7 @@ import nbkode_b200 as nbk
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 rng = np.random.default_rng(0)
 src = nbk.CudaRHS("NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n) { return -p[i] * y[i]; }")
-for n in (8, 12, 16, 24, 32, 48, 64):
+for n in [int(x) for x in os.environ.get('NBK_NS', '8,12,16,24,32,48,64').split(',')]:
     y0 = torch.from_numpy(rng.uniform(0.5, 2, (B, n))).cuda()
     p = torch.from_numpy(rng.uniform(0.1, 1.0, (B, n))).cuda()
     times = []
