@@ -26,6 +26,9 @@ typedef nbk::tab_rk23 nbk_tab_t;
 #ifndef NBK_CTA_MAXT
 #define NBK_CTA_MAXT 512  // largest block the kernels are compiled for: n <= NBK_E * NBK_CTA_MAXT
 #endif
+#ifndef NBK_CTA_MINB
+#define NBK_CTA_MINB 1    // resident CTAs per SM the advance kernels are compiled for (register budget)
+#endif
 
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
@@ -35,7 +38,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(cons
     nbk::cta_init_fixed<NBK_METHOD, nbk_rhs_t, NBK_E>(a, nbk_smem);
 #endif
 }
-extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
@@ -43,7 +46,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(run)(const
     nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
 #endif
 }
-extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
