@@ -55,28 +55,55 @@ struct smem_vec {
 
 // =====================================================================================
 // Right-hand sides of the CTA regime:
-//   template <int E> static void eval(t, yown[E], ysm (whole vector, shared memory), p, i0, n, dy[E])
-// `yown` is the thread's slice of the vector that is also in `ysm`.
+//   struct prm;  static prm load(const double *p)      -- a trajectory's parameters, fetched ONCE per trajectory
+//                                                         (a pointer for parameter blocks that do not fit registers)
+//   template <int E, bool FULL> static void eval(t, yown[E], ysm (whole vector, shared memory), prm, i0, n, dy[E])
+// `yown` is the thread's slice of the vector that is also in `ysm`.  FULL: n == blockDim.x * E, every thread owns E
+// valid components -- the kernels then compile without any per-component bounds check (branch-free stages whose
+// E dependency chains interleave; with the checks the chains ran one after the other).
 // =====================================================================================
+
+template <bool FULL>
+NBK_DEV bool cta_inb(int i, int n) { return FULL || i < n; }
 
 struct rhs_rd1d_cta {  // periodic 1-D reaction-diffusion: d (y[i+1] - 2 y[i] + y[i-1]) + r y (1 - y)
     static constexpr int NP = 2;
-    template <int E>
-    static NBK_DEV void eval(double, const double (&yown)[E], smem_vec<E> ysm, const double *p, int i0, int n,
+    struct prm { double d, r; };
+    static NBK_DEV prm load(const double *p) { return prm{p[0], p[1]}; }
+    // 5 FP64 instructions.  The association of the stencil matters: (right - 2 y) + left cancels exactly, whereas
+    // (left + right) - 2 y rounds the sum first and feeds 2-4x more noise into the highest grid mode, which a
+    // stability-limited explicit pair amplifies up to the tolerance (measured on the C5 ensemble with a CPU restatement:
+    // 4.1x (rtol |y| + atol) between the two associations, 0.07x between this one and the reference's expression).
+    static NBK_DEV double point(const prm &q, double left, double y, double right) {
+        const double ry = q.r * y;
+        return fma(q.d, fma(-2.0, y, right) + left, fma(-ry, y, ry));
+    }
+    template <int E, bool FULL = false>
+    static NBK_DEV void eval(double, const double (&yown)[E], smem_vec<E> ysm, const prm &q, int i0, int n,
                              double (&dy)[E]) {
-        const double d = __ldg(p), r = __ldg(p + 1);
-        if (i0 >= n) return;
         // only the two halo values come from shared memory, the interior from registers
-        double left = ysm[i0 == 0 ? n - 1 : i0 - 1];
-        const int ilast = i0 + E - 1 < n ? i0 + E - 1 : n - 1;
-        const double halo_right = ysm[ilast + 1 == n ? 0 : ilast + 1];
+        if constexpr (FULL) {
+            const int tid = threadIdx.x, T = ysm.T;
+            double left = ysm.at(tid == 0 ? T - 1 : tid - 1, E - 1);
+            const double halo_right = ysm.at(tid + 1 == T ? 0 : tid + 1, 0);
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int i = i0 + e;
-            if (i < n) {
-                const double right = (i == ilast) ? halo_right : yown[e + 1 < E ? e + 1 : e];
-                dy[e] = d * (right - 2 * yown[e] + left) + r * yown[e] * (1 - yown[e]);
+            for (int e = 0; e < E; ++e) {
+                dy[e] = point(q, left, yown[e], e + 1 < E ? yown[e + 1 < E ? e + 1 : e] : halo_right);
                 left = yown[e];
+            }
+        } else {
+            if (i0 >= n) return;
+            double left = ysm[i0 == 0 ? n - 1 : i0 - 1];
+            const int ilast = i0 + E - 1 < n ? i0 + E - 1 : n - 1;
+            const double halo_right = ysm[ilast + 1 == n ? 0 : ilast + 1];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = i0 + e;
+                if (i < n) {
+                    const double right = (i == ilast) ? halo_right : yown[e + 1 < E ? e + 1 : e];
+                    dy[e] = point(q, left, yown[e], right);
+                    left = yown[e];
+                }
             }
         }
     }
@@ -85,9 +112,12 @@ struct rhs_rd1d_cta {  // periodic 1-D reaction-diffusion: d (y[i+1] - 2 y[i] + 
 struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANSPOSED ([j][i]) so that
                          // consecutive threads read consecutive addresses; y[j] is a broadcast smem read
     static constexpr int NP = -1;  // n*n, run-time
-    template <int E>
-    static NBK_DEV void eval(double, const double (&)[E], smem_vec<E> ysm, const double *At, int i0, int n,
+    struct prm { const double *At; };
+    static NBK_DEV prm load(const double *p) { return prm{p}; }
+    template <int E, bool FULL = false>
+    static NBK_DEV void eval(double, const double (&)[E], smem_vec<E> ysm, const prm &q, int i0, int n,
                              double (&dy)[E]) {
+        const double *At = q.At;
         double acc[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) acc[e] = 0.0;
@@ -95,7 +125,7 @@ struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANS
             const double yj = ysm[j];
 #pragma unroll
             for (int e = 0; e < E; ++e)
-                if (i0 + e < n) acc[e] = fma(__ldg(At + (long long)j * n + i0 + e), yj, acc[e]);
+                if (cta_inb<FULL>(i0 + e, n)) acc[e] = fma(__ldg(At + (long long)j * n + i0 + e), yj, acc[e]);
         }
 #pragma unroll
         for (int e = 0; e < E; ++e) dy[e] = acc[e];
@@ -108,12 +138,14 @@ struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANS
 // where y[j] reads component j of the whole stage-argument vector (shared memory).
 struct rhs_user_cta {
     static constexpr int NP = -1;
-    template <int E>
-    static NBK_DEV void eval(double t, const double (&)[E], smem_vec<E> ysm, const double *p, int i0, int n,
+    struct prm { const double *p; };
+    static NBK_DEV prm load(const double *p) { return prm{p}; }
+    template <int E, bool FULL = false>
+    static NBK_DEV void eval(double t, const double (&)[E], smem_vec<E> ysm, const prm &q, int i0, int n,
                              double (&dy)[E]) {
 #pragma unroll
         for (int e = 0; e < E; ++e)
-            if (i0 + e < n) dy[e] = nbk_rhs_i(t, ysm, p, i0 + e, n);
+            if (cta_inb<FULL>(i0 + e, n)) dy[e] = nbk_rhs_i(t, ysm, q.p, i0 + e, n);
     }
 };
 #endif
@@ -121,10 +153,10 @@ struct rhs_user_cta {
 // =====================================================================================
 // One FSAL attempt of the whole CTA.  K[0] holds this thread's slice of f(t, y).
 // =====================================================================================
-template <class Tab, class Rhs, int E>
-NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[Tab::S + 1][E], const double *p, int i0,
-                         int n, double *buf0, double *buf1, double *red, int nwarps, double (&ynew)[E], double &err2,
-                         double rtol, double atol) {
+template <class Tab, class Rhs, int E, bool FULL = false>
+NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[Tab::S + 1][E], const typename Rhs::prm &p,
+                         int i0, int n, double inv_n, double *buf0, double *buf1, double *red, int nwarps,
+                         double (&ynew)[E], double &err2, double rtol, double atol) {
     constexpr int S = Tab::S;
 #pragma unroll
     for (int s = 1; s <= S; ++s) {
@@ -149,8 +181,8 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
 #pragma unroll
         for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = ys[e];  // transposed, conflict-free (see smem_vec)
         __syncthreads();
-        Rhs::template eval<E>(s < S ? fma(h, Tab::cb().c[s < S ? s : 0], t) : t + h, ys, smem_vec<E>{buf, T}, p, i0, n,
-                              K[s]);
+        Rhs::template eval<E, FULL>(s < S ? fma(h, Tab::cb().c[s < S ? s : 0], t) : t + h, ys, smem_vec<E>{buf, T}, p, i0,
+                                    n, K[s]);
         if (s == S) {
 #pragma unroll
             for (int e = 0; e < E; ++e) ynew[e] = ys[e];
@@ -168,13 +200,13 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
                 first = false;
             }
         }
-        if (i0 + e < n) {
+        if (cta_inb<FULL>(i0 + e, n)) {
             const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
             const double r = ee * fast_rcp(sc);
             part = fma(r, r, part);
         }
     }
-    err2 = block_sum(part, red, nwarps) * (h * h / (double)n);
+    err2 = block_sum(part, red, nwarps) * (h * h * inv_n);  // inv_n = 1/n, computed once per kernel
 }
 
 // rms(x / scale) over the whole vector (cold path)
@@ -208,7 +240,7 @@ NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
                 a.params[idx * a.n_params + c] = a.p0[idx * a.p0_sb + c * a.p0_sc];
             __syncthreads();  // made visible to the block before the first right-hand side call
         }
-        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
         double y[E], f[E], sc[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -270,11 +302,12 @@ NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
 // =====================================================================================
 // Advance: persistent CTAs pulling trajectories from the global queue.
 // =====================================================================================
-template <class Tab, class Rhs, int E, int MODE>
+template <class Tab, class Rhs, int E, int MODE, bool FULL = false>
 NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
     constexpr int S = Tab::S;
     const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
     const long long nn = n;
+    const double inv_n = 1.0 / (double)n;
     double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
     long long *s_idx = (long long *)(red + 32);
     const double rtol = a.rtol, atol = a.atol, bound = a.bound;
@@ -287,16 +320,16 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
         const long long idx = *s_idx;
         if (idx >= a.B) break;
 
-        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
         double t = a.ts[idx * 2 + 1], h = a.h[idx];
         double y[E], K[S + 1][E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int i = i0 + e;
-            y[e] = i < n ? a.ys[(idx * 2 + 1) * nn + i] : 0.0;
+            y[e] = cta_inb<FULL>(i, n) ? a.ys[(idx * 2 + 1) * nn + i] : 0.0;
 #pragma unroll
             for (int s = 0; s < S; ++s) K[s][e] = 0.0;
-            K[S][e] = i < n ? a.fs[(idx * 2 + 1) * nn + i] : 0.0;  // f(t, y): K[0] of the first attempt
+            K[S][e] = cta_inb<FULL>(i, n) ? a.fs[(idx * 2 + 1) * nn + i] : 0.0;  // f(t, y): K[0] of the first attempt
         }
         int status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
         int nacc = 0, natt = 0, kout = 0;
@@ -310,16 +343,16 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = i0 + e;
-                    y_old[e] = i < n ? a.ys[(idx * 2) * nn + i] : 0.0;
+                    y_old[e] = cta_inb<FULL>(i, n) ? a.ys[(idx * 2) * nn + i] : 0.0;
 #pragma unroll
-                    for (int s = 0; s <= S; ++s) Kh[s][e] = (i < n && !a.pristine) ? a.K[(idx * (S + 1) + s) * nn + i] : 0.0;
+                    for (int s = 0; s <= S; ++s) Kh[s][e] = (cta_inb<FULL>(i, n) && !a.pristine) ? a.K[(idx * (S + 1) + s) * nn + i] : 0.0;
                 }
                 while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
                     double out[E];
                     rk_dense<Tab, E>(__ldg(a.tgrid + kout), t_old, t, y_old, y, Kh, out);
 #pragma unroll
                     for (int e = 0; e < E; ++e)
-                        if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                        if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
                     ++kout;
                 }
             }
@@ -331,7 +364,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
         if (status >= NBK_TRAJ_NONFINITE && MODE == NBK_MODE_RUN) {
             for (int k = 0; k < a.m; ++k)
                 for (int e = 0; e < E; ++e)
-                    if (i0 + e < n) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)(i0 + e) * a.o_sc] = d_nan();
+                    if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)(i0 + e) * a.o_sc] = d_nan();
         }
         if (running && (t + h > bound)) {  // guard of the first step (core.py:176-184)
             status = NBK_TRAJ_BOUND;
@@ -344,7 +377,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
                 for (int e = 0; e < E; ++e) K[0][e] = K[S][e];
             }
             double ynew[E], err2;
-            cta_attempt<Tab, Rhs, E>(t, h, y, K, p, i0, n, buf0, buf1, red, nwarps, ynew, err2, rtol, atol);
+            cta_attempt<Tab, Rhs, E, FULL>(t, h, y, K, p, i0, n, inv_n, buf0, buf1, red, nwarps, ynew, err2, rtol, atol);
             const bool accept = (unsigned)__double2hiint(err2) < 0x3ff00000u;
             const double t_new = t + h;
             h *= step_factor<Tab>(err2, a.safety, a.min_factor, a.max_factor, a.x_lo, a.x_hi);
@@ -357,7 +390,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
                         rk_dense<Tab, E>(te_next, t, t_new, y, ynew, K, out);
 #pragma unroll
                         for (int e = 0; e < E; ++e)
-                            if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                            if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
                         ++kout;
                         te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
                     }
@@ -367,7 +400,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
                         if (tid == 0) a.t_out[idx * a.to_sb + nacc] = t_new;
 #pragma unroll
                         for (int e = 0; e < E; ++e)
-                            if (i0 + e < n) a.y_out[idx * a.o_sb + nacc * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
+                            if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + nacc * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
                     }
                     done = nacc + 1 >= a.n_steps;
                 }
@@ -388,7 +421,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
                 if (tid == 0) a.ts[idx * 2] = t;
 #pragma unroll
                 for (int e = 0; e < E; ++e)
-                    if (i0 + e < n) a.ys[(idx * 2) * nn + i0 + e] = y[e];
+                    if (cta_inb<FULL>(i0 + e, n)) a.ys[(idx * 2) * nn + i0 + e] = y[e];
                 running = false;
             }
             if (accept) {
@@ -405,7 +438,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int i = i0 + e;
-                if (i < n) {
+                if (cta_inb<FULL>(i, n)) {
                     a.ys[(idx * 2 + 1) * nn + i] = y[e];
                     a.fs[(idx * 2) * nn + i] = K[0][e];
                     a.fs[(idx * 2 + 1) * nn + i] = clean ? K[S][e] : K[0][e];
@@ -458,7 +491,8 @@ NBK_DEV void cta_hermite(double te, const double (&ts)[L], const double (&ys)[L]
 
 // f(t, y) of the whole CTA: stage the vector (transposed, see smem_vec), one barrier, evaluate the slice
 template <class Rhs, int E>
-NBK_DEV void cta_eval(double t, const double (&y)[E], const double *p, int i0, int n, double *buf, double (&f)[E]) {
+NBK_DEV void cta_eval(double t, const double (&y)[E], const typename Rhs::prm &p, int i0, int n, double *buf,
+                      double (&f)[E]) {
     const int T = blockDim.x;
 #pragma unroll
     for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = y[e];
@@ -471,7 +505,7 @@ NBK_DEV void cta_eval(double t, const double (&y)[E], const double *p, int i0, i
 // Start-up points of an adaptive first stepper with DEFAULT tolerances (rtol 1e-3, atol 1e-6): dense output at the
 // absolute times hfix, 2 hfix, ... pushed into the history window (multistep/core.py:60-65).  Returns false on failure.
 template <class Tab, class Rhs, int E, int L>
-NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)[E], const double *p, int i0, int n,
+NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)[E], const typename Rhs::prm &p, int i0, int n,
                             double hfix, int npts, double *buf0, double *buf1, double *red, int nwarps, double (&ts)[L],
                             double (&ys)[L][E], double (&fs)[L][E]) {
     constexpr int S = Tab::S;
@@ -503,6 +537,7 @@ NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)
     double h = fmin(100 * h0, h1);
     bool fresh = true;
     int budget = 1000000;
+    const double inv_n = 1.0 / (double)n;
     for (int j = 1; j <= npts; ++j) {
         const double ti = j * hfix;
         while (t < ti) {
@@ -512,7 +547,7 @@ NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)
             }
             double ynew[E], err2;
             __syncthreads();
-            cta_attempt<Tab, Rhs, E>(t, h, y, K, p, i0, n, buf0, buf1, red, nwarps, ynew, err2, rtol, atol);
+            cta_attempt<Tab, Rhs, E>(t, h, y, K, p, i0, n, inv_n, buf0, buf1, red, nwarps, ynew, err2, rtol, atol);
             const bool accept = pos_less(err2, 1.0);
             const double t_new = t + h;
             h *= step_factor<Tab>(err2, 0.9, 0.2, 10.0, 1e-13, 1e8);
@@ -574,7 +609,7 @@ NBK_DEV void cta_init_fixed(const nbk_kargs &a, double *sm) {
                 a.params[idx * a.n_params + c] = a.p0[idx * a.p0_sb + c * a.p0_sc];
             __syncthreads();
         }
-        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
         double y[E], f[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) y[e] = i0 + e < n ? a.y0[idx * a.y0_sb + (long long)(i0 + e) * a.y0_sc] : 0.0;
@@ -634,7 +669,7 @@ NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
     double *buf0 = sm, *buf1 = sm + npad;
     for (long long idx = blockIdx.x; idx < a.B; idx += gridDim.x) {
         __syncthreads();
-        const double *p = a.params_shared ? a.params : a.params + idx * a.n_params;
+        const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
         double ts[L], ys[L][E], fs[L][E], K[KS][E];
 #pragma unroll
         for (int l = 0; l < L; ++l) {

@@ -12,6 +12,7 @@ struct nbk_jit_request {
     std::string user_src;   // user source defining nbk_rhs(...) / nbk_rhs_i(...) (used when rhs_type is empty)
     int cta_elems = 0;      // > 0: CTA-per-trajectory regime (nbk_program_cta.cu) with E components per thread
     int cta_maxt = 0;       // block-size cap the CTA kernels are compiled for
+    int cta_full = 0;       // 1: n == block * E (every thread owns E valid components): no bounds checks compiled in
     int n_events = 0;       // > 0: also build the run_events kernel with event_src's nbk_event(k, t, y, p) inlined
     std::string event_src;
 };

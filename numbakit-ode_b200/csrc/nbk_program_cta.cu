@@ -30,6 +30,23 @@ typedef nbk::tab_rk23 nbk_tab_t;
 #define NBK_CTA_MINB 1    // resident CTAs per SM the advance kernels are compiled for (register budget)
 #endif
 
+// NBK_CTA_FULL (NVRTC programs: n is known when the program is compiled): 1 = every thread owns NBK_E valid
+// components (n == blockDim.x * NBK_E), the adaptive kernels are compiled without bounds checks; 0 = generic.
+// Undefined (ahead-of-time catalogue, any n): both bodies, chosen once per launch.
+#if NBK_CTA_ADAPTIVE
+template <int MODE>
+__device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *sm) {
+#if defined(NBK_CTA_FULL) && NBK_CTA_FULL
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, true>(a, sm);
+#elif defined(NBK_CTA_FULL)
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, false>(a, sm);
+#else
+    if (a.n == (int)blockDim.x * NBK_E) nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, true>(a, sm);
+    else nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, false>(a, sm);
+#endif
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
@@ -41,7 +58,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(cons
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
-    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
+    nbk_cta_advance_any<NBK_MODE_RUN>(a, nbk_smem);
 #else
     nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
 #endif
@@ -49,7 +66,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KER
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
-    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
+    nbk_cta_advance_any<NBK_MODE_STEP>(a, nbk_smem);
 #else
     nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
 #endif

@@ -108,7 +108,10 @@ def test_user_cuda_rhs_and_api_in_cta_regime():
     c.skip(n=3)
     o = onp.AdaptiveRK("RungeKutta45", onp.rhs_rd1d, 0.0, y0[0], p[0], rtol=1e-6, atol=1e-9)
     tr, yr = onp.steps(o, n=8)
-    assert rel(t1[0], tr[:5]) < 1e-3 and rel(y1[0], yr[:5]) < 1e-5 and rel(c.t[0], tr[-1]) < 1e-3
+    # the second step (h grows 10x, far outside the stability region) amplifies rounding noise into the error
+    # estimate, so the step SIZES of two correct implementations differ at the 1e-5 level from the third step on
+    # (emulating either FMA contraction of the stencil in NumPy gives rel t 2-3e-5, rel y 0.8-1.1e-5)
+    assert rel(t1[0], tr[:5]) < 1e-3 and rel(y1[0], yr[:5]) < 5e-5 and rel(c.t[0], tr[-1]) < 1e-3
     tc, yc = c.run([3.0])  # resumed: continues from the 8 steps above
     tf, yf = nbk.RungeKutta45("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9).run([3.0])
     assert np.array_equal(yc, yf)  # same kernels, same arithmetic: the split run is bit-identical
