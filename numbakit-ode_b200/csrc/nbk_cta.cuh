@@ -92,18 +92,16 @@ struct rhs_rd1d_cta {  // periodic 1-D reaction-diffusion: d (y[i+1] - 2 y[i] + 
                 left = yown[e];
             }
         } else {
-            if (i0 >= n) return;
+            // ragged tail (n < blockDim.x * E): no branches either -- slots beyond n are computed from whatever
+            // finite values sit there and never reach a reduction or a store
             double left = ysm[i0 == 0 ? n - 1 : i0 - 1];
             const int ilast = i0 + E - 1 < n ? i0 + E - 1 : n - 1;
             const double halo_right = ysm[ilast + 1 == n ? 0 : ilast + 1];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int i = i0 + e;
-                if (i < n) {
-                    const double right = (i == ilast) ? halo_right : yown[e + 1 < E ? e + 1 : e];
-                    dy[e] = point(q, left, yown[e], right);
-                    left = yown[e];
-                }
+                const double right = (i0 + e == ilast) ? halo_right : yown[e + 1 < E ? e + 1 : e];
+                dy[e] = point(q, left, yown[e], right);
+                left = yown[e];
             }
         }
     }
@@ -121,11 +119,13 @@ struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANS
         double acc[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) acc[e] = 0.0;
+        int col[E];  // slots beyond n recompute row n-1 (never stored): no branch in the inner loop
+#pragma unroll
+        for (int e = 0; e < E; ++e) col[e] = cta_inb<FULL>(i0 + e, n) ? i0 + e : n - 1;
         for (int j = 0; j < n; ++j) {
             const double yj = ysm[j];
 #pragma unroll
-            for (int e = 0; e < E; ++e)
-                if (cta_inb<FULL>(i0 + e, n)) acc[e] = fma(__ldg(At + (long long)j * n + i0 + e), yj, acc[e]);
+            for (int e = 0; e < E; ++e) acc[e] = fma(__ldg(At + (long long)j * n + col[e]), yj, acc[e]);
         }
 #pragma unroll
         for (int e = 0; e < E; ++e) dy[e] = acc[e];
@@ -144,8 +144,8 @@ struct rhs_user_cta {
     static NBK_DEV void eval(double t, const double (&)[E], smem_vec<E> ysm, const prm &q, int i0, int n,
                              double (&dy)[E]) {
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-            if (cta_inb<FULL>(i0 + e, n)) dy[e] = nbk_rhs_i(t, ysm, q.p, i0 + e, n);
+        for (int e = 0; e < E; ++e)  // slots beyond n recompute component n-1 (never stored): no branches
+            dy[e] = nbk_rhs_i(t, ysm, q.p, cta_inb<FULL>(i0 + e, n) ? i0 + e : n - 1, n);
     }
 };
 #endif
@@ -200,11 +200,9 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
                 first = false;
             }
         }
-        if (cta_inb<FULL>(i0 + e, n)) {
-            const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
-            const double r = ee * fast_rcp(sc);
-            part = fma(r, r, part);
-        }
+        const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
+        const double r = ee * fast_rcp(sc);
+        part = cta_inb<FULL>(i0 + e, n) ? fma(r, r, part) : part;  // a select, not a branch
     }
     err2 = block_sum(part, red, nwarps) * (h * h * inv_n);  // inv_n = 1/n, computed once per kernel
 }

@@ -30,20 +30,16 @@ typedef nbk::tab_rk23 nbk_tab_t;
 #define NBK_CTA_MINB 1    // resident CTAs per SM the advance kernels are compiled for (register budget)
 #endif
 
-// NBK_CTA_FULL (NVRTC programs: n is known when the program is compiled): 1 = every thread owns NBK_E valid
-// components (n == blockDim.x * NBK_E), the adaptive kernels are compiled without bounds checks; 0 = generic.
-// Undefined (ahead-of-time catalogue, any n): both bodies, chosen once per launch.
+// NBK_CTA_FULL: 1 = every thread owns NBK_E valid components (n == blockDim.x * NBK_E) and the adaptive kernels are
+// compiled without bounds checks; 0 = any n.  Separate programs, not a branch inside one kernel: with both bodies in
+// one function ptxas spills in the hot loop of the full body (C5: 568 -> 670 ms).
+#ifndef NBK_CTA_FULL
+#define NBK_CTA_FULL 0
+#endif
 #if NBK_CTA_ADAPTIVE
 template <int MODE>
 __device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *sm) {
-#if defined(NBK_CTA_FULL) && NBK_CTA_FULL
-    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, true>(a, sm);
-#elif defined(NBK_CTA_FULL)
-    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, false>(a, sm);
-#else
-    if (a.n == (int)blockDim.x * NBK_E) nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, true>(a, sm);
-    else nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, false>(a, sm);
-#endif
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, NBK_CTA_FULL != 0>(a, sm);
 }
 #endif
 
@@ -79,6 +75,7 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->n = -1;  // any n: run-time
     out->n_params = nbk_rhs_t::NP;
     out->cta_elems = NBK_E;
+    out->cta_full = NBK_CTA_FULL;
     out->mma_tile = 0;
     out->mma_smem = 0;
     out->k_init = (const void *)&NBK_KERNEL(init);

@@ -36,6 +36,7 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->n = -1;
     out->n_params = -1;
     out->cta_elems = 1;
+    out->cta_full = 0;
     out->mma_tile = nbk::MMA_NT;
     out->mma_smem = sizeof(double) * (2 * 128 * nbk::MMA_LD + nbk::MMA_WARPS * nbk::MMA_NT) + sizeof(nbk::mma_cols);
     out->k_init = (const void *)&NBK_KERNEL(init);
