@@ -33,6 +33,17 @@ NBK_DEV double block_sum(double v, double *red, int nwarps) {
     const int lane = threadIdx.x & 31;
     if (lane == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
+    if (nwarps == 16) {
+        // the 512-thread blocks of the large systems: every thread reads the 16 warp partials as broadcast 16-byte
+        // loads and adds them as a tree (one shared round trip + 4 dependent additions instead of 5 shuffle rounds)
+        const double2 *r2 = reinterpret_cast<const double2 *>(red);
+        double2 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = r2[i];
+        const double a = (q[0].x + q[0].y) + (q[1].x + q[1].y), b = (q[2].x + q[2].y) + (q[3].x + q[3].y);
+        const double c = (q[4].x + q[4].y) + (q[5].x + q[5].y), d = (q[6].x + q[6].y) + (q[7].x + q[7].y);
+        return (a + b) + (c + d);
+    }
     // every warp reduces the (<= 32) warp partials with the same butterfly: identical total everywhere
     double tot = lane < nwarps ? red[lane] : 0.0;
 #pragma unroll

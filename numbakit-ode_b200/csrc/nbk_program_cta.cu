@@ -44,7 +44,7 @@ __device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *
 #endif
 
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
-    extern __shared__ double nbk_smem[];
+    extern __shared__ __align__(16) double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk::cta_init_adaptive<nbk_tab_t, nbk_rhs_t, NBK_E>(a, nbk_smem);
 #else
@@ -52,7 +52,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(cons
 #endif
 }
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
-    extern __shared__ double nbk_smem[];
+    extern __shared__ __align__(16) double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk_cta_advance_any<NBK_MODE_RUN>(a, nbk_smem);
 #else
@@ -60,7 +60,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KER
 #endif
 }
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
-    extern __shared__ double nbk_smem[];
+    extern __shared__ __align__(16) double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk_cta_advance_any<NBK_MODE_STEP>(a, nbk_smem);
 #else
