@@ -20,7 +20,7 @@ y0d, pd = torch.from_numpy(y0).cuda(), torch.from_numpy(p).cuda()
 ts = np.linspace(0, 20, m)
 for cls, kw in (("RungeKutta23", dict(rtol=1e-6, atol=1e-9)), ("AdamsBashforth4", dict(h=0.01))):
     times = []
-    for it in range(3):
+    for it in range(6):
         s = getattr(nbk, cls)("vdp", 0.0, y0d, pd, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
