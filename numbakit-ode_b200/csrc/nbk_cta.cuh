@@ -199,24 +199,124 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
             for (int e = 0; e < E; ++e) ynew[e] = ys[e];
         }
     }
-    double part = 0.0;
+    if constexpr (Tab::DOP) {
+        // DOP853: err5 = h E5.K, err3 = h E3.K, norm^2 = a^2 / (a + b / 100) with a = mean((err5/sc)^2), b = mean((err3/sc)^2)
+        // (explicit.py:325-336; same squared form as the per-thread kernel)
+        double p5 = 0.0, p3 = 0.0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        double ee = 0.0;
-        bool first = true;
+        for (int e = 0; e < E; ++e) {
+            double e5 = 0.0, e3 = 0.0;
+            bool f5 = true, f3 = true;
 #pragma unroll
-        for (int j = 0; j <= S; ++j) {
-            if (Tab::e(j) != 0.0) {
-                ee = first ? Tab::cb().e[j] * K[j][e] : fma(Tab::cb().e[j], K[j][e], ee);
-                first = false;
+            for (int j = 0; j <= S; ++j) {
+                if (Tab::e5(j) != 0.0) {
+                    e5 = f5 ? Tab::cb().e5[j] * K[j][e] : fma(Tab::cb().e5[j], K[j][e], e5);
+                    f5 = false;
+                }
+                if (Tab::e3(j) != 0.0) {
+                    e3 = f3 ? Tab::cb().e3[j] * K[j][e] : fma(Tab::cb().e3[j], K[j][e], e3);
+                    f3 = false;
+                }
             }
+            const double rs = fast_rcp(pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol)));
+            const double r5 = e5 * rs, r3 = e3 * rs;
+            p5 = cta_inb<FULL>(i0 + e, n) ? fma(r5, r5, p5) : p5;
+            p3 = cta_inb<FULL>(i0 + e, n) ? fma(r3, r3, p3) : p3;
         }
-        const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
-        const double r = ee * fast_rcp(sc);
-        part = cta_inb<FULL>(i0 + e, n) ? fma(r, r, part) : part;  // a select, not a branch
+        const double hh = h * h * inv_n;
+        const double a5 = block_sum(p5, red, nwarps) * hh;
+        __syncthreads();  // `red` is reused
+        const double a3 = block_sum(p3, red, nwarps) * hh;
+        const double den = fma(0.01, a3, a5);
+        err2 = den > 0.0 ? a5 * a5 / den : a5;  // exact step: the reference divides 0/0 here
+    } else {
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            double ee = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j <= S; ++j) {
+                if (Tab::e(j) != 0.0) {
+                    ee = first ? Tab::cb().e[j] * K[j][e] : fma(Tab::cb().e[j], K[j][e], ee);
+                    first = false;
+                }
+            }
+            const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
+            const double r = ee * fast_rcp(sc);
+            part = cta_inb<FULL>(i0 + e, n) ? fma(r, r, part) : part;  // a select, not a branch
+        }
+        err2 = block_sum(part, red, nwarps) * (h * h * inv_n);  // inv_n = 1/n, computed once per kernel
     }
-    err2 = block_sum(part, red, nwarps) * (h * h * inv_n);  // inv_n = 1/n, computed once per kernel
 }
+
+// f(t, y) of the whole CTA: stage the vector (transposed, see smem_vec), one barrier, evaluate the slice
+template <class Rhs, int E>
+NBK_DEV void cta_eval(double t, const double (&y)[E], const typename Rhs::prm &p, int i0, int n, double *buf,
+                      double (&f)[E]) {
+    const int T = blockDim.x;
+#pragma unroll
+    for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = y[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) f[e] = 0.0;
+    Rhs::template eval<E>(t, y, smem_vec<E>{buf, T}, p, i0, n, f);
+}
+
+// Dense output of one step for the whole CTA (RkInterpolator / DOP853Interpolator): prepare() builds the step's
+// interpolant once -- for DOP853 that takes three more right-hand-side evaluations of the whole vector (rows 13..15 of
+// the extended tableau, explicit.py:406-481), i.e. three barriers every thread of the CTA must reach -- and
+// eval() evaluates a thread's slice at a time inside the step.
+template <class Tab, class Rhs, int E>
+struct cta_dense {
+    double F[Tab::DOP ? 7 : E][Tab::DOP ? E : Tab::M];
+    NBK_DEV void prepare(double t_old, double t, const double (&y_old)[E], const double (&y)[E],
+                         const double (&K)[Tab::S + 1][E], const typename Rhs::prm &p, int i0, int n, double *buf0,
+                         double *buf1) {
+        if constexpr (Tab::DOP) {
+            const double h = t - t_old;
+            double Ke[3][E];
+#pragma unroll
+            for (int s = 13; s < 16; ++s) {
+                double ys[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < s; ++j)
+                        if (Tab::a(s, j) != 0.0)
+                            acc = fma(Tab::cb().a[s][j], j < 13 ? K[j < 13 ? j : 0][e] : Ke[j >= 13 ? j - 13 : 0][e], acc);
+                    ys[e] = fma(acc, h, y_old[e]);
+                }
+                __syncthreads();  // the previous users of the buffer are done
+                cta_eval<Rhs, E>(fma(Tab::cb().c[s], h, t_old), ys, p, i0, n, (s & 1) ? buf1 : buf0, Ke[s - 13]);
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const double dy = y[e] - y_old[e];
+                F[0][e] = dy;
+                F[1][e] = h * K[0][e] - dy;
+                F[2][e] = 2 * dy - h * (K[12][e] + K[0][e]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (Tab::d(r, j) != 0.0)
+                            acc = fma(Tab::cb().d[r][j], j < 13 ? K[j < 13 ? j : 0][e] : Ke[j >= 13 ? j - 13 : 0][e], acc);
+                    F[3 + r][e] = h * acc;
+                }
+            }
+        } else {
+            rk_dense_coeffs<Tab, E>(K, F);
+        }
+    }
+    NBK_DEV void eval(double te, double t_old, double t, const double (&y_old)[E], const double (&y)[E],
+                      double (&out)[E]) const {
+        if constexpr (Tab::DOP) dop853_eval<E>(te, t_old, t, y_old, y, F, out);
+        else rk_dense_eval<Tab, E>(te, t_old, t, y_old, y, F, out);
+    }
+};
 
 // rms(x / scale) over the whole vector (cold path)
 template <int E>
@@ -356,9 +456,11 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
 #pragma unroll
                     for (int s = 0; s <= S; ++s) Kh[s][e] = (cta_inb<FULL>(i, n) && !a.pristine) ? a.K[(idx * (S + 1) + s) * nn + i] : 0.0;
                 }
+                cta_dense<Tab, Rhs, E> dn;
+                dn.prepare(t_old, t, y_old, y, Kh, p, i0, n, buf0, buf1);
                 while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
                     double out[E];
-                    rk_dense<Tab, E>(__ldg(a.tgrid + kout), t_old, t, y_old, y, Kh, out);
+                    dn.eval(__ldg(a.tgrid + kout), t_old, t, y_old, y, out);
 #pragma unroll
                     for (int e = 0; e < E; ++e)
                         if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
@@ -394,14 +496,18 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
             bool done = false;
             if (accept) {
                 if (MODE == NBK_MODE_RUN) {
-                    while (t_new >= te_next) {
-                        double out[E];
-                        rk_dense<Tab, E>(te_next, t, t_new, y, ynew, K, out);
+                    if (t_new >= te_next) {  // the same for every thread of the CTA: prepare() may use barriers
+                        cta_dense<Tab, Rhs, E> dn;
+                        dn.prepare(t, t_new, y, ynew, K, p, i0, n, buf0, buf1);
+                        do {
+                            double out[E];
+                            dn.eval(te_next, t, t_new, y, ynew, out);
 #pragma unroll
-                        for (int e = 0; e < E; ++e)
-                            if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
-                        ++kout;
-                        te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                            for (int e = 0; e < E; ++e)
+                                if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                            ++kout;
+                            te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                        } while (t_new >= te_next);
                     }
                     done = kout >= a.m;
                 } else {
@@ -496,19 +602,6 @@ NBK_DEV void cta_hermite(double te, const double (&ts)[L], const double (&ys)[L]
         const double dy = ys[L - 1][e] - ys[0][e];
         out[e] = ys[0][e] + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * fs[0][e] + T * fs[L - 1][e]));
     }
-}
-
-// f(t, y) of the whole CTA: stage the vector (transposed, see smem_vec), one barrier, evaluate the slice
-template <class Rhs, int E>
-NBK_DEV void cta_eval(double t, const double (&y)[E], const typename Rhs::prm &p, int i0, int n, double *buf,
-                      double (&f)[E]) {
-    const int T = blockDim.x;
-#pragma unroll
-    for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = y[e];
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < E; ++e) f[e] = 0.0;
-    Rhs::template eval<E>(t, y, smem_vec<E>{buf, T}, p, i0, n, f);
 }
 
 // Start-up points of an adaptive first stepper with DEFAULT tolerances (rtol 1e-3, atol 1e-6): dense output at the

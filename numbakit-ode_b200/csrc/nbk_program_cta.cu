@@ -1,5 +1,5 @@
 // nbk_program_cta.cu -- init / run / step kernels of one (method, RHS) pair in the
-// CTA-per-trajectory regime (nbk_cta.cuh).  Macros: NBK_METHOD (23 | 45), NBK_RHS_T (a CTA
+// CTA-per-trajectory regime (nbk_cta.cuh).  Macros: NBK_METHOD (23 | 45 | 853 | 1..5 | 202.. fixed-step), NBK_RHS_T (a CTA
 // right-hand side type), NBK_E (state components per thread), NBK_TAG.  The block size is chosen at
 // launch: ceil(n / NBK_E) rounded up to a warp; dynamic shared memory = (2*T*E + 34) doubles.
 #include "nbk_cta.cuh"
@@ -15,10 +15,13 @@ typedef nbk::tab_rk45 nbk_tab_t;
 #elif NBK_METHOD == 23
 typedef nbk::tab_rk23 nbk_tab_t;
 #define NBK_CTA_ADAPTIVE 1
+#elif NBK_METHOD == 853
+typedef nbk::tab_dop853 nbk_tab_t;  // 13 stage vectors per thread: one or two components per thread (n <= 1024)
+#define NBK_CTA_ADAPTIVE 1
 #elif (NBK_METHOD >= 1 && NBK_METHOD <= 5) || NBK_METHOD == 202 || NBK_METHOD == 203 || NBK_METHOD == 213 || NBK_METHOD == 204 || NBK_METHOD == 238
 #define NBK_CTA_ADAPTIVE 0  // fixed step: Adams-Bashforth-k / ForwardEuler and the fixed-step Runge-Kutta classes
 #else
-#error "the CTA regime implements RungeKutta23/45, AdamsBashforth1..5 and the fixed-step Runge-Kutta classes"
+#error "the CTA regime implements RungeKutta23/45, DOP853, AdamsBashforth1..5 and the fixed-step Runge-Kutta classes"
 #endif
 #ifndef NBK_E
 #define NBK_E 4

@@ -30,7 +30,7 @@ from .util import CaseInsensitiveDict
 
 _INT_MAX = 2**31 - 1
 # method ids the CTA-per-trajectory kernels implement (include/nbkode_b200.h)
-_CTA_METHODS = frozenset({23, 45, 1, 2, 3, 4, 5, 202, 203, 213, 204, 238})
+_CTA_METHODS = frozenset({23, 45, 853, 1, 2, 3, 4, 5, 202, 203, 213, 204, 238})
 
 # device copies of recently used output grids: uploading a grid from pageable host memory makes the
 # driver synchronise the stream, which would serialise back-to-back passes on the same grid

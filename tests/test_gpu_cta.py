@@ -268,9 +268,12 @@ def test_fixed_step_cta_api_linear_and_traced_python():
     a = nbk.RungeKutta4(rd, 0.0, y0, p, h=1e-3)
     b = nbk.RungeKutta4("rd1d", 0.0, y0, p, h=1e-3)
     assert rel(a.run([0.02])[1], b.run([0.02])[1]) <= 1e-11
-    # DOP853 / implicit families are per-thread only: clear errors
-    with pytest.raises(ValueError, match="CTA"):
-        nbk.DOP853("rd1d", 0.0, y0, p)
+    # the implicit families are per-thread only, DOP853 stops at n = 1024: clear errors
+    with pytest.raises(ValueError, match="per-thread"):
+        nbk.BDF2("rd1d", 0.0, y0, p, h=1e-3)
+    y0b, pb = onp.rd1d_ensemble(2, n=2048, seed=2)
+    with pytest.raises(ValueError, match="1024"):
+        nbk.DOP853("rd1d", 0.0, y0b, pb)
 
 
 def test_auto_regime_for_mid_size_traced_systems():
@@ -312,6 +315,83 @@ def test_auto_regime_for_mid_size_traced_systems():
     assert c._regime == 1
     refc = oc.run_ensemble("RungeKutta23", "linear", y0, A, [2.0], rtol=1e-5, atol=1e-8, params_shared=True, nthreads=4)
     assert within(c.run([2.0])[1], refc["ys"], 1e-5, 1e-8).all()
-    # solver classes without a CTA regime stay per-thread (and keep events / DOP853 usable on mid-size systems)
+    # DOP853 has a CTA regime too; regime="thread" keeps the per-thread kernels (e.g. for run_events)
     d = nbk.DOP853(lin, 0.0, y0[:4], rtol=1e-6, atol=1e-9)
-    assert d._regime == 0
+    e = nbk.DOP853(lin, 0.0, y0[:4], rtol=1e-6, atol=1e-9, regime="thread")
+    assert d._regime == 1 and e._regime == 0
+    assert within(d.run([1.0, 2.0])[1], e.run([1.0, 2.0])[1], 1e-6, 1e-9).all() and np.abs(d.n_accepted - e.n_accepted).max() <= 1
+
+
+def test_dop853_in_cta_regime():
+    """DOP853 (explicit.py:282-351, 406-481) with one CTA per trajectory: 13 stage vectors per thread, E5/E3 error norm as
+    two block reductions, dense output with the three extra stages evaluated by the whole CTA.  Against the C oracle on
+    the reaction-diffusion generator: n = 100 (one component per thread, ragged), 512 (the "full" program), 700 (two
+    components per thread); resumed runs, step(), interpolate()."""
+    for n, B in ((100, 6), (512, 4), (700, 4)):
+        y0, p = onp.rd1d_ensemble(B, n=n, seed=11)
+        # keep the grid non-stiff (d = kappa n^2 of order 0.1): the 8th-order pair crosses t = 0.3 in 2-9 steps, and on a
+        # stiff grid two CPU restatements that differ only in FMA contraction are already 6x (n = 512) to 112x (n = 700)
+        # the tolerance apart -- nothing to pin a kernel against
+        p[:, 0] *= 0.1 * (100.0 / n) ** 2
+        ts = [0.5, 2.0, 6.0]
+        ref = oc.run_ensemble("DOP853", "rd1d", y0, p, ts, rtol=1e-6, atol=1e-9, nthreads=4)
+        s = nbk.DOP853("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+        assert s._regime == 1 and rel(s.h, ref["h0"]) < 1e-12
+        t, y = s.run(ts)
+        assert y.shape == (B, 3, n) and (s.status == 0).all() and s.K.shape == (B, 13, n)
+        assert np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
+        assert within(y, ref["ys"], 1e-6, 1e-9).all()
+        r = nbk.DOP853("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+        _, y1 = r.run(ts[:1])
+        _, y2 = r.run(ts[1:])
+        assert np.array_equal(np.concatenate([y1, y2], 1), y)  # split run: same kernels, same arithmetic
+        lo, hi = r.cache.ts
+        mid = float(max(lo.max(), hi.min() - 1e-5))
+        if lo.max() <= mid <= hi.min():
+            assert np.isfinite(r.interpolate(mid)).all()
+    q = nbk.DOP853("rd1d", 0.0, y0[0], p[0], rtol=1e-6, atol=1e-9)
+    tq, yq = q.step(n=4)
+    o = onp.AdaptiveRK("DOP853", onp.rhs_rd1d, 0.0, y0[0], p[0], rtol=1e-6, atol=1e-9)
+    tr, yr = onp.steps(o, n=4)
+    assert rel(tq, tr) < 1e-3 and rel(yq, yr) < 5e-5  # step sizes carry amplified rounding noise (see above)
+    # dense output inside a step against the NumPy restatement's interpolator on a smooth (non-stiff) problem
+    y0s, ps = onp.rd1d_ensemble(1, n=64, seed=12)
+    ps[:, 0] *= 1e-3
+    u = nbk.DOP853("rd1d", 0.0, y0s[0], ps[0], rtol=1e-8, atol=1e-11, regime="cta")
+    v = onp.AdaptiveRK("DOP853", onp.rhs_rd1d, 0.0, y0s[0], ps[0], rtol=1e-8, atol=1e-11)
+    grid = np.linspace(0.05, 2.0, 40)
+    _, yu = u.run(grid)
+    _, yv = onp.run(v, grid)
+    assert u._regime == 1 and rel(yu, yv) < 1e-10
+
+
+def test_cta_edge_shapes():
+    """Limits of the regime: the largest state (n = 8192: 32 components per thread), one above it (refused with the
+    C-ABI's message), a single unbatched trajectory, a grid point at t0, and one trajectory more than resident CTAs."""
+    # n = 8192, B = 3 against the C oracle (stability-limited grid: 3x bar, see test_rd1d_vs_oracle)
+    n = 8192
+    y0, p = onp.rd1d_ensemble(3, n=n, seed=7)
+    p[:, 0] *= 1.0 / 64  # keep the step count small: kappa / dx^2 grows with n^2
+    ref = oc.run_ensemble("RungeKutta45", "rd1d", y0, p, [0.05], rtol=1e-6, atol=1e-9, nthreads=3)
+    s = nbk.RungeKutta45("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    _, y = s.run([0.05])
+    assert s.last_launch()["block"] == 256 and np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
+    assert within(y, ref["ys"], 1e-6, 1e-9, slack=3).all()
+    with pytest.raises((ValueError, nbk.NbkError), match="8192"):
+        nbk.RungeKutta45("rd1d", 0.0, np.zeros((2, 8193)), np.ones((2, 2)))
+    # one unbatched trajectory: reference shapes (m, n), scalar t; the first grid point is t0 itself
+    y1, p1 = onp.rd1d_ensemble(1, n=256, seed=8)
+    u = nbk.RungeKutta45("rd1d", 0.0, y1[0], p1[0], rtol=1e-6, atol=1e-9)
+    t, yy = u.run([0.0, 0.1])
+    assert yy.shape == (2, 256) and np.array_equal(yy[0], y1[0]) and np.ndim(u.t) == 0
+    o = oc.run_ensemble("RungeKutta45", "rd1d", y1, p1, [0.1], rtol=1e-6, atol=1e-9, nthreads=1)
+    assert within(yy[1], o["ys"][0, 0], 1e-6, 1e-9, slack=3).all()
+    # more trajectories than resident CTAs by one: the queue hands the last one to whichever CTA finishes first
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    B = sm * 8 + 1
+    y2, p2 = onp.rd1d_ensemble(B, n=128, seed=9)
+    a = nbk.RungeKutta45("rd1d", 0.0, y2, p2, rtol=1e-6, atol=1e-9)
+    _, ya = a.run([0.2])
+    b = nbk.RungeKutta45("rd1d", 0.0, y2[::-1].copy(), p2[::-1].copy(), rtol=1e-6, atol=1e-9)
+    _, yb = b.run([0.2])
+    assert np.array_equal(ya, yb[::-1])  # position in the ensemble does not change a trajectory's result
