@@ -1155,10 +1155,12 @@ NBK_DEV void hermite_window(double te, const double (&ts)[L], const double (&ys)
 
 // The same with the two end points of the window given explicitly (the ring-buffered advance loops below keep the
 // window rotated in registers) and the quotient by fast_div (T within ~1 ulp of the reference's division).
-template <int N>
+// PAST_T0: the caller knows te > t0 (the emission loops: every grid point up to the start of the step was written by an
+// earlier step), so the reference's exact return at the window start is dead code there.
+template <int N, bool PAST_T0 = false>
 NBK_DEV void hermite_ends(double te, double t0, const double (&y0)[N], const double (&f0)[N], double t1, const double (&y1)[N],
                           const double (&f1)[N], double (&out)[N]) {
-    if (te == t0) {
+    if (!PAST_T0 && te == t0) {
 #pragma unroll
         for (int i = 0; i < N; ++i) out[i] = y0[i];
         return;
@@ -1254,75 +1256,84 @@ NBK_DEV void advance_ab(const nbk_kargs &a) {
         // Ring-buffered loop: L consecutive steps are unrolled with the window rotating through the same registers
         // (logical slot l of rotation r is physical slot (l + r) % L), so a push overwrites the oldest slot instead
         // of moving L - 1 slots (AdamsBashforth4 on n = 2: 30 register moves per step in the shifting version).
-        int rot = 0;
+        // A trajectory that stops inside a block SKIPS the block's remaining steps instead of leaving the loop: control
+        // flow rejoins right behind each step, so no values have to be marshalled into fixed registers for a far
+        // exit (the `break` version paid 10 register moves per step for that); `rot` remembers the rotation the
+        // window was left in.  Step counters are 32-bit (the budget is clamped like in the adaptive kernels).
+        int nst = 0, rot = 0;
+        const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
+        const int n_steps = a.n_steps > 2147483647LL ? 2147483647 : (int)a.n_steps;
         double *dst = MODE == NBK_MODE_RUN ? a.y_out + (idx * a.o_sb + kout * a.o_sk) : a.y_out + idx * a.o_sb;
+        const double *tg = a.tgrid + kout + 1;  // RUN: the grid time after te_next, fetched one point ahead
+        double te_after = (MODE == NBK_MODE_RUN && running && kout + 1 < a.m) ? __ldg(tg) : d_inf();
         while (running) {
 #pragma unroll
             for (int r = 0; r < L; ++r) {
                 const int newest = (L - 1 + r) % L, oldest = r % L;
-                if (ts[newest] + h > a.bound) {
+                const double t_new = ts[newest] + h;
+                if (running && t_new > a.bound) {  // guard of this step (core.py:176-184)
                     status = NBK_TRAJ_BOUND;
                     running = false;
-                    rot = r;
-                    break;
                 }
-                const double t_new = ts[newest] + h;
-                double ynew[N], fnew[N];
+                if (running) {
+                    double ynew[N], fnew[N];
 #pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    double acc = hB[0] * fs[(L - ORDER + r) % L][c];
+                    for (int c = 0; c < N; ++c) {
+                        double acc = hB[0] * fs[(L - ORDER + r) % L][c];
 #pragma unroll
-                    for (int j = 1; j < ORDER; ++j) acc = fma(hB[j], fs[(L - ORDER + j + r) % L][c], acc);
-                    ynew[c] = acc + ys[newest][c];
-                }
-                Rhs::eval(t_new, ynew, p, fnew);
-                ts[oldest] = t_new;  // push: the oldest slot becomes the newest one of rotation r + 1
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    ys[oldest][c] = ynew[c];
-                    fs[oldest][c] = fnew[c];
-                }
-                ++nsteps;
-                rot = r + 1;
-                if (MODE == NBK_MODE_RUN) {
-                    while (t_new >= te_next) {
-                        double out[N];
-                        hermite_ends<N>(te_next, ts[(r + 1) % L], ys[(r + 1) % L], fs[(r + 1) % L], t_new, ynew, fnew, out);
-#pragma unroll
-                        for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
-                        dst += a.o_sk;
-                        ++kout;
-                        te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                        for (int j = 1; j < ORDER; ++j) acc = fma(hB[j], fs[(L - ORDER + j + r) % L][c], acc);
+                        ynew[c] = acc + ys[newest][c];
                     }
-                    running = kout < a.m;
-                } else {
-                    if (a.emit) {
-                        a.t_out[idx * a.to_sb + (nsteps - 1)] = t_new;
+                    Rhs::eval(t_new, ynew, p, fnew);
+                    ts[oldest] = t_new;  // push: the oldest slot becomes the newest one of rotation r + 1
 #pragma unroll
-                        for (int c = 0; c < N; ++c) dst[c * a.o_sc] = ynew[c];
-                        dst += a.o_sk;
+                    for (int c = 0; c < N; ++c) {
+                        ys[oldest][c] = ynew[c];
+                        fs[oldest][c] = fnew[c];
                     }
-                    running = nsteps < a.n_steps;
+                    ++nst;
+                    rot = (r + 1) % L;
+                    if (MODE == NBK_MODE_RUN) {
+                        while (t_new >= te_next) {
+                            double out[N];
+                            hermite_ends<N, true>(te_next, ts[(r + 1) % L], ys[(r + 1) % L], fs[(r + 1) % L], t_new, ynew, fnew, out);
+#pragma unroll
+                            for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
+                            dst += a.o_sk;
+                            ++kout;
+                            ++tg;
+                            te_next = te_after;
+                            te_after = kout + 1 < a.m ? __ldg(tg) : d_inf();
+                        }
+                        running = kout < a.m;
+                    } else {
+                        if (a.emit) {
+                            a.t_out[idx * a.to_sb + (nst - 1)] = t_new;
+#pragma unroll
+                            for (int c = 0; c < N; ++c) dst[c * a.o_sc] = ynew[c];
+                            dst += a.o_sk;
+                        }
+                        running = nst < n_steps;
+                    }
+                    if (running && nst >= max_att) {
+                        status = NBK_TRAJ_MAXATTEMPTS;
+                        running = false;
+                    }
                 }
-                if (running && nsteps >= a.max_attempts) {
-                    status = NBK_TRAJ_MAXATTEMPTS;
-                    running = false;
-                }
-                if (!running) break;
             }
         }
-        if (nsteps > 0) {
-            switch (rot % L) {
+        if (nst > 0) {
+            switch (rot) {
                 case 0: store_window<L, N, 0>(a, idx, ts, ys, fs); break;
                 case 1: store_window<L, N, 1 % L>(a, idx, ts, ys, fs); break;
                 case 2: store_window<L, N, 2 % L>(a, idx, ts, ys, fs); break;
                 case 3: store_window<L, N, 3 % L>(a, idx, ts, ys, fs); break;
                 default: store_window<L, N, 4 % L>(a, idx, ts, ys, fs); break;
             }
-            a.n_acc[idx] += nsteps;
+            a.n_acc[idx] += nst;
         }
         store_status(a, idx, status);
-        a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : (int)nsteps;
+        a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nst;
         return;
     }
     while (running) {
