@@ -10,6 +10,8 @@ import nbkode_b200 as nbk
 from oracle import nbk_oracle_np as onp
 
 which = sys.argv[1] if len(sys.argv) > 1 else "rd1d"
+cls = sys.argv[4] if len(sys.argv) > 4 else "RungeKutta45"  # a fixed-step class runs rd1d with h = 5e-4 to T = 0.1
+fixed = getattr(nbk, cls).FIXED_STEP
 B = int(sys.argv[2]) if len(sys.argv) > 2 else (16384 if which == "rd1d" else 65536)
 peak, _ = nbk.fp64_peak(0, 20000)
 if which == "rd1d":
@@ -18,6 +20,18 @@ if which == "rd1d":
     p[:, 0] *= (n / 2048.0) ** 2  # same h*d (stability-limited step count) on coarser grids
     flop = 6 * 8 * n + 66 * n + 18
     mk = lambda: nbk.RungeKutta45("rd1d", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
+    if cls != "RungeKutta45":
+        if fixed:
+            T = 0.1
+            stages = {"RungeKutta4": 4, "RungeKutta3_8": 4, "Runge3": 4, "Heun3": 3, "Runge2": 2}.get(cls, 1)
+            k = int(cls[-1]) if cls.startswith("AdamsBashforth") else 1
+            # R + 2 k n + k + 1 (Adams-Bashforth-k) / S R + (stage arguments + y_new) (Runge-Kutta), SURVEY.md 8(d)
+            flop = 8 * n + 2 * k * n + k + 1 if stages == 1 else stages * 8 * n + (stages * (stages - 1) + 2 * stages) * n
+            mk = lambda: getattr(nbk, cls)("rd1d", 0.0, y0d, pd, h=5e-4)
+        else:
+            S = {"RungeKutta23": 3, "DOP853": 12}[cls]
+            flop = S * 8 * n + (27 if S == 3 else 171) * n + 18
+            mk = lambda: getattr(nbk, cls)("rd1d", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
 else:
     n, T = 128, 10.0
     y0, p = onp.linear_ensemble(B, n=n, seed=2)
