@@ -38,7 +38,8 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->cta_elems = 1;
     out->cta_full = 0;
     out->mma_tile = nbk::MMA_NT;
-    out->mma_smem = sizeof(double) * (2 * 128 * nbk::MMA_LD + nbk::MMA_WARPS * nbk::MMA_NT) + sizeof(nbk::mma_cols);
+    out->mma_smem = sizeof(double) * (2 * 128 * nbk::MMA_LD + nbk::MMA_WARPS * nbk::MMA_NT) + sizeof(nbk::mma_cols) + 16 +
+                    sizeof(double) * 128 * nbk::MMA_LDA;  // Y staging (2 buffers), reduction scratch, columns, the matrix
     out->k_init = (const void *)&NBK_KERNEL(init);
     out->k_run = (const void *)&NBK_KERNEL(run);
     out->k_step = (const void *)&NBK_KERNEL(step);
