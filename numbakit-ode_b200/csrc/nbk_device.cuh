@@ -2073,14 +2073,20 @@ NBK_DEV void advance_erk(const nbk_kargs &a) {
         if (MODE == NBK_MODE_RUN) {
             if (t_new >= te_next) {
                 double *dst = a.y_out + (idx * a.o_sb + kout * a.o_sk);
+                // te_next > ts[0] here (earlier grid points were written by earlier steps); the grid time after the
+                // next one is fetched one point ahead so that the loop condition never waits for a load
+                const double *tg = a.tgrid + kout + 1;
+                double te_after = kout + 1 < a.m ? __ldg(tg) : d_inf();
                 do {
                     double out[N];
-                    hermite_ends<N>(te_next, ts[0], ys[0], fs[0], ts[1], ys[1], fs[1], out);
+                    hermite_ends<N, true>(te_next, ts[0], ys[0], fs[0], ts[1], ys[1], fs[1], out);
 #pragma unroll
                     for (int c = 0; c < N; ++c) dst[c * a.o_sc] = out[c];
                     dst += a.o_sk;
                     ++kout;
-                    te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                    ++tg;
+                    te_next = te_after;
+                    te_after = kout + 1 < a.m ? __ldg(tg) : d_inf();
                 } while (t_new >= te_next);
             }
             running = kout < a.m;

@@ -18,7 +18,10 @@ except Exception:
 y0, p = onp.vdp_ensemble(B, seed=1)
 y0d, pd = torch.from_numpy(y0).cuda(), torch.from_numpy(p).cuda()
 ts = np.linspace(0, 20, m)
-for cls, kw in (("RungeKutta23", dict(rtol=1e-6, atol=1e-9)), ("AdamsBashforth4", dict(h=0.01))):
+CASES = [("RungeKutta23", dict(rtol=1e-6, atol=1e-9)), ("AdamsBashforth4", dict(h=0.01))]
+if len(sys.argv) > 3:  # e.g. "RungeKutta4": only that fixed-step class, h = 0.01
+    CASES = [(sys.argv[3], dict(h=0.01))]
+for cls, kw in CASES:
     times = []
     for it in range(6):
         s = getattr(nbk, cls)("vdp", 0.0, y0d, pd, **kw)
