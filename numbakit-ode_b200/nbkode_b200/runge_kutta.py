@@ -51,6 +51,9 @@ class ERK(RungeKutta, abstract=True):
     """Fixed-step explicit Runge-Kutta (nbkode/runge_kutta/explicit.py:9-46, 102-129): default h = 1,
     dense output by the Hermite cubic over the last step."""
 
+    # all trajectories advance in lock-step: dense output written as [m][n][B] (coalesced), like the multistep kernels
+    OUT_LAYOUT = "mnb"
+
     @classproperty
     def stages(cls):
         return len(cls.A)
