@@ -545,7 +545,9 @@ class Solver(ABC):
             return self.run(t) + ([], [])
         torch = _torch()
         if self._regime != 0:
-            raise NotImplementedError("events are implemented for the one-trajectory-per-thread regime (n <= 64)")
+            raise NotImplementedError(
+                "events are implemented for the one-trajectory-per-thread regime (n <= 64)"
+                + ('; construct the solver with regime="thread" to use run_events on this system' if self.n <= 64 else ""))
         ev = _rhs.trace_events(events, self.n, self._p_shape, self.params is not None)
         if not (1 <= ev.n_events <= _lib.MAX_EVENTS):
             raise ValueError(f"between 1 and {_lib.MAX_EVENTS} event functions are supported")
