@@ -28,13 +28,20 @@ AB = ("ForwardEuler", "AdamsBashforth1", "AdamsBashforth2", "AdamsBashforth3", "
 
 
 def make_pair(cls, rname, y0, p, rng):
-    fn = RHS[rname][0]
+    fn = RHS[rname][0] if rname in RHS else onp.rhs_rd1d
     if cls in ADAPTIVE:
         rtol, atol = 10.0 ** rng.uniform(-8, -4), 10.0 ** rng.uniform(-11, -7)
         g = getattr(nbk, cls)(rname, 0.0, y0, p, rtol=rtol, atol=atol)
         o = [onp.AdaptiveRK(cls, fn, 0.0, y0[b], p[b], rtol=rtol, atol=atol) for b in range(len(y0))]
         return g, o, ("adaptive", rtol, atol)
     h = float(rng.choice([0.004, 0.01, 0.02]))
+    if rname == "rd1d" and cls in AB and cls not in ("ForwardEuler", "AdamsBashforth1"):
+        # CTA regime: the start-up is RungeKutta45 (default) or none
+        fs = [None, "RungeKutta45"][int(rng.integers(0, 2))]
+        order = int(cls[-1])
+        g = getattr(nbk, cls)(rname, 0.0, y0, p, h=h, first_stepper_cls=fs)
+        o = [onp.AdamsBashforth(order, fn, 0.0, y0[b], p[b], h=h, first_stepper=fs) for b in range(len(y0))]
+        return g, o, ("fixed", h, 0.0)
     if cls in FIXED_RK:
         g = getattr(nbk, cls)(rname, 0.0, y0, p, h=h)
         o = [onp.FixedRK(cls, fn, 0.0, y0[b], p[b], h=h) for b in range(len(y0))]
@@ -76,6 +83,24 @@ def test_random_call_sequences(seed):
     rname = str(rng.choice(list(RHS)))
     B = int(rng.integers(2, 6))
     y0, p = RHS[rname][2](rng, B)
+    _drive(rng, cls, rname, y0, p)
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_call_sequences_cta_regime(seed):
+    """The same through the CTA-per-trajectory kernels: reaction-diffusion grids of assorted sizes (ragged and "full"
+    shapes, one / two / four components per thread), diffusion scaled down so that the grid is not stiff."""
+    rng = np.random.default_rng(5000 + seed)
+    cls = str(rng.choice(ADAPTIVE + FIXED_RK + AB))
+    n = int(rng.choice([40, 64, 100, 128, 300, 512]))
+    B = int(rng.integers(2, 5))
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=int(rng.integers(0, 1 << 30)))
+    p[:, 0] *= 0.05 * (100.0 / n) ** 2
+    g = _drive(rng, cls, "rd1d", y0, p)
+    assert g._regime == 1
+
+
+def _drive(rng, cls, rname, y0, p):
     g, o, kind = make_pair(cls, rname, y0, p, rng)
     # step times of the adaptive pairs: the controller feeds the rounding of the error estimate back into h.  E.K cancels
     # down to the local error (8+ digits at rtol 1e-8; more for DOP853's E5.K / E3.K), so an FMA-contracted and a plain
@@ -130,3 +155,4 @@ def test_random_call_sequences(seed):
                 lim = kind[1] * np.abs(s.y) + kind[2] + 2 * np.abs(s.f) * dt
                 assert (np.abs(np.atleast_2d(g.y)[b] - s.y) <= lim).all(), (cls, rname, op, "y", b)
     assert (np.asarray(g.status) <= 1).all()
+    return g
