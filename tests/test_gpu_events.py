@@ -133,3 +133,43 @@ def test_events_with_implicit_solvers(c):
     assert [len(x) for x in te] == [len(x) for x in c["t_events"]]
     for a, b in zip(te, c["t_events"]):
         assert rel(a, b) < 1e-6
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_events_random_sets_vs_oracle(seed):
+    """Seeded random combinations: solver class (adaptive and fixed-step) x right-hand side x a subset of the oracle's
+    event functions (directional, terminal, time events) x a small ensemble, every trajectory against the NumPy
+    restatement of event_handler.py: the same events in the same order, the same truncation by terminal events."""
+    rng = np.random.default_rng(7000 + seed)
+    rname = str(rng.choice(["lorenz", "vdp"]))
+    names = ["y0", "y1_down", "time", "y0_up_terminal"] + (["z25_up", "x_m8_terminal"] if rname == "lorenz" else [])
+    events = [onp.EVENTS[e] for e in rng.choice(names, size=int(rng.integers(1, 4)), replace=False)]
+    B = int(rng.integers(2, 7))
+    y0, p = (onp.lorenz_ensemble if rname == "lorenz" else onp.vdp_ensemble)(B, seed=int(rng.integers(0, 1 << 30)))
+    fn = onp.RHS[rname]
+    cls = str(rng.choice(["RungeKutta45", "RungeKutta23", "DOP853", "RungeKutta4", "AdamsBashforth2", "ForwardEuler"]))
+    if cls in ("RungeKutta45", "RungeKutta23", "DOP853"):
+        kw = dict(rtol=1e-8, atol=1e-10)
+        mk = lambda b: onp.AdaptiveRK(cls, fn, 0.0, y0[b], p[b], **kw)  # noqa: E731
+    elif cls == "RungeKutta4":
+        kw = dict(h=0.002)
+        mk = lambda b: onp.FixedRK(cls, fn, 0.0, y0[b], p[b], **kw)  # noqa: E731
+    else:
+        kw = dict(h=0.0005)
+        mk = lambda b: onp.AdamsBashforth(1 if cls == "ForwardEuler" else 2, fn, 0.0, y0[b], p[b], **kw)  # noqa: E731
+    ts = np.sort(rng.uniform(0.2, 3.0 if rname == "lorenz" else 6.0, int(rng.integers(2, 9))))
+    s = getattr(nbk, cls)(rname, 0.0, y0, p, **kw)
+    t, y, te, ye = s.run_events(ts, events)
+    # Lorenz separates nearby trajectories by e^(0.9 t): event times inherit the amplified rounding differences
+    tol_t, tol_y = (2e-5, 2e-3) if rname == "lorenz" else (1e-6, 1e-4)
+    for i in range(B):
+        to, yo, teo, yeo = onp.run_events(mk(i), ts, events)
+        k = len(to)
+        ti = t[i] if t.ndim == 2 else t
+        assert np.isnan(y[i, k:]).all() and np.isfinite(y[i, :k]).all(), (cls, rname, i)
+        assert rel(ti[:k], to) < tol_t and rel(y[i, :k], np.asarray(yo).reshape(k, -1)) < tol_y, (cls, rname, i)
+        for j in range(len(events)):
+            assert s.event_counts[i, j] == len(teo[j]), (cls, rname, [e.__name__ for e in events], i, j)
+            if teo[j]:
+                assert rel(te[j][i, :len(teo[j])], teo[j]) < tol_t
+                assert rel(ye[j][i, :len(teo[j])], np.array(yeo[j])) < tol_y
