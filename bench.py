@@ -220,6 +220,11 @@ def main():
     import nbkode_b200 as nbk
     from oracle import nbk_oracle_np as onp  # input generator only (SURVEY.md 8(d) distribution)
 
+    # one process per GPU: keep the process (and the pinned buffers it is about to allocate) on the GPU's NUMA node
+    from nbkode_b200 import distributed as nd
+
+    numa_bound = world > 1 and nd.bind_to_gpu_numa(local_rank)
+
     B = args.batch
     y0_np, p_np = onp.lorenz_ensemble(B, seed=rank)
     # host inputs live in pinned memory (e2e arm); device-resident copies for the kernel-only arm
@@ -331,7 +336,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": {**workload_config(world), "trajectories_per_gpu": B},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "host_numa_bound": bool(numa_bound)},
             "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,

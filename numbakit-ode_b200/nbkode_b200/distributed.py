@@ -12,6 +12,33 @@ def rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin this process to the CPUs NVML reports as closest to the GPU (its NUMA node), so that pinned host buffers
+    allocated afterwards (first touch) and the copies that use them stay on the GPU's side of the machine -- what
+    ``numactl --cpunodebind`` would do for a one-process-per-GPU job.  Best effort: returns False and changes nothing
+    if NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            entry = visible.split(",")[device_index].strip()
+            handle = pynvml.nvmlDeviceGetHandleByUUID(entry) if entry.startswith("GPU-") else pynvml.nvmlDeviceGetHandleByIndex(int(entry))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def shard_bounds(n_total: int, rank: int, world: int):
     """Contiguous, near-equal slices: rank r owns [lo, hi); sizes differ by at most one."""
     base, extra = divmod(int(n_total), int(world))
