@@ -96,7 +96,10 @@ typedef struct {
                              (per-thread regime, y/dy in registers) or, for large systems,
                                NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n)
                              (CTA regime: returns component i; y[j] reads component j of the whole vector, which lives in
-                             shared memory).
+                             shared memory).  Shape of the CTA: a right-hand side whose source contains a loop (cost per
+                             component growing with n, e.g. a matrix-vector product) runs with one component per thread
+                             as long as the block allows; loop-free (stencil-like) source with four components per thread
+                             from n = 128 on (measured crossover).
                              Replaces numba.njit(rhs) of nbkode/core.py:125-132. */
     /* VariableStepOptions, nbkode/core.py:661-679 (min_step/max_step are never enforced by
        the reference and therefore absent) */
