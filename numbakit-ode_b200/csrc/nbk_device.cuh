@@ -1064,7 +1064,10 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                             double F[Tab::DOP ? 7 : N][Tab::DOP ? N : Tab::M];
                             if constexpr (Tab::DOP) dop853_prepare<Rhs>(t, t_new, y, ynew, K, p, F);
                             else rk_dense_coeffs<Tab, N>(K, F);
-                            const double inv_H = 1.0 / (t_new - t);
+                            // 1 / H by the reciprocal seed + two Newton steps (truncation 2^-92: the rounded result is
+                            // within an ulp of the IEEE quotient, 5 instructions instead of ~20 with a slow-path call)
+                            const double H = t_new - t, r0 = fast_rcp(H);
+                            const double inv_H = fma(r0, fma(-H, r0, 1.0), r0);
                             double *dst = a.y_out + (idx * a.o_sb + kout * a.o_sk);
                             // the grid time after the next one is fetched one iteration ahead: the loop condition
                             // never waits for a load (it did: 9 % of the warp samples of C3 sat on that compare)
