@@ -149,14 +149,29 @@ struct rhs_linear_cta {  // y' = A y with a shared dense A; params holds A TRANS
 // where y[j] reads component j of the whole stage-argument vector (shared memory).
 struct rhs_user_cta {
     static constexpr int NP = -1;
+#if defined(NBK_CTA_NP) && NBK_CTA_NP > 0
+    // a small per-trajectory parameter block (NBK_CTA_NP <= 16 doubles, known when NVRTC compiles the program) is
+    // copied into registers once per trajectory: the user's p[k] with constant k never touches memory again (it was
+    // a global load behind every barrier)
+    struct prm { double v[NBK_CTA_NP]; };
+    static NBK_DEV prm load(const double *p) {
+        prm q;
+#pragma unroll
+        for (int k = 0; k < NBK_CTA_NP; ++k) q.v[k] = p[k];
+        return q;
+    }
+    static NBK_DEV const double *ptr(const prm &q) { return q.v; }
+#else
     struct prm { const double *p; };
     static NBK_DEV prm load(const double *p) { return prm{p}; }
+    static NBK_DEV const double *ptr(const prm &q) { return q.p; }
+#endif
     template <int E, bool FULL = false>
     static NBK_DEV void eval(double t, const double (&)[E], smem_vec<E> ysm, const prm &q, int i0, int n,
                              double (&dy)[E]) {
 #pragma unroll
         for (int e = 0; e < E; ++e)  // slots beyond n recompute component n-1 (never stored): no branches
-            dy[e] = nbk_rhs_i(t, ysm, q.p, cta_inb<FULL>(i0 + e, n) ? i0 + e : n - 1, n);
+            dy[e] = nbk_rhs_i(t, ysm, ptr(q), cta_inb<FULL>(i0 + e, n) ? i0 + e : n - 1, n);
     }
 };
 #endif

@@ -14,12 +14,21 @@ cls = sys.argv[4] if len(sys.argv) > 4 else "RungeKutta45"  # a fixed-step class
 fixed = getattr(nbk, cls).FIXED_STEP
 B = int(sys.argv[2]) if len(sys.argv) > 2 else (16384 if which == "rd1d" else 65536)
 peak, _ = nbk.fp64_peak(0, 20000)
+traced = which == "rd1d_py"  # the same right-hand side as a NumPy-style Python callable (vector tracer -> nbk_rhs_i -> NVRTC)
+if traced:
+    which = "rd1d"
+
+
+def rd1d_py(t, y, p):
+    return p[0] * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + p[1] * y * (1 - y)
+
+
 if which == "rd1d":
     n, T = (int(sys.argv[3]) if len(sys.argv) > 3 else 2048), 1.0
     y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
     p[:, 0] *= (n / 2048.0) ** 2  # same h*d (stability-limited step count) on coarser grids
     flop = 6 * 8 * n + 66 * n + 18
-    mk = lambda: nbk.RungeKutta45("rd1d", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
+    mk = lambda: nbk.RungeKutta45(rd1d_py if traced else "rd1d", 0.0, y0d, pd, rtol=1e-6, atol=1e-9)
     if cls != "RungeKutta45":
         if fixed:
             T = 0.1
