@@ -776,6 +776,42 @@ NBK_DEV void cta_init_fixed(const nbk_kargs &a, double *sm) {
     }
 }
 
+// window Hermite with the two ends given explicitly, for te behind the window start (the emission loop of the
+// ring-buffered Adams-Bashforth path below)
+template <int E>
+NBK_DEV void cta_hermite_ends(double te, double t0, const double (&y0)[E], const double (&f0)[E], double t1,
+                              const double (&y1)[E], const double (&f1)[E], double (&out)[E]) {
+    const double dt = t1 - t0;
+    const double T = (te - t0) / dt;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const double dy = y1[e] - y0[e];
+        out[e] = y0[e] + T * dy + T * (T - 1) * ((1 - 2 * T) * dy + dt * ((T - 1) * f0[e] + T * f1[e]));
+    }
+}
+
+// history window of a CTA -> HBM, logical slot l living in physical slot (l + ROT) % L
+template <int L, int E, int ROT>
+NBK_DEV void cta_store_window(const nbk_kargs &a, long long idx, int n, int i0, const double (&ts)[L],
+                              const double (&ys)[L][E], const double (&fs)[L][E]) {
+    const long long nn = n;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = i0 + e;
+        if (i < n) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                a.ys[(idx * L + l) * nn + i] = ys[(l + ROT) % L][e];
+                a.fs[(idx * L + l) * nn + i] = fs[(l + ROT) % L][e];
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) a.ts[idx * L + l] = ts[(l + ROT) % L];
+    }
+}
+
 template <int METHOD, class Rhs, int E, int MODE>
 NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
     using TR = cta_fixed_traits<METHOD>;
@@ -828,6 +864,86 @@ NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
             running = a.n_steps > 0;
         }
         int flip = 0;
+        if constexpr (!TR::ERK && (L > 2)) {
+            // AdamsBashforth3..5: the window is a ring in registers like in the per-thread kernel (advance_ab) -- L
+            // steps unrolled, a push overwrites the oldest slot (the shifting loop below moved (L-1)(2E+1) doubles per
+            // step), a trajectory that stops inside the block skips the rest of it.  Control flow is the same in every
+            // thread of the CTA, so the barriers inside cta_eval are safe.
+            constexpr int ORDER = METHOD;
+            int nst = 0, rot = 0;
+            const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
+            const int n_steps = a.n_steps > 2147483647LL ? 2147483647 : (int)a.n_steps;
+            while (running) {
+#pragma unroll
+                for (int r = 0; r < L; ++r) {
+                    const int newest = (L - 1 + r) % L, oldest = r % L;
+                    const double t_new = ts[newest] + h;
+                    if (running && t_new > a.bound) {
+                        status = NBK_TRAJ_BOUND;
+                        running = false;
+                    }
+                    if (running) {
+                        double ynew[E], fnew[E];
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            double acc = (h * tab_ab<ORDER>::b(0)) * fs[(L - ORDER + r) % L][e];
+#pragma unroll
+                            for (int j = 1; j < ORDER; ++j) acc = fma(h * tab_ab<ORDER>::b(j), fs[(L - ORDER + j + r) % L][e], acc);
+                            ynew[e] = acc + ys[newest][e];
+                        }
+                        cta_eval<Rhs, E>(t_new, ynew, p, i0, n, (flip ^= 1) ? buf1 : buf0, fnew);
+                        ts[oldest] = t_new;
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            ys[oldest][e] = ynew[e];
+                            fs[oldest][e] = fnew[e];
+                        }
+                        ++nst;
+                        rot = (r + 1) % L;
+                        if (MODE == NBK_MODE_RUN) {
+                            while (t_new >= te_next) {
+                                double out[E];
+                                cta_hermite_ends<E>(te_next, ts[(r + 1) % L], ys[(r + 1) % L], fs[(r + 1) % L], t_new, ynew, fnew, out);
+#pragma unroll
+                                for (int e = 0; e < E; ++e)
+                                    if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                                ++kout;
+                                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                            }
+                            running = kout < a.m;
+                        } else {
+                            if (a.emit) {
+                                if (tid == 0) a.t_out[idx * a.to_sb + (nst - 1)] = t_new;
+#pragma unroll
+                                for (int e = 0; e < E; ++e)
+                                    if (i0 + e < n) a.y_out[idx * a.o_sb + (nst - 1) * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
+                            }
+                            running = nst < n_steps;
+                        }
+                        if (running && nst >= max_att) {
+                            status = NBK_TRAJ_MAXATTEMPTS;
+                            running = false;
+                        }
+                    }
+                }
+            }
+            if (nst > 0) {
+                switch (rot) {
+                    case 0: cta_store_window<L, E, 0>(a, idx, n, i0, ts, ys, fs); break;
+                    case 1: cta_store_window<L, E, 1 % L>(a, idx, n, i0, ts, ys, fs); break;
+                    case 2: cta_store_window<L, E, 2 % L>(a, idx, n, i0, ts, ys, fs); break;
+                    case 3: cta_store_window<L, E, 3 % L>(a, idx, n, i0, ts, ys, fs); break;
+                    default: cta_store_window<L, E, 4 % L>(a, idx, n, i0, ts, ys, fs); break;
+                }
+            }
+            if (tid == 0) {
+                if (nst > 0) a.n_acc[idx] += nst;
+                a.status[idx] = status;
+                if (status >= NBK_TRAJ_NONFINITE) atomicAdd(a.work_counter + 1, 1ULL);
+                a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nst;
+            }
+            continue;  // next trajectory of this CTA
+        }
         while (running) {  // identical control flow in every thread of the CTA
             if (ts[L - 1] + h > a.bound) {
                 status = NBK_TRAJ_BOUND;
