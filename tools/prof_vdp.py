@@ -9,7 +9,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 cls = sys.argv[3] if len(sys.argv) > 3 else "RungeKutta23"
 y0, p = onp.vdp_ensemble(B, seed=1)
-s = getattr(nbk, cls)("vdp", 0.0, torch.from_numpy(y0).cuda(), torch.from_numpy(p).cuda(), rtol=1e-6, atol=1e-9)
+kw = dict(h=0.01) if getattr(nbk, cls).FIXED_STEP else dict(rtol=1e-6, atol=1e-9)
+s = getattr(nbk, cls)("vdp", 0.0, torch.from_numpy(y0).cuda(), torch.from_numpy(p).cuda(), **kw)
 t, y = s.run(np.linspace(0, 20, m))
 torch.cuda.synchronize()
 print(int(s._nacc.sum()), int(s._nrej.sum()), s.last_launch())
