@@ -236,7 +236,15 @@ class Vec:
             fn = "fmax" if name == "maximum" else "fmin"
             return _vec_binary(inputs[0], inputs[1], None, lambda a, b: f"{fn}({a}, {b})")
         if name == "matmul" and len(inputs) == 2:
-            return _vec_matmul(inputs[0], inputs[1])
+            return _vec_matmul(inputs[0], inputs[1]) if isinstance(inputs[1], Vec) and not isinstance(inputs[0], Vec) \
+                else _vec_dot(inputs[0], inputs[1])
+        compare = {"less": "<", "less_equal": "<=", "greater": ">", "greater_equal": ">="}
+        if name in compare and len(inputs) == 2:
+            return _vec_binary(inputs[0], inputs[1], compare[name])
+        if name == "sign" and len(inputs) == 1:
+            return _vec_unary(inputs[0], lambda a: f"(({a}) > 0.0 ? 1.0 : (({a}) < 0.0 ? -1.0 : 0.0))")
+        if name == "reciprocal" and len(inputs) == 1:
+            return _vec_unary(inputs[0], lambda a: f"(1.0 / ({a}))")
         raise TraceError(f"numpy.{name} cannot be traced into a component-wise right-hand side")
 
     def __array_function__(self, func, types, args, kwargs):
@@ -259,6 +267,14 @@ class Vec:
     def __abs__(self): return _vec_unary(self, lambda a: f"fabs({a})")
     def __pow__(self, e): return _vec_pow(self, e)
     def __rmatmul__(self, m): return _vec_matmul(m, self)
+    def __matmul__(self, o): return _vec_dot(self, o)
+    def __lt__(self, o): return _vec_binary(self, o, "<")
+    def __le__(self, o): return _vec_binary(self, o, "<=")
+    def __gt__(self, o): return _vec_binary(self, o, ">")
+    def __ge__(self, o): return _vec_binary(self, o, ">=")
+    def sum(self, axis=None): return _vec_sum(self)
+    def mean(self, axis=None): return _vec_sum(self) / float(self.length)
+    def dot(self, o): return _vec_dot(self, o)
     def __len__(self): return self.length
 
     @property
@@ -284,7 +300,8 @@ class Vec:
         if isinstance(key, slice):
             a, b, st = key.indices(self.length)
             if st != 1:
-                raise TraceError("only unit-stride slices can be traced")
+                count = len(range(a, b, st))  # any stride, e.g. y[::-1] or y[::2]
+                return Vec(count, lambda j, a=a, st=st, c=self.code: c(f"({a} + ({st}) * ({j}))"))
             return Vec(max(b - a, 0), lambda j, a=a, c=self.code: c(f"({j} + {a})" if a else j))
         raise TraceError("only integer and slice indices can be traced")
 
@@ -471,6 +488,86 @@ def _vec_matmul(m, v):
         "__device__ __forceinline__ double {name}(int i, double t, nbk_vec y, const double* p) {{\n"
         f"    double s = 0.0;\n    for (int j = 0; j < {n}; ++j) s = fma({row('i')}, {v.code('j')}, s);\n    return s;\n}}}}")
     return Vec(m.shape[0], lambda i, fn=fn: f"{fn}({i}, t, y, p)")
+
+
+def _vec_sum(v):
+    """Sum of all elements: a scalar every component can use, emitted as one helper function with a loop (each
+    component re-evaluates it: O(n) work per component, like a matrix row)."""
+    if not isinstance(v, Vec):
+        raise TraceError("only traced vectors can be summed")
+    fn = _TABLES.add_function(
+        "__device__ __forceinline__ double {name}(double t, nbk_vec y, const double* p) {{\n"
+        f"    double s = 0.0;\n    for (int j = 0; j < {v.length}; ++j) s += {v.code('j')};\n    return s;\n}}}}")
+    return Sc(f"{fn}(t, y, p)")
+
+
+def _vec_dot(a, b):
+    """vector . vector (one of them may be a captured 1-D NumPy array)."""
+    length = _len_of(a) if _len_of(a) is not None else _len_of(b)
+    if length is None or not (isinstance(a, Vec) or isinstance(b, Vec)):
+        raise TraceError("only dot products that involve a traced vector can be traced")
+    return _vec_sum(_vec_binary(a, b, "*"))
+
+
+@_implements(np.sum)
+def _np_sum(a, axis=None, **kw):
+    return _vec_sum(a)
+
+
+@_implements(np.mean)
+def _np_mean(a, axis=None, **kw):
+    return _vec_sum(a) / float(a.length)
+
+
+@_implements(np.dot)
+def _np_dot(a, b, **kw):
+    if isinstance(b, Vec) and isinstance(a, np.ndarray) and a.ndim == 2:
+        return _vec_matmul(a, b)
+    return _vec_dot(a, b)
+
+
+@_implements(np.diff)
+def _np_diff(a, n=1, axis=-1, **kw):
+    if kw or int(n) < 0:
+        raise TraceError("np.diff(a, n) without prepend / append can be traced")
+    for _ in range(int(n)):
+        a = a[1:] - a[:-1]
+    return a
+
+
+@_implements(np.where)
+def _np_where(cond, a=None, b=None):
+    if a is None or b is None:
+        raise TraceError("np.where(cond, a, b) needs both branches to be traced")
+    length = next((L for L in (_len_of(cond), _len_of(a), _len_of(b)) if L is not None), None)
+    vc, va, vb = _as_vec(cond, length), _as_vec(a, length), _as_vec(b, length)
+    return Vec(length, lambda j, c=vc.code, x=va.code, y=vb.code: f"({c(j)} ? {x(j)} : {y(j)})")
+
+
+@_implements(np.clip)
+def _np_clip(a, a_min=None, a_max=None, **kw):
+    out = a
+    if a_min is not None:
+        out = _vec_binary(out, a_min, None, lambda x, y: f"fmax({x}, {y})")
+    if a_max is not None:
+        out = _vec_binary(out, a_max, None, lambda x, y: f"fmin({x}, {y})")
+    return out
+
+
+@_implements(np.hstack)
+def _np_hstack(parts, **kw):
+    return _np_concatenate(parts)
+
+
+@_implements(np.append)
+def _np_append(a, values, axis=None):
+    return _np_concatenate((a, values))
+
+
+@_implements(np.flip)
+def _np_flip(a, axis=None):
+    n = a.length
+    return Vec(n, lambda j, c=a.code: c(f"({n - 1} - ({j}))"))
 
 
 @_implements(np.roll)
@@ -663,7 +760,13 @@ def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", c
             if n > MAX_TRACED_N:
                 raise ValueError(f"n = {n} needs the CTA regime, which this solver class does not have "
                                  "(RungeKutta23/45, AdamsBashforth*, ForwardEuler and the fixed-step Runge-Kutta classes do)")
-            return None, trace(rhs, n, params_shape, has_params).source
+            try:
+                return None, trace(rhs, n, params_shape, has_params).source
+            except TraceError:
+                # e.g. np.where / comparisons: only the whole-vector tracer can express them (as selects)
+                if regime != "auto" or not cta_ok:
+                    raise
+                return None, trace_cta(rhs, n, params_shape, has_params).source
         # large (and mid-size) systems run one CTA per trajectory: the right-hand side is traced as a whole-vector
         # expression; a function the vector tracer cannot handle falls back to the per-thread form while it can
         try:

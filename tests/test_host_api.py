@@ -272,6 +272,14 @@ def test_vector_tracer_emits_componentwise_cuda_and_compiles():
     assert "nbk_rhs(" in rhs.resolve(rd, 40, (2,), True, "thread")[1]
     assert "nbk_rhs_i" in rhs.resolve(rd, 8, (2,), True, "cta")[1]
     assert "nbk_rhs(" in rhs.resolve(lambda t, y: np.cumsum(y) * 0 + y, 30, (), False)[1]  # cumsum: scalar tracer only
+    # comparisons / np.where are selects in the whole-vector tracer only: a small system that uses them is traced
+    # that way (CTA regime) instead of failing in the component-by-component tracer
+    relu = lambda t, y, p: np.where(y > 0, -y, p[0] * y) + np.diff(np.append(y, 0.0)).sum()  # noqa: E731
+    with pytest.raises(rhs.TraceError):
+        rhs.trace(relu, 6, (1,), True)
+    s3 = rhs.resolve(relu, 6, (1,), True)[1]
+    assert "nbk_rhs_i" in s3 and "?" in s3
+    _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 6, 1, src=s3.encode())), C.byref(sz)))
     with pytest.raises(ValueError):
         rhs.resolve(rd, 100, (2,), True, "auto", False)
     with pytest.raises(rhs.TraceError):
@@ -314,8 +322,18 @@ def test_vector_tracer_values_match_numpy(tmp_path):
         x, yy, z = y
         return np.array([p[0] * (yy - x), x * (p[1] - z) - yy, x * yy - p[2] * z])
 
+    w = rng.standard_normal(40)
+
+    def limiter(t, y, p):  # comparisons / np.where / np.diff / clip / sign / reductions / reversed and strided slices
+        d = np.diff(y)
+        flux = np.where(d > 0, d, 0.5 * d) * (np.abs(d) <= 1.5)
+        out = np.hstack(([0.0], flux)) * p[0] + np.clip(y, -0.5, 0.5) - y.mean() + (y @ y) * 1e-3
+        out = out + y[::-1] * 0.1 + np.sign(y) * 0.01 + np.dot(w, y) * 1e-2 - np.sum(y * y) * p[1] + np.flip(y) * np.exp(-t)
+        return out + np.append(np.diff(y, 2), [1.0, 2.0]) * 0.3 + np.concatenate((y[::2], y[1::2])) * 0.2
+
     for k, (fn, n, par) in enumerate(((heat, 100, [2.5]), (rd, 257, [0.7, 1.3]), (upwind, 90, [3.0]), (lin_const, 33, [0.3]),
-                                      (lin_param, 33, list(rng.standard_normal(33 * 33))), (lorenz_scalar_style, 3, [10.0, 28.0, 2.6]))):
+                                      (lin_param, 33, list(rng.standard_normal(33 * 33))), (lorenz_scalar_style, 3, [10.0, 28.0, 2.6]),
+                                      (limiter, 40, [0.8, 0.05]))):
         src = rhs.trace_cta(fn, n, (33, 33) if fn is lin_param else (len(par),), True).source
         cfile = tmp_path / f"t{k}.cpp"
         cfile.write_text(
