@@ -60,3 +60,13 @@ def test_two_rank_sharding_and_gather():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_bind_to_gpu_numa_is_best_effort():
+    """Without NVML / a GPU the helper changes nothing and says so (bench.py calls it unconditionally for N > 1)."""
+    import os
+
+    before = os.sched_getaffinity(0)
+    assert nd.bind_to_gpu_numa(0) in (True, False)
+    assert os.sched_getaffinity(0) <= before and len(os.sched_getaffinity(0)) > 0
+    os.sched_setaffinity(0, before)
