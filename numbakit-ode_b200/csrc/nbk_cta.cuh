@@ -306,6 +306,11 @@ struct cta_dense {
                 __syncthreads();  // the previous users of the buffer are done
                 cta_eval<Rhs, E>(fma(Tab::cb().c[s], h, t_old), ys, p, i0, n, (s & 1) ? buf1 : buf0, Ke[s - 13]);
             }
+            // the last evaluation read buf1, which the first stage of the NEXT attempt writes without a barrier of its
+            // own in between (stages rely on the alternation of the two buffers): close the window here.  Found by the
+            // host emulation of the block (tests/test_cta_logic_host.py); real warps run close enough to lock-step
+            // that the GPU tests never saw it.
+            __syncthreads();
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const double dy = y[e] - y_old[e];

@@ -200,3 +200,118 @@ class EmulEnsemble:
     t = property(lambda self: self.ts[-1].copy())
     y = property(lambda self: self.ys[-1].T.copy())
     f = property(lambda self: self.fs[-1].T.copy())
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CTA-per-trajectory regime (csrc/nbk_cta.cuh) on the host: one block of T POSIX threads (nbk_emul_cta.cpp)
+# --------------------------------------------------------------------------------------------------------------------
+CTA_RHS_TYPES = {"rd1d": ("nbk::rhs_rd1d_cta", 2), "linear": ("nbk::rhs_linear_cta", -1)}
+
+
+def cta_shape(mid, rhs, n):
+    """Mirror of cta_shape() / cta_block() in csrc/nbk_api.cu -> (components per thread, block, full)."""
+    if n > 2048:
+        e = (n + 255) // 256
+    elif mid == 853:
+        e = 1 if n <= 512 else 2
+    elif rhs == "linear":
+        e = 1 if n <= 512 else (2 if n <= 1024 else 4)
+    else:
+        e = 1 if n <= 64 else (2 if n < 128 else 4)
+    t = ((n + e - 1) // e + 31) // 32 * 32
+    return e, t, int(mid in (23, 45, 853) and t * e == n)
+
+
+def _program_cta(method, rhs, elems, full):
+    tag = f"m{method}_{rhs}_e{elems}{'f' if full else ''}"
+    if ("cta", tag) in _libs:
+        return _libs[("cta", tag)]
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, f"libemul_cta_{tag}.so")
+    deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_cta.cuh", "nbk_kargs.h", "nbk_program_cta.cu", "nbk_dop853_coeffs.h")]
+    deps += [os.path.join(HERE, f) for f in ("nbk_emul_cta.cpp", "cuda_host_shim.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call([
+            "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-ffp-contract=off",
+            "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}", f"-DNBK_RHS_T={CTA_RHS_TYPES[rhs][0]}",
+            f"-DNBK_TAG={tag}", f"-DNBK_E={elems}", "-DNBK_CTA_MAXT=512", f"-DNBK_CTA_FULL={full}",
+            os.path.join(HERE, "nbk_emul_cta.cpp"), "-o", so,
+        ])
+    fn = getattr(C.CDLL(so), f"emul_cta_{tag}")
+    fn.argtypes = [C.c_int, C.POINTER(KArgs), C.c_int]
+    _libs[("cta", tag)] = fn
+    return fn
+
+
+class EmulCtaEnsemble:
+    """Host mirror of the Solver around the C-ABI for the CTA regime (trajectory-major state: ts [B][L], ys/fs [B][L][n],
+    K [B][rows][n]); same methods as EmulEnsemble."""
+
+    def __init__(self, method, rhs, y0, params, *, t0=0.0, h=None, first_step=None, rtol=1e-3, atol=1e-6,
+                 min_factor=0.2, max_factor=10.0, safety_factor=0.9, first_stepper=45, params_shared=False):
+        self.mid = METHOD_IDS[method]
+        y0 = np.ascontiguousarray(np.atleast_2d(np.asarray(y0, float)))
+        self.B, self.n = y0.shape
+        params = np.ascontiguousarray(np.asarray(params, float))
+        params = params.reshape(1, -1) if params_shared else params.reshape(self.B, -1)
+        self.np_ = params.shape[1]
+        self.E, self.T, self.full = cta_shape(self.mid, rhs, self.n)
+        self.fn = _program_cta(self.mid, rhs, self.E, self.full)
+        adaptive = self.mid in (23, 45, 853)
+        self.L = 2 if (adaptive or self.mid in ERK_STAGES) else max(self.mid, 2)
+        self.SR = {23: 4, 45: 7, 853: 13, **ERK_STAGES}.get(self.mid, 0)
+        B, n = self.B, self.n
+        self.ts = np.zeros((B, self.L)); self.ys = np.zeros((B, self.L, n)); self.fs = np.zeros((B, self.L, n))
+        self.K = np.zeros((B, max(self.SR, 1), n)); self.h = np.zeros(B)
+        self.p = np.zeros((self.np_,) if params_shared else (B, self.np_))
+        if params_shared:
+            self.p[:] = params[0]
+        self.nacc = np.zeros(B, np.int64); self.nrej = np.zeros(B, np.int64)
+        self.status = np.zeros(B, np.int32); self.nout = np.zeros(B, np.int32)
+        self.counter = np.zeros(2, np.uint64)
+        root = {45: 10, 853: 16}.get(self.mid, 6)
+        self.base = dict(
+            B=B, n=n, n_params=self.np_, ts=self.ts.ctypes.data, ys=self.ys.ctypes.data, fs=self.fs.ctypes.data,
+            K=self.K.ctypes.data, h=self.h.ctypes.data, params=self.p.ctypes.data, n_acc=self.nacc.ctypes.data,
+            n_rej=self.nrej.ctypes.data, status=self.status.ctypes.data, n_out=self.nout.ctypes.data,
+            params_shared=int(params_shared), first_stepper=first_stepper or 0, rtol=rtol, atol=atol,
+            min_factor=min_factor, max_factor=max_factor, safety=safety_factor,
+            x_lo=0.5 * (safety_factor / max_factor) ** root, x_hi=2.0 * (safety_factor / min_factor) ** root,
+            bound=math.inf, max_attempts=2**31 - 1, work_counter=self.counter.ctypes.data,
+        )
+        hh = first_step if adaptive else (1.0 if h is None else h)
+        a = KArgs(**self.base)
+        a.y0, a.y0_sb, a.y0_sc = y0.ctypes.data, n, 1
+        a.p0, a.p0_sb, a.p0_sc = params.ctypes.data, self.np_, 1
+        a.t0, a.h_init = t0, (math.nan if hh is None else hh)
+        self._keep = (y0, params)
+        assert self.fn(0, C.byref(a), self.T) == 0
+        self._pristine = True
+
+    def run(self, ts, t_bound=math.inf):
+        ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
+        m = ts.size
+        out = np.full((self.B, m, self.n), np.nan)
+        a = KArgs(**self.base)
+        a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
+        a.pristine, self._pristine = int(self._pristine), False
+        a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
+        self.counter[:] = 0
+        assert self.fn(1, C.byref(a), self.T) == 0
+        return out
+
+    def step(self, n_steps, bound=math.inf, emit=True):
+        t_out = np.full((self.B, max(n_steps, 1)), np.nan)
+        y_out = np.full((self.B, max(n_steps, 1), self.n), np.nan)
+        a = KArgs(**self.base)
+        a.bound, a.n_steps, a.emit = bound, n_steps, int(emit)
+        a.pristine, self._pristine = int(self._pristine), False
+        a.t_out, a.to_sb = t_out.ctypes.data, max(n_steps, 1)
+        a.y_out, a.o_sb, a.o_sk, a.o_sc = y_out.ctypes.data, max(n_steps, 1) * self.n, self.n, 1
+        self.counter[:] = 0
+        assert self.fn(2, C.byref(a), self.T) == 0
+        return t_out, y_out, self.nout.copy()
+
+    t = property(lambda self: self.ts[:, -1].copy())
+    y = property(lambda self: self.ys[:, -1].copy())
+    f = property(lambda self: self.fs[:, -1].copy())

@@ -1,0 +1,108 @@
+"""Kernel-logic tests of the CTA-per-trajectory regime without a GPU: csrc/nbk_cta.cuh + nbk_program_cta.cu compiled
+for the host, a thread block emulated by T POSIX threads (tests/emul/nbk_emul_cta.cpp: __syncthreads = barrier, warp
+shuffles = exchange through a scratch array), against the NumPy restatement of the reference.  Covers what the
+single-lane emulation of the per-thread kernels cannot: stage arguments through "shared memory", halo reads, block
+reductions, ragged and "full" shapes, the ring-buffered multistep window, DOP853's two-norm error estimate and its
+dense output evaluated by the whole block.  GPU-only aspects (FMA contraction, MUFU seeds, real warps) are covered by
+the -m gpu parity tests."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+from emul import EmulCtaEnsemble, cta_shape  # noqa: E402
+
+from oracle import nbk_oracle_np as onp  # noqa: E402
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b))) / max(1.0, float(np.max(np.abs(b)))) if a.size else 0.0
+
+
+def ensemble(B, n, seed, scale=0.05):
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=seed)
+    p[:, 0] *= scale * (100.0 / n) ** 2  # a non-stiff grid: rounding differences stay at rounding level
+    return y0, p
+
+
+def test_shape_rule_matches_the_launcher():
+    """emul.cta_shape restates cta_shape() / cta_block() of csrc/nbk_api.cu (components per thread, block, full)."""
+    assert cta_shape(45, "rd1d", 48) == (1, 64, 0)
+    assert cta_shape(45, "rd1d", 64) == (1, 64, 1)
+    assert cta_shape(45, "rd1d", 100) == (2, 64, 0)
+    assert cta_shape(45, "rd1d", 128) == (4, 32, 1)
+    assert cta_shape(45, "rd1d", 1000) == (4, 256, 0)
+    assert cta_shape(45, "rd1d", 2048) == (4, 512, 1)
+    assert cta_shape(4, "rd1d", 2048) == (4, 512, 0)      # fixed step: the any-n program
+    assert cta_shape(853, "rd1d", 512) == (1, 512, 1) and cta_shape(853, "rd1d", 700) == (2, 352, 0)
+    assert cta_shape(45, "linear", 128) == (1, 128, 1)
+    assert cta_shape(45, "rd1d", 3000) == (12, 256, 0)
+
+
+@pytest.mark.parametrize("cls,n", [("RungeKutta45", 48), ("RungeKutta45", 100), ("RungeKutta45", 128), ("RungeKutta23", 128),
+                                   ("RungeKutta23", 70), ("DOP853", 100), ("DOP853", 96)])
+def test_adaptive_cta_vs_numpy_restatement(cls, n):
+    """run() with dense output, a resumed run, step() and the t_bound guard for the adaptive classes; ragged shapes
+    (n = 48, 70, 100), the "full" programs (n = 96, 128)."""
+    B = 3
+    y0, p = ensemble(B, n, seed=21)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    # step SIZES carry the rounding of the error estimate (std::fma in the stencil against NumPy's two roundings);
+    # DOP853's E5.K / E3.K cancel more digits than the 5(4) and 3(2) pairs' E.K
+    tol_t = 1e-6 if cls == "DOP853" else 1e-9
+    g = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+    ts = [0.4, 1.0, 2.5]
+    out = g.run(ts[:2])
+    out2 = g.run(ts[2:])
+    assert (g.status == 0).all()
+    for b in range(B):
+        o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **kw)
+        _, yo = onp.run(o, ts)
+        got = np.concatenate([out[b], out2[b]])
+        assert np.all(np.abs(got - yo) <= 1e-3 * (1e-6 * np.abs(yo) + 1e-9)), (cls, n, b)
+        assert g.nacc[b] == o.n_accepted and g.nrej[b] == o.n_rejected
+        assert rel(g.t[b], o.t) < tol_t and rel(g.y[b], o.y) < tol_t
+    # step(): every accepted step of each trajectory
+    s = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+    t_out, y_out, counts = s.step(4)
+    for b in range(B):
+        o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **kw)
+        to, yo = onp.steps(o, n=4)
+        assert counts[b] == 4 and rel(t_out[b], to) < tol_t and rel(y_out[b], yo) < tol_t
+    # t_bound: trajectories stop before the first step that would pass it, later grid points stay NaN
+    q = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+    outb = q.run([0.2, 5.0], t_bound=0.6)
+    assert (q.status == 1).all() and np.isnan(outb[:, 1]).all() and (q.t <= 0.6).all()
+
+
+@pytest.mark.parametrize("cls,n,fs", [("AdamsBashforth4", 100, 45), ("AdamsBashforth4", 128, 0), ("AdamsBashforth3", 48, 45),
+                                      ("AdamsBashforth5", 70, 23), ("AdamsBashforth2", 100, 45), ("ForwardEuler", 128, 0),
+                                      ("RungeKutta4", 100, 0), ("Heun3", 128, 0)])
+def test_fixed_step_cta_vs_numpy_restatement(cls, n, fs):
+    """Fixed-step classes in the CTA regime: AdamsBashforth3..5 through the ring-buffered loop (start-up RungeKutta45 /
+    RungeKutta23 / none), AdamsBashforth2 / ForwardEuler through the shifting loop, the fixed-step Runge-Kutta classes;
+    dense output on a grid that straddles steps, a resumed run and step(), all to 1e-12."""
+    B, h = 2, 0.01
+    y0, p = ensemble(B, n, seed=33)
+    g = EmulCtaEnsemble(cls, "rd1d", y0, p, h=h, first_stepper=fs)
+    ts = np.array([0.005, 0.0312, 0.1, 0.1049, 0.25])
+    out = np.concatenate([g.run(ts[:3]), g.run(ts[3:])], axis=1)
+    tq, yq, counts = g.step(5)
+    assert (g.status == 0).all() and (counts == 5).all()
+    for b in range(B):
+        if cls in ("RungeKutta4", "Heun3"):
+            o = onp.FixedRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], h=h)
+        else:
+            order = 1 if cls == "ForwardEuler" else int(cls[-1])
+            o = onp.AdamsBashforth(order, onp.rhs_rd1d, 0.0, y0[b], p[b], h=h,
+                                   first_stepper={45: "RungeKutta45", 23: "RungeKutta23", 0: None}[fs])
+        _, yo = onp.run(o, ts)
+        assert rel(out[b], yo) < 1e-12, (cls, n, fs, b, rel(out[b], yo))
+        to, ys = onp.steps(o, n=5)
+        assert rel(tq[b], to) < 1e-12 and rel(yq[b], ys) < 1e-12
+        assert rel(g.t[b], o.t) < 1e-12 and rel(g.y[b], o.y) < 1e-12 and rel(g.f[b], o.f) < 1e-11
