@@ -106,3 +106,43 @@ def test_fixed_step_cta_vs_numpy_restatement(cls, n, fs):
         to, ys = onp.steps(o, n=5)
         assert rel(tq[b], to) < 1e-12 and rel(yq[b], ys) < 1e-12
         assert rel(g.t[b], o.t) < 1e-12 and rel(g.y[b], o.y) < 1e-12 and rel(g.f[b], o.f) < 1e-11
+
+
+@pytest.mark.parametrize("cls,n,kw", [("RungeKutta45", 100, dict(rtol=1e-6, atol=1e-9)), ("RungeKutta23", 128, dict(rtol=1e-5, atol=1e-8)),
+                                      ("DOP853", 100, dict(rtol=1e-6, atol=1e-9)), ("DOP853", 96, dict(rtol=1e-7, atol=1e-10)),
+                                      ("AdamsBashforth4", 100, dict(h=0.01)), ("AdamsBashforth2", 70, dict(h=0.01)),
+                                      ("RungeKutta4", 128, dict(h=0.01))])
+def test_cta_kernels_are_race_free_under_real_thread_scheduling(cls, n, kw):
+    """The emulated block's threads are scheduled by the OS, far from lock-step: any missing barrier shows up as a
+    run-to-run difference.  Five repetitions of run (several grid points per step and per call, resumed) + step must be
+    bit-identical, and must equal a run at one output point per call."""
+    B = 3
+    y0, p = ensemble(B, n, seed=5)
+    ts = np.array([0.05, 0.06, 0.3, 0.31, 0.32, 0.9])
+    results = []
+    for _ in range(5):
+        g = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+        out = np.concatenate([g.run(ts[:4]), g.run(ts[4:])], axis=1)
+        tq, yq, _ = g.step(3)
+        results.append((out, tq, yq, g.y, g.h.copy(), g.K.copy()))
+    for r in results[1:]:
+        for a, b in zip(results[0], r):
+            assert np.array_equal(a, b, equal_nan=True)
+    one = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+    single = np.concatenate([one.run([t]) for t in ts], axis=1)
+    assert np.array_equal(single, results[0][0])
+
+
+def test_linear_rhs_cta_vs_numpy_restatement():
+    """y' = A y with one shared dense A through the generic CTA kernel (one component per thread, the whole vector read
+    from "shared memory" by every thread)."""
+    B, n = 3, 40
+    y0, A = onp.linear_ensemble(B, n=n, seed=2)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    g = EmulCtaEnsemble("RungeKutta45", "linear", y0, A.T.copy(), params_shared=True, **kw)  # the kernel takes A transposed
+    ts = [0.5, 1.0, 4.0]
+    out = g.run(ts)
+    for b in range(B):
+        o = onp.AdaptiveRK("RungeKutta45", onp.rhs_linear, 0.0, y0[b], A, **kw)
+        _, yo = onp.run(o, ts)
+        assert np.all(np.abs(out[b] - yo) <= 1e-2 * (1e-6 * np.abs(yo) + 1e-9)) and g.nacc[b] == o.n_accepted
