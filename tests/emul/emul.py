@@ -222,19 +222,36 @@ def cta_shape(mid, rhs, n):
     return e, t, int(mid in (23, 45, 853) and t * e == n)
 
 
-def _program_cta(method, rhs, elems, full):
+def _program_cta(method, rhs, elems, full, user_src=None, n_params=0):
     tag = f"m{method}_{rhs}_e{elems}{'f' if full else ''}"
+    extra = []
+    if user_src is not None:
+        import hashlib
+
+        tag += "_u" + hashlib.sha1((user_src + str(n_params)).encode()).hexdigest()[:10]
     if ("cta", tag) in _libs:
         return _libs[("cta", tag)]
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, f"libemul_cta_{tag}.so")
+    if user_src is not None:
+        # the translation-unit prelude of nbk_jit_compile() for a CTA user right-hand side
+        pre = os.path.join(BUILD, f"pre_cta_{tag}.h")
+        with open(pre, "w") as fh:
+            fh.write("#define NBK_RHS_I static inline double\n"
+                     "namespace nbk { template <int E> struct smem_vec; }\ntypedef nbk::smem_vec<NBK_E> nbk_vec;\n"
+                     + (f"#define NBK_CTA_NP {n_params}\n" if 0 < n_params <= 16 else "")
+                     + "#define NBK_USER_RHS_CTA 1\n"
+                     "NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n);\n"
+                     '#include "nbk_cta.cuh"\n' + user_src + "\n")
+        extra = [f'-DEMUL_USER_PRELUDE="{pre}"']
     deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_cta.cuh", "nbk_kargs.h", "nbk_program_cta.cu", "nbk_dop853_coeffs.h")]
     deps += [os.path.join(HERE, f) for f in ("nbk_emul_cta.cpp", "cuda_host_shim.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call([
             "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-ffp-contract=off",
-            "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}", f"-DNBK_RHS_T={CTA_RHS_TYPES[rhs][0]}",
-            f"-DNBK_TAG={tag}", f"-DNBK_E={elems}", "-DNBK_CTA_MAXT=512", f"-DNBK_CTA_FULL={full}",
+            "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}",
+            f"-DNBK_RHS_T={'nbk::rhs_user_cta' if user_src is not None else CTA_RHS_TYPES[rhs][0]}",
+            f"-DNBK_TAG={tag}", f"-DNBK_E={elems}", "-DNBK_CTA_MAXT=512", f"-DNBK_CTA_FULL={full}", *extra,
             os.path.join(HERE, "nbk_emul_cta.cpp"), "-o", so,
         ])
     fn = getattr(C.CDLL(so), f"emul_cta_{tag}")
@@ -249,14 +266,18 @@ class EmulCtaEnsemble:
 
     def __init__(self, method, rhs, y0, params, *, t0=0.0, h=None, first_step=None, rtol=1e-3, atol=1e-6,
                  min_factor=0.2, max_factor=10.0, safety_factor=0.9, first_stepper=45, params_shared=False):
+        """rhs: a built-in name ("rd1d", "linear") or CUDA C source defining nbk_rhs_i (e.g. rhs.trace_cta(...).source)"""
         self.mid = METHOD_IDS[method]
         y0 = np.ascontiguousarray(np.atleast_2d(np.asarray(y0, float)))
         self.B, self.n = y0.shape
         params = np.ascontiguousarray(np.asarray(params, float))
         params = params.reshape(1, -1) if params_shared else params.reshape(self.B, -1)
         self.np_ = params.shape[1]
+        user_src = rhs if "nbk_rhs_i" in rhs else None
+        if user_src is not None:  # shape rule of csrc/nbk_api.cu for source: a loop means dense coupling
+            rhs = "linear" if ("for (" in user_src or "for(" in user_src or "while" in user_src) else "rd1d"
         self.E, self.T, self.full = cta_shape(self.mid, rhs, self.n)
-        self.fn = _program_cta(self.mid, rhs, self.E, self.full)
+        self.fn = _program_cta(self.mid, "user" if user_src is not None else rhs, self.E, self.full, user_src, self.np_)
         adaptive = self.mid in (23, 45, 853)
         self.L = 2 if (adaptive or self.mid in ERK_STAGES) else max(self.mid, 2)
         self.SR = {23: 4, 45: 7, 853: 13, **ERK_STAGES}.get(self.mid, 0)

@@ -27,6 +27,9 @@ static inline double __shfl_xor_sync(unsigned, double v, int o) {
     return r;
 }
 
+#ifdef EMUL_USER_PRELUDE  // a user right-hand side (nbk_rhs_i), spliced in the way csrc/nbk_jit.cpp does for NVRTC
+#include EMUL_USER_PRELUDE
+#endif
 #include "nbk_program_cta.cu"
 
 #define EMUL_NAME NBK_CAT(emul_cta_, NBK_TAG)

@@ -146,3 +146,37 @@ def test_linear_rhs_cta_vs_numpy_restatement():
         o = onp.AdaptiveRK("RungeKutta45", onp.rhs_linear, 0.0, y0[b], A, **kw)
         _, yo = onp.run(o, ts)
         assert np.all(np.abs(out[b] - yo) <= 1e-2 * (1e-6 * np.abs(yo) + 1e-9)) and g.nacc[b] == o.n_accepted
+
+
+def test_traced_python_rhs_through_the_emulated_block():
+    """A NumPy-style Python right-hand side -> vector tracer -> nbk_rhs_i -> the user path of the CTA kernels (the
+    parameter block held in registers, NBK_CTA_NP), spliced in as csrc/nbk_jit.cpp does for NVRTC: the same results
+    as the built-in right-hand side, for an adaptive and a fixed-step class, plus operations only the tracer has."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "numbakit-ode_b200"))
+    from nbkode_b200 import rhs
+
+    def rd(t, y, p):
+        return p[0] * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + p[1] * y * (1 - y)
+
+    B, n = 2, 100
+    y0, p = ensemble(B, n, seed=8)
+    src = rhs.trace_cta(rd, n, (2,), True).source
+    ts = [0.3, 1.1]
+    for cls, kw, tol in (("RungeKutta45", dict(rtol=1e-6, atol=1e-9), 1e-9), ("AdamsBashforth4", dict(h=0.01), 1e-12)):
+        a = EmulCtaEnsemble(cls, src, y0, p, **kw)
+        b = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+        assert (a.E, a.T) == (b.E, b.T)
+        assert rel(a.run(ts), b.run(ts)) < tol and np.array_equal(a.nacc, b.nacc)
+
+    def limited(t, y, p):  # comparisons / np.where / np.diff / a reduction (a loop in the source: one component per thread)
+        d = np.diff(np.append(y, y[0]))
+        return p[0] * np.where(d > 0, d, 0.5 * d) - p[1] * (y - y.mean())
+
+    src2 = rhs.trace_cta(limited, n, (2,), True).source
+    c = EmulCtaEnsemble("RungeKutta23", src2, y0, p, rtol=1e-6, atol=1e-9)
+    assert c.E == 1 and "for (" in src2
+    out = c.run(ts)
+    for k in range(B):
+        o = onp.AdaptiveRK("RungeKutta23", limited, 0.0, y0[k], p[k], rtol=1e-6, atol=1e-9)
+        _, yo = onp.run(o, ts)
+        assert np.all(np.abs(out[k] - yo) <= 1e-2 * (1e-6 * np.abs(yo) + 1e-9)) and c.nacc[k] == o.n_accepted
