@@ -36,9 +36,13 @@ constexpr int MMA_LDA = 128 + 4;    // padded row length of the matrix staged in
                                     // half-warp into 16 different 8-byte banks
 
 NBK_DEV void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+#ifdef NBK_HOST_EMUL
+    nbk_emul_dmma(c0, c1, a, b);  // tests/emul: the fragment exchange of one warp through a scratch array
+#else
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+#endif
 }
 
 // per-column bookkeeping kept in shared memory (written by the column leaders only)

@@ -336,3 +336,44 @@ class EmulCtaEnsemble:
     t = property(lambda self: self.ts[:, -1].copy())
     y = property(lambda self: self.ys[:, -1].copy())
     f = property(lambda self: self.fs[:, -1].copy())
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# K4 (csrc/nbk_mma.cuh): shared-matrix linear systems, right-hand side as FP64 DMMA tiles -- host build with the
+# fragment exchange emulated (nbk_emul_mma.cpp)
+# --------------------------------------------------------------------------------------------------------------------
+def _program_mma(method):
+    tag = f"m{method}_linear_mma"
+    if ("mma", tag) in _libs:
+        return _libs[("mma", tag)]
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, f"libemul_mma_{tag}.so")
+    deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_cta.cuh", "nbk_mma.cuh", "nbk_kargs.h", "nbk_program_mma.cu")]
+    deps += [os.path.join(HERE, f) for f in ("nbk_emul_mma.cpp", "cuda_host_shim.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call([
+            "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-ffp-contract=off",
+            "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}", f"-DNBK_TAG={tag}",
+            os.path.join(HERE, "nbk_emul_mma.cpp"), "-o", so,
+        ])
+    fn = getattr(C.CDLL(so), f"emul_mma_{tag}")
+    fn.argtypes = [C.c_int, C.POINTER(KArgs)]
+    _libs[("mma", tag)] = fn
+    return fn
+
+
+class EmulMmaEnsemble(EmulCtaEnsemble):
+    """y' = A y, one shared dense A (n <= 128), through the DMMA tile kernel; `A` is given as the matrix itself."""
+
+    def __init__(self, method, y0, A, **kw):
+        fn = _program_mma(METHOD_IDS[method])
+        self._mma = fn
+        super().__init__(method, "linear", y0, np.ascontiguousarray(np.asarray(A, float).T), params_shared=True, **kw)
+
+    def __setattr__(self, name, value):
+        if name == "fn" and "_mma" in self.__dict__:
+            # the construction kernel is the CTA regime's (256 threads), run / step are the tile kernels: all three
+            # live in the K4 program, launched with 256 threads
+            mma = self.__dict__["_mma"]
+            value = lambda kernel, a, _t: mma(kernel, a)  # noqa: E731
+        object.__setattr__(self, name, value)

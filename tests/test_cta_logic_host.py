@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
-from emul import EmulCtaEnsemble, cta_shape  # noqa: E402
+from emul import EmulCtaEnsemble, EmulMmaEnsemble, cta_shape  # noqa: E402
 
 from oracle import nbk_oracle_np as onp  # noqa: E402
 
@@ -180,3 +180,25 @@ def test_traced_python_rhs_through_the_emulated_block():
         o = onp.AdaptiveRK("RungeKutta23", limited, 0.0, y0[k], p[k], rtol=1e-6, atol=1e-9)
         _, yo = onp.run(o, ts)
         assert np.all(np.abs(out[k] - yo) <= 1e-2 * (1e-6 * np.abs(yo) + 1e-9)) and c.nacc[k] == o.n_accepted
+
+
+def test_dmma_tile_kernel_k4_on_the_host():
+    """K4 (csrc/nbk_mma.cuh) with the mma.sync fragment exchange emulated per warp: a partial tile (5 of 16 columns),
+    n = 40 zero-padded to 128, per-column controllers and emission from the accumulator layout, against the NumPy
+    restatement; two OS-scheduled repetitions must be bit-identical (race detector); a resumed run continues."""
+    B, n = 5, 40
+    y0, A = onp.linear_ensemble(B, n=n, seed=2)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    ts = [0.2, 0.6]
+    runs = []
+    for _ in range(2):
+        g = EmulMmaEnsemble("RungeKutta45", y0, A, **kw)
+        runs.append((g.run(ts[:1]), g.run(ts[1:]), g.y, g.h.copy(), g.nacc.copy(), g.K.copy()))
+    for a, b in zip(*runs):
+        assert np.array_equal(a, b)
+    out = np.concatenate(runs[0][:2], axis=1)
+    for b in range(B):
+        o = onp.AdaptiveRK("RungeKutta45", onp.rhs_linear, 0.0, y0[b], A, **kw)
+        _, yo = onp.run(o, ts)
+        assert np.all(np.abs(out[b] - yo) <= 1e-3 * (1e-6 * np.abs(yo) + 1e-9))
+        assert runs[0][4][b] == o.n_accepted and rel(runs[0][2][b], o.y) < 1e-7 and rel(runs[0][3][b], o.h) < 1e-6  # summation order of A.y
