@@ -202,3 +202,27 @@ def test_dmma_tile_kernel_k4_on_the_host():
         _, yo = onp.run(o, ts)
         assert np.all(np.abs(out[b] - yo) <= 1e-3 * (1e-6 * np.abs(yo) + 1e-9))
         assert runs[0][4][b] == o.n_accepted and rel(runs[0][2][b], o.y) < 1e-7 and rel(runs[0][3][b], o.h) < 1e-6  # summation order of A.y
+
+
+@pytest.mark.parametrize("cls,n", [("RungeKutta45", 130), ("RungeKutta45", 300), ("RungeKutta23", 2100), ("AdamsBashforth3", 300)])
+def test_more_cta_shapes_on_the_host(cls, n):
+    """Further shapes: four components per thread with a ragged last thread (n = 130, 300), the large-n shape
+    (n = 2100: nine components per thread, 256 threads), against the NumPy restatement and repeated for determinism."""
+    B = 2
+    y0, p = ensemble(B, n, seed=13)
+    kw = dict(h=0.01) if cls.startswith("Adams") else dict(rtol=1e-6, atol=1e-9)
+    ts = [0.15, 0.4]
+    outs = []
+    for _ in range(2):
+        g = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+        outs.append((g.run(ts), g.y, g.nacc.copy()))
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))
+    for b in range(B):
+        if cls.startswith("Adams"):
+            o = onp.AdamsBashforth(int(cls[-1]), onp.rhs_rd1d, 0.0, y0[b], p[b], h=0.01)
+            _, yo = onp.run(o, ts)
+            assert rel(outs[0][0][b], yo) < 1e-12
+        else:
+            o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **kw)
+            _, yo = onp.run(o, ts)
+            assert np.all(np.abs(outs[0][0][b] - yo) <= 1e-3 * (1e-6 * np.abs(yo) + 1e-9)) and outs[0][2][b] == o.n_accepted
