@@ -226,3 +226,41 @@ def test_more_cta_shapes_on_the_host(cls, n):
             o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **kw)
             _, yo = onp.run(o, ts)
             assert np.all(np.abs(outs[0][0][b] - yo) <= 1e-3 * (1e-6 * np.abs(yo) + 1e-9)) and outs[0][2][b] == o.n_accepted
+
+
+@pytest.mark.parametrize("cls", ["RungeKutta45", "DOP853", "AdamsBashforth4"])
+def test_failure_paths_of_the_cta_kernels(cls):
+    """A trajectory whose right-hand side turns non-finite (NaN parameter) fails alone: status NONFINITE for the
+    adaptive classes (the reference would spin forever), NaN rows in the output, the neighbours untouched; the status is
+    sticky across calls; the attempt budget stops a run with MAXATTEMPTS."""
+    B, n = 3, 100
+    y0, p = ensemble(B, n, seed=17)
+    p[1, 1] = np.nan
+    kw = dict(h=0.01) if cls.startswith("Adams") else dict(rtol=1e-6, atol=1e-9)
+    g = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+    out = g.run([0.2, 0.5])
+    good = [0, 2]
+    assert np.isfinite(out[good]).all() and (g.status[good] == 0).all()
+    if cls.startswith("Adams"):
+        # a fixed-step solver has no error estimate to notice: the start-up (adaptive RungeKutta45) fails the trajectory
+        assert g.status[1] == 2 and np.isnan(out[1]).all()
+    else:
+        assert g.status[1] == 2 and np.isnan(out[1]).all() and g.counter[1] >= 1
+    out2 = g.run([0.6])
+    assert g.status[1] == 2 and np.isnan(out2[1]).all() and np.isfinite(out2[good]).all()
+    for b in good:
+        q = dict(kw)
+        if cls.startswith("Adams"):
+            o = onp.AdamsBashforth(4, onp.rhs_rd1d, 0.0, y0[b], p[b], h=0.01)
+            _, yo = onp.run(o, [0.2, 0.5, 0.6])
+            assert rel(np.concatenate([out[b], out2[b]]), yo) < 1e-12
+        else:
+            o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **q)
+            _, yo = onp.run(o, [0.2, 0.5, 0.6])
+            assert np.all(np.abs(np.concatenate([out[b], out2[b]]) - yo) <= 1e-3 * (1e-6 * np.abs(yo) + 1e-9))
+    if not cls.startswith("Adams"):
+        y1, p1 = ensemble(2, n, seed=18)
+        m = EmulCtaEnsemble(cls, "rd1d", y1, p1, **kw)
+        m.base["max_attempts"] = 2
+        m.run([5.0])
+        assert (m.status == 3).all() and (m.nacc + m.nrej == 2).all()
