@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of BASELINE.json: accepted RK45 steps/s on the Lorenz-63
-ensemble (configs[1]: 1M trajectories per GPU, random y0, sigma/rho/beta sweep, rtol=1e-6,
-atol=1e-9, t in [0, 10], FP64).
+ensemble (configs[1]: ONE ensemble of 1M trajectories, random y0, sigma/rho/beta sweep,
+rtol=1e-6, atol=1e-9, t in [0, 10], FP64).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 One "step" = one pass of the hot path over the ensemble: constructor kernel (f0 + initial
-step size) and the persistent RK45 kernel to t = 10.  Under torchrun every rank integrates its
-own 1M-trajectory ensemble (weak scaling, no data-path collective).
+step size) and the persistent RK45 kernel to t = 10.  Under torchrun the ONE 1M-trajectory
+ensemble of the north star is sharded by trajectory over the N ranks (strong scaling, no
+data-path collective); the weak-scaling figure (1M per GPU) of the same
+run sits in `extra.weak_scaling`.
 
-Printed JSON line (rank 0): see the contract in the task statement; additionally
-  roofline     FP64 vector pipe: algorithmic FLOPs (264 per attempted step)
-               / run-kernel time, against the DFMA peak measured in this run (nbk_fp64_peak)
-  cpu_baseline the C oracle (oracle/nbk_oracle.c, a port of the reference's algorithm) on all
-               host cores over a bounded sample of the same ensemble
-  e2e          the same metric through the public API with pinned HOST buffers in and out
-`--impl reference` times the oracle port alone (the reference is pure Python + numba and
-cannot travel to the GPU box).
+Printed JSON line (rank 0): the contract of the task statement; additionally
+  roofline      FP64 vector pipe: algorithmic FLOPs (264 per attempted step)
+                / run-kernel time, against the DFMA peak measured in this run (nbk_fp64_peak)
+  cpu_baseline  N = 1: the LIVE reference (nbkode's numba path from baseline/_ref, one Solver
+                object per trajectory, fork()ed workers on all host cores) over a 65 536-trajectory
+                prefix of the same ensemble (kind "reference"); `cpu_baseline_port` = the C port
+                (oracle/nbk_oracle.c, pthreads) over the full ensemble
+  parity        N = 1: the GPU result of the full 1M ensemble against the C port, and of the
+                prefix against the live reference: fraction within rtol*|y|+atol, fraction with
+                accepted-step counts within +-1, outliers listed
+  e2e           the same metric through the public API with pinned HOST buffers in and out
+  extra.configs N = 1: one timed pass each of BASELINE configs[2..4] at full size
+`--impl reference` times the live reference (numba) on the host cores, each step a bounded
+sample of the same ensemble (the C port only if baseline/_ref is absent).
 """
 
 from __future__ import annotations
@@ -34,7 +42,8 @@ for _p in (ROOT, os.path.join(ROOT, "numbakit-ode_b200")):
 
 import numpy as np  # noqa: E402
 
-B_PER_GPU = 1_000_000
+B_TOTAL = 1_000_000
+N_PREFIX = 65_536  # trajectories the live reference integrates beside the kernels
 T_END = 10.0
 RTOL, ATOL = 1e-6, 1e-9
 FLOP_PER_ATTEMPT = 264  # 6R + 66n + 18 with R = 8, n = 3
@@ -58,14 +67,28 @@ def ncu_traffic_bytes():
     return None
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, b_total=B_TOTAL, l2=None):
+    per = -(-b_total // n_gpus)
+    mb = per * (368 + 48) / 1e6
     return {
         "workload": "Lorenz-63 ensemble, RungeKutta45 rtol=1e-6 atol=1e-9, t in [0,10], run([10.0])",
-        "trajectories_per_gpu": B_PER_GPU,
-        "trajectories_total": B_PER_GPU * n_gpus,
-        "parallelism": f"trajectory sharding x{n_gpus}, no collective",
-        "l2": "working set (inputs 48 MB + state 344 MB per GPU) exceeds the 126 MB L2; no explicit flush",
+        "trajectories_total": b_total,
+        "trajectories_per_gpu": per,
+        "parallelism": f"one ensemble sharded by trajectory x{n_gpus}, no collective",
+        "l2": l2 or l2_policy(per)[1],
     }
+
+
+def l2_policy(per_gpu):
+    """Working set of one pass per GPU (inputs 48 B + state 368 B per trajectory) against the 126 MB L2: when it
+    does not exceed the L2 by itself, consecutive passes rotate over R distinct input copies and R live solver
+    states, so that no pass finds its data in L2."""
+    mb = per_gpu * (368 + 48) / 1e6
+    ring = 1 if mb > 252 else int(252 // mb) + 1
+    if ring == 1:
+        return 1, f"working set ({mb:.0f} MB per GPU: inputs + resumable state) exceeds the 126 MB L2; no explicit flush"
+    return ring, (f"working set is {mb:.0f} MB per GPU: passes rotate over {ring} input copies and {ring} live states "
+                  f"({ring * mb:.0f} MB > 2 x 126 MB L2); no explicit flush")
 
 
 # ----------------------------------------------------------------------------------------
@@ -127,64 +150,219 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
-def cpu_oracle_throughput(y0, p, budget_s=12.0, threads=None):
-    """C oracle (port of the reference algorithm) on all host cores over a bounded sample."""
+# CPU legs (never on the product path): the live reference and the C port
+# ----------------------------------------------------------------------------------------
+def live_reference_pool():
+    """fork()ed numba workers of the LIVE reference (baseline/nbkode_ref.py); None + reason if baseline/_ref is
+    absent.  Must be called before CUDA is initialised in this process (the workers are fork()ed)."""
+    try:
+        from baseline import nbkode_ref
+
+        if not nbkode_ref.installed():
+            return None, nbkode_ref.install()  # build container only; "unavailable: ..." on the GPU box
+        return nbkode_ref.Pool(os.cpu_count() or 1, "lorenz", "RungeKutta45", rtol=RTOL, atol=ATOL), "ok"
+    except Exception as exc:  # noqa: BLE001
+        return None, f"unavailable: {type(exc).__name__}: {exc}"
+
+
+def parity_stats(y, nacc, y_ref, nacc_ref, max_list=16):
+    """Final states within rtol*|y|+atol and accepted-step counts within +-1 (the north-star bars), as fractions
+    over the ensemble, with the outliers listed."""
+    y, y_ref = np.asarray(y).reshape(len(y_ref), -1), np.asarray(y_ref).reshape(len(y_ref), -1)
+    ratio = np.max(np.abs(y - y_ref) / (RTOL * np.abs(y_ref) + ATOL), axis=1)
+    dn = np.abs(np.asarray(nacc, dtype=np.int64) - np.asarray(nacc_ref, dtype=np.int64))
+    bad = np.nonzero((ratio > 1.0) | (dn > 1) | ~np.isfinite(ratio))[0]
+    order = bad[np.argsort(-np.nan_to_num(ratio[bad], nan=np.inf))][:max_list]
+    q = np.quantile(ratio, [0.5, 0.99, 0.9999])
+    return {
+        "trajectories": int(len(y_ref)),
+        "frac_within_tol": float(np.mean(ratio <= 1.0)),
+        "frac_steps_within_1": float(np.mean(dn <= 1)),
+        "frac_steps_identical": float(np.mean(dn == 0)),
+        "err_over_tol": {"p50": float(q[0]), "p99": float(q[1]), "p9999": float(q[2]), "max": float(np.max(ratio))},
+        "n_outliers": int(len(bad)),
+        "outliers": [{"trajectory": int(i), "err_over_tol": float(ratio[i]), "d_steps": int(dn[i])} for i in order],
+        "bars": "final state |dy| <= rtol*|y_ref| + atol (rtol=1e-6, atol=1e-9); accepted steps within +-1; a flipped "
+                "accept/reject decision on a chaotic trajectory is amplified beyond the bar -- those are the outliers",
+    }
+
+
+def cpu_port(y0, p, threads=None):
+    """C port of the reference algorithm (oracle/nbk_oracle.c, pthreads) over the whole ensemble."""
     from oracle import nbk_oracle_c as oc
 
     threads = threads or os.cpu_count() or 1
-    probe = min(len(y0), 4096 * max(1, threads // 4))
     t0 = time.perf_counter()
-    r = oc.run_ensemble("RungeKutta45", "lorenz", y0[:probe], p[:probe], [T_END], rtol=RTOL, atol=ATOL, nthreads=threads, dense=False)
+    r = oc.run_ensemble("RungeKutta45", "lorenz", y0, p, [T_END], rtol=RTOL, atol=ATOL, nthreads=threads, dense=True)
     dt = time.perf_counter() - t0
-    rate = r["n_accepted"].sum() / dt
-    n = int(min(len(y0), max(probe, budget_s * probe / max(dt, 1e-6))))
-    t0 = time.perf_counter()
-    r = oc.run_ensemble("RungeKutta45", "lorenz", y0[:n], p[:n], [T_END], rtol=RTOL, atol=ATOL, nthreads=threads, dense=False)
-    dt = time.perf_counter() - t0
-    return {
+    return r, {
         "value": float(r["n_accepted"].sum() / dt), "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": f"first {n} trajectories of the rank-0 ensemble, {dt:.2f} s wall, C oracle (oracle/nbk_oracle.c) with pthreads",
-        "probe_rate": float(rate),
+        "sample": f"all {len(y0)} trajectories of the ensemble, {dt:.2f} s wall, C port (oracle/nbk_oracle.c) with pthreads",
+    }
+
+
+def cpu_live(pool, y0, p, n=N_PREFIX):
+    """nbkode's numba path over a prefix of the ensemble: throughput = accepted steps / slowest worker's time."""
+    n = min(n, len(y0))
+    r = pool.run(y0[:n], p[:n], [T_END], count=True)
+    return r, {
+        "value": float(r["n_accepted"].sum() / r["wall"]), "unit": UNIT, "cores": pool.workers, "kind": "reference",
+        "sample": (f"first {n} trajectories of the ensemble, one nbkode.RungeKutta45 object per trajectory, run([10.0]), "
+                   f"{pool.workers} fork()ed workers, slowest worker {r['wall']:.2f} s; numba JIT ({pool.jit_s:.1f} s, once, "
+                   "in the parent) and the accepted-step recount are outside the timed region"),
+        "jit_s": pool.jit_s,
     }
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     if rank != 0:
         return
-    from oracle import nbk_oracle_c as oc
-    from oracle import nbk_oracle_np as onp
+    from nbkode_b200 import ensembles
 
-    threads = os.cpu_count() or 1
-    y0, p = onp.lorenz_ensemble(B_PER_GPU, seed=0)
-    # bounded sample per step: ~3 s of CPU work
-    probe = 8192
-    t0 = time.perf_counter()
-    oc.run_ensemble("RungeKutta45", "lorenz", y0[:probe], p[:probe], [T_END], rtol=RTOL, atol=ATOL, nthreads=threads, dense=False)
-    dt = time.perf_counter() - t0
-    n = int(min(B_PER_GPU, max(probe, 3.0 * probe / dt)))
-    total_steps, times = 0, []
-    for it in range(args.warmup + args.steps):
-        lo = (it * n) % max(1, B_PER_GPU - n)
-        t0 = time.perf_counter()
-        r = oc.run_ensemble("RungeKutta45", "lorenz", y0[lo:lo + n], p[lo:lo + n], [T_END], rtol=RTOL, atol=ATOL,
-                            nthreads=threads, dense=True)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-            total_steps += int(r["n_accepted"].sum())
-    value = total_steps / sum(times)
+    y0, p = ensembles.lorenz_ensemble(B_TOTAL, seed=0)
+    pool, why = live_reference_pool()
+    n_iter = args.warmup + args.steps
+    if pool is not None:
+        # bounded sample per step: ~2.5 s of wall time on this host, a fixed prefix of the ensemble
+        probe = 64 * pool.workers
+        pool.run(y0[:probe], p[:probe], [T_END])  # first call in every worker: page faults after fork(), cold caches
+        r = pool.run(y0[:probe], p[:probe], [T_END])
+        n = int(min(B_TOTAL, max(probe, 2.5 * probe / r["wall"])))
+        times = []
+        for it in range(n_iter):
+            r = pool.run(y0[:n], p[:n], [T_END])
+            if it >= args.warmup:
+                times.append(r["wall"])
+        steps_per_pass = int(pool.run(y0[:n], p[:n], [T_END], count=True)["n_accepted"].sum())
+        kind, cores = "reference", pool.workers
+        sample = (f"first {n} trajectories of the ensemble per step, the unmodified nbkode (numba) from baseline/_ref: one "
+                  f"RungeKutta45 object per trajectory, run([10.0]), {cores} fork()ed workers; time = slowest worker; JIT "
+                  f"({pool.jit_s:.1f} s) excluded")
+        pool.close()
+    else:
+        from oracle import nbk_oracle_c as oc
+
+        cores = os.cpu_count() or 1
+        n, times = B_TOTAL, []
+        for it in range(n_iter):
+            t0 = time.perf_counter()
+            r = oc.run_ensemble("RungeKutta45", "lorenz", y0, p, [T_END], rtol=RTOL, atol=ATOL, nthreads=cores, dense=True)
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        steps_per_pass = int(r["n_accepted"].sum())
+        kind = "port"
+        sample = f"all {n} trajectories per step, C port of nbkode's RK45 path (pthreads); live reference {why}"
+    value = steps_per_pass * len(times) / sum(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {**workload_config(args.gpus), "sample_trajectories_per_step": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} trajectories per step, C oracle port of nbkode's RK45 path (pthreads)"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# BASELINE configs[2..4], one timed pass each at full size (N = 1)
+# ----------------------------------------------------------------------------------------
+def extra_configs(nbk, torch, dev, peak_tf, sizes=None):
+    from nbkode_b200 import _lib, ensembles
+
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:  # noqa: BLE001
+        hbm, hbm_src = 6650.0, "B200_PROFILING.md fallback"
+    sizes = sizes or {"c3": 4_000_000, "c4": 262_144, "c5": 65_536}
+    rows = []
+
+    def timed(make, run, reps=2):
+        best = None
+        for _ in range(reps):  # the first pass also warms the allocator (and NVRTC, where a program is not ahead-of-time)
+            s = make()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = run(s)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+            acc, att = int(s._nacc.sum().item()), int((s._nacc.sum() + s._nrej.sum()).item())
+            s.raise_for_status()
+            launch = s.last_launch()
+            del out, s
+        return best, acc, att, launch
+
+    def guarded(name, fn):
+        try:
+            rows.append(fn())
+        except Exception as exc:  # noqa: BLE001  (a secondary config must not take the headline line down)
+            rows.append({"config": name, "error": f"{type(exc).__name__}: {exc}"[:300]})
+        torch.cuda.empty_cache()
+
+    # ---- C3: Van der Pol, 1000-point dense output (64 GB per solver at 4M trajectories)
+    B3, m = sizes["c3"], 1000
+    y0, p = ensembles.vdp_ensemble(B3, seed=1)
+    y0d, pd = torch.from_numpy(y0).to(dev), torch.from_numpy(p).to(dev)
+    ts = np.linspace(0, 20, m)
+    out_gb = B3 * m * 2 * 8 / 1e9
+
+    def c3(cls, kw, flop, kernel, what):
+        def fn():
+            ms, acc, att, launch = timed(lambda: getattr(nbk, cls)("vdp", 0.0, y0d, pd, **kw), lambda s: s.run(ts))
+            tf = att * flop / ms * 1e3 / 1e12
+            return {"config": f"C3 Van der Pol {B3} x {m}-point grid, {what}", "kernel": kernel, "ms": ms, "accepted_steps": acc,
+                    "steps_per_s": acc / ms * 1e3,
+                    "roofline": {"bound": "hbm", "achieved": out_gb / ms * 1e3, "peak": hbm, "unit": "GB/s",
+                                 "frac": out_gb / ms * 1e3 / hbm, "peak_source": hbm_src, "algorithmic_bytes": out_gb * 1e9},
+                    "fp64": {"achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "flop_per_attempt": flop},
+                    "launch": launch}
+        return fn
+
+    # FLOP per attempt (SURVEY.md 8(d)): RK23 3R + 27n + 18, Adams-Bashforth-k R + 2kn + k + 1; Van der Pol R = 5, n = 2
+    guarded("C3 AdamsBashforth4", c3("AdamsBashforth4", dict(h=0.01), 5 + 16 + 5, "nbk_run_ab4_vdp (K2)", "AdamsBashforth4 h=0.01"))
+    guarded("C3 RungeKutta23", c3("RungeKutta23", dict(rtol=RTOL, atol=ATOL), 15 + 54 + 18, "nbk_run_rk23_vdp (K1)",
+                                   "RungeKutta23 rtol=1e-6 atol=1e-9"))
+    del y0d, pd
+
+    # ---- C4: linear y' = A y, n = 128, shared dense A: right-hand side on the FP64 tensor pipe (DMMA)
+    def c4():
+        B4, n = sizes["c4"], 128
+        y0, A = ensembles.linear_ensemble(B4, n=n, seed=2)
+        y0d, Ad = torch.from_numpy(y0).to(dev), torch.from_numpy(A).to(dev)
+        flop = 6 * 2 * n * n + 66 * n + 18
+        ms, acc, att, launch = timed(lambda: nbk.RungeKutta45("linear", 0.0, y0d, Ad, rtol=RTOL, atol=ATOL), lambda s: s.run([10.0]))
+        mma_peak, _ = _lib.fp64_mma_peak(dev.index or 0, 4000)
+        tf = att * flop / ms * 1e3 / 1e12
+        return {"config": f"C4 linear n={n} x {B4}, RungeKutta45, shared dense A", "kernel": "nbk_run_rk45_linear_mma (K4, DMMA)",
+                "ms": ms, "accepted_steps": acc, "steps_per_s": acc / ms * 1e3,
+                "roofline": {"bound": "fp64 tensor pipe (DMMA m8n8k4)", "achieved": tf, "peak": mma_peak, "unit": "TFLOP/s",
+                             "frac": tf / mma_peak, "frac_of_dfma_peak": tf / peak_tf, "flop_per_attempt": flop},
+                "launch": launch}
+
+    guarded("C4 linear", c4)
+
+    # ---- C5: reaction-diffusion method of lines, n = 2048, one CTA per trajectory
+    def c5():
+        B5, n = sizes["c5"], 2048
+        y0, p5 = ensembles.rd1d_ensemble(B5, n=n, seed=3)
+        y0d, p5d = torch.from_numpy(y0).to(dev), torch.from_numpy(p5).to(dev)
+        flop = 6 * 8 * n + 66 * n + 18
+        ms, acc, att, launch = timed(lambda: nbk.RungeKutta45("rd1d", 0.0, y0d, p5d, rtol=RTOL, atol=ATOL), lambda s: s.run([1.0]))
+        tf = att * flop / ms * 1e3 / 1e12
+        return {"config": f"C5 reaction-diffusion n={n} x {B5}, RungeKutta45, t in [0,1]", "kernel": "nbk_run_rk45_rd1d_cta (K3)",
+                "ms": ms, "accepted_steps": acc, "steps_per_s": acc / ms * 1e3,
+                "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                             "flop_per_attempt": flop},
+                "launch": launch}
+
+    guarded("C5 rd1d", c5)
+    return rows
 
 
 # ----------------------------------------------------------------------------------------
@@ -194,8 +372,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (default: the BASELINE config)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=B_TOTAL, help="trajectories of the whole ensemble (default: the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (live reference, C port, parity block)")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra.configs / extra.weak_scaling")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,6 +384,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    # the live reference's workers are fork()ed BEFORE this process touches CUDA (N = 1 only, rank 0)
+    cpu_legs = world == 1 and not args.no_cpu_baseline
+    pool, pool_note = live_reference_pool() if cpu_legs else (None, "not requested")
 
     import torch
     import torch.distributed as dist
@@ -218,23 +401,23 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import nbkode_b200 as nbk
-    from oracle import nbk_oracle_np as onp  # input generator only (SURVEY.md 8(d) distribution)
+    from nbkode_b200 import distributed as nd
+    from nbkode_b200 import ensembles
 
     # one process per GPU: keep the process (and the pinned buffers it is about to allocate) on the GPU's NUMA node
-    from nbkode_b200 import distributed as nd
-
     numa_bound = world > 1 and nd.bind_to_gpu_numa(local_rank)
 
-    B = args.batch
-    y0_np, p_np = onp.lorenz_ensemble(B, seed=rank)
+    # ONE ensemble, sharded by trajectory: every rank draws the same B_total rows and keeps its contiguous slice
+    B_total = args.batch
+    lo, hi = nd.shard_bounds(B_total, rank, world)
+    y0_all, p_all = ensembles.lorenz_ensemble(B_total, seed=0)
+    y0_np, p_np = np.ascontiguousarray(y0_all[lo:hi]), np.ascontiguousarray(p_all[lo:hi])
+    B = hi - lo
+    ring_n, l2_note = l2_policy(-(-B_total // world))
     # host inputs live in pinned memory (e2e arm); device-resident copies for the kernel-only arm
     y0_host = torch.from_numpy(y0_np).pin_memory()
     p_host = torch.from_numpy(p_np).pin_memory()
-    y0_dev, p_dev = y0_host.to(dev), p_host.to(dev)
-
-    def one_pass(y0, p):
-        s = nbk.RungeKutta45("lorenz", 0.0, y0, p, rtol=RTOL, atol=ATOL, device=local_rank)
-        return s, s.run([T_END])
+    inputs = [(y0_host.to(dev), p_host.to(dev)) for _ in range(ring_n)]
 
     def barrier():
         if world > 1:
@@ -243,39 +426,47 @@ def main():
 
     peak_tf, _ = nbk.fp64_peak(local_rank, 20000)
 
-    # ------------------------------------------------------------ kernel-only arm (inputs resident in HBM)
-    for _ in range(max(args.warmup, 3)):
-        s, (t, y) = one_pass(y0_dev, p_dev)
-    launch = s.last_launch()
+    def kernel_arm(inputs, steps, warmup):
+        """Inputs resident in HBM; nothing but the path itself is queued inside the timed region."""
+        import collections
+
+        live = collections.deque(maxlen=len(inputs))  # keeps the last R states alive: the allocator hands out other memory
+        for i in range(warmup):
+            s = nbk.RungeKutta45("lorenz", 0.0, *inputs[i % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
+            s.run([T_END])
+            live.append(s)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        run_ev = []
+        barrier()
+        ev[0].record()
+        for i in range(steps):
+            s = nbk.RungeKutta45("lorenz", 0.0, *inputs[i % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t, y = s.run([T_END])
+            e1.record()
+            run_ev.append((e0, e1))
+            live.append(s)
+        ev[1].record()
+        barrier()
+        s.raise_for_status()  # device-resident results are checked lazily: once, outside the timed region
+        # every step integrates the same ensemble (deterministic kernels): count once, after the clock stopped
+        acc = float(s._nacc.sum().item())
+        att = acc + float(s._nrej.sum().item())
+        return s, y, ev[0].elapsed_time(ev[1]), sum(a.elapsed_time(b) for a, b in run_ev), acc * steps, att * steps
+
+    # ------------------------------------------------------------ kernel-only arm
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    run_ev = []
-    barrier()
-    ev[0].record()
-    for _ in range(args.steps):
-        # nothing but the path itself is queued inside the timed region: no host sync, no reductions
-        s = nbk.RungeKutta45("lorenz", 0.0, y0_dev, p_dev, rtol=RTOL, atol=ATOL, device=local_rank)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t, y = s.run([T_END])
-        e1.record()
-        run_ev.append((e0, e1))
-    ev[1].record()
-    barrier()
-    s.raise_for_status()  # device-resident results are checked lazily: do it once, outside the timed region
-    # every step integrates the same ensemble (deterministic kernels): count once, after the clock stopped
-    steps_acc = s._nacc.sum() * args.steps
-    attempts = (s._nacc.sum() + s._nrej.sum()) * args.steps
+    s, y_dev, ms_total, ms_run, steps_acc, attempts = kernel_arm(inputs, args.steps, max(args.warmup, 3))
     clocks = sampler.finish()
-    ms_total = ev[0].elapsed_time(ev[1])
-    ms_run = sum(a.elapsed_time(b) for a, b in run_ev)
-    from nbkode_b200 import distributed as nd
-
+    launch = s.last_launch()
     # device-timed, max over ranks; work summed over ranks (the driver computes efficiency itself)
-    (ms_total, ms_run), (total_steps, total_attempts) = nd.reduce_max_sum(
-        [ms_total, ms_run], [float(steps_acc.item()), float(attempts.item())], device=dev)
+    (ms_total, ms_run), (total_steps, total_attempts) = nd.reduce_max_sum([ms_total, ms_run], [steps_acc, attempts], device=dev)
     value = total_steps / (ms_total * 1e-3)
+    y_gpu = y_dev.cpu().numpy() if cpu_legs else None
+    nacc_gpu = s._nacc.cpu().numpy() if cpu_legs else None
+    del s, y_dev
 
     # ------------------------------------------------------------ e2e arm (pinned host buffers in and out)
     # Every pass copies its inputs host->device and its results (final states, step counts) device->host.
@@ -308,49 +499,84 @@ def main():
     barrier()
     t0 = time.perf_counter()
     e2e_steps, pending = 0, None
-    dbg = []
     for i in range(args.steps):
-        ta = time.perf_counter()
         item = e2e_pass(i)
-        tb = time.perf_counter()
         if pending is not None:
             n_i, y, nacc = e2e_finish(pending)
             e2e_steps += n_i
-        dbg.append((1e3 * (tb - ta), 1e3 * (time.perf_counter() - tb)))
         pending = item
     n_i, y, nacc = e2e_finish(pending)
     e2e_steps += n_i
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    if os.environ.get("NBK_BENCH_DEBUG"):
-        print("e2e (enqueue, finish) ms per pass:", " ".join(f"({a:.2f},{b:.2f})" for a, b in dbg), file=sys.stderr)
     h2d = y0_host.numel() * 8 + p_host.numel() * 8
     d2h = y.numel() * 8 + 2 * nacc.numel() * 8
-    (e2e_s,), (e2e_total,) = nd.reduce_max_sum([e2e_s], [float(e2e_steps)], device=dev)
+    # latency of ONE pass, nothing overlapped: host buffers -> result in host memory, wall clock
+    lat = []
+    for i in range(max(3, min(args.steps, 10))):
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        e2e_finish(e2e_pass(i))
+        lat.append(1e3 * (time.perf_counter() - t1))
+    (e2e_s, lat_ms), (e2e_total,) = nd.reduce_max_sum([e2e_s, float(np.median(lat))], [float(e2e_steps)], device=dev)
     e2e_value = e2e_total / e2e_s
+
+    # ------------------------------------------------------------ weak-scaling figure of the same run (N > 1)
+    extra = {}
+    if world > 1 and not args.no_extra:
+        yw, pw = ensembles.lorenz_ensemble(B_TOTAL, seed=rank)
+        w_in = [(torch.from_numpy(yw).to(dev), torch.from_numpy(pw).to(dev))]
+        _s, _y, w_ms, w_run, w_steps, _att = kernel_arm(w_in, args.steps, 3)
+        (w_ms,), (w_steps,) = nd.reduce_max_sum([w_ms], [w_steps], device=dev)
+        extra["weak_scaling"] = {"value": w_steps / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms / args.steps,
+                                 "trajectories_per_gpu": B_TOTAL, "trajectories_total": B_TOTAL * world,
+                                 "note": "every rank integrates its own 1M-trajectory ensemble (seed = rank)"}
+        del _s, _y, w_in
+
     if rank == 0:
         achieved_tf = (total_attempts / world) * FLOP_PER_ATTEMPT / (ms_run * 1e-3) / 1e12  # per GPU
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {**workload_config(world), "trajectories_per_gpu": B},
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world, B_total, l2_note),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "host_numa_bound": bool(numa_bound)},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "host_numa_bound": bool(numa_bound),
+                    "note": "throughput of back-to-back passes alternating between two streams (copies overlap the other "
+                            "pass's kernel); one_pass_latency_ms = one pass alone, host buffers in -> results in host memory",
+                    "one_pass_latency_ms": lat_ms},
             "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": ncu_traffic_bytes(), "traffic_unit": "bytes of DRAM traffic per launch (ncu); algorithmic: ~100 B in + ~330 B out per trajectory",
+                "traffic": ncu_traffic_bytes() if B == B_TOTAL else None,
+                "traffic_unit": "bytes of DRAM traffic per launch (ncu, 1M trajectories); algorithmic: ~100 B in + ~330 B out per trajectory",
                 "note": "FP64 vector (DFMA) pipe; achieved = attempted steps x 264 algorithmic FLOP / persistent-kernel time "
                         "(CUDA events); peak = nbk_fp64_peak DFMA chain measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "kernel": "nbk_run_rk45_lorenz", "kernel_ms_per_step": ms_run / args.steps,
                 "kernel_share_of_step": ms_run / ms_total, "attempts_per_step": total_attempts / world / args.steps,
                 "launch": launch,
             },
-            "accepted_steps_per_pass": total_steps / world / args.steps,
+            "accepted_steps_per_pass": total_steps / args.steps,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_oracle_throughput(y0_np, p_np)
+        if cpu_legs:
+            ref_c, line["cpu_baseline_port"] = cpu_port(y0_np, p_np)
+            line["parity"] = {"vs_c_port_full_ensemble": parity_stats(y_gpu, nacc_gpu, ref_c["ys"], ref_c["n_accepted"])}
+            if pool is not None:
+                ref_l, live = cpu_live(pool, y0_np, p_np)
+                pool.close()
+                n = len(ref_l["ys"])
+                line["cpu_baseline"] = live
+                line["cpu_baseline_numba"] = live
+                line["parity"]["vs_live_nbkode_prefix"] = parity_stats(y_gpu[:n], nacc_gpu[:n], ref_l["ys"], ref_l["n_accepted"])
+                line["parity"]["c_port_vs_live_nbkode_prefix"] = parity_stats(
+                    ref_c["ys"][:n], ref_c["n_accepted"][:n], ref_l["ys"], ref_l["n_accepted"])
+            else:
+                line["cpu_baseline"] = line["cpu_baseline_port"]
+                line["cpu_baseline_numba"] = {"unavailable": pool_note}
+        if world == 1 and not args.no_extra:
+            extra["configs"] = extra_configs(nbk, torch, dev, peak_tf)
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

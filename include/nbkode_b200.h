@@ -73,7 +73,7 @@ extern "C" {
 #define NBK_TRAJ_OK 0
 #define NBK_TRAJ_BOUND 1       /* stopped by the t_bound / upto_t guard, nbkode/core.py:176-184 */
 #define NBK_TRAJ_NONFINITE 2   /* non-finite error norm or collapsed step (the reference spins forever) */
-#define NBK_TRAJ_MAXATTEMPTS 3 /* attempt budget of the call exhausted */
+#define NBK_TRAJ_MAXATTEMPTS 3 /* attempt budget of a call exhausted; terminal (sticky) like every status >= 2 */
 #define NBK_TRAJ_EVBRACKET 4   /* nbk_run_events: an event function does not change sign on the step's interpolant
                                   (the reference's bisect raises ValueError, nbkode/nbcompat/zeros.py:516-520) */
 #define NBK_TRAJ_NEWTON 5      /* implicit multistep: Newton / secant iteration did not converge (the reference raises

@@ -31,7 +31,9 @@ bool nbk_jit_compile(const nbk_jit_request &rq, std::vector<char> &cubin, std::s
 
 // Load a cubin into the current context and resolve the three kernels.
 bool nbk_jit_load(const std::vector<char> &cubin, nbk_jit_module &mod, std::string &err);
+// Drop one reference; modules nobody references stay loaded up to a small bound (least recently used are unloaded).
 void nbk_jit_unload(nbk_jit_module &mod);
+long nbk_jit_modules_loaded();
 
 // cuLaunchKernel with a single by-value argument block.
 bool nbk_jit_launch(void *func, unsigned grid, unsigned block, size_t smem, void *arg_block, void *stream,

@@ -8,7 +8,8 @@
 #define NBK_TRAJ_OK 0          // reached the end of the request
 #define NBK_TRAJ_BOUND 1       // stopped by the t_bound / upto_t guard (nbkode/core.py:176-184)
 #define NBK_TRAJ_NONFINITE 2   // non-finite error norm or step size collapsed to 0
-#define NBK_TRAJ_MAXATTEMPTS 3 // attempt budget of this call exhausted
+#define NBK_TRAJ_MAXATTEMPTS 3 // attempt budget of a call exhausted -- terminal like the other failures (status >= 2 is sticky:
+                               // the stage rows of the interrupted step are overwritten, so the trajectory is not resumed)
 #define NBK_TRAJ_EVBRACKET 4   // run_events: the event function has the same sign at both ends of the step on the
                                // interpolant (the reference's bisect raises ValueError, nbcompat/zeros.py:516-520)
 #define NBK_TRAJ_NEWTON 5      // implicit step: Newton / secant iteration did not converge (the reference raises RuntimeError)

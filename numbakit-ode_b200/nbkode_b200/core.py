@@ -165,6 +165,11 @@ class Solver(ABC):
             else:
                 self.params = params
             per_traj = self._batched and p_t.ndim >= 2 and p_t.shape[0] == self.B and params_batched is not False
+            if per_traj and params_batched is None and p_t.ndim >= 2 and self.B > 1 and tuple(p_t.shape) == (self.n, self.n):
+                # an n x n matrix with B == n: one shared matrix or one parameter row per trajectory?
+                raise ValueError(
+                    f"params of shape {tuple(p_t.shape)} is ambiguous for a batch of {self.B} trajectories with n = {self.n}: "
+                    "pass params_batched=True (one row per trajectory) or params_batched=False (one shared array)")
             if params_batched and not per_traj:
                 raise ValueError("params_batched=True needs params of shape (B, ...)")
             if per_traj:
@@ -257,8 +262,8 @@ class Solver(ABC):
         if self.FIXED_STEP:
             # like the reference, a fixed-step solver keeps the user's value (or the integer 1)
             self.h = np.array(h, dtype=float) if h is not None and np.ndim(h) == 0 else (1 if h is None else h)
-        # the constructor kernel's status is checked at the first synchronising call (run / step /
-        # any property read), so constructing a solver does not stall the stream
+        # the constructor kernel's status is checked at the first synchronising call (run / step / a read of
+        # t, y, f, status, cache, ...), so constructing a solver does not stall the stream
         self._unchecked = "constructor"
         self._oldest_host = float(t0)  # oldest history time, known on the host until the first advance
 
@@ -334,10 +339,18 @@ class Solver(ABC):
             raise ValueError(f"Time {t} is larger than solver bound time t_bound={self.t_bound}")
 
     # ------------------------------------------------------------------ state
+    def _checked(self):
+        """Deferred failure report: a state read is a synchronising call (it copies to the host or hands out
+        device data the caller will trust), so a failure of an earlier, unchecked kernel surfaces here instead
+        of as silent NaN rows."""
+        if self._unchecked:
+            self._raise_on_failure(self._unchecked)
+
     @property
     def cache(self):
         # built on demand: a stored view would form a reference cycle and keep the ensemble's HBM
         # alive until the cyclic garbage collector runs
+        self._checked()
         return _Cache(self)
 
     def _slot_t(self, slot):  # (B,) history times of one slot (0 oldest, -1 newest)
@@ -348,16 +361,19 @@ class Solver(ABC):
 
     @property
     def t(self):
+        self._checked()
         cur = self._slot_t(-1)
         return float(cur[0].item()) if not self._batched else self._out(cur)
 
     @property
     def y(self):
+        self._checked()
         cur = self._slot(self._ys, -1)
         return self._out(cur[0].reshape(self._y0_shape)) if not self._batched else self._out(cur)
 
     @property
     def f(self):
+        self._checked()
         cur = self._slot(self._fs, -1)
         return self._out(cur[0].reshape(self._y0_shape)) if not self._batched else self._out(cur)
 

@@ -146,7 +146,10 @@ class Expr:
     def _cmp(self, *_):
         raise TraceError("comparisons on traced values are not supported; use CudaRHS for branching right-hand sides")
 
-    __lt__ = __le__ = __gt__ = __ge__ = _cmp
+    # == and != too: Python's default identity comparison would evaluate `if y[0] == 0.0:` to a constant at trace
+    # time and freeze one arm of the branch into the CUDA source without any error
+    __lt__ = __le__ = __gt__ = __ge__ = __eq__ = __ne__ = _cmp
+    __hash__ = None
 
     def __getattr__(self, item):
         # NumPy's object-dtype ufunc loops call a method named like the ufunc (np.sin -> .sin())
@@ -238,7 +241,7 @@ class Vec:
         if name == "matmul" and len(inputs) == 2:
             return _vec_matmul(inputs[0], inputs[1]) if isinstance(inputs[1], Vec) and not isinstance(inputs[0], Vec) \
                 else _vec_dot(inputs[0], inputs[1])
-        compare = {"less": "<", "less_equal": "<=", "greater": ">", "greater_equal": ">="}
+        compare = {"less": "<", "less_equal": "<=", "greater": ">", "greater_equal": ">=", "equal": "==", "not_equal": "!="}
         if name in compare and len(inputs) == 2:
             return _vec_binary(inputs[0], inputs[1], compare[name])
         if name == "sign" and len(inputs) == 1:
@@ -272,6 +275,9 @@ class Vec:
     def __le__(self, o): return _vec_binary(self, o, "<=")
     def __gt__(self, o): return _vec_binary(self, o, ">")
     def __ge__(self, o): return _vec_binary(self, o, ">=")
+    def __eq__(self, o): return _vec_binary(self, o, "==")  # a mask for np.where, like the other comparisons
+    def __ne__(self, o): return _vec_binary(self, o, "!=")
+    __hash__ = None
     def sum(self, axis=None): return _vec_sum(self)
     def mean(self, axis=None): return _vec_sum(self) / float(self.length)
     def dot(self, o): return _vec_dot(self, o)
@@ -364,6 +370,15 @@ class Sc:
     def __pos__(self): return self
     def __abs__(self): return Sc(f"fabs({self.c})")
     def __pow__(self, e): return Sc(_pow_code(self.c, e))
+
+    def _cmp(self, o):
+        if isinstance(o, Vec):
+            return NotImplemented  # scalar (x) vector comparison: the vector builds the mask
+        raise TraceError("comparisons on traced scalars are not supported (an `if t == 0:` would be frozen at trace "
+                         "time); use np.where on vectors, or write the right-hand side as CUDA C")
+
+    __lt__ = __le__ = __gt__ = __ge__ = __eq__ = __ne__ = _cmp
+    __hash__ = None
 
     def __bool__(self):
         raise TraceError("data-dependent control flow cannot be traced; write the right-hand side as CUDA C")

@@ -754,41 +754,12 @@ EVENTS = {"y0_up_terminal": ev_y0_up_terminal, "y0": ev_y0, "y1_down": ev_y1_dow
 RHS = {"decay": rhs_decay, "lorenz": rhs_lorenz, "vdp": rhs_vdp, "linear": rhs_linear, "rd1d": rhs_rd1d}
 
 
-def lorenz_ensemble(B, seed=0):
-    """C2 generator of SURVEY.md section 8(d): draw order x0,y0,z0,sigma,rho,beta."""
-    rng = np.random.default_rng(seed)
-    x0 = rng.uniform(-15, 15, B)
-    y0 = rng.uniform(-20, 20, B)
-    z0 = rng.uniform(5, 45, B)
-    sg = rng.uniform(8, 12, B)
-    rh = rng.uniform(20, 36, B)
-    be = rng.uniform(2, 3.5, B)
-    return np.stack([x0, y0, z0], 1), np.stack([sg, rh, be], 1)
+# input generators of the BASELINE configurations: defined in the package (so that the product harness never
+# needs oracle/), re-exported here for the tests and the CPU baseline
+import os as _os
+import sys as _sys
 
-
-def vdp_ensemble(B, seed=1):
-    """C3 generator of SURVEY.md section 8(d)."""
-    rng = np.random.default_rng(seed)
-    mu = np.linspace(0.1, 5, B)
-    y0 = np.stack([rng.uniform(-2.5, 2.5, B), rng.uniform(-2.5, 2.5, B)], 1)
-    return y0, mu[:, None].copy()
-
-
-def linear_ensemble(B, n=128, seed=2):
-    """C4 generator: A = G/sqrt(n) - I (shared), y0 ~ N(0,1)."""
-    rng = np.random.default_rng(seed)
-    A = rng.standard_normal((n, n)) / math.sqrt(n) - np.eye(n)
-    y0 = rng.standard_normal((B, n))
-    return y0, A
-
-
-def rd1d_ensemble(B, n=2048, seed=3):
-    """C5 generator: kappa~U(0.5e-4,2e-4), r~U(0.5,2), y0=0.5+0.4 sin(2 pi x + phi)."""
-    rng = np.random.default_rng(seed)
-    kappa = rng.uniform(0.5e-4, 2e-4, B)
-    r = rng.uniform(0.5, 2, B)
-    phi = rng.uniform(0, 2 * np.pi, B)
-    x = np.arange(n) / n
-    y0 = 0.5 + 0.4 * np.sin(2 * np.pi * x[None, :] + phi[:, None])
-    d = kappa * n * n  # kappa / dx^2
-    return y0, np.stack([d, r], 1)
+_pkg = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "numbakit-ode_b200")
+if _pkg not in _sys.path:
+    _sys.path.insert(0, _pkg)
+from nbkode_b200.ensembles import lorenz_ensemble, linear_ensemble, rd1d_ensemble, vdp_ensemble  # noqa: E402,F401

@@ -136,6 +136,29 @@ def test_trace_rejects_untraceable():
     with pytest.raises(rhs.TraceError):
         rhs.trace(branching, 1, (), False)
 
+    # == / != must not fall back to Python's identity comparison (that would freeze one arm of the branch into the
+    # CUDA source at trace time, silently diverging from the reference, which branches at run time)
+    def eq_branch(t, y):
+        if y[0] == 0.0:
+            return np.array([1.0 + 0 * y[0]])
+        return -y
+
+    def ne_time(t, y):
+        if t != 0:
+            return -y
+        return y
+
+    for fn in (eq_branch, ne_time):
+        with pytest.raises(rhs.TraceError):
+            rhs.trace(fn, 1, (), False)
+        with pytest.raises(rhs.TraceError):
+            rhs.trace_cta(fn, 1, (), False)
+    with pytest.raises(TypeError):
+        hash(rhs.Sc("t"))
+    # vectors: == builds a mask for np.where, like the other comparisons
+    src = rhs.trace_cta(lambda t, y: np.where(y == 0.0, 1.0, -y), 128, (), False).source
+    assert "==" in src
+
     def wrong_size(t, y):
         return np.array([y[0], y[0]])
 

@@ -11,7 +11,7 @@ import numpy as np, torch
 import torch.distributed as dist
 import nbkode_b200 as nbk
 from nbkode_b200 import distributed as nd
-from oracle import nbk_oracle_np as onp  # input generator only (the C5 ensemble of SURVEY.md 8(d))
+from nbkode_b200 import ensembles as onp  # input generators
 
 B_total = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 n = 2048

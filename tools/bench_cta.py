@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "numbakit-ode_b200")]
 import numpy as np, torch
 import nbkode_b200 as nbk
-from oracle import nbk_oracle_np as onp
+from nbkode_b200 import ensembles as onp  # input generators
 
 which = sys.argv[1] if len(sys.argv) > 1 else "rd1d"
 cls = sys.argv[4] if len(sys.argv) > 4 else "RungeKutta45"  # a fixed-step class runs rd1d with h = 5e-4 to T = 0.1

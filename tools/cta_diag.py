@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "numbakit-ode_b200")]
 import numpy as np, torch
 import nbkode_b200 as nbk
-from oracle import nbk_oracle_c as oc, nbk_oracle_np as onp
+from oracle import nbk_oracle_c as oc, nbk_oracle_np as onp  # diagnostic tool: compares against the oracle on purpose
 for cls, n, B in (("RungeKutta45", 2048, 48), ("RungeKutta45", 100, 40), ("RungeKutta23", 2048, 8)):
     y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
     ts = [0.25, 0.5]

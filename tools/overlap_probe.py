@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "numbakit-ode_b200")]
 import numpy as np, torch
 import nbkode_b200 as nbk
-from oracle import nbk_oracle_np as onp
+from nbkode_b200 import ensembles as onp  # input generators
 
 B = 1_000_000
 y0, p = onp.lorenz_ensemble(B, 0)

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "numbakit-ode_b200")]
 import numpy as np, torch
 import nbkode_b200 as nbk
-from oracle import nbk_oracle_np as onp
+from nbkode_b200 import ensembles as onp  # input generators
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 cls = sys.argv[3] if len(sys.argv) > 3 else "RungeKutta23"

@@ -7,18 +7,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "numbakit-ode_b200")]
 import numpy as np, torch
 import nbkode_b200 as nbk
-from oracle import nbk_oracle_np as onp
+from nbkode_b200 import ensembles as onp  # input generators
 
 method = os.environ.get("NBK_TUNE_METHOD", "RungeKutta45")
 FLOP = {"RungeKutta45": 264, "RungeKutta23": 123, "DOP853": 635}[method]
 B = int(os.environ.get("NBK_TUNE_B", 1_000_000)); reps = int(os.environ.get("NBK_TUNE_REPS", 6))
 rtol, atol = float(os.environ.get("NBK_TUNE_RTOL", 1e-6)), float(os.environ.get("NBK_TUNE_ATOL", 1e-9))
 y0, p = onp.lorenz_ensemble(B, 0)
+
+
+def rhs_lorenz(t, y, p):
+    return np.array([p[0] * (y[1] - y[0]), y[0] * (p[1] - y[2]) - y[1], y[0] * y[1] - p[2] * y[2]])
+
+
 y0d, pd = torch.from_numpy(y0).cuda(), torch.from_numpy(p).cuda()
 times, att = [], 0
 for it in range(reps + 3):
     # NBK_TUNE_JIT=1: the same right-hand side as a Python callable (traced -> CUDA C -> NVRTC) instead of the catalogue kernel
-    s = getattr(nbk, method)(onp.rhs_lorenz if os.environ.get("NBK_TUNE_JIT") else "lorenz", 0.0, y0d, pd, rtol=rtol, atol=atol)
+    s = getattr(nbk, method)(rhs_lorenz if os.environ.get("NBK_TUNE_JIT") else "lorenz", 0.0, y0d, pd, rtol=rtol, atol=atol)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); s.run([10.0]); e1.record(); torch.cuda.synchronize()
     if it >= 3: times.append(e0.elapsed_time(e1))
