@@ -101,20 +101,24 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_ms=100):
-        self.index, self.period_ms, self.proc = index, period_ms, None
+    def __init__(self, index, period_ms=None):
+        self.index, self.proc, self.first = index, None, None
+        self.period_ms = int(period_ms or os.environ.get("NBK_BENCH_SMI_MS", 100))
 
     def start(self):
         import shutil
         import subprocess
 
         exe = shutil.which("nvidia-smi")
-        if exe is None:
+        if exe is None or self.period_ms <= 0:
             return
         try:
             self.proc = subprocess.Popen(
                 [exe, f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                  f"-lms={self.period_ms}"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            # nvidia-smi's start-up (NVML initialisation, ~100 ms) must not overlap the timed region: wait for its
+            # first sample before going on
+            self.first = self.proc.stdout.readline()
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -128,6 +132,7 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
             out = ""
+        out = (self.first or "") + out
         sm, mx, power, reasons = [], None, [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in out.strip().splitlines():

@@ -54,6 +54,19 @@ static __device__ __forceinline__ float nbk_ex2(float x) { float r; asm("ex2.app
 #ifndef NBK_FULL_MASK
 #define NBK_FULL_MASK 0xffffffffu  // tests/emul compiles the kernels for the host as 1-lane warps
 #endif
+// Tail compaction of the persistent adaptive kernels (advance_adaptive): once the trajectory queue is empty, the warps
+// of a CTA merge their surviving trajectories through a shared-memory pool so that whole warps retire instead of
+// running on with a few live lanes each.  Off in the host emulation (one-lane warps, no shared memory).
+#ifndef NBK_COMPACT
+#ifdef NBK_HOST_EMUL
+#define NBK_COMPACT 0
+#else
+#define NBK_COMPACT 1
+#endif
+#endif
+#ifndef NBK_POOL_BYTES
+#define NBK_POOL_BYTES (36 * 1024)  // shared memory a CTA may spend on the pool
+#endif
 
 namespace nbk {
 
@@ -876,6 +889,27 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     int kout = 0;            // RUN: next grid index
     bool fresh = true;       // the next attempt opens a new step (K[S] holds f(t, y))
     int status = NBK_TRAJ_OK;
+
+    // ---- tail compaction (see NBK_COMPACT above).  A parked trajectory is its loop-carried state: t, h, te_next, y, K,
+    // p (NFD doubles), its index and four counters.  The pool holds at most CAP of them, field-major so that the lanes
+    // of a warp touch consecutive words.  Everything below the lock is warp-uniform control flow.
+    constexpr int NWARP_MAX = NBK_BLOCK / 32;
+    constexpr int NFD = 3 + N + (S + 1) * N + NPX;
+    constexpr int CAP0 = NBK_POOL_BYTES / ((NFD + 3) * 8);
+    constexpr int CAP = CAP0 > 32 * (NWARP_MAX - 1) ? 32 * (NWARP_MAX - 1) : CAP0;
+    constexpr bool COMPACT = NBK_COMPACT && !EV && NWARP_MAX > 1 && CAP >= 16;
+    constexpr int CAPS = COMPACT ? CAP : 1;
+#if NBK_COMPACT
+    __shared__ double pool_d[COMPACT ? NFD : 1][CAPS];
+    __shared__ long long pool_idx[CAPS];
+    __shared__ int pool_i[4][CAPS];
+    __shared__ int pool_lock, pool_count, pool_live, warp_idle[NWARP_MAX];
+    if constexpr (COMPACT) {
+        if (threadIdx.x == 0) pool_lock = 0, pool_count = 0, pool_live = (int)(blockDim.x >> 5);
+        if (threadIdx.x < NWARP_MAX) warp_idle[threadIdx.x] = 0;
+        __syncthreads();
+    }
+#endif
 #ifdef NBK_NEVENTS
     double ev_last[NBK_NEVENTS];  // EV: value of every event function at the last accepted point
 #endif
@@ -914,6 +948,91 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
         const unsigned idle = __ballot_sync(FULL, !running);
         if (idle) {
             if (queue_empty) {
+#if NBK_COMPACT
+                if constexpr (COMPACT) {
+                    // The queue is empty: from here on trajectories only finish.  Under the CTA's pool lock this warp
+                    // (1) fills its idle lanes with parked trajectories, then (2) if it is still not full and the other
+                    // live warps of the CTA have room for all of its trajectories, parks them and retires.  The last
+                    // live warp of a CTA never parks, and a warp only leaves empty-handed when the pool is empty
+                    // (it would have taken otherwise), so no trajectory is orphaned.
+                    const int warp = (int)(threadIdx.x >> 5), nwarp = (int)(blockDim.x >> 5);
+                    if (lane == 0)
+                        while (atomicCAS(&pool_lock, 0, 1) != 0) {}
+                    __syncwarp();
+                    __threadfence_block();
+                    int cnt = *(volatile int *)&pool_count;
+                    int live = *(volatile int *)&pool_live;
+                    const int nidle = __popc(idle);
+                    const int take = nidle < cnt ? nidle : cnt;
+                    const int irank = __popc(idle & ((1u << lane) - 1u));
+                    if (!running && irank < take) {
+                        const int slot = cnt - 1 - irank;
+                        int f = 0;
+                        t = pool_d[f++][slot];
+                        h = pool_d[f++][slot];
+                        te_next = pool_d[f++][slot];
+#pragma unroll
+                        for (int c = 0; c < N; ++c) y[c] = pool_d[f++][slot];
+#pragma unroll
+                        for (int q = 0; q <= S; ++q)
+#pragma unroll
+                            for (int c = 0; c < N; ++c) K[q][c] = pool_d[f++][slot];
+#pragma unroll
+                        for (int c = 0; c < NPX; ++c) p[c] = pool_d[f++][slot];
+                        idx = pool_idx[slot];
+                        nacc = pool_i[0][slot];
+                        natt = pool_i[1][slot];
+                        kout = pool_i[2][slot];
+                        fresh = pool_i[3][slot] != 0;
+                        status = NBK_TRAJ_OK;
+                        running = true;
+                    }
+                    cnt -= take;
+                    const int act = 32 - nidle + take;
+                    bool leave = act == 0;
+                    if (act > 0 && act < 32 && live > 1 && cnt + act <= CAP) {
+                        int room = -cnt;
+                        for (int w = 0; w < nwarp; ++w)
+                            if (w != warp) room += *(volatile int *)&warp_idle[w];
+                        if (room >= act) {
+                            const unsigned busy = __ballot_sync(FULL, running);
+                            if (running) {
+                                const int slot = cnt + __popc(busy & ((1u << lane) - 1u));
+                                int f = 0;
+                                pool_d[f++][slot] = t;
+                                pool_d[f++][slot] = h;
+                                pool_d[f++][slot] = te_next;
+#pragma unroll
+                                for (int c = 0; c < N; ++c) pool_d[f++][slot] = y[c];
+#pragma unroll
+                                for (int q = 0; q <= S; ++q)
+#pragma unroll
+                                    for (int c = 0; c < N; ++c) pool_d[f++][slot] = K[q][c];
+#pragma unroll
+                                for (int c = 0; c < NPX; ++c) pool_d[f++][slot] = p[c];
+                                pool_idx[slot] = idx;
+                                pool_i[0][slot] = nacc;
+                                pool_i[1][slot] = natt;
+                                pool_i[2][slot] = kout;
+                                pool_i[3][slot] = fresh ? 1 : 0;
+                                running = false;
+                                idx = -1;
+                            }
+                            cnt += act;
+                            leave = true;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        warp_idle[warp] = leave ? 0 : 32 - act;
+                        pool_count = cnt;
+                        pool_live = live - (leave ? 1 : 0);
+                        __threadfence_block();
+                        atomicExch(&pool_lock, 0);
+                    }
+                    if (leave) break;
+                } else
+#endif
                 if (idle == FULL) break;
             } else if (__popc(idle) >= NBK_REFILL_MIN) {
                 const int nidle = __popc(idle);

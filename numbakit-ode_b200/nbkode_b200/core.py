@@ -165,11 +165,17 @@ class Solver(ABC):
             else:
                 self.params = params
             per_traj = self._batched and p_t.ndim >= 2 and p_t.shape[0] == self.B and params_batched is not False
-            if per_traj and params_batched is None and p_t.ndim >= 2 and self.B > 1 and tuple(p_t.shape) == (self.n, self.n):
-                # an n x n matrix with B == n: one shared matrix or one parameter row per trajectory?
-                raise ValueError(
-                    f"params of shape {tuple(p_t.shape)} is ambiguous for a batch of {self.B} trajectories with n = {self.n}: "
-                    "pass params_batched=True (one row per trajectory) or params_batched=False (one shared array)")
+            if per_traj and params_batched is None and self.B > 1 and tuple(p_t.shape) == (self.n, self.n):
+                # an n x n array with B == n: one shared matrix or one parameter row per trajectory?
+                if isinstance(rhs, str) and rhs == "linear":
+                    per_traj = False  # the built-in y' = A y takes exactly one shared n x n matrix
+                elif not isinstance(rhs, str):
+                    import warnings
+
+                    warnings.warn(
+                        f"params of shape {tuple(p_t.shape)} is ambiguous for a batch of {self.B} trajectories with n = {self.n}; "
+                        "taken as one parameter row per trajectory -- pass params_batched=False for one shared array "
+                        "(or params_batched=True to silence this warning)", stacklevel=3)
             if params_batched and not per_traj:
                 raise ValueError("params_batched=True needs params of shape (B, ...)")
             if per_traj:
