@@ -905,7 +905,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     __shared__ int pool_i[4][CAPS];
     __shared__ int pool_lock, pool_count, pool_live, warp_idle[NWARP_MAX];
     if constexpr (COMPACT) {
-        if (threadIdx.x == 0) pool_lock = 0, pool_count = 0, pool_live = (int)(blockDim.x >> 5);
+        if (threadIdx.x == 0) pool_lock = 0, pool_count = 0, pool_live = (1 << (blockDim.x >> 5)) - 1;  // bit w: warp w is live
         if (threadIdx.x < NWARP_MAX) warp_idle[threadIdx.x] = 0;
         __syncthreads();
     }
@@ -914,6 +914,14 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     double ev_last[NBK_NEVENTS];  // EV: value of every event function at the last accepted point
 #endif
 
+#ifdef NBK_DEBUG_COMPACT
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        a.work_counter[6] = ns;
+    }
+    unsigned long long dbg_reps = 0;  // attempts (loop iterations) this warp executed after it saw the queue empty
+#endif
     for (;;) {
         // ---------------------------------------------------------------- (1) retire
         if (finishing) {
@@ -952,9 +960,9 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 if constexpr (COMPACT) {
                     // The queue is empty: from here on trajectories only finish.  Under the CTA's pool lock this warp
                     // (1) fills its idle lanes with parked trajectories, then (2) if it is still not full and the other
-                    // live warps of the CTA have room for all of its trajectories, parks them and retires.  The last
-                    // live warp of a CTA never parks, and a warp only leaves empty-handed when the pool is empty
-                    // (it would have taken otherwise), so no trajectory is orphaned.
+                    // live warps of the CTA have room for all of its trajectories, parks them and retires.  Warp 0
+                    // never parks and only leaves when it is the last live warp with nothing to do (the pool is empty
+                    // then: it would have taken otherwise), so no trajectory is orphaned.
                     const int warp = (int)(threadIdx.x >> 5), nwarp = (int)(blockDim.x >> 5);
                     if (lane == 0)
                         while (atomicCAS(&pool_lock, 0, 1) != 0) {}
@@ -989,8 +997,15 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     }
                     cnt -= take;
                     const int act = 32 - nidle + take;
-                    bool leave = act == 0;
-                    if (act > 0 && act < 32 && live > 1 && cnt + act <= CAP) {
+                    // Warps retire in a fixed order -- 3, then 2, then 1; warp 0 is the collector that never parks and
+                    // leaves last.  Measured on B200 (tools/micro/fp64_smsp.cu): the warps with the SAME index of the four
+                    // resident CTAs of an SM sit on four different sub-partitions, warps with different indices may
+                    // share one.  With "whoever is last" as the survivor the four survivors of an SM collided on the FP64
+                    // pipes and ran at half speed (no gain at all from compacting); with warp 0 as the only survivor
+                    // 125 000 trajectories took 1.17 instead of 1.28 ms, with the fixed retirement order 1.12 ms.
+                    bool leave = act == 0 && (warp != 0 || live == 1);
+                    const bool may_park = warp != 0 && (live >> (warp + 1)) == 0;
+                    if (act > 0 && act < 32 && may_park && cnt + act <= CAP) {
                         int room = -cnt;
                         for (int w = 0; w < nwarp; ++w)
                             if (w != warp) room += *(volatile int *)&warp_idle[w];
@@ -1023,14 +1038,23 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                         }
                     }
                     __syncwarp();
+#ifdef NBK_DEBUG_COMPACT
+                    if (lane == 0) {  // diagnostics only (tools/compact_debug.py): the Python shell allocates 8 words
+                        atomicAdd(a.work_counter + 2, 1ULL);                                   // lock acquisitions
+                        atomicAdd(a.work_counter + 3, (unsigned long long)take);               // trajectories taken
+                        if (leave && act > 0) atomicAdd(a.work_counter + 4, (unsigned long long)act);  // parked
+                        if (leave) atomicAdd(a.work_counter + 5, 1ULL);                        // warps retired here
+                    }
+#endif
                     if (lane == 0) {
                         warp_idle[warp] = leave ? 0 : 32 - act;
                         pool_count = cnt;
-                        pool_live = live - (leave ? 1 : 0);
+                        pool_live = leave ? (live & ~(1 << warp)) : live;
                         __threadfence_block();
                         atomicExch(&pool_lock, 0);
                     }
                     if (leave) break;
+                    if (act == 0) __nanosleep(400);  // the collector waits for the other warps to park or finish
                 } else
 #endif
                 if (idle == FULL) break;
@@ -1040,7 +1064,16 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                 const int leader = __ffs(idle) - 1;
                 if (lane == leader) base = atomicAdd(a.work_counter, (unsigned long long)nidle);
                 base = __shfl_sync(FULL, base, leader);
-                if ((long long)(base + nidle) >= B) queue_empty = true;
+                if ((long long)(base + nidle) >= B) {
+#ifdef NBK_DEBUG_COMPACT
+                    if (!queue_empty && lane == 0) {
+                        unsigned long long ns;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                        a.work_counter[8 + 4096 + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % 4096] = ns;
+                    }
+#endif
+                    queue_empty = true;
+                }
                 const long long mine = (long long)base + __popc(idle & ((1u << lane) - 1u));
                 if (!running && mine < B) {
                     idx = mine;
@@ -1134,6 +1167,9 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
         // (of ~500 per trajectory) and the vote/branch overhead is paid once per NBK_INNER.
 #pragma unroll 1
         for (int rep = 0; rep < NBK_INNER; ++rep) {
+#ifdef NBK_DEBUG_COMPACT
+            if (queue_empty) ++dbg_reps;
+#endif
             if (running) {
                 if (fresh) {  // FSAL: last stage of the accepted step opens the next one
 #pragma unroll
@@ -1250,6 +1286,14 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
             }
         }
     }
+#ifdef NBK_DEBUG_COMPACT
+    if (lane == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        a.work_counter[8 + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % 4096] = ns;
+        a.work_counter[8 + 8192 + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % 4096] = dbg_reps;
+    }
+#endif
 }
 
 // =====================================================================================

@@ -239,7 +239,7 @@ class Solver(ABC):
         self._nrej = torch.empty((B,), dtype=torch.int64, device=dev)
         self._status = torch.empty((B,), dtype=torch.int32, device=dev)
         self._nout = torch.zeros((B,), dtype=torch.int32, device=dev)
-        self._queue = torch.zeros((2,), dtype=torch.int64, device=dev)  # [queue head, failures of the last call]
+        self._queue = torch.zeros((8 + (3 * 4096 if os.environ.get('NBK_DEBUG_COMPACT') else 0),), dtype=torch.int64, device=dev)  # [queue head, failures of the last call, 6 diagnostic words]
         ptr = lambda x: x.data_ptr() if x is not None else None  # noqa: E731
         self._state = _lib.NbkState(
             ptr(self._ts), ptr(self._ys), ptr(self._fs), ptr(self._K), ptr(self._h), ptr(self._p),
