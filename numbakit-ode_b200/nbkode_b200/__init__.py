@@ -10,7 +10,10 @@ a ctypes C-ABI; there is no CPU fallback.
 from . import multistep, runge_kutta  # noqa: F401  (importing registers the solver classes)
 from .core import Solver, get_groups, get_solver, get_solvers, list_solvers
 from .rhs import CudaEvents, CudaRHS
+from .sharded import ShardedSolver
 from ._lib import CompileError, NbkError, fp64_peak
+
+Solver.register(ShardedSolver)  # isinstance(solver, Solver) holds for the multi-device object, too
 
 __version__ = "0.1.0"
 

@@ -134,14 +134,28 @@ class Solver(ABC):
         cls.SOLVERS_BY_GROUP[cls.GROUP].append(cls)
 
     # ------------------------------------------------------------------ construction
-    def __init__(self, rhs, t0, y0, params=None, *, h=None, t_bound=np.inf, device=None,
+    def __new__(cls, *args, devices=None, **kwargs):
+        # devices=[0, 1, ...]: one solver per device behind one object (one device / stream per slice,
+        # launch all, one gather) -- see sharded.py
+        if devices is not None and len(devices) > 1:
+            from .sharded import ShardedSolver
+
+            return ShardedSolver(cls, *args, devices=list(devices), **kwargs)
+        return super().__new__(cls)
+
+    def __init__(self, rhs, t0, y0, params=None, *, h=None, t_bound=np.inf, device=None, devices=None,
                  params_batched: Optional[bool] = None, regime: str = "auto", _options=None, _first_step=None,
                  _first_stepper=0):
         torch = _torch()
         self.t_bound = t_bound
         self.user_rhs = rhs
         self._handle = None
-        self._dev_index = default_device() if device is None else int(torch.device(device).index or 0)
+        if devices is not None:
+            if len(devices) != 1 or device is not None:
+                raise ValueError("pass either device= or devices=[...]")
+            device = devices[0]
+        self._dev_index = default_device() if device is None else (
+            int(device) if isinstance(device, (int, np.integer)) else int(torch.device(device).index or 0))
         self._device = torch.device("cuda", self._dev_index)
 
         # ---- y0: () / (n,) unbatched, (B, n) batched

@@ -29,3 +29,33 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Parity bars that are not the plain north-star bar are stated as "measured + margin": `parity_bar` computes
+# max |got - ref| / (rtol |ref| + atol), records it (gpurun_out/parity_measured.json, copied into profiles/ per
+# round) and asserts it against the limit given at the call site.
+# ---------------------------------------------------------------------------------------------------------------
+_MEASURED = {}
+
+
+def parity_bar(name, got, ref, rtol, atol, limit):
+    import numpy as np
+
+    got, ref = np.asarray(got, dtype=float), np.asarray(ref, dtype=float)
+    ratio = float(np.max(np.abs(got - ref) / (rtol * np.abs(ref) + atol)))
+    _MEASURED[name] = {"max_err_over_tol": ratio, "limit": limit, "n": int(ref.size)}
+    assert ratio <= limit, f"{name}: max |d| / (rtol |y| + atol) = {ratio:.3f} > {limit}"
+    return ratio
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _MEASURED:
+        return
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.json"), "w") as fh:
+            json.dump(_MEASURED, fh, indent=1, sort_keys=True)
+    except OSError:
+        pass

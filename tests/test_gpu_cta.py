@@ -7,7 +7,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import load_golden, parity_bar
 
 pytestmark = pytest.mark.gpu
 
@@ -46,12 +46,24 @@ def test_rd1d_vs_oracle(cls, n, B):
     t, y = s.run(ts)
     assert y.shape == (B, 2, n)
     assert np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
-    # The explicit pairs run this stiff grid at the edge of their stability region (h d ~ 0.8, first
-    # step far outside it), where rounding noise in the highest grid mode is amplified ~40x per stage and
-    # reaches the error estimate.  Two correct implementations therefore differ by O(tolerance): the
-    # bit-exact NumPy restatement of the reference and the C oracle themselves differ by up to 1.22x
-    # (rtol |y| + atol) on this ensemble (trajectory 15), the same figure the GPU shows.  Bar: 3x.
-    assert within(y, ref["ys"], 1e-6, 1e-9, slack=3).all()
+    # The explicit pairs run this stiff grid at the edge of their stability region (h d ~ 0.8, first step far outside
+    # it), where rounding noise in the highest grid mode is amplified ~40x per stage and reaches the error estimate: two
+    # faithful implementations differ by O(tolerance).  The checker here is the BIT-EXACT NumPy restatement of the
+    # reference; bars = measured + margin (profiles/r02_parity.json, B200):
+    #   RungeKutta45 (the pair of BASELINE configs[4]): GPU vs restatement <= 0.63x on every shape (0.08x at n = 2048,
+    #     0.04x on configs[4] itself to t = 1) -> the plain north-star bar, 1x;
+    #   RungeKutta23 (not a BASELINE pair on this grid): GPU vs restatement 1.54x / 1.91x at n = 2048 / 1000, while the
+    #     C port differs from the SAME restatement by 0.76x / 1.91x -- the noise floor of the problem itself -> 2.5x.
+    # Against the C port (all B trajectories): measured <= 1.14x (RungeKutta45, n = 700), 1.42x (RungeKutta23) -> 1.5x / 2.5x.
+    nnp = min(B, 12 if n >= 2048 else 8)
+    ynp = []
+    for i in range(nnp):
+        o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[i], p[i], rtol=1e-6, atol=1e-9)
+        ynp.append(onp.run(o, ts)[1])
+        assert abs(int(s.n_accepted[i]) - o.n_accepted) <= 1
+    rk45 = cls == "RungeKutta45"
+    parity_bar(f"c5/{cls}/n{n}/gpu_vs_numpy_restatement", y[:nnp], np.array(ynp), 1e-6, 1e-9, 1.0 if rk45 else 2.5)
+    parity_bar(f"c5/{cls}/n{n}/gpu_vs_c_port", y, ref["ys"], 1e-6, 1e-9, 1.5 if rk45 else 2.5)
     # (two CPU restatements with different FMA contraction differ by up to 0.99x on the RungeKutta23 / n = 1000 case)
     assert within(y, ref["ys"], 1e-6, 1e-9).mean() > 0.99
     # the end state sits at each implementation's own (noise-dependent) last step: loose check only
@@ -104,7 +116,8 @@ def test_user_cuda_rhs_and_api_in_cta_regime():
     tb, yb = b.run([0.2, 0.4])
     # same counts; values agree to tolerance (a different FMA contraction of the stencil is enough to
     # change the amplified rounding noise, see test_rd1d_vs_oracle)
-    assert np.abs(a.n_accepted - b.n_accepted).max() <= 1 and within(yb, ya, 1e-6, 1e-9, slack=3).all()
+    assert np.abs(a.n_accepted - b.n_accepted).max() <= 1
+    parity_bar("c5/user_cuda_rhs_vs_builtin/n600", yb, ya, 1e-6, 1e-9, 1.5)
     # step / skip / resumed run / interpolate / t_bound in the CTA regime
     c = nbk.RungeKutta45("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
     t1, y1 = c.step(n=5)
@@ -188,7 +201,7 @@ def test_python_vector_rhs_traced_into_cta_regime():
     tb, yb = b.run([0.05, 0.1])
     assert np.abs(s.n_accepted - b.n_accepted).max() <= 1
     tol = 1e-6 * np.abs(yb) + 1e-9
-    assert (np.abs(y - yb) <= 3 * tol).all()  # stability-limited grid: 3x bar as for the built-in
+    parity_bar("c5/traced_python_rhs_vs_builtin", y, yb, 1e-6, 1e-9, 1.5)  # stability-limited grid (test_rd1d_vs_oracle)
 
     # non-periodic stencil assembled by slice assignment, captured grid, time-dependent source: against the NumPy oracle
     m = 100
@@ -210,7 +223,7 @@ def test_python_vector_rhs_traced_into_cta_regime():
         o = onp.AdaptiveRK("RungeKutta23", heat, 0.0, y0h[i], ph[i], rtol=1e-5, atol=1e-8)
         _, yo = onp.run(o, [0.02, 0.05])
         assert abs(s.n_accepted[i] - o.n_accepted) <= 1
-        assert (np.abs(y[i] - yo) <= 3 * (1e-5 * np.abs(yo) + 1e-8)).all()
+        parity_bar(f"cta/heat_rk23_vs_numpy_restatement/{i}", y[i], yo, 1e-5, 1e-8, 2.5)
 
 
 FIXED_CTA = [("ForwardEuler", {}), ("AdamsBashforth2", {}), ("AdamsBashforth4", {}), ("AdamsBashforth5", {"first_stepper_cls": "RungeKutta23"}),
@@ -368,7 +381,7 @@ def test_dop853_in_cta_regime():
 def test_cta_edge_shapes():
     """Limits of the regime: the largest state (n = 8192: 32 components per thread), one above it (refused with the
     C-ABI's message), a single unbatched trajectory, a grid point at t0, and one trajectory more than resident CTAs."""
-    # n = 8192, B = 3 against the C oracle (stability-limited grid: 3x bar, see test_rd1d_vs_oracle)
+    # n = 8192, B = 3 against the C oracle (stability-limited grid: measured + margin, see test_rd1d_vs_oracle)
     n = 8192
     y0, p = onp.rd1d_ensemble(3, n=n, seed=7)
     p[:, 0] *= 1.0 / 64  # keep the step count small: kappa / dx^2 grows with n^2
@@ -376,7 +389,7 @@ def test_cta_edge_shapes():
     s = nbk.RungeKutta45("rd1d", 0.0, y0, p, rtol=1e-6, atol=1e-9)
     _, y = s.run([0.05])
     assert s.last_launch()["block"] == 256 and np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1
-    assert within(y, ref["ys"], 1e-6, 1e-9, slack=3).all()
+    parity_bar("c5/RungeKutta45/n8192/gpu_vs_c_port", y, ref["ys"], 1e-6, 1e-9, 1.5)
     with pytest.raises((ValueError, nbk.NbkError), match="8192"):
         nbk.RungeKutta45("rd1d", 0.0, np.zeros((2, 8193)), np.ones((2, 2)))
     # one unbatched trajectory: reference shapes (m, n), scalar t; the first grid point is t0 itself
@@ -385,7 +398,7 @@ def test_cta_edge_shapes():
     t, yy = u.run([0.0, 0.1])
     assert yy.shape == (2, 256) and np.array_equal(yy[0], y1[0]) and np.ndim(u.t) == 0
     o = oc.run_ensemble("RungeKutta45", "rd1d", y1, p1, [0.1], rtol=1e-6, atol=1e-9, nthreads=1)
-    assert within(yy[1], o["ys"][0, 0], 1e-6, 1e-9, slack=3).all()
+    parity_bar("c5/RungeKutta45/n256_unbatched/gpu_vs_c_port", yy[1], o["ys"][0, 0], 1e-6, 1e-9, 1.5)
     # more trajectories than resident CTAs by one: the queue hands the last one to whichever CTA finishes first
     sm = torch.cuda.get_device_properties(0).multi_processor_count
     B = sm * 8 + 1

@@ -94,7 +94,7 @@ def test_adaptive_single(c):
 def test_fixed_single(c):
     kw = {k: (None if v == "None" else v) for k, v in c["kw"].items()}
     s = getattr(nbk, c["cls"])(c["rhs"], 0.0, np.array(c["y0"]), np.array(c["p"]), h=c["h"], **kw)
-    tol = 1e-9 if c["rhs"] == "lorenz" else FIXED_TOL  # Lorenz: chaotic growth of rounding differences
+    tol = FIXED_TOL  # Lorenz rows included: measured 1.8e-14 at most (profiles/r02_parity.json)
     assert rel(s.cache.ts, c["init_ts"]) < 1e-15
     assert rel(s.cache.ys, c["init_ys"]) <= tol and rel(s.cache.fs, c["init_fs"]) <= tol
     t, y = s.run(c["ts"])
@@ -107,7 +107,7 @@ def test_fixed_single(c):
 def test_fixed_rk_single(c):
     """Fixed-step explicit Runge-Kutta classes (SURVEY.md 8(f) #1): 1e-12 bar."""
     s = getattr(nbk, c["cls"])(c["rhs"], 0.0, np.array(c["y0"]), np.array(c["p"]), h=c["h"])
-    tol = 1e-9 if c["rhs"] == "lorenz" else FIXED_TOL
+    tol = FIXED_TOL
     t, y = s.run(c["ts"])
     assert rel(y, c["ys"]) <= tol and s.t == c["t_end"]
     assert rel(s.y, c["y_end"]) <= tol and rel(s.f, c["f_end"]) <= tol
@@ -323,14 +323,15 @@ def test_dop853_golden_rows_and_oracle_ensemble():
     s = nbk.DOP853("lorenz", 0.0, y0, p, rtol=1e-6, atol=1e-9)
     t, y = s.run(ts)
     dn = np.abs(s.n_accepted - ref["n_accepted"])
-    # Lorenz to t = 10 amplifies rounding differences ~1e4x and the 8(5,3) tableau (coefficients up to ~43)
-    # starts from larger ones than RK45: the bit-exact NumPy restatement of the reference and the C oracle
-    # themselves disagree beyond rtol|y|+atol on 4 of 3000 of these trajectories (0.13 %, identical step
-    # counts; measured in the build container).  Bar: >= 99.5 % within tolerance, step counts within +-1.
+    # Lorenz to t = 10 amplifies rounding differences ~1e4x and the 8(5,3) tableau (coefficients up to ~43) starts from
+    # larger ones than RK45: the bit-exact NumPy restatement of the reference and the C oracle themselves disagree beyond
+    # rtol|y|+atol on 4 of 3000 of these trajectories (0.13 %, identical step counts).  Measured on B200
+    # (profiles/r02_parity.json): 33 of 20 000 trajectories (0.165 %) leave the bar somewhere on the grid, none before
+    # t = 4, step counts identical on all 20 000.  Bars = measured + margin.
     ok = within(y, ref["ys"], 1e-6, 1e-9).all(axis=(1, 2))
-    assert ok.mean() >= 0.995, ok.mean()
-    assert within(y[:, :8], ref["ys"][:, :8], 1e-6, 1e-9).all(axis=(1, 2)).mean() >= 0.9995  # t <= 4: little amplification
-    assert (dn <= 1).mean() >= 0.999 and (dn == 0).mean() > 0.99
+    assert ok.mean() >= 0.9975, ok.mean()
+    assert within(y[:, :8], ref["ys"][:, :8], 1e-6, 1e-9).all(axis=(1, 2)).all()  # t <= 4: little amplification
+    assert (dn <= 1).all() and (dn == 0).mean() >= 0.9995
     assert (s.status == 0).all()
 
 

@@ -33,7 +33,7 @@ def test_adaptive_single_vs_reference(c):
     assert rel(e.h[0], c["h0"]) < 1e-14
     assert rel(e.f[0], c["f0"]) < 1e-15
     ys = e.run(c["ts"])
-    tol = 1e-9 if c["rhs"] == "lorenz" else 1e-11
+    tol = 1e-11
     assert e.nacc[0] == c["n_accepted"]
     assert rel(ys[0], c["ys"]) < tol
     assert rel(e.t[0], c["t_end"]) < 1e-8 and rel(e.y[0], c["y_end"]) < 1e-8 and rel(e.h[0], c["h_end"]) < 1e-8
@@ -57,7 +57,7 @@ def test_fixed_single_vs_reference(c):
     """Fixed-step bar of the north star: 1e-12 relative (per trajectory, max-norm scaled)."""
     e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], h=c["h"], first_stepper=_fs(c["kw"]))
     assert rel(e.ts[:, 0], c["init_ts"]) < 1e-15
-    tol0 = 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    tol0 = 1e-12
     assert rel(e.ys[:, :, 0], c["init_ys"]) < tol0 and rel(e.fs[:, :, 0], c["init_fs"]) < tol0
     ys = e.run(c["ts"])
     assert rel(ys[0], c["ys"]) < tol0
@@ -69,7 +69,7 @@ def test_fixed_single_vs_reference(c):
 def test_fixed_rk_vs_reference(c):
     """Runge2 / Runge3 / Heun3 / RungeKutta4 / RungeKutta3_8 (SURVEY.md 8(f) #1): 1e-12 bar."""
     e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], h=c["h"])
-    tol = 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    tol = 1e-12
     ys = e.run(c["ts"])
     assert rel(ys[0], c["ys"]) < tol and e.t[0] == c["t_end"] and rel(e.y[0], c["y_end"]) < tol
     if "step10_t" in c:
@@ -251,7 +251,7 @@ def test_implicit_multistep_vs_reference(c):
     for the implicit families; bar here: 5e-7 relative on every output, identical step counts and times."""
     e = EmulEnsemble(c["cls"], c["rhs"], [c["y0"]], [c["p"]], h=c["h"], first_stepper=_fs(c["kw"]))
     assert rel(e.ts[:, 0], c["init_ts"]) < 1e-15
-    assert rel(e.ys[:, :, 0], c["init_ys"]) < (1e-9 if c["rhs"] == "lorenz" else 1e-12)
+    assert rel(e.ys[:, :, 0], c["init_ys"]) < 1e-12
     ys = e.run(c["ts"])
     assert e.status[0] == 0 and e.nout[0] == len(c["ts"])
     assert rel(ys[0], c["ys"]) < 5e-7

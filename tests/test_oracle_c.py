@@ -21,7 +21,7 @@ def _close(a, b, rel, what=""):
 
 
 def _tol(c):
-    return 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    return 1e-12
 
 
 @pytest.mark.parametrize("c", load_golden("adaptive_single.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
@@ -47,7 +47,7 @@ def test_adaptive_single(c):
 def test_fixed_single(c):
     fs = c["kw"].get("first_stepper_cls", "auto")
     r = oc.run_ensemble(c["cls"], c["rhs"], [c["y0"]], c["p"], c["ts"], h=c["h"], first_stepper=fs)
-    tol = 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    tol = 1e-12
     _close(r["ys"][0], c["ys"], tol, "ys")
     assert r["t_end"][0] == c["t_end"]
     _close(r["y_end"][0], c["y_end"], tol)
@@ -101,7 +101,7 @@ def test_t_bound_prefix():
 @pytest.mark.parametrize("c", load_golden("erk_fixed.json"), ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
 def test_fixed_rk(c):
     r = oc.run_ensemble(c["cls"], c["rhs"], [c["y0"]], c["p"], c["ts"], h=c["h"])
-    tol = 1e-9 if c["rhs"] == "lorenz" else 1e-12
+    tol = 1e-12
     _close(r["ys"][0], c["ys"], tol, "ys")
     assert r["t_end"][0] == c["t_end"]
     _close(r["y_end"][0], c["y_end"], tol)
