@@ -32,7 +32,7 @@ def test_devices_list_with_one_entry_is_the_plain_solver():
 
 @multi
 @pytest.mark.parametrize("cls,kw", [("RungeKutta45", dict(rtol=1e-6, atol=1e-9)), ("RungeKutta23", dict(rtol=1e-5, atol=1e-8)),
-                                    ("AdamsBashforth4", dict(h=0.005)), ("RungeKutta4", dict(h=0.01)), ("DOP853", dict(rtol=1e-7, atol=1e-9))])
+                                    ("AdamsBashforth4", dict(h=0.002)), ("RungeKutta4", dict(h=0.01)), ("DOP853", dict(rtol=1e-7, atol=1e-9))])
 def test_sharded_equals_single_gpu_bitwise(cls, kw):
     B = 10_007  # odd: shards differ in size
     y0, p = ensembles.lorenz_ensemble(B, seed=11)
@@ -45,21 +45,22 @@ def test_sharded_equals_single_gpu_bitwise(cls, kw):
     t1, y1 = one.run(ts)
     tm, ym = many.run(ts)
     assert np.array_equal(t1, tm) and ym.shape == (B, 3, 3)
-    assert np.array_equal(y1, ym)
-    assert np.array_equal(one.t, many.t) and np.array_equal(one.y, many.y) and np.array_equal(one.f, many.f)
+    # (equal_nan: a fixed-step method may overflow on a few of the random Lorenz systems -- on both solvers alike)
+    assert np.array_equal(y1, ym, equal_nan=True) and np.isfinite(y1).mean() > 0.99
+    assert np.array_equal(one.t, many.t) and np.array_equal(one.y, many.y, equal_nan=True) and np.array_equal(one.f, many.f, equal_nan=True)
     assert np.array_equal(one.n_accepted, many.n_accepted) and (many.status == 0).all()
-    assert np.array_equal(one.cache.ys, many.cache.ys) and np.array_equal(one.cache.ts, many.cache.ts)
+    assert np.array_equal(one.cache.ys, many.cache.ys, equal_nan=True) and np.array_equal(one.cache.ts, many.cache.ts)
     # step / skip / interpolate go through the same per-device fan-out
     a1, b1 = one.step(n=3)
     am, bm = many.step(n=3)
-    assert np.array_equal(a1, am) and np.array_equal(b1, bm)
+    assert np.array_equal(a1, am) and np.array_equal(b1, bm, equal_nan=True)
     one.skip(n=2)
     many.skip(n=2)
-    assert np.array_equal(one.y, many.y)
+    assert np.array_equal(one.y, many.y, equal_nan=True)
     if cls != "AdamsBashforth4":  # (its window Hermite spans the whole history: interpolate inside the last step only)
         ti = float(np.max(one.cache.ts[0]) * 0.5 + np.min(one.cache.ts[-1]) * 0.5)
         if np.max(one.cache.ts[0]) <= ti <= np.min(one.cache.ts[-1]):
-            assert np.array_equal(one.interpolate(ti), many.interpolate(ti))
+            assert np.array_equal(one.interpolate(ti), many.interpolate(ti), equal_nan=True)
 
 
 @multi
