@@ -138,6 +138,10 @@ int nbk_is_jit(const nbk_solver *s);
         user source defining nbk_rhs_i): ts [B][2], ys/fs [B][2][n], K [B][S+1][n], params [B][np]
         (a trajectory's n values are contiguous).  h, counters and status are [B] in both. */
 int nbk_regime(const nbk_solver *s);
+/* Regime 1 only: lanes of a warp that integrate one trajectory in the advance kernels (sub-warp regime for small and
+   mid-size component-wise systems under RungeKutta23 / RungeKutta45: 2, 4, 8, 16 or 32; the reference has one code path
+   for every n, nbkode/runge_kutta/explicit.py:60-79); 0 = the whole CTA (or regime 0). */
+int nbk_group_lanes(const nbk_solver *s);
 
 /* Replaces Solver.__init__ / VariableStep.__init__ / Multistep.__init__
    (nbkode/core.py:106-141, :687-706, nbkode/multistep/core.py:37-65): f0 = rhs(t0, y0), history

@@ -1,0 +1,348 @@
+// nbk_group.cuh -- sub-warp regime for mid-size systems (n ~ 13..64): G lanes of a warp (G = 4, 8, 16 or 32)
+// integrate one trajectory, 32 / G trajectories per warp.
+//
+// Between the two regimes of the north star there is a band where neither fits: one trajectory per thread needs
+// 7n + 2n doubles of registers (spills from n ~ 13 on), and one CTA (>= one warp) per trajectory pays the whole
+// controller -- error norm, step-size factor, accept / reject, guards, ~100 instructions -- per warp for 32 or fewer
+// components.  Here a lane owns E = ceil(n / G) consecutive components, so a warp's controller instructions are shared by
+// 32 / G trajectories x E components per lane:
+//  * y, K0..K_S, y_new of a lane's slice live in registers (7E + 2E doubles: 36 for E = 4);
+//  * the stage ARGUMENT vector is staged in the group's own 2 x (G E) doubles of shared memory (same transposed layout
+//    and the same component-wise right-hand-side interface as the CTA regime, nbk_cta.cuh: built-ins, NVRTC nbk_rhs_i,
+//    traced Python callables); the barrier is a __syncwarp of the group's lanes;
+//  * the error norm is a log2(G)-round shuffle butterfly inside the group: every lane of the group gets the same sum,
+//    hence the same accept / reject decision and step-size factor -- a group never diverges internally;
+//  * groups of one warp differ in their decisions: like the per-thread kernel (advance_adaptive) every loop iteration is
+//    one ATTEMPT for every running group, accept / reject is committed with selects, and a group that finishes takes the
+//    next trajectory from the global queue without waiting for its neighbours;
+//  * state layout = CTA regime (trajectory-major: ts [B][2], ys/fs [B][2][n], K [B][S+1][n], params [B][np]); the
+//    construction kernel is the CTA regime's (cta_init_adaptive, one small block per trajectory).
+//
+// Reference rows restated: as nbk_cta.cuh (FSAL stage loop explicit.py:60-79, error norm / controller
+// runge_kutta/core.py:73-99, accept loop explicit.py:81-99, t_bound guard core.py:176-184, RkInterpolator
+// explicit.py:354-403, drivers core.py:483-537, 598-619).
+#ifndef NBK_GROUP_CUH
+#define NBK_GROUP_CUH
+
+#include "nbk_cta.cuh"
+
+#ifndef NBK_GRP_BLOCK
+#define NBK_GRP_BLOCK 128
+#endif
+#ifndef NBK_GRP_INNER
+#define NBK_GRP_INNER 4  // attempts between two looks at the queue / retire code
+#endif
+
+namespace nbk {
+
+#ifdef NBK_HOST_EMUL
+// tests/emul/nbk_emul_group.cpp provides the warp primitives for a warp of 32 POSIX threads
+#else
+NBK_DEV void group_sync(unsigned gmask) { __syncwarp(gmask); }
+NBK_DEV double group_shfl_xor(unsigned gmask, double v, int o) { return __shfl_xor_sync(gmask, v, o); }
+NBK_DEV long long group_bcast(unsigned gmask, long long v, int src_lane) { return __shfl_sync(gmask, v, src_lane); }
+NBK_DEV bool warp_all(bool p) { return __all_sync(0xffffffffu, p); }
+#endif
+
+// Sum over the G lanes of a group; the xor butterfly gives every lane the same value (each round adds the same pair
+// of numbers on both sides).
+template <int G>
+NBK_DEV double group_sum(double v, unsigned gmask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += group_shfl_xor(gmask, v, o);
+    return v;
+}
+
+// Element-wise decay y' = -k y for the component-wise regimes (k scalar or per component): needs no neighbour, so the
+// stage argument is not staged at all (LOCAL).
+template <bool SCALAR>
+struct rhs_decay_cta {
+    static constexpr int NP = SCALAR ? 1 : -1;  // one rate for all components, or n of them (run-time)
+    static constexpr bool LOCAL = true;
+    struct prm { const double *p; };
+    static NBK_DEV prm load(const double *p) { return prm{p}; }
+    template <int E, bool FULL = false>
+    static NBK_DEV void eval(double, const double (&yown)[E], smem_vec<E>, const prm &q, int i0, int n, double (&dy)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e < n ? i0 + e : n - 1;
+            dy[e] = -q.p[SCALAR ? 0 : i] * yown[e];
+        }
+    }
+};
+
+template <class Rhs, class = void>
+struct rhs_is_local { static constexpr bool value = false; };
+template <class Rhs>
+struct rhs_is_local<Rhs, decltype((void)Rhs::LOCAL)> { static constexpr bool value = Rhs::LOCAL; };
+
+// One FSAL attempt of a group.  K[0] holds the lane's slice of f(t, y).
+template <class Tab, class Rhs, int G, int E>
+NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)[Tab::S + 1][E], const typename Rhs::prm &p,
+                           int gl, int i0, int n, double inv_n, double *buf0, double *buf1, unsigned gmask,
+                           double (&ynew)[E], double &err2, double rtol, double atol) {
+    constexpr int S = Tab::S;
+    constexpr bool LOCAL = rhs_is_local<Rhs>::value;
+#pragma unroll
+    for (int s = 1; s <= S; ++s) {
+        double ys[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                const bool nz = s < S ? Tab::a(s < S ? s : 0, j) != 0.0 : Tab::b(j) != 0.0;
+                if (nz) {
+                    const double c = s < S ? Tab::cb().a[s < S ? s : 0][j] : Tab::cb().b[j];
+                    acc = first ? c * K[j][e] : fma(c, K[j][e], acc);
+                    first = false;
+                }
+            }
+            ys[e] = fma(h, acc, y[e]);
+        }
+        double *buf = (s & 1) ? buf1 : buf0;
+        if constexpr (!LOCAL) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) buf[e * G + gl] = ys[e];
+            group_sync(gmask);
+        }
+        Rhs::template eval<E, false>(s < S ? fma(h, Tab::cb().c[s < S ? s : 0], t) : t + h, ys, smem_vec<E>{buf, G}, p, i0, n,
+                                     K[s]);
+        if (s == S) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) ynew[e] = ys[e];
+        }
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        double ee = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j <= S; ++j) {
+            if (Tab::e(j) != 0.0) {
+                ee = first ? Tab::cb().e[j] * K[j][e] : fma(Tab::cb().e[j], K[j][e], ee);
+                first = false;
+            }
+        }
+        const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
+        const double r = ee * fast_rcp(sc);
+        part = i0 + e < n ? fma(r, r, part) : part;  // a select, not a branch
+    }
+    // the butterfly is also the execution barrier between this attempt's last reads of the stage buffers and the next
+    // attempt's first writes (all lanes of a group belong to one warp: shared-memory accesses execute in issue order)
+    err2 = group_sum<G>(part, gmask) * (h * h * inv_n);
+}
+
+// =====================================================================================
+// Advance: persistent warps, every group pulls trajectories from the global queue.
+// MODE RUN / STEP as in advance_adaptive (nbk_device.cuh) and cta_advance (nbk_cta.cuh).
+// =====================================================================================
+template <class Tab, class Rhs, int G, int E, int MODE>
+NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
+    static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
+    static_assert(!Tab::DOP, "the sub-warp regime implements RungeKutta23 / RungeKutta45");
+    constexpr int S = Tab::S;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), gbase = lane - gl;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    const int n = a.n, i0 = gl * E;
+    const long long nn = n, B = a.B;
+    const double inv_n = 1.0 / (double)n;
+    double *buf0 = sm + (size_t)(threadIdx.x / G) * (2 * G * E), *buf1 = buf0 + G * E;
+    const double rtol = a.rtol, atol = a.atol, bound = a.bound;
+    const double safety = a.safety, min_factor = a.min_factor, max_factor = a.max_factor;
+    const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
+
+    // loop-carried state of the group's trajectory; the scalars are replicated in every lane of the group
+    long long idx = -1;
+    bool running = false, finishing = false, queue_empty = false, fresh = true;
+    double t = 0, h = 0, te_next = 0;
+    double y[E], K[S + 1][E];
+    typename Rhs::prm p{};
+    int nacc = 0, natt = 0, kout = 0, status = NBK_TRAJ_OK;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        y[e] = 0.0;
+#pragma unroll
+        for (int s = 0; s <= S; ++s) K[s][e] = 0.0;
+    }
+
+    for (;;) {
+        // ---------------------------------------------------------------- (1) retire
+        if (finishing) {
+            if (nacc > 0) {
+                const bool clean = status == NBK_TRAJ_OK || status == NBK_TRAJ_BOUND;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = i0 + e;
+                    if (i < n) {
+                        a.ys[(idx * 2 + 1) * nn + i] = y[e];
+                        a.fs[(idx * 2) * nn + i] = K[0][e];
+                        a.fs[(idx * 2 + 1) * nn + i] = clean ? K[S][e] : K[0][e];
+#pragma unroll
+                        for (int s = 0; s <= S; ++s) a.K[(idx * (S + 1) + s) * nn + i] = K[s][e];
+                    }
+                }
+            }
+            if (gl == 0) {
+                if (nacc > 0) a.ts[idx * 2 + 1] = t;
+                a.h[idx] = h;
+                if (a.pristine) {
+                    a.n_acc[idx] = nacc;
+                    a.n_rej[idx] = natt - nacc;
+                } else {
+                    a.n_acc[idx] += nacc;
+                    a.n_rej[idx] += natt - nacc;
+                }
+                store_status(a, idx, status);
+                a.n_out[idx] = MODE == NBK_MODE_RUN ? kout : nacc;
+            }
+            finishing = false;
+            idx = -1;
+        }
+        // ---------------------------------------------------------------- (2) refill (group-uniform branch)
+        if (!running && !queue_empty) {
+            long long mine = 0;
+            if (gl == 0) mine = (long long)atomicAdd(a.work_counter, 1ULL);
+            mine = group_bcast(gmask, mine, gbase);
+            if (mine >= B) {
+                queue_empty = true;
+            } else {
+                idx = mine;
+                p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
+                t = a.ts[idx * 2 + 1];
+                h = a.h[idx];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = i0 + e;
+                    y[e] = i < n ? a.ys[(idx * 2 + 1) * nn + i] : 0.0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) K[s][e] = 0.0;
+                    K[S][e] = i < n ? a.fs[(idx * 2 + 1) * nn + i] : 0.0;  // f(t, y): K[0] of the first attempt
+                }
+                status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
+                nacc = natt = kout = 0;
+                fresh = true;
+                te_next = d_inf();
+                running = status == NBK_TRAJ_OK;
+                if (running && MODE == NBK_MODE_RUN) {
+                    if (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                        // grid points inside the stored last step: answered from history (core.py:401-408)
+                        const double t_old = a.ts[idx * 2];
+                        double y_old[E], Kh[S + 1][E];
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            const int i = i0 + e;
+                            y_old[e] = i < n ? a.ys[(idx * 2) * nn + i] : 0.0;
+#pragma unroll
+                            for (int s = 0; s <= S; ++s) Kh[s][e] = (i < n && !a.pristine) ? a.K[(idx * (S + 1) + s) * nn + i] : 0.0;
+                        }
+                        double Q[E][Tab::M];
+                        rk_dense_coeffs<Tab, E>(Kh, Q);
+                        while (kout < a.m && __ldg(a.tgrid + kout) <= t) {
+                            double out[E];
+                            rk_dense_eval<Tab, E>(__ldg(a.tgrid + kout), t_old, t, y_old, y, Q, out);
+#pragma unroll
+                            for (int e = 0; e < E; ++e)
+                                if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                            ++kout;
+                        }
+                    }
+                    running = kout < a.m;
+                    if (running) te_next = __ldg(a.tgrid + kout);
+                } else if (running) {
+                    running = a.n_steps > 0;
+                }
+                if (status >= NBK_TRAJ_NONFINITE && MODE == NBK_MODE_RUN) {
+                    for (int k = 0; k < a.m; ++k)
+                        for (int e = 0; e < E; ++e)
+                            if (i0 + e < n) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)(i0 + e) * a.o_sc] = d_nan();
+                }
+                if (running && (t + h > bound)) {  // guard of the first step (core.py:176-184)
+                    status = NBK_TRAJ_BOUND;
+                    running = false;
+                }
+                finishing = !running;
+            }
+        }
+        // the warp leaves when the queue is empty and none of its groups has anything left
+        if (warp_all(!running && !finishing && queue_empty)) break;
+        // ---------------------------------------------------------------- (3) attempts
+#pragma unroll 1
+        for (int rep = 0; rep < NBK_GRP_INNER; ++rep) {
+            if (running) {
+                if (fresh) {  // FSAL
+#pragma unroll
+                    for (int e = 0; e < E; ++e) K[0][e] = K[S][e];
+                }
+                double ynew[E], err2;
+                group_attempt<Tab, Rhs, G, E>(t, h, y, K, p, gl, i0, n, inv_n, buf0, buf1, gmask, ynew, err2, rtol, atol);
+                const bool accept = (unsigned)__double2hiint(err2) < 0x3ff00000u;
+                const double t_new = t + h;
+                h *= step_factor<Tab>(err2, safety, min_factor, max_factor, a.x_lo, a.x_hi);
+                ++natt;
+                bool done = false;
+                if (accept) {
+                    if (MODE == NBK_MODE_RUN) {
+                        if (t_new >= te_next) {
+                            double Q[E][Tab::M];
+                            rk_dense_coeffs<Tab, E>(K, Q);
+                            const double H = t_new - t, r0 = fast_rcp(H);
+                            const double inv_H = fma(r0, fma(-H, r0, 1.0), r0);
+                            do {
+                                double out[E];
+                                rk_dense_eval_in_step<Tab, E>(te_next, t, t_new, y, ynew, Q, out, inv_H);
+#pragma unroll
+                                for (int e = 0; e < E; ++e)
+                                    if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                                ++kout;
+                                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                            } while (t_new >= te_next);
+                            done = kout >= a.m;
+                        }
+                    } else {
+                        if (a.emit) {
+                            if (gl == 0) a.t_out[idx * a.to_sb + nacc] = t_new;
+#pragma unroll
+                            for (int e = 0; e < E; ++e)
+                                if (i0 + e < n) a.y_out[idx * a.o_sb + nacc * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
+                        }
+                        done = nacc + 1 >= a.n_steps;
+                    }
+                }
+                if (d_nonfinite(err2) || d_collapsed(h)) {
+                    status = NBK_TRAJ_NONFINITE;
+                    done = true;
+                } else if (!done && natt >= max_att) {
+                    status = NBK_TRAJ_MAXATTEMPTS;
+                    done = true;
+                }
+                if (accept && !done && (t_new + h > bound)) {  // guard of the next step
+                    status = NBK_TRAJ_BOUND;
+                    done = true;
+                }
+                if (done) {
+                    // history slot 0 = start of the last accepted step (see advance_adaptive)
+                    if (gl == 0) a.ts[idx * 2] = t;
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (i0 + e < n) a.ys[(idx * 2) * nn + i0 + e] = y[e];
+                    running = false;
+                    finishing = true;
+                }
+                if (accept) {  // commit (predicated moves)
+                    t = t_new;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) y[e] = ynew[e];
+                    ++nacc;
+                }
+                fresh = accept;
+            }
+        }
+    }
+}
+
+}  // namespace nbk
+
+#endif

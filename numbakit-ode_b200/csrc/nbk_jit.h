@@ -13,6 +13,7 @@ struct nbk_jit_request {
     int cta_elems = 0;      // > 0: CTA-per-trajectory regime (nbk_program_cta.cu) with E components per thread
     int cta_maxt = 0;       // block-size cap the CTA kernels are compiled for
     int cta_full = 0;       // 1: n == block * E (every thread owns E valid components): no bounds checks compiled in
+    int group = 0;          // CTA regime: G > 0 = sub-warp run / step kernels (nbk_group.cuh), G lanes per trajectory
     int n_events = 0;       // > 0: also build the run_events kernel with event_src's nbk_event(k, t, y, p) inlined
     std::string event_src;
 };

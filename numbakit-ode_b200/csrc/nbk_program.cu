@@ -107,6 +107,7 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->n_params = nbk_rhs_t::NP;
     out->cta_elems = 0;
     out->cta_full = 0;
+    out->group = 0;
     out->mma_tile = 0;
     out->mma_smem = 0;
     out->k_init = (const void *)&NBK_KERNEL(init);

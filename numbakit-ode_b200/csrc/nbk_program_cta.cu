@@ -2,7 +2,16 @@
 // CTA-per-trajectory regime (nbk_cta.cuh).  Macros: NBK_METHOD (23 | 45 | 853 | 1..5 | 202.. fixed-step), NBK_RHS_T (a CTA
 // right-hand side type), NBK_E (state components per thread), NBK_TAG.  The block size is chosen at
 // launch: ceil(n / NBK_E) rounded up to a warp; dynamic shared memory = (2*T*E + 34) doubles.
+// NBK_GROUP = G > 0: sub-warp regime (nbk_group.cuh) -- the run / step kernels are persistent 128-thread blocks in which
+// G lanes integrate one trajectory (RungeKutta23 / RungeKutta45, n <= G * NBK_E); the construction kernel stays the CTA one.
+#ifndef NBK_GROUP
+#define NBK_GROUP 0
+#endif
+#if NBK_GROUP > 0
+#include "nbk_group.cuh"
+#else
 #include "nbk_cta.cuh"
+#endif
 
 #define NBK_CAT2(a, b) a##b
 #define NBK_CAT(a, b) NBK_CAT2(a, b)
@@ -39,11 +48,26 @@ typedef nbk::tab_dop853 nbk_tab_t;  // 13 stage vectors per thread: one or two c
 #ifndef NBK_CTA_FULL
 #define NBK_CTA_FULL 0
 #endif
+#if NBK_GROUP > 0
+#if !NBK_CTA_ADAPTIVE || NBK_METHOD == 853
+#error "the sub-warp regime implements RungeKutta23 / RungeKutta45"
+#endif
+#ifndef NBK_GRP_MINB
+#define NBK_GRP_MINB 4
+#endif
+#define NBK_ADV_BOUNDS __launch_bounds__(NBK_GRP_BLOCK, NBK_GRP_MINB)
+template <int MODE>
+__device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *sm) {
+    nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, MODE>(a, sm);
+}
+#else
+#define NBK_ADV_BOUNDS __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB)
 #if NBK_CTA_ADAPTIVE
 template <int MODE>
 __device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *sm) {
     nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, NBK_CTA_FULL != 0>(a, sm);
 }
+#endif
 #endif
 
 extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
@@ -54,7 +78,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(cons
     nbk::cta_init_fixed<NBK_METHOD, nbk_rhs_t, NBK_E>(a, nbk_smem);
 #endif
 }
-extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ __align__(16) double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk_cta_advance_any<NBK_MODE_RUN>(a, nbk_smem);
@@ -62,7 +86,7 @@ extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KER
     nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_RUN>(a, nbk_smem);
 #endif
 }
-extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ __align__(16) double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk_cta_advance_any<NBK_MODE_STEP>(a, nbk_smem);
@@ -79,6 +103,7 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->n_params = nbk_rhs_t::NP;
     out->cta_elems = NBK_E;
     out->cta_full = NBK_CTA_FULL;
+    out->group = NBK_GROUP;
     out->mma_tile = 0;
     out->mma_smem = 0;
     out->k_init = (const void *)&NBK_KERNEL(init);

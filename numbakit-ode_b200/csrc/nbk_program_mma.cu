@@ -37,6 +37,7 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->n_params = -1;
     out->cta_elems = 1;
     out->cta_full = 0;
+    out->group = 0;
     out->mma_tile = nbk::MMA_NT;
     out->mma_smem = sizeof(double) * (2 * 128 * nbk::MMA_LD + nbk::MMA_WARPS * nbk::MMA_NT) + sizeof(nbk::mma_cols) + 16 +
                     sizeof(double) * 128 * nbk::MMA_LDA;  // Y staging (2 buffers), reduction scratch, columns, the matrix

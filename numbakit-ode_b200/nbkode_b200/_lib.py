@@ -50,7 +50,7 @@ class CompileError(NbkError):
 _lib = None
 
 EXPORTS = (
-    "nbk_version", "nbk_last_error", "nbk_create", "nbk_destroy", "nbk_layout", "nbk_is_jit", "nbk_regime", "nbk_init",
+    "nbk_version", "nbk_last_error", "nbk_create", "nbk_destroy", "nbk_layout", "nbk_is_jit", "nbk_regime", "nbk_group_lanes", "nbk_init",
     "nbk_run", "nbk_step", "nbk_last_launch", "nbk_jit_compile_only", "nbk_fp64_peak", "nbk_fp64_mma_peak",
     "nbk_set_events", "nbk_run_events", "nbk_jit_compile_events_only",
 )
@@ -76,6 +76,7 @@ def lib():
     L.nbk_layout.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
     L.nbk_is_jit.argtypes = [vp]
     L.nbk_regime.argtypes = [vp]
+    L.nbk_group_lanes.argtypes = [vp]
     L.nbk_init.argtypes = [vp, C.POINTER(NbkState), dbl, vp, ll, ll, vp, ll, ll, dbl, vp, vp]
     L.nbk_run.argtypes = [vp, C.POINTER(NbkState), vp, i, dbl, vp, ll, ll, ll, ll, vp]
     L.nbk_step.argtypes = [vp, C.POINTER(NbkState), ll, dbl, i, vp, ll, vp, ll, ll, ll, ll, vp]

@@ -210,7 +210,7 @@ class Solver(ABC):
         # one, e.g. "thread" to use run_events or DOP853 on a mid-size system)
         cta_ok = self.METHOD_ID in _CTA_METHODS and not (2 <= self.METHOD_ID <= 5 and 1 <= _first_stepper <= 5)
         name, src = _rhs.resolve(rhs, self.n, p_shape if p_shape else (self.n_params,), params is not None, regime, cta_ok)
-        if name == "decay" and self.n_params not in (1, self.n):
+        if name in ("decay", "decay:thread") and self.n_params not in (1, self.n):
             raise ValueError("built-in 'decay' needs 1 or n parameters")
         self.rhs = name if name is not None else _rhs.CudaRHS(src)
 
@@ -416,7 +416,11 @@ class Solver(ABC):
     def last_launch(self):
         g, b, r = C.c_int(0), C.c_int(0), C.c_int(0)
         _lib.check(_lib.lib().nbk_last_launch(self._handle, C.byref(g), C.byref(b), C.byref(r)))
-        return {"grid": g.value, "block": b.value, "regs": r.value}
+        out = {"grid": g.value, "block": b.value, "regs": r.value}
+        lanes = int(_lib.lib().nbk_group_lanes(self._handle))
+        if lanes:
+            out["lanes_per_trajectory"] = lanes
+        return out
 
     # ------------------------------------------------------------------ step / skip
     def _advance(self, n_steps, bound, emit):

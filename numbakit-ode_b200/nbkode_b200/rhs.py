@@ -764,7 +764,11 @@ def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", c
         return None, rhs.source
     if isinstance(rhs, str):
         if rhs.lower() in BUILTINS:
-            return rhs.lower(), None
+            # "decay" exists per thread and component-wise: mid-size systems under RungeKutta23 / RungeKutta45 take the
+            # component-wise form (sub-warp regime) unless regime="thread" asks for the per-thread kernels
+            return ("decay:thread" if rhs.lower() == "decay" and regime == "thread" else rhs.lower()), None
+        if rhs.lower() == "decay:thread":
+            return "decay:thread", None
         if "nbk_rhs" in rhs:
             return None, rhs
         raise ValueError(f"unknown built-in right-hand side {rhs!r}; known: {sorted(BUILTINS)}")
