@@ -69,6 +69,34 @@ struct rhs_decay_cta {
             dy[e] = -q.p[SCALAR ? 0 : i] * yown[e];
         }
     }
+    // sub-warp regime: a lane's rates are fetched once per trajectory and stay in registers (see group_prm)
+    template <int E>
+    struct lane_prm { double k[E]; };
+    template <int E>
+    static NBK_DEV lane_prm<E> load_lane(const double *p, int i0, int n) {
+        lane_prm<E> q;
+#pragma unroll
+        for (int e = 0; e < E; ++e) q.k[e] = p[SCALAR ? 0 : (i0 + e < n ? i0 + e : n - 1)];
+        return q;
+    }
+    template <int E, bool FULL = false>
+    static NBK_DEV void eval(double, const double (&yown)[E], smem_vec<E>, const lane_prm<E> &q, int, int, double (&dy)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) dy[e] = -q.k[e] * yown[e];
+    }
+};
+
+// Parameter block of a group's lane: the CTA regime's Rhs::prm, or -- when the right-hand side offers it -- a per-lane
+// block Rhs::lane_prm<E> loaded by Rhs::load_lane<E>(p, i0, n) (parameters that belong to the lane's own components).
+template <class Rhs, int E, class = void>
+struct group_prm {
+    using type = typename Rhs::prm;
+    static NBK_DEV type load(const double *p, int, int) { return Rhs::load(p); }
+};
+template <class Rhs, int E>
+struct group_prm<Rhs, E, decltype((void)sizeof(typename Rhs::template lane_prm<E>))> {
+    using type = typename Rhs::template lane_prm<E>;
+    static NBK_DEV type load(const double *p, int i0, int n) { return Rhs::template load_lane<E>(p, i0, n); }
 };
 
 template <class Rhs, class = void>
@@ -77,8 +105,8 @@ template <class Rhs>
 struct rhs_is_local<Rhs, decltype((void)Rhs::LOCAL)> { static constexpr bool value = Rhs::LOCAL; };
 
 // One FSAL attempt of a group.  K[0] holds the lane's slice of f(t, y).
-template <class Tab, class Rhs, int G, int E>
-NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)[Tab::S + 1][E], const typename Rhs::prm &p,
+template <class Tab, class Rhs, int G, int E, class P>
+NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)[Tab::S + 1][E], const P &p,
                            int gl, int i0, int n, double inv_n, double *buf0, double *buf1, unsigned gmask,
                            double (&ynew)[E], double &err2, double rtol, double atol) {
     constexpr int S = Tab::S;
@@ -130,9 +158,10 @@ NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)
         const double r = ee * fast_rcp(sc);
         part = i0 + e < n ? fma(r, r, part) : part;  // a select, not a branch
     }
-    // the butterfly is also the execution barrier between this attempt's last reads of the stage buffers and the next
-    // attempt's first writes (all lanes of a group belong to one warp: shared-memory accesses execute in issue order)
     err2 = group_sum<G>(part, gmask) * (h * h * inv_n);
+    // closes the window between this attempt's last reads of a stage buffer and the next attempt's first writes (for
+    // RungeKutta23 the last stage and the next first stage use the same buffer)
+    if constexpr (!LOCAL) group_sync(gmask);
 }
 
 // =====================================================================================
@@ -159,7 +188,8 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
     bool running = false, finishing = false, queue_empty = false, fresh = true;
     double t = 0, h = 0, te_next = 0;
     double y[E], K[S + 1][E];
-    typename Rhs::prm p{};
+    using PRM = group_prm<Rhs, E>;
+    typename PRM::type p{};
     int nacc = 0, natt = 0, kout = 0, status = NBK_TRAJ_OK;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -210,7 +240,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                 queue_empty = true;
             } else {
                 idx = mine;
-                p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
+                p = PRM::load(a.params_shared ? a.params : a.params + idx * a.n_params, i0, n);
                 t = a.ts[idx * 2 + 1];
                 h = a.h[idx];
 #pragma unroll

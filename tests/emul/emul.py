@@ -100,8 +100,9 @@ def _program(method, rhs, n, npar, events=None):
         subprocess.check_call([
             "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
             "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", "-include", pre,
-            os.path.join(HERE, "nbk_emul.cpp"), "-o", so,
+            os.path.join(HERE, "nbk_emul.cpp"), "-o", so + f".{os.getpid()}.tmp",
         ])
+        os.replace(so + f".{os.getpid()}.tmp", so)  # atomic: pytest-xdist workers may build the same program
     lib = C.CDLL(so)
     fn = getattr(lib, f"emul_{tag}")
     fn.argtypes = [C.c_int, C.POINTER(KArgs), C.c_longlong]
@@ -252,8 +253,9 @@ def _program_cta(method, rhs, elems, full, user_src=None, n_params=0):
             "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}",
             f"-DNBK_RHS_T={'nbk::rhs_user_cta' if user_src is not None else CTA_RHS_TYPES[rhs][0]}",
             f"-DNBK_TAG={tag}", f"-DNBK_E={elems}", "-DNBK_CTA_MAXT=512", f"-DNBK_CTA_FULL={full}", *extra,
-            os.path.join(HERE, "nbk_emul_cta.cpp"), "-o", so,
+            os.path.join(HERE, "nbk_emul_cta.cpp"), "-o", so + f".{os.getpid()}.tmp",
         ])
+        os.replace(so + f".{os.getpid()}.tmp", so)  # atomic: pytest-xdist workers may build the same program
     fn = getattr(C.CDLL(so), f"emul_cta_{tag}")
     fn.argtypes = [C.c_int, C.POINTER(KArgs), C.c_int]
     _libs[("cta", tag)] = fn
@@ -339,6 +341,81 @@ class EmulCtaEnsemble:
 
 
 # --------------------------------------------------------------------------------------------------------------------
+# Sub-warp regime (csrc/nbk_group.cuh) on the host: the run / step kernels as one warp of 32 POSIX threads
+# (nbk_emul_group.cpp); the construction kernel is the CTA regime's
+# --------------------------------------------------------------------------------------------------------------------
+GROUP_RHS_TYPES = {"rd1d": "nbk::rhs_rd1d_cta", "decay": "nbk::rhs_decay_cta<false>", "decay1": "nbk::rhs_decay_cta<true>"}
+
+
+def group_shape(n, lanes=None):
+    """Mirror of group_shape() in csrc/nbk_api.cu -> (lanes per trajectory, components per lane, construction block)."""
+    g = 2
+    while g < 32 and (n + g - 1) // g > 4:
+        g *= 2
+    g = lanes or g
+    e = (n + g - 1) // g
+    return g, e, ((n + e - 1) // e + 31) // 32 * 32
+
+
+def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0):
+    tag = f"m{method}_{rhs}_g{lanes}e{elems}"
+    extra = []
+    if user_src is not None:
+        import hashlib
+
+        tag += "_u" + hashlib.sha1((user_src + str(n_params)).encode()).hexdigest()[:10]
+    if ("group", tag) in _libs:
+        return _libs[("group", tag)]
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, f"libemul_group_{tag}.so")
+    pre = os.path.join(BUILD, f"pre_group_{tag}.{os.getpid()}.h")
+    with open(pre, "w") as fh:
+        if user_src is not None:
+            fh.write("#define NBK_RHS_I static inline double\n"
+                     "namespace nbk { template <int E> struct smem_vec; }\ntypedef nbk::smem_vec<NBK_E> nbk_vec;\n"
+                     + (f"#define NBK_CTA_NP {n_params}\n" if 0 < n_params <= 16 else "")
+                     + "#define NBK_USER_RHS_CTA 1\n"
+                     "NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n);\n"
+                     '#include "nbk_cta.cuh"\n' + user_src + "\n#define NBK_RHS_T nbk::rhs_user_cta\n")
+        else:
+            fh.write(f"#define NBK_RHS_T {GROUP_RHS_TYPES[rhs]}\n")  # (a -D value cannot carry the template brackets portably)
+    extra = [f'-DEMUL_USER_PRELUDE="{pre}"']
+    deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_cta.cuh", "nbk_group.cuh", "nbk_kargs.h", "nbk_program_cta.cu")]
+    deps += [os.path.join(HERE, f) for f in ("nbk_emul_group.cpp", "cuda_host_shim.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call([
+            "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-ffp-contract=off",
+            "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}", f"-DNBK_TAG={tag}", f"-DNBK_E={elems}",
+            f"-DNBK_GROUP={lanes}", "-DNBK_CTA_MAXT=128", "-DNBK_CTA_FULL=0", *extra,
+            os.path.join(HERE, "nbk_emul_group.cpp"), "-o", so + f".{os.getpid()}.tmp",
+        ])
+        os.replace(so + f".{os.getpid()}.tmp", so)  # atomic: pytest-xdist workers may build the same program
+    fn = getattr(C.CDLL(so), f"emul_group_{tag}")
+    fn.argtypes = [C.c_int, C.POINTER(KArgs), C.c_int]
+    _libs[("group", tag)] = fn
+    return fn
+
+
+class EmulGroupEnsemble(EmulCtaEnsemble):
+    """RungeKutta23 / RungeKutta45 through the sub-warp kernels: up to 32 / G trajectories are in flight in the one emulated
+    warp and the rest is pulled from the queue.  `rhs`: "rd1d", "decay" (n rates), "decay1" (one rate) or nbk_rhs_i source."""
+
+    def __init__(self, method, rhs, y0, params, lanes=None, **kw):
+        n = np.atleast_2d(np.asarray(y0)).shape[1]
+        self._shape = group_shape(n, lanes)
+        self._rhs = rhs
+        super().__init__(method, rhs if "nbk_rhs_i" in rhs else "rd1d", y0, params, **kw)
+
+    def __setattr__(self, name, value):
+        if name in ("E", "T", "full") and "_shape" in self.__dict__:
+            value = {"E": self._shape[1], "T": self._shape[2], "full": 0}[name]
+        if name == "fn" and "_shape" in self.__dict__:
+            user = self._rhs if "nbk_rhs_i" in self._rhs else None
+            value = _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_)
+        object.__setattr__(self, name, value)
+
+
+# --------------------------------------------------------------------------------------------------------------------
 # K4 (csrc/nbk_mma.cuh): shared-matrix linear systems, right-hand side as FP64 DMMA tiles -- host build with the
 # fragment exchange emulated (nbk_emul_mma.cpp)
 # --------------------------------------------------------------------------------------------------------------------
@@ -354,8 +431,9 @@ def _program_mma(method):
         subprocess.check_call([
             "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-ffp-contract=off",
             "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}", f"-DNBK_TAG={tag}",
-            os.path.join(HERE, "nbk_emul_mma.cpp"), "-o", so,
+            os.path.join(HERE, "nbk_emul_mma.cpp"), "-o", so + f".{os.getpid()}.tmp",
         ])
+        os.replace(so + f".{os.getpid()}.tmp", so)  # atomic: pytest-xdist workers may build the same program
     fn = getattr(C.CDLL(so), f"emul_mma_{tag}")
     fn.argtypes = [C.c_int, C.POINTER(KArgs)]
     _libs[("mma", tag)] = fn
