@@ -367,6 +367,32 @@ def extra_configs(nbk, torch, dev, peak_tf, sizes=None):
                 "launch": launch}
 
     guarded("C5 rd1d", c5)
+
+    # ---- mid-size systems (the north star's register regime up to n = 32 and the band above it): sub-warp kernels,
+    # G lanes of a warp per trajectory (nbk_group.cuh).  Element-wise decay with per-component rates (R = n) and the
+    # periodic reaction-diffusion stencil (R = 8 per component), RungeKutta45, 262 144 trajectories to t = 10.
+    def mid(rhs_name, n):
+        def fn():
+            Bm = sizes.get("mid", 262_144)
+            if rhs_name == "decay":
+                rng = np.random.default_rng(0)
+                y0, pm, flop = rng.uniform(0.5, 2, (Bm, n)), rng.uniform(0.1, 1.0, (Bm, n)), 6 * n + 66 * n + 18
+            else:
+                y0, pm = ensembles.rd1d_ensemble(Bm, n=n, seed=3)
+                flop = 6 * 8 * n + 66 * n + 18
+            y0d, pmd = torch.from_numpy(y0).to(dev), torch.from_numpy(pm).to(dev)
+            ms, acc, att, launch = timed(lambda: nbk.RungeKutta45(rhs_name, 0.0, y0d, pmd, rtol=RTOL, atol=ATOL), lambda s: s.run([10.0]), reps=3)
+            tf = att * flop / ms * 1e3 / 1e12
+            return {"config": f"mid-size {rhs_name} n={n} x {Bm}, RungeKutta45, t in [0,10]",
+                    "kernel": f"nbk_run_jit (sub-warp regime, {launch.get('lanes_per_trajectory', 0)} lanes per trajectory)", "ms": ms,
+                    "accepted_steps": acc, "steps_per_s": acc / ms * 1e3,
+                    "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                                 "flop_per_attempt": flop},
+                    "launch": launch}
+        return fn
+
+    for rhs_name, n in (("decay", 16), ("decay", 32), ("rd1d", 32), ("rd1d", 64)):
+        guarded(f"mid-size {rhs_name} n={n}", mid(rhs_name, n))
     return rows
 
 

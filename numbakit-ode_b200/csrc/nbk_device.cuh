@@ -1214,6 +1214,18 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                         }
 #endif
                     } else if (MODE == NBK_MODE_RUN) {
+#ifdef NBK_EXP_NO_EMIT
+                        // EXPERIMENT ONLY (tuning variant, never in the shipped library): grid points are counted but
+                        // neither evaluated nor stored -- the time of this build is the floor of ANY restructuring of
+                        // the emission path (profiles/r02_c3_rk23_emission_bound.json)
+                        if (t_new >= te_next) {
+                            do {
+                                ++kout;
+                                te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
+                            } while (t_new >= te_next);
+                            done = kout >= a.m;
+                        }
+#else
                         if (t_new >= te_next) {
                             // interpolant of this step, built once and evaluated at every grid point inside it
                             double F[Tab::DOP ? 7 : N][Tab::DOP ? N : Tab::M];
@@ -1242,6 +1254,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                             } while (t_new >= te_next);
                             done = kout >= a.m;
                         }
+#endif
                     } else {
                         if (a.emit) {
                             a.t_out[idx * a.to_sb + nacc] = t_new;

@@ -58,13 +58,13 @@ for rhs in RHS:
             tf = att * flop / ms * 1e3 / 1e12
             row[label] = {"ms": round(ms, 3), "tflops": round(tf, 2), "frac": round(tf / peak, 3), "launch": s.last_launch(),
                           "regime": s._regime}
-            if label == "group":
+            if True:
                 k = 256
                 ref = oc.run_ensemble("RungeKutta45", rhs, y0[:k], p[:k], [T], rtol=RTOL, atol=ATOL, nthreads=8)
                 yy = y[:k, 0].cpu().numpy()
                 err = np.abs(yy - ref["ys"][:, 0]) / (RTOL * np.abs(ref["ys"][:, 0]) + ATOL)
                 dn = np.abs(s._nacc[:k].cpu().numpy() - ref["n_accepted"])
-                row["parity"] = {"max_err_over_tol": float(err.max()), "max_dsteps": int(dn.max())}
+                row[label]["parity"] = {"max_err_over_tol": float(err.max()), "max_dsteps": int(dn.max())}
         os.environ.pop("NBK_NO_GROUP", None)
         if "ms" in row.get("group", {}) and "ms" in row.get("before", {}):
             row["speedup"] = round(row["before"]["ms"] / row["group"]["ms"], 2)
