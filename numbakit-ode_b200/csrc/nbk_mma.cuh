@@ -51,7 +51,10 @@ struct mma_cols {
     long long idx[MMA_NT];
     int nacc[MMA_NT], natt[MMA_NT], kout[MMA_NT], status[MMA_NT];
     int running[MMA_NT], fresh[MMA_NT], accept[MMA_NT], done[MMA_NT], emit_from[MMA_NT];
-    int any_running;
+    // what the element threads need of the attempt that was just decided, after the leaders have already moved the
+    // column on (one barrier per attempt tail instead of four): was the column active, its start time and step count
+    double t_prev[MMA_NT];
+    int act[MMA_NT], nacc_prev[MMA_NT];
     long long tile;
 };
 
@@ -161,15 +164,11 @@ _Pragma("unroll")
                 for (int k = 0; k < a.m; ++k) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)row * a.o_sc] = d_nan();
             }
         })
-        if (tid == 0) {
-            int any = 0;
-            for (int c = 0; c < MMA_NT; ++c) any |= cs->running[c];
-            cs->any_running = any;
-        }
-        __syncthreads();
+        // (the barrier doubles as the OR over the columns' running flags)
+        int any_running = __syncthreads_or(tid < MMA_NT ? cs->running[tid] : 0);
 
         // ---------------------------------------------------------------- lock-step attempts
-        while (cs->any_running) {
+        while (any_running) {
             // columns that already finished keep their registers frozen until the tile retires
             double hcol[2][2], ynew[2][2][2];
             bool runc[2][2];
@@ -306,16 +305,30 @@ _Pragma("unroll")
                     cs->done[c] = done;
                     cs->t_new[c] = t_new;
                     cs->h[c] = h_new;
+                    // the column moves on here; the element threads finish the attempt below from act / t_prev / nacc_prev
+                    cs->act[c] = 1;
+                    cs->t_prev[c] = cs->t[c];
+                    cs->nacc_prev[c] = cs->nacc[c];
+                    if (done) {
+                        a.ts[cs->idx[c] * 2] = cs->t[c];  // history slot 0 (see nbk_cta.cuh)
+                        cs->running[c] = 0;
+                    }
+                    if (accept) {
+                        cs->t[c] = t_new;
+                        ++cs->nacc[c];
+                    }
+                    cs->fresh[c] = accept;
                 } else {
+                    cs->act[c] = 0;
                     cs->accept[c] = 0;
                     cs->done[c] = 0;
                 }
             }
-            __syncthreads();
+            any_running = __syncthreads_or(tid < MMA_NT ? cs->running[tid] : 0);
             // ---- emission, history stash, commit (every thread for its own elements)
             NBK_MMA_FOR_ELEMS({
                 const long long idx = cs->idx[col];
-                if (cs->running[col] && row < n) {
+                if (cs->act[col] && row < n) {
                     const bool accept = cs->accept[col];
                     if (accept) {
                         if (MODE == NBK_MODE_RUN) {
@@ -325,40 +338,20 @@ _Pragma("unroll")
 _Pragma("unroll")
                                 for (int s = 0; s <= S; ++s) Ke[s][0] = K[s][mt][nt][q];
                                 for (int k = cs->emit_from[col]; k < k1; ++k) {
-                                    rk_dense<Tab, 1>(__ldg(a.tgrid + k), cs->t[col], cs->t_new[col], yo, yn, Ke, out);
+                                    rk_dense<Tab, 1>(__ldg(a.tgrid + k), cs->t_prev[col], cs->t_new[col], yo, yn, Ke, out);
                                     a.y_out[idx * a.o_sb + k * a.o_sk + (long long)row * a.o_sc] = out[0];
                                 }
                             }
                         } else if (a.emit) {
-                            a.y_out[idx * a.o_sb + cs->nacc[col] * a.o_sk + (long long)row * a.o_sc] = ynew[mt][nt][q];
+                            a.y_out[idx * a.o_sb + cs->nacc_prev[col] * a.o_sk + (long long)row * a.o_sc] = ynew[mt][nt][q];
                         }
                     }
                     if (cs->done[col]) a.ys[(idx * 2) * nn + row] = y[mt][nt][q];  // history slot 0 (see nbk_cta.cuh)
                     if (accept) y[mt][nt][q] = ynew[mt][nt][q];
                 }
             })
-            __syncthreads();
-            if (tid < MMA_NT) {
-                const int c = tid;
-                if (cs->running[c]) {
-                    if (cs->done[c]) {
-                        a.ts[cs->idx[c] * 2] = cs->t[c];
-                        cs->running[c] = 0;
-                    }
-                    if (cs->accept[c]) {
-                        cs->t[c] = cs->t_new[c];
-                        ++cs->nacc[c];
-                    }
-                    cs->fresh[c] = cs->accept[c];
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int any = 0;
-                for (int c = 0; c < MMA_NT; ++c) any |= cs->running[c];
-                cs->any_running = any;
-            }
-            __syncthreads();
+            // no barrier here: the next attempt's first writes to the fields read above (act, accept, kout, emit_from,
+            // t_prev, t_new, done, nacc_prev) come from its leaders, S + 1 barriers further on
         }
         // ---------------------------------------------------------------- retire the tile
         NBK_MMA_FOR_ELEMS({

@@ -755,9 +755,10 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
 # RungeKutta45, 1 M decay trajectories: n = 16: 7.9 vs 11.4 ms, n = 24: 28 vs 11.8 ms, n = 32: 73 vs 11.8 ms,
 # n = 64: 202 vs 22.5 ms, per-thread vs CTA).
 CTA_AUTO_N = 16
+GROUP_AUTO_N = 10
 
 
-def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", cta_ok: bool = True):
+def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", cta_ok: bool = True, group_ok: bool = False):
     """-> (builtin_name or None, cuda_source or None).  ``regime``: "auto" | "thread" | "cta" (Python callables only:
     built-ins and CUDA C source fix their regime themselves)."""
     if isinstance(rhs, CudaRHS):
@@ -775,7 +776,10 @@ def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", c
     if callable(rhs):
         if regime not in ("auto", "thread", "cta"):
             raise ValueError("regime must be 'auto', 'thread' or 'cta'")
-        if regime == "thread" or (regime == "auto" and (n <= CTA_AUTO_N or not cta_ok)):
+        # RungeKutta23 / RungeKutta45 have the sub-warp kernels (csrc/nbk_group.cuh) for component-wise right-hand sides:
+        # they overtake the per-thread kernels from n = 11 on (decay, n = 12 / 16: 1.4x / 2.2x)
+        auto_n = GROUP_AUTO_N if group_ok else CTA_AUTO_N
+        if regime == "thread" or (regime == "auto" and (n <= auto_n or not cta_ok)):
             if n > MAX_TRACED_N:
                 raise ValueError(f"n = {n} needs the CTA regime, which this solver class does not have "
                                  "(RungeKutta23/45, AdamsBashforth*, ForwardEuler and the fixed-step Runge-Kutta classes do)")

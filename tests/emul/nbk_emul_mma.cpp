@@ -18,6 +18,17 @@ static double g_shfl[256], g_ma[256], g_mb[256];
 alignas(16) double nbk_smem[1 << 16];
 
 static inline void __syncthreads() { pthread_barrier_wait(&g_bar); }
+static int g_or[2];
+static thread_local unsigned g_or_phase;
+static inline int __syncthreads_or(int p) {  // barrier + OR over the block; two accumulators used alternately
+    const unsigned k = g_or_phase++ & 1u;
+    if (p) __atomic_store_n(&g_or[k], 1, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&g_bar);
+    const int r = __atomic_load_n(&g_or[k], __ATOMIC_SEQ_CST);
+    if (threadIdx.x == 0) __atomic_store_n(&g_or[k ^ 1u], 0, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&g_bar);
+    return r;
+}
 static inline double __shfl_xor_sync(unsigned, double v, int o) {
     const int t = (int)threadIdx.x;
     g_shfl[t] = v;
@@ -60,6 +71,7 @@ void *emul_worker(void *p) {
 extern "C" int EMUL_NAME(int kernel, const nbk_kargs *a) {
     if (kernel < 0 || kernel > 2) return -1;
     pthread_barrier_init(&g_bar, nullptr, 256);
+    g_or[0] = g_or[1] = 0;
     for (int w = 0; w < 8; ++w) pthread_barrier_init(&g_wbar[w], nullptr, 32);
     pthread_t th[256];
     emul_arg args[256];
