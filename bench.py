@@ -22,7 +22,9 @@ Printed JSON line (rank 0): the contract of the task statement; additionally
                 prefix against the live reference: fraction within rtol*|y|+atol, fraction with
                 accepted-step counts within +-1, outliers listed
   e2e           the same metric through the public API with pinned HOST buffers in and out
-  extra.configs N = 1: one timed pass each of BASELINE configs[2..4] at full size
+  extra.configs N = 1: one timed pass each of BASELINE configs[2..4] at full size and of four mid-size systems
+                (sub-warp regime); N > 1: extra.weak_scaling (1M trajectories per GPU) and extra.c5_strong_scaling
+                (configs[4]'s 65 536 grids of n = 2048 sharded over the ranks)
 `--impl reference` times the live reference (numba) on the host cores, each step a bounded
 sample of the same ensemble (the C port only if baseline/_ref is absent).
 """
@@ -563,6 +565,42 @@ def main():
                                  "trajectories_per_gpu": B_TOTAL, "trajectories_total": B_TOTAL * world,
                                  "note": "every rank integrates its own 1M-trajectory ensemble (seed = rank)"}
         del _s, _y, w_in
+        # BASELINE configs[4] "sharded across 8 GPUs": the 65 536 reaction-diffusion grids of n = 2048, one contiguous slice
+        # per rank, one CTA per trajectory (K3); strong scaling, no collective in the data path
+        B5, n5 = 65_536, 2048
+        ms5, acc5, att5, err5 = 0.0, 0.0, 0.0, None
+        try:  # (no collective inside: a failing rank must not leave the others waiting)
+            lo5, hi5 = nd.shard_bounds(B5, rank, world)
+            y5, p5 = ensembles.rd1d_ensemble(B5, n=n5, seed=3)
+            y5d, p5d = torch.from_numpy(np.ascontiguousarray(y5[lo5:hi5])).to(dev), torch.from_numpy(np.ascontiguousarray(p5[lo5:hi5])).to(dev)
+            del y5, p5
+            best = None
+            for _ in range(2):
+                s5 = nbk.RungeKutta45("rd1d", 0.0, y5d, p5d, rtol=RTOL, atol=ATOL, device=local_rank)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                s5.run([1.0])
+                e1.record()
+                torch.cuda.synchronize(dev)
+                t5 = e0.elapsed_time(e1)
+                best = t5 if best is None else min(best, t5)
+            s5.raise_for_status()
+            ms5, acc5 = best, float(s5._nacc.sum().item())
+            att5 = acc5 + float(s5._nrej.sum().item())
+            del s5, y5d, p5d
+        except Exception as exc:  # noqa: BLE001  (a secondary config must not take the headline line down)
+            err5 = f"{type(exc).__name__}: {exc}"[:300]
+        (ms5, bad5), (acc5, att5) = nd.reduce_max_sum([ms5, 1.0 if err5 else 0.0], [acc5, att5], device=dev)
+        flop5 = 6 * 8 * n5 + 66 * n5 + 18
+        if bad5 or ms5 <= 0:
+            extra["c5_strong_scaling"] = {"error": err5 or "failed on another rank"}
+        else:
+            extra["c5_strong_scaling"] = {
+                "config": f"C5 reaction-diffusion n={n5} x {B5} in total, RungeKutta45, t in [0,1], {B5 // world} trajectories per GPU",
+                "kernel": "nbk_run_rk45_rd1d_cta (K3)", "ms": ms5, "accepted_steps": acc5, "steps_per_s": acc5 / ms5 * 1e3,
+                "fp64_tflops_per_gpu": att5 / world * flop5 / ms5 * 1e3 / 1e12, "fp64_frac_per_gpu": att5 / world * flop5 / ms5 * 1e3 / 1e12 / peak_tf,
+                "note": "device-timed per rank (CUDA events), max over ranks; strong scaling of BASELINE configs[4]"}
 
     if rank == 0:
         achieved_tf = (total_attempts / world) * FLOP_PER_ATTEMPT / (ms_run * 1e-3) / 1e12  # per GPU
