@@ -164,11 +164,109 @@ NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)
     if constexpr (!LOCAL) group_sync(gmask);
 }
 
+#ifdef NBK_NEVENTS
+// =====================================================================================
+// run_events in the sub-warp regime (nbkode/core.py:334-447, :621-647, event_handler.py, nbcompat/zeros.py:508-533).
+// The event functions take the WHOLE state vector -- nbk_event(k, t, y, p) with plain pointers, the same source as in
+// the per-thread regime -- so the group's lanes publish their slices in natural order into the group's `evbuf` (n
+// doubles of shared memory) and every lane then evaluates the event functions redundantly: all lanes see the same
+// values, take the same branches, and the group stays converged through detection and bisection.
+// =====================================================================================
+template <int E>
+NBK_DEV void group_publish(double *evbuf, const double (&v)[E], int i0, int n, unsigned gmask) {
+    group_sync(gmask);  // the readers of the previous vector are done
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (i0 + e < n) evbuf[i0 + e] = v[e];
+    group_sync(gmask);
+}
+
+// After an accepted step [t_old, t_new]: sign changes, bisection of each root on the step's dense output, recording.
+// Returns true if the trajectory stops (terminal event -> t_term, or status = NBK_TRAJ_EVBRACKET).
+template <class Tab, int E>
+NBK_DEV bool group_events_after_step(const nbk_kargs &a, long long idx, double t_old, double t_new, const double (&y_old)[E],
+                                     const double (&y_new)[E], const double (&K)[Tab::S + 1][E], const double *pp,
+                                     double (&ev_last)[NBK_NEVENTS], double *evbuf, int gl, int i0, int n, unsigned gmask,
+                                     double &t_term, int &status) {
+    // every event function at the new point first (the bisections below reuse the buffer)
+    double value[NBK_NEVENTS];
+    group_publish<E>(evbuf, y_new, i0, n, gmask);
+#pragma unroll
+    for (int k = 0; k < NBK_NEVENTS; ++k) value[k] = nbk_event(k, t_new, evbuf, pp);
+    double Q[E][Tab::M];
+    bool have_q = false;
+    bool terminate = false;
+#pragma unroll
+    for (int k = 0; k < NBK_NEVENTS; ++k) {
+        const double last = ev_last[k];
+        const bool up = last <= 0.0 && value[k] >= 0.0, down = last >= 0.0 && value[k] <= 0.0;
+        const int dir = a.ev_dir[k];
+        const bool trigger = (up && dir > 0) || (down && dir < 0) || ((up || down) && dir == 0);
+        ev_last[k] = value[k];
+        if (!trigger) continue;
+        if (!have_q) {
+            rk_dense_coeffs<Tab, E>(K, Q);
+            have_q = true;
+        }
+        double root = t_new, out[E];
+        if (value[k] != 0.0) {
+            double left = t_old, right = t_new;
+            rk_dense_eval<Tab, E>(left, t_old, t_new, y_old, y_new, Q, out);
+            group_publish<E>(evbuf, out, i0, n, gmask);
+            double yl = nbk_event(k, left, evbuf, pp);
+            if (yl == 0.0) {
+                root = left;
+            } else if (!(yl * value[k] < 0.0)) {
+                status = NBK_TRAJ_EVBRACKET;
+                return true;
+            } else {
+                double mid = left;
+                for (int it = 0; it < 50; ++it) {
+                    mid = (left + right) / 2;
+                    rk_dense_eval<Tab, E>(mid, t_old, t_new, y_old, y_new, Q, out);
+                    group_publish<E>(evbuf, out, i0, n, gmask);
+                    const double ym = nbk_event(k, mid, evbuf, pp);
+                    if (fabs(ym) <= 1.48e-8) break;
+                    if ((ym > 0.0) == (yl > 0.0)) {
+                        left = mid;
+                        yl = ym;
+                    } else {
+                        right = mid;
+                    }
+                }
+                root = mid;
+            }
+        }
+        const long long slot = idx * NBK_NEVENTS + k;
+        const int cnt = a.ev_count[slot];  // written by this group only; the group barrier below orders it
+        // "This is required to avoid duplicates" (event_handler.py:158-160)
+        const bool dup = cnt > 0 && cnt <= a.ev_cap && a.ev_t[slot * a.ev_cap + cnt - 1] == root;
+        group_sync(gmask);  // every lane has read the counter and the last time before the first lane updates them
+        if (!dup) {
+            if (cnt < a.ev_cap) {
+                rk_dense_eval<Tab, E>(root, t_old, t_new, y_old, y_new, Q, out);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (i0 + e < n) a.ev_y[(slot * a.ev_cap + cnt) * n + i0 + e] = out[e];
+                if (gl == 0) a.ev_t[slot * a.ev_cap + cnt] = root;
+            }
+            if (gl == 0) a.ev_count[slot] = cnt + 1;
+        }
+        if ((a.ev_terminal >> k) & 1) {
+            // EventHandler.evaluate: min_t is never raised, so the LAST terminal event of the list wins
+            terminate = true;
+            t_term = root;
+        }
+    }
+    return terminate;
+}
+#endif  // NBK_NEVENTS
+
 // =====================================================================================
 // Advance: persistent warps, every group pulls trajectories from the global queue.
 // MODE RUN / STEP as in advance_adaptive (nbk_device.cuh) and cta_advance (nbk_cta.cuh).
 // =====================================================================================
-template <class Tab, class Rhs, int G, int E, int MODE>
+template <class Tab, class Rhs, int G, int E, int MODE, bool EV = false>
 NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
     static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
     static_assert(!Tab::DOP, "the sub-warp regime implements RungeKutta23 / RungeKutta45");
@@ -179,6 +277,12 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
     const long long nn = n, B = a.B;
     const double inv_n = 1.0 / (double)n;
     double *buf0 = sm + (size_t)(threadIdx.x / G) * (2 * G * E), *buf1 = buf0 + G * E;
+#ifdef NBK_NEVENTS
+    // EV: the whole-vector buffer of the group's event functions sits behind the stage buffers of the block
+    double *evbuf = sm + (size_t)(NBK_GRP_BLOCK / G) * (2 * G * E) + (size_t)(threadIdx.x / G) * (G * E);
+    double ev_last[NBK_NEVENTS];
+    const double *pp = a.params;
+#endif
     const double rtol = a.rtol, atol = a.atol, bound = a.bound;
     const double safety = a.safety, min_factor = a.min_factor, max_factor = a.max_factor;
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
@@ -202,7 +306,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
         // ---------------------------------------------------------------- (1) retire
         if (finishing) {
             if (nacc > 0) {
-                const bool clean = status == NBK_TRAJ_OK || status == NBK_TRAJ_BOUND;
+                const bool clean = status != NBK_TRAJ_NONFINITE && status != NBK_TRAJ_MAXATTEMPTS;
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = i0 + e;
@@ -281,6 +385,19 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                     }
                     running = kout < a.m;
                     if (running) te_next = __ldg(a.tgrid + kout);
+#ifdef NBK_NEVENTS
+                    if constexpr (EV) {
+                        // build_handler(events, self.t, self.y): last_value = func(t, y), empty lists (event_handler.py:127-135)
+                        pp = a.params_shared ? a.params : a.params + idx * a.n_params;
+                        group_publish<E>(evbuf, y, i0, n, gmask);
+#pragma unroll
+                        for (int k = 0; k < NBK_NEVENTS; ++k) {
+                            ev_last[k] = nbk_event(k, t, evbuf, pp);
+                            if (gl == 0) a.ev_count[idx * NBK_NEVENTS + k] = 0;
+                        }
+                        group_sync(gmask);
+                    }
+#endif
                 } else if (running) {
                     running = a.n_steps > 0;
                 }
@@ -314,7 +431,30 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                 ++natt;
                 bool done = false;
                 if (accept) {
-                    if (MODE == NBK_MODE_RUN) {
+                    bool stopped_by_event = false;
+#ifdef NBK_NEVENTS
+                    if constexpr (MODE == NBK_MODE_RUN && EV) {
+                        // events first, then the grid points inside the step (core.py:638-645)
+                        double t_term = 0.0;
+                        if (group_events_after_step<Tab, E>(a, idx, t, t_new, y, ynew, K, pp, ev_last, evbuf, gl, i0, n, gmask, t_term,
+                                                            status)) {
+                            if (status != NBK_TRAJ_EVBRACKET) {
+                                double out[E];
+                                rk_dense<Tab, E>(t_term, t, t_new, y, ynew, K, out);
+#pragma unroll
+                                for (int e = 0; e < E; ++e)
+                                    if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                                if (gl == 0) a.ev_tterm[idx] = t_term;
+                                ++kout;
+                                status = NBK_TRAJ_EVENT;
+                            }
+                            done = true;
+                            stopped_by_event = true;
+                        }
+                    }
+#endif
+                    if (stopped_by_event) {
+                    } else if (MODE == NBK_MODE_RUN) {
                         if (t_new >= te_next) {
                             double Q[E][Tab::M];
                             rk_dense_coeffs<Tab, E>(K, Q);

@@ -94,6 +94,14 @@ extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(step)(const __grid_constant
     nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
 #endif
 }
+#if defined(NBK_NEVENTS) && NBK_GROUP > 0
+// run_events variant of the sub-warp run kernel (nbk_set_events): dynamic shared memory = stage buffers + one whole-vector
+// buffer per group for the event functions (3 * NBK_GRP_BLOCK * NBK_E doubles)
+extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
+    extern __shared__ __align__(16) double nbk_smem[];
+    nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, NBK_MODE_RUN, true>(a, nbk_smem);
+}
+#endif
 
 #ifndef __CUDACC_RTC__
 #include "nbk_host.h"

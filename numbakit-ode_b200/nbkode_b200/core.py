@@ -232,6 +232,8 @@ class Solver(ABC):
         # 0: one trajectory per thread (trajectory index fastest); 1: one CTA per trajectory (a trajectory's
         # n values contiguous) -- see nbk_regime() in include/nbkode_b200.h
         self._regime = int(_lib.lib().nbk_regime(handle))
+        # regime 1 only: lanes of a warp per trajectory in the advance kernels (sub-warp regime), 0 = the whole CTA
+        self._group = int(_lib.lib().nbk_group_lanes(handle))
 
         # ---- ensemble state in HBM
         B, n, dev = self.B, self.n, self._device
@@ -585,9 +587,10 @@ class Solver(ABC):
         if not events:
             return self.run(t) + ([], [])
         torch = _torch()
-        if self._regime != 0:
+        if self._regime != 0 and self._group == 0:
             raise NotImplementedError(
-                "events are implemented for the one-trajectory-per-thread regime (n <= 64)"
+                "events are implemented for the one-trajectory-per-thread regime (n <= 64) and the sub-warp regime "
+                "(component-wise right-hand sides, n <= 127, RungeKutta23 / RungeKutta45), not with one CTA per trajectory"
                 + ('; construct the solver with regime="thread" to use run_events on this system' if self.n <= 64 else ""))
         ev = _rhs.trace_events(events, self.n, self._p_shape, self.params is not None)
         if not (1 <= ev.n_events <= _lib.MAX_EVENTS):

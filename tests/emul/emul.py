@@ -357,13 +357,16 @@ def group_shape(n, lanes=None):
     return g, e, ((n + e - 1) // e + 31) // 32 * 32
 
 
-def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0):
+def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0, events=None):
+    """events: (n_events, CUDA C source defining nbk_event) -> also builds the run_events kernel (kernel 3)"""
+    import hashlib
+
     tag = f"m{method}_{rhs}_g{lanes}e{elems}"
     extra = []
     if user_src is not None:
-        import hashlib
-
         tag += "_u" + hashlib.sha1((user_src + str(n_params)).encode()).hexdigest()[:10]
+    if events:
+        tag += "_ev" + hashlib.sha1(events[1].encode()).hexdigest()[:10]
     if ("group", tag) in _libs:
         return _libs[("group", tag)]
     os.makedirs(BUILD, exist_ok=True)
@@ -379,6 +382,8 @@ def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0):
                      '#include "nbk_cta.cuh"\n' + user_src + "\n#define NBK_RHS_T nbk::rhs_user_cta\n")
         else:
             fh.write(f"#define NBK_RHS_T {GROUP_RHS_TYPES[rhs]}\n")  # (a -D value cannot carry the template brackets portably)
+        if events:
+            fh.write(f"#define NBK_NEVENTS {events[0]}\n#define NBK_EVENT static inline double\n{events[1]}\n")
     extra = [f'-DEMUL_USER_PRELUDE="{pre}"']
     deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_cta.cuh", "nbk_group.cuh", "nbk_kargs.h", "nbk_program_cta.cu")]
     deps += [os.path.join(HERE, f) for f in ("nbk_emul_group.cpp", "cuda_host_shim.h")]
@@ -413,6 +418,28 @@ class EmulGroupEnsemble(EmulCtaEnsemble):
             user = self._rhs if "nbk_rhs_i" in self._rhs else None
             value = _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_)
         object.__setattr__(self, name, value)
+
+    def run_events(self, ts, events, cap=64, t_bound=math.inf):
+        """events: nbkode_b200.rhs.CudaEvents (e.g. from rhs.trace_events).  Mirrors Solver.run_events' buffers."""
+        user = self._rhs if "nbk_rhs_i" in self._rhs else None
+        fn = _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_,
+                            (events.n_events, events.source))
+        ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
+        m, NE = ts.size, events.n_events
+        out = np.full((self.B, m, self.n), np.nan)
+        ev_t = np.full((self.B, NE, cap), np.nan); ev_y = np.full((self.B, NE, cap, self.n), np.nan)
+        ev_c = np.zeros((self.B, NE), np.int32); t_term = np.full(self.B, np.nan)
+        a = KArgs(**self.base)
+        a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
+        a.pristine, self._pristine = int(self._pristine), False
+        a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
+        a.ev_cap, a.ev_terminal = cap, sum(1 << k for k, x in enumerate(events.terminal) if x)
+        for k, d in enumerate(events.direction):
+            a.ev_dir[k] = d
+        a.ev_t, a.ev_y, a.ev_count, a.ev_tterm = ev_t.ctypes.data, ev_y.ctypes.data, ev_c.ctypes.data, t_term.ctypes.data
+        self.counter[:] = 0
+        assert fn(3, C.byref(a), 32) == 0
+        return out, ev_t, ev_y, ev_c, t_term
 
 
 # --------------------------------------------------------------------------------------------------------------------

@@ -82,14 +82,17 @@ void *emul_worker(void *p) {
     gridDim.x = 1;
     if (g->kernel == 0) NBK_KERNEL(init)(*g->a);
     else if (g->kernel == 1) NBK_KERNEL(run)(*g->a);
+#ifdef NBK_NEVENTS
+    else if (g->kernel == 3) NBK_KERNEL(runev)(*g->a);
+#endif
     else NBK_KERNEL(step)(*g->a);
     return nullptr;
 }
 }  // namespace
 
-// kernel 0: construction with a block of T threads; 1 / 2: run / step with one warp (T is ignored)
+// kernel 0: construction with a block of T threads; 1 / 2 / 3: run / step / run_events with one warp (T is ignored)
 extern "C" int EMUL_NAME(int kernel, const nbk_kargs *a, int T) {
-    if (kernel < 0 || kernel > 2) return -1;
+    if (kernel < 0 || kernel > 3) return -1;
     if (kernel != 0) T = 32;
     if (T < 32 || T > 1024 || T % 32) return -1;
     g_group = NBK_GROUP;

@@ -164,3 +164,59 @@ def test_position_invariance_and_failures():
         s3.run(ts)
     st = s3.status
     assert st[17] == 2 and (np.delete(st, 17) == 0).all()
+
+
+def test_run_events_in_the_sub_warp_regime():
+    """run_events for a mid-size system: traced event callables (non-terminal, directional, terminal) through the
+    sub-warp kernels against the NumPy restatement of the reference's run_events, and against the per-thread kernels
+    (regime="thread") on the same ensemble: same events in the same order, times to the bisection's resolution."""
+    n, B = 12, 300
+    y0, k = decay_ensemble(B, n, seed=9)
+
+    def half(t, y):
+        return y[0] - 0.25
+
+    def cross(t, y):
+        return y[3] - y[7]
+
+    cross.direction = 0
+
+    def low(t, y):
+        return y[1] + y[2] - 0.2
+
+    low.terminal = True
+    low.direction = -1
+    evs = [half, cross, low]
+    ts = [1.0, 3.0, 8.0]
+    g = nbk.RungeKutta45("decay", 0.0, y0, k, rtol=RTOL, atol=ATOL)
+    th = nbk.RungeKutta45("decay", 0.0, y0, k, rtol=RTOL, atol=ATOL, regime="thread")
+    assert g._regime == 1 and g._group == 4 and th._regime == 0
+    tg, yg, teg, yeg = g.run_events(ts, evs)
+    tt, yt, tet, yet = th.run_events(ts, evs)
+    assert np.array_equal(g.event_counts, th.event_counts) and g.event_counts.sum() > B
+    assert np.array_equal(g.status, th.status) and (g.status == -1).sum() > 0
+    assert np.array_equal(np.isnan(yg), np.isnan(yt)) and np.nanmax(np.abs(yg - yt)) < 1e-6
+    for j in range(3):
+        assert np.array_equal(np.isnan(teg[j]), np.isnan(tet[j]))
+        if teg[j].size:
+            assert np.nanmax(np.abs(teg[j] - tet[j])) < 1e-6 and np.nanmax(np.abs(yeg[j] - yet[j])) < 1e-5
+    for b in range(6):
+        o = onp.AdaptiveRK("RungeKutta45", onp.rhs_decay, 0.0, y0[b], k[b], rtol=RTOL, atol=ATOL)
+        t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, ts, evs)
+        for j in range(3):
+            assert g.event_counts[b, j] == len(te_ref[j])
+            if len(te_ref[j]):
+                assert np.abs(teg[j][b, :len(te_ref[j])] - np.array(te_ref[j])).max() < 1e-6
+    # the stencil right-hand side (stage buffers in use next to the event buffer), user CUDA C events
+    y0r, pr = onp.rd1d_ensemble(200, n=24, seed=3)
+    ev = nbk.CudaEvents("NBK_EVENT nbk_event(int k, double t, const double* y, const double* p) { return y[5] - y[17]; }", 1)
+    r = nbk.RungeKutta45("rd1d", 0.0, y0r, pr, rtol=RTOL, atol=ATOL)
+    assert r._group == 8
+    tr_, yr_, ter, yer = r.run_events([0.25, 0.5], ev)
+    _, yplain = nbk.RungeKutta45("rd1d", 0.0, y0r, pr, rtol=RTOL, atol=ATOL).run([0.25, 0.5])
+    assert np.array_equal(yr_, yplain)  # a non-terminal event does not change the trajectory
+    cnt = r.event_counts
+    assert cnt.shape == (200, 1)
+    for b in np.nonzero(cnt[:, 0] > 0)[0][:20]:
+        for i in range(cnt[b, 0]):
+            assert abs(yer[0][b, i, 5] - yer[0][b, i, 17]) < 1e-7  # the recorded state is a root of the event function

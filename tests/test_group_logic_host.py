@@ -152,3 +152,65 @@ def test_failure_paths_of_one_group_leave_its_neighbours_alone():
     ok = EmulGroupEnsemble("RungeKutta45", "rd1d", np.delete(y0, 4, axis=0), np.delete(p, 4, axis=0), rtol=1e-6, atol=1e-9)
     assert np.array_equal(np.concatenate([ok.run([0.3, 0.6]), ok.run([0.9])], axis=1),
                           np.delete(np.concatenate([out, out2], axis=1), 4, axis=0))
+
+
+def _events(n, terminal_at=None):
+    def crossing(t, y):
+        return y[0] - 0.5
+
+    def gap(t, y):
+        return y[n // 2] - y[n // 2 + 2]
+
+    gap.direction = -1
+
+    def level(t, y):
+        return y[1] + y[2] - (1.0 if terminal_at is None else terminal_at)
+
+    level.terminal = terminal_at is not None
+    return [crossing, gap, level]
+
+
+@pytest.mark.parametrize("cls,n,terminal_at", [("RungeKutta45", 12, None), ("RungeKutta45", 12, 0.9), ("RungeKutta23", 20, None),
+                                               ("RungeKutta45", 7, 1.1)])
+def test_run_events_in_the_group_kernels(cls, n, terminal_at):
+    """run_events in the sub-warp regime (the group's lanes publish the whole vector for the event functions, every lane
+    evaluates them): same events in the same order as the NumPy restatement of the reference's run_events, event times to
+    the bisection's resolution, terminal events truncate the output; bit-identical across OS-scheduled repetitions."""
+    from nbkode_b200 import rhs as nrhs
+
+    B = 9
+    y0, p = ensemble(B, n, seed=17, scale=0.4)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    evs = _events(n, terminal_at)
+    ev = nrhs.trace_events(evs, n, (2,), True)
+    ts = [0.5, 1.5, 3.0]
+    first = None
+    for rep in range(3):
+        g = EmulGroupEnsemble(cls, "rd1d", y0, p, **kw)
+        got = g.run_events(ts, ev)
+        if first is None:
+            first = (g, got)
+        else:
+            for a, b in zip(got, first[1]):
+                assert np.array_equal(a, b, equal_nan=True)
+    g, (out, ev_t, ev_y, ev_c, t_term) = first
+    n_events = 0
+    for b in range(B):
+        o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **kw)
+        t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, ts, evs)
+        k = int(g.nout[b])
+        assert k == len(t_ref)
+        if g.status[b] == -1:
+            assert rel(t_term[b], t_ref[-1]) < 1e-7 and rel(out[b, k - 1], y_ref[-1]) < 1e-6
+            if k > 1:
+                assert rel(out[b, :k - 1], y_ref[:k - 1]) < 1e-7
+        else:
+            assert g.status[b] == 0 and rel(out[b, :k], y_ref) < 1e-7
+        assert np.isnan(out[b, k:]).all()
+        for j in range(3):
+            assert ev_c[b, j] == len(te_ref[j])
+            n_events += len(te_ref[j])
+            if len(te_ref[j]):
+                assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-6
+                assert rel(ev_y[b, j, :len(te_ref[j])], np.array(ye_ref[j])) < 1e-5
+    assert n_events > 0
