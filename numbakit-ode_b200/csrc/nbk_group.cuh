@@ -105,7 +105,7 @@ template <class Rhs>
 struct rhs_is_local<Rhs, decltype((void)Rhs::LOCAL)> { static constexpr bool value = Rhs::LOCAL; };
 
 // One FSAL attempt of a group.  K[0] holds the lane's slice of f(t, y).
-template <class Tab, class Rhs, int G, int E, class P>
+template <class Tab, class Rhs, int G, int E, bool FULL, class P>
 NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)[Tab::S + 1][E], const P &p,
                            int gl, int i0, int n, double inv_n, double *buf0, double *buf1, unsigned gmask,
                            double (&ynew)[E], double &err2, double rtol, double atol) {
@@ -156,7 +156,7 @@ NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)
         }
         const double sc = pos_max(fma(rtol, fabs(ynew[e]), atol), fma(rtol, fabs(y[e]), atol));
         const double r = ee * fast_rcp(sc);
-        part = i0 + e < n ? fma(r, r, part) : part;  // a select, not a branch
+        part = cta_inb<FULL>(i0 + e, n) ? fma(r, r, part) : part;  // a select, not a branch (nothing at all in a full group)
     }
     err2 = group_sum<G>(part, gmask) * (h * h * inv_n);
     // closes the window between this attempt's last reads of a stage buffer and the next attempt's first writes (for
@@ -266,7 +266,7 @@ NBK_DEV bool group_events_after_step(const nbk_kargs &a, long long idx, double t
 // Advance: persistent warps, every group pulls trajectories from the global queue.
 // MODE RUN / STEP as in advance_adaptive (nbk_device.cuh) and cta_advance (nbk_cta.cuh).
 // =====================================================================================
-template <class Tab, class Rhs, int G, int E, int MODE, bool EV = false>
+template <class Tab, class Rhs, int G, int E, int MODE, bool EV = false, bool FULL = false>
 NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
     static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
     static_assert(!Tab::DOP, "the sub-warp regime implements RungeKutta23 / RungeKutta45");
@@ -310,7 +310,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = i0 + e;
-                    if (i < n) {
+                    if (cta_inb<FULL>(i, n)) {
                         a.ys[(idx * 2 + 1) * nn + i] = y[e];
                         a.fs[(idx * 2) * nn + i] = K[0][e];
                         a.fs[(idx * 2 + 1) * nn + i] = clean ? K[S][e] : K[0][e];
@@ -350,10 +350,10 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = i0 + e;
-                    y[e] = i < n ? a.ys[(idx * 2 + 1) * nn + i] : 0.0;
+                    y[e] = cta_inb<FULL>(i, n) ? a.ys[(idx * 2 + 1) * nn + i] : 0.0;
 #pragma unroll
                     for (int s = 0; s < S; ++s) K[s][e] = 0.0;
-                    K[S][e] = i < n ? a.fs[(idx * 2 + 1) * nn + i] : 0.0;  // f(t, y): K[0] of the first attempt
+                    K[S][e] = cta_inb<FULL>(i, n) ? a.fs[(idx * 2 + 1) * nn + i] : 0.0;  // f(t, y): K[0] of the first attempt
                 }
                 status = a.status[idx] >= NBK_TRAJ_NONFINITE ? a.status[idx] : NBK_TRAJ_OK;
                 nacc = natt = kout = 0;
@@ -368,9 +368,9 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
 #pragma unroll
                         for (int e = 0; e < E; ++e) {
                             const int i = i0 + e;
-                            y_old[e] = i < n ? a.ys[(idx * 2) * nn + i] : 0.0;
+                            y_old[e] = cta_inb<FULL>(i, n) ? a.ys[(idx * 2) * nn + i] : 0.0;
 #pragma unroll
-                            for (int s = 0; s <= S; ++s) Kh[s][e] = (i < n && !a.pristine) ? a.K[(idx * (S + 1) + s) * nn + i] : 0.0;
+                            for (int s = 0; s <= S; ++s) Kh[s][e] = (cta_inb<FULL>(i, n) && !a.pristine) ? a.K[(idx * (S + 1) + s) * nn + i] : 0.0;
                         }
                         double Q[E][Tab::M];
                         rk_dense_coeffs<Tab, E>(Kh, Q);
@@ -379,7 +379,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                             rk_dense_eval<Tab, E>(__ldg(a.tgrid + kout), t_old, t, y_old, y, Q, out);
 #pragma unroll
                             for (int e = 0; e < E; ++e)
-                                if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                                if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
                             ++kout;
                         }
                     }
@@ -404,7 +404,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                 if (status >= NBK_TRAJ_NONFINITE && MODE == NBK_MODE_RUN) {
                     for (int k = 0; k < a.m; ++k)
                         for (int e = 0; e < E; ++e)
-                            if (i0 + e < n) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)(i0 + e) * a.o_sc] = d_nan();
+                            if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + k * a.o_sk + (long long)(i0 + e) * a.o_sc] = d_nan();
                 }
                 if (running && (t + h > bound)) {  // guard of the first step (core.py:176-184)
                     status = NBK_TRAJ_BOUND;
@@ -424,7 +424,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                     for (int e = 0; e < E; ++e) K[0][e] = K[S][e];
                 }
                 double ynew[E], err2;
-                group_attempt<Tab, Rhs, G, E>(t, h, y, K, p, gl, i0, n, inv_n, buf0, buf1, gmask, ynew, err2, rtol, atol);
+                group_attempt<Tab, Rhs, G, E, FULL>(t, h, y, K, p, gl, i0, n, inv_n, buf0, buf1, gmask, ynew, err2, rtol, atol);
                 const bool accept = (unsigned)__double2hiint(err2) < 0x3ff00000u;
                 const double t_new = t + h;
                 h *= step_factor<Tab>(err2, safety, min_factor, max_factor, a.x_lo, a.x_hi);
@@ -443,7 +443,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                                 rk_dense<Tab, E>(t_term, t, t_new, y, ynew, K, out);
 #pragma unroll
                                 for (int e = 0; e < E; ++e)
-                                    if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                                    if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
                                 if (gl == 0) a.ev_tterm[idx] = t_term;
                                 ++kout;
                                 status = NBK_TRAJ_EVENT;
@@ -465,7 +465,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                                 rk_dense_eval_in_step<Tab, E>(te_next, t, t_new, y, ynew, Q, out, inv_H);
 #pragma unroll
                                 for (int e = 0; e < E; ++e)
-                                    if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                                    if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
                                 ++kout;
                                 te_next = kout < a.m ? __ldg(a.tgrid + kout) : d_inf();
                             } while (t_new >= te_next);
@@ -476,7 +476,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                             if (gl == 0) a.t_out[idx * a.to_sb + nacc] = t_new;
 #pragma unroll
                             for (int e = 0; e < E; ++e)
-                                if (i0 + e < n) a.y_out[idx * a.o_sb + nacc * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
+                                if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + nacc * a.o_sk + (long long)(i0 + e) * a.o_sc] = ynew[e];
                         }
                         done = nacc + 1 >= a.n_steps;
                     }
@@ -497,7 +497,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                     if (gl == 0) a.ts[idx * 2] = t;
 #pragma unroll
                     for (int e = 0; e < E; ++e)
-                        if (i0 + e < n) a.ys[(idx * 2) * nn + i0 + e] = y[e];
+                        if (cta_inb<FULL>(i0 + e, n)) a.ys[(idx * 2) * nn + i0 + e] = y[e];
                     running = false;
                     finishing = true;
                 }

@@ -58,7 +58,7 @@ typedef nbk::tab_dop853 nbk_tab_t;  // 13 stage vectors per thread: one or two c
 #define NBK_ADV_BOUNDS __launch_bounds__(NBK_GRP_BLOCK, NBK_GRP_MINB)
 template <int MODE>
 __device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *sm) {
-    nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, MODE>(a, sm);
+    nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, MODE, false, NBK_CTA_FULL != 0>(a, sm);
 }
 #else
 #define NBK_ADV_BOUNDS __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB)
@@ -99,7 +99,7 @@ extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(step)(const __grid_constant
 // buffer per group for the event functions (3 * NBK_GRP_BLOCK * NBK_E doubles)
 extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ __align__(16) double nbk_smem[];
-    nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, NBK_MODE_RUN, true>(a, nbk_smem);
+    nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, NBK_MODE_RUN, true, NBK_CTA_FULL != 0>(a, nbk_smem);
 }
 #endif
 

@@ -357,11 +357,12 @@ def group_shape(n, lanes=None):
     return g, e, ((n + e - 1) // e + 31) // 32 * 32
 
 
-def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0, events=None):
-    """events: (n_events, CUDA C source defining nbk_event) -> also builds the run_events kernel (kernel 3)"""
+def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0, events=None, full=0):
+    """events: (n_events, CUDA C source defining nbk_event) -> also builds the run_events kernel (kernel 3);
+    full: 1 = every lane of a group owns `elems` valid components (n == lanes x elems): no bounds checks compiled in"""
     import hashlib
 
-    tag = f"m{method}_{rhs}_g{lanes}e{elems}"
+    tag = f"m{method}_{rhs}_g{lanes}e{elems}{'f' if full else ''}"
     extra = []
     if user_src is not None:
         tag += "_u" + hashlib.sha1((user_src + str(n_params)).encode()).hexdigest()[:10]
@@ -391,7 +392,7 @@ def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0, events=
         subprocess.check_call([
             "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-ffp-contract=off",
             "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}", f"-DNBK_TAG={tag}", f"-DNBK_E={elems}",
-            f"-DNBK_GROUP={lanes}", "-DNBK_CTA_MAXT=128", "-DNBK_CTA_FULL=0", *extra,
+            f"-DNBK_GROUP={lanes}", "-DNBK_CTA_MAXT=128", f"-DNBK_CTA_FULL={int(full)}", *extra,
             os.path.join(HERE, "nbk_emul_group.cpp"), "-o", so + f".{os.getpid()}.tmp",
         ])
         os.replace(so + f".{os.getpid()}.tmp", so)  # atomic: pytest-xdist workers may build the same program
@@ -416,14 +417,15 @@ class EmulGroupEnsemble(EmulCtaEnsemble):
             value = {"E": self._shape[1], "T": self._shape[2], "full": 0}[name]
         if name == "fn" and "_shape" in self.__dict__:
             user = self._rhs if "nbk_rhs_i" in self._rhs else None
-            value = _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_)
+            value = _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_,
+                                   full=int(self._shape[0] * self._shape[1] == self.n))
         object.__setattr__(self, name, value)
 
     def run_events(self, ts, events, cap=64, t_bound=math.inf):
         """events: nbkode_b200.rhs.CudaEvents (e.g. from rhs.trace_events).  Mirrors Solver.run_events' buffers."""
         user = self._rhs if "nbk_rhs_i" in self._rhs else None
         fn = _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_,
-                            (events.n_events, events.source))
+                            (events.n_events, events.source), full=int(self._shape[0] * self._shape[1] == self.n))
         ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
         m, NE = ts.size, events.n_events
         out = np.full((self.B, m, self.n), np.nan)
