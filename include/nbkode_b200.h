@@ -176,9 +176,9 @@ int nbk_step(nbk_solver *s, const nbk_state *st, long long n_steps, double bound
    nbkode/core.py:334-447, :621-647).  nbk_set_events compiles (NVRTC) a variant of the run kernel with the
    n_events event functions inlined; event_src is CUDA C defining
        NBK_EVENT nbk_event(int k, double t, const double* y, const double* p)     (returns g_k(t, y))
-   Per-thread regime and sub-warp regime (nbk_group_lanes() > 0: the group's lanes publish the whole state vector in shared
-   memory for the event functions, so the same source serves both); not with one CTA per trajectory.  nbk_run_events is
-   nbk_run plus, after every accepted step, sign-change detection per
+   Every regime takes the same source: per-thread, and -- for RungeKutta23 / RungeKutta45 / DOP853 -- the sub-warp groups and
+   one CTA per trajectory, where the team's threads publish the whole state vector in shared memory for the event
+   functions.  nbk_run_events is nbk_run plus, after every accepted step, sign-change detection per
    event (direction[k] in {-1, 0, +1}), bisection of the root on the step's dense output (|g| <= 1.48e-8, <= 50
    halvings: nbkode/nbcompat/zeros.py:508-533) and recording of (t, y(t)); a terminal event (terminal[k] != 0) stops
    its trajectory: output row n_out-1 holds the event state, t_terminal[b] its time, status NBK_TRAJ_EVENT. */

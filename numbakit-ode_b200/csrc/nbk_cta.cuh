@@ -428,10 +428,145 @@ NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
     }
 }
 
+#ifdef NBK_NEVENTS
+// =====================================================================================
+// run_events for a TEAM of threads that integrates one trajectory together -- the whole CTA here, a sub-warp group in
+// nbk_group.cuh (nbkode/core.py:334-447, :621-647, event_handler.py, nbcompat/zeros.py:508-533).
+// The event functions take the WHOLE state vector -- nbk_event(k, t, y, p) with plain pointers, the same source as in the
+// per-thread regime -- so the team's threads publish their slices in natural order into `evbuf` (n doubles of shared
+// memory) and every thread then evaluates the event functions redundantly: all threads see the same values, take the same
+// branches, and the team stays converged through detection, bisection and recording.
+//   Barrier: functor, the team's barrier.   Dense: functor (te, out[E]) -> the thread's slice of the step's dense output
+//   (it may itself contain team barriers: every thread of the team calls it at the same places).
+// =====================================================================================
+template <int E, class Barrier>
+NBK_DEV void team_publish(double *evbuf, const double (&v)[E], int i0, int n, Barrier sync) {
+    sync();  // the readers of the previous vector are done
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (i0 + e < n) evbuf[i0 + e] = v[e];
+    sync();
+}
+
+// build_handler(events, self.t, self.y): last_value = func(t, y), empty lists (event_handler.py:127-135)
+template <int E, class Barrier>
+NBK_DEV void team_events_start(const nbk_kargs &a, long long idx, double t, const double (&y)[E], const double *pp,
+                               double (&ev_last)[NBK_NEVENTS], double *evbuf, bool lead, int i0, int n, Barrier sync) {
+    team_publish<E>(evbuf, y, i0, n, sync);
+#pragma unroll
+    for (int k = 0; k < NBK_NEVENTS; ++k) {
+        ev_last[k] = nbk_event(k, t, evbuf, pp);
+        if (lead) a.ev_count[idx * NBK_NEVENTS + k] = 0;
+    }
+    sync();
+}
+
+// After an accepted step [t_old, t_new]: sign changes, bisection of each root on the step's dense output, recording.
+// Returns true if the trajectory stops (terminal event -> t_term, or status = NBK_TRAJ_EVBRACKET).
+template <int E, class Barrier, class Dense>
+NBK_DEV bool team_events_after_step(const nbk_kargs &a, long long idx, double t_old, double t_new, const double (&y_new)[E],
+                                    const double *pp, double (&ev_last)[NBK_NEVENTS], double *evbuf, bool lead, int i0, int n,
+                                    Barrier sync, Dense &dense, double &t_term, int &status) {
+    // every event function at the new point first (the bisections below reuse the buffer)
+    double value[NBK_NEVENTS];
+    team_publish<E>(evbuf, y_new, i0, n, sync);
+#pragma unroll
+    for (int k = 0; k < NBK_NEVENTS; ++k) value[k] = nbk_event(k, t_new, evbuf, pp);
+    bool terminate = false;
+#pragma unroll
+    for (int k = 0; k < NBK_NEVENTS; ++k) {
+        const double last = ev_last[k];
+        const bool up = last <= 0.0 && value[k] >= 0.0, down = last >= 0.0 && value[k] <= 0.0;
+        const int dir = a.ev_dir[k];
+        const bool trigger = (up && dir > 0) || (down && dir < 0) || ((up || down) && dir == 0);
+        ev_last[k] = value[k];
+        if (!trigger) continue;
+        double root = t_new, out[E];
+        if (value[k] != 0.0) {
+            double left = t_old, right = t_new;
+            dense(left, out);
+            team_publish<E>(evbuf, out, i0, n, sync);
+            double yl = nbk_event(k, left, evbuf, pp);
+            if (yl == 0.0) {
+                root = left;
+            } else if (!(yl * value[k] < 0.0)) {
+                status = NBK_TRAJ_EVBRACKET;
+                return true;
+            } else {
+                double mid = left;
+                for (int it = 0; it < 50; ++it) {
+                    mid = (left + right) / 2;
+                    dense(mid, out);
+                    team_publish<E>(evbuf, out, i0, n, sync);
+                    const double ym = nbk_event(k, mid, evbuf, pp);
+                    if (fabs(ym) <= 1.48e-8) break;
+                    if ((ym > 0.0) == (yl > 0.0)) {
+                        left = mid;
+                        yl = ym;
+                    } else {
+                        right = mid;
+                    }
+                }
+                root = mid;
+            }
+        }
+        const long long slot = idx * NBK_NEVENTS + k;
+        const int cnt = a.ev_count[slot];  // written by this team only; the barrier below orders it
+        // "This is required to avoid duplicates" (event_handler.py:158-160)
+        const bool dup = cnt > 0 && cnt <= a.ev_cap && a.ev_t[slot * a.ev_cap + cnt - 1] == root;
+        sync();  // every thread has read the counter and the last time before the leader updates them
+        if (!dup) {
+            if (cnt < a.ev_cap) {
+                dense(root, out);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (i0 + e < n) a.ev_y[(slot * a.ev_cap + cnt) * n + i0 + e] = out[e];
+                if (lead) a.ev_t[slot * a.ev_cap + cnt] = root;
+            }
+            if (lead) a.ev_count[slot] = cnt + 1;
+        }
+        if ((a.ev_terminal >> k) & 1) {
+            // EventHandler.evaluate: min_t is never raised, so the LAST terminal event of the list wins
+            terminate = true;
+            t_term = root;
+        }
+    }
+    return terminate;
+}
+
+struct cta_barrier {
+    NBK_DEV void operator()() const { __syncthreads(); }
+};
+// dense output of the step just accepted, for the whole CTA (prepared lazily; for DOP853 the preparation evaluates three
+// more stages with block barriers -- every thread reaches it at the same call)
+template <class Tab, class Rhs, int E>
+struct cta_step_dense {
+    double t_old, t_new;
+    const double (&y_old)[E];
+    const double (&y_new)[E];
+    const double (&K)[Tab::S + 1][E];
+    const typename Rhs::prm &p;
+    int i0, n;
+    double *buf0, *buf1;
+    cta_dense<Tab, Rhs, E> dn;
+    bool prepared;
+    NBK_DEV cta_step_dense(double t0, double t1, const double (&y0)[E], const double (&y1)[E], const double (&K_)[Tab::S + 1][E],
+                           const typename Rhs::prm &p_, int i0_, int n_, double *b0, double *b1)
+        : t_old(t0), t_new(t1), y_old(y0), y_new(y1), K(K_), p(p_), i0(i0_), n(n_), buf0(b0), buf1(b1), prepared(false) {}
+    NBK_DEV void operator()(double te, double (&out)[E]) {
+        if (!prepared) {
+            dn.prepare(t_old, t_new, y_old, y_new, K, p, i0, n, buf0, buf1);
+            prepared = true;
+        }
+        dn.eval(te, t_old, t_new, y_old, y_new, out);
+    }
+};
+#endif  // NBK_NEVENTS
+
 // =====================================================================================
 // Advance: persistent CTAs pulling trajectories from the global queue.
 // =====================================================================================
-template <class Tab, class Rhs, int E, int MODE, bool FULL = false>
+template <class Tab, class Rhs, int E, int MODE, bool FULL = false, bool EV = false>
 NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
     constexpr int S = Tab::S;
     const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
@@ -439,6 +574,10 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
     const double inv_n = 1.0 / (double)n;
     double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
     long long *s_idx = (long long *)(red + 32);
+#ifdef NBK_NEVENTS
+    double *evbuf = sm + 2 * npad + 34;  // EV: the whole vector in natural order for the event functions (npad doubles)
+    double ev_last[NBK_NEVENTS];
+#endif
     const double rtol = a.rtol, atol = a.atol, bound = a.bound;
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
 
@@ -492,6 +631,12 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
         } else if (running) {
             running = a.n_steps > 0;
         }
+#ifdef NBK_NEVENTS
+        const double *pp = a.params_shared ? a.params : a.params + idx * a.n_params;
+        if constexpr (EV && MODE == NBK_MODE_RUN) {
+            if (status == NBK_TRAJ_OK) team_events_start<E>(a, idx, t, y, pp, ev_last, evbuf, tid == 0, i0, n, cta_barrier{});
+        }
+#endif
         if (status >= NBK_TRAJ_NONFINITE && MODE == NBK_MODE_RUN) {
             for (int k = 0; k < a.m; ++k)
                 for (int e = 0; e < E; ++e)
@@ -514,7 +659,33 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
             h *= step_factor<Tab>(err2, a.safety, a.min_factor, a.max_factor, a.x_lo, a.x_hi);
             ++natt;
             bool done = false;
-            if (accept) {
+            bool stopped_by_event = false;
+#ifdef NBK_NEVENTS
+            if constexpr (EV && MODE == NBK_MODE_RUN) {
+                if (accept) {
+                    // events first, then the grid points inside the step (core.py:638-645)
+                    cta_step_dense<Tab, Rhs, E> dense(t, t_new, y, ynew, K, p, i0, n, buf0, buf1);
+                    double t_term = 0.0;
+                    if (team_events_after_step<E>(a, idx, t, t_new, ynew, pp, ev_last, evbuf, tid == 0, i0, n, cta_barrier{}, dense,
+                                                  t_term, status)) {
+                        if (status != NBK_TRAJ_EVBRACKET) {
+                            double out[E];
+                            dense(t_term, out);
+#pragma unroll
+                            for (int e = 0; e < E; ++e)
+                                if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                            if (tid == 0) a.ev_tterm[idx] = t_term;
+                            ++kout;
+                            status = NBK_TRAJ_EVENT;
+                        }
+                        done = true;
+                        stopped_by_event = true;
+                    }
+                    __syncthreads();  // the event path's last readers of the stage buffers (DOP853 dense output) are done
+                }
+            }
+#endif
+            if (accept && !stopped_by_event) {
                 if (MODE == NBK_MODE_RUN) {
                     if (t_new >= te_next) {  // the same for every thread of the CTA: prepare() may use barriers
                         cta_dense<Tab, Rhs, E> dn;
@@ -569,7 +740,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
         }
         // ---- retire
         if (nacc > 0) {
-            const bool clean = status == NBK_TRAJ_OK || status == NBK_TRAJ_BOUND;
+            const bool clean = status != NBK_TRAJ_NONFINITE && status != NBK_TRAJ_MAXATTEMPTS;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int i = i0 + e;

@@ -165,101 +165,30 @@ NBK_DEV void group_attempt(double t, double h, const double (&y)[E], double (&K)
 }
 
 #ifdef NBK_NEVENTS
-// =====================================================================================
-// run_events in the sub-warp regime (nbkode/core.py:334-447, :621-647, event_handler.py, nbcompat/zeros.py:508-533).
-// The event functions take the WHOLE state vector -- nbk_event(k, t, y, p) with plain pointers, the same source as in
-// the per-thread regime -- so the group's lanes publish their slices in natural order into the group's `evbuf` (n
-// doubles of shared memory) and every lane then evaluates the event functions redundantly: all lanes see the same
-// values, take the same branches, and the group stays converged through detection and bisection.
-// =====================================================================================
-template <int E>
-NBK_DEV void group_publish(double *evbuf, const double (&v)[E], int i0, int n, unsigned gmask) {
-    group_sync(gmask);  // the readers of the previous vector are done
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-        if (i0 + e < n) evbuf[i0 + e] = v[e];
-    group_sync(gmask);
-}
-
-// After an accepted step [t_old, t_new]: sign changes, bisection of each root on the step's dense output, recording.
-// Returns true if the trajectory stops (terminal event -> t_term, or status = NBK_TRAJ_EVBRACKET).
+// run_events in the sub-warp regime: the team routine of nbk_cta.cuh (team_events_after_step) with the group's barrier and
+// the RkInterpolator of the lane's slice.
+struct group_barrier {
+    unsigned gmask;
+    NBK_DEV void operator()() const { group_sync(gmask); }
+};
 template <class Tab, int E>
-NBK_DEV bool group_events_after_step(const nbk_kargs &a, long long idx, double t_old, double t_new, const double (&y_old)[E],
-                                     const double (&y_new)[E], const double (&K)[Tab::S + 1][E], const double *pp,
-                                     double (&ev_last)[NBK_NEVENTS], double *evbuf, int gl, int i0, int n, unsigned gmask,
-                                     double &t_term, int &status) {
-    // every event function at the new point first (the bisections below reuse the buffer)
-    double value[NBK_NEVENTS];
-    group_publish<E>(evbuf, y_new, i0, n, gmask);
-#pragma unroll
-    for (int k = 0; k < NBK_NEVENTS; ++k) value[k] = nbk_event(k, t_new, evbuf, pp);
+struct group_step_dense {
+    double t_old, t_new;
+    const double (&y_old)[E];
+    const double (&y_new)[E];
+    const double (&K)[Tab::S + 1][E];
     double Q[E][Tab::M];
-    bool have_q = false;
-    bool terminate = false;
-#pragma unroll
-    for (int k = 0; k < NBK_NEVENTS; ++k) {
-        const double last = ev_last[k];
-        const bool up = last <= 0.0 && value[k] >= 0.0, down = last >= 0.0 && value[k] <= 0.0;
-        const int dir = a.ev_dir[k];
-        const bool trigger = (up && dir > 0) || (down && dir < 0) || ((up || down) && dir == 0);
-        ev_last[k] = value[k];
-        if (!trigger) continue;
+    bool have_q;
+    NBK_DEV group_step_dense(double t0, double t1, const double (&y0)[E], const double (&y1)[E], const double (&K_)[Tab::S + 1][E])
+        : t_old(t0), t_new(t1), y_old(y0), y_new(y1), K(K_), have_q(false) {}
+    NBK_DEV void operator()(double te, double (&out)[E]) {
         if (!have_q) {
             rk_dense_coeffs<Tab, E>(K, Q);
             have_q = true;
         }
-        double root = t_new, out[E];
-        if (value[k] != 0.0) {
-            double left = t_old, right = t_new;
-            rk_dense_eval<Tab, E>(left, t_old, t_new, y_old, y_new, Q, out);
-            group_publish<E>(evbuf, out, i0, n, gmask);
-            double yl = nbk_event(k, left, evbuf, pp);
-            if (yl == 0.0) {
-                root = left;
-            } else if (!(yl * value[k] < 0.0)) {
-                status = NBK_TRAJ_EVBRACKET;
-                return true;
-            } else {
-                double mid = left;
-                for (int it = 0; it < 50; ++it) {
-                    mid = (left + right) / 2;
-                    rk_dense_eval<Tab, E>(mid, t_old, t_new, y_old, y_new, Q, out);
-                    group_publish<E>(evbuf, out, i0, n, gmask);
-                    const double ym = nbk_event(k, mid, evbuf, pp);
-                    if (fabs(ym) <= 1.48e-8) break;
-                    if ((ym > 0.0) == (yl > 0.0)) {
-                        left = mid;
-                        yl = ym;
-                    } else {
-                        right = mid;
-                    }
-                }
-                root = mid;
-            }
-        }
-        const long long slot = idx * NBK_NEVENTS + k;
-        const int cnt = a.ev_count[slot];  // written by this group only; the group barrier below orders it
-        // "This is required to avoid duplicates" (event_handler.py:158-160)
-        const bool dup = cnt > 0 && cnt <= a.ev_cap && a.ev_t[slot * a.ev_cap + cnt - 1] == root;
-        group_sync(gmask);  // every lane has read the counter and the last time before the first lane updates them
-        if (!dup) {
-            if (cnt < a.ev_cap) {
-                rk_dense_eval<Tab, E>(root, t_old, t_new, y_old, y_new, Q, out);
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if (i0 + e < n) a.ev_y[(slot * a.ev_cap + cnt) * n + i0 + e] = out[e];
-                if (gl == 0) a.ev_t[slot * a.ev_cap + cnt] = root;
-            }
-            if (gl == 0) a.ev_count[slot] = cnt + 1;
-        }
-        if ((a.ev_terminal >> k) & 1) {
-            // EventHandler.evaluate: min_t is never raised, so the LAST terminal event of the list wins
-            terminate = true;
-            t_term = root;
-        }
+        rk_dense_eval<Tab, E>(te, t_old, t_new, y_old, y_new, Q, out);
     }
-    return terminate;
-}
+};
 #endif  // NBK_NEVENTS
 
 // =====================================================================================
@@ -389,13 +318,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                     if constexpr (EV) {
                         // build_handler(events, self.t, self.y): last_value = func(t, y), empty lists (event_handler.py:127-135)
                         pp = a.params_shared ? a.params : a.params + idx * a.n_params;
-                        group_publish<E>(evbuf, y, i0, n, gmask);
-#pragma unroll
-                        for (int k = 0; k < NBK_NEVENTS; ++k) {
-                            ev_last[k] = nbk_event(k, t, evbuf, pp);
-                            if (gl == 0) a.ev_count[idx * NBK_NEVENTS + k] = 0;
-                        }
-                        group_sync(gmask);
+                        team_events_start<E>(a, idx, t, y, pp, ev_last, evbuf, gl == 0, i0, n, group_barrier{gmask});
                     }
 #endif
                 } else if (running) {
@@ -436,11 +359,12 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                     if constexpr (MODE == NBK_MODE_RUN && EV) {
                         // events first, then the grid points inside the step (core.py:638-645)
                         double t_term = 0.0;
-                        if (group_events_after_step<Tab, E>(a, idx, t, t_new, y, ynew, K, pp, ev_last, evbuf, gl, i0, n, gmask, t_term,
-                                                            status)) {
+                        group_step_dense<Tab, E> dense(t, t_new, y, ynew, K);
+                        if (team_events_after_step<E>(a, idx, t, t_new, ynew, pp, ev_last, evbuf, gl == 0, i0, n, group_barrier{gmask},
+                                                      dense, t_term, status)) {
                             if (status != NBK_TRAJ_EVBRACKET) {
                                 double out[E];
-                                rk_dense<Tab, E>(t_term, t, t_new, y, ynew, K, out);
+                                dense(t_term, out);
 #pragma unroll
                                 for (int e = 0; e < E; ++e)
                                     if (cta_inb<FULL>(i0 + e, n)) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];

@@ -94,12 +94,16 @@ extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(step)(const __grid_constant
     nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
 #endif
 }
-#if defined(NBK_NEVENTS) && NBK_GROUP > 0
-// run_events variant of the sub-warp run kernel (nbk_set_events): dynamic shared memory = stage buffers + one whole-vector
-// buffer per group for the event functions (3 * NBK_GRP_BLOCK * NBK_E doubles)
+#if defined(NBK_NEVENTS) && NBK_CTA_ADAPTIVE
+// run_events variant of the run kernel (nbk_set_events).  Dynamic shared memory: the run kernel's + one whole-vector buffer
+// for the event functions -- sub-warp regime 3 * NBK_GRP_BLOCK * NBK_E doubles, one CTA per trajectory 3 * T * NBK_E + 34.
 extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ __align__(16) double nbk_smem[];
+#if NBK_GROUP > 0
     nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, NBK_MODE_RUN, true, NBK_CTA_FULL != 0>(a, nbk_smem);
+#else
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_RUN, NBK_CTA_FULL != 0, true>(a, nbk_smem);
+#endif
 }
 #endif
 

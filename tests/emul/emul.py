@@ -223,13 +223,16 @@ def cta_shape(mid, rhs, n):
     return e, t, int(mid in (23, 45, 853) and t * e == n)
 
 
-def _program_cta(method, rhs, elems, full, user_src=None, n_params=0):
+def _program_cta(method, rhs, elems, full, user_src=None, n_params=0, events=None):
+    """events: (n_events, CUDA C source defining nbk_event) -> also builds the run_events kernel (kernel 3)"""
+    import hashlib
+
     tag = f"m{method}_{rhs}_e{elems}{'f' if full else ''}"
     extra = []
     if user_src is not None:
-        import hashlib
-
         tag += "_u" + hashlib.sha1((user_src + str(n_params)).encode()).hexdigest()[:10]
+    if events:
+        tag += "_ev" + hashlib.sha1(events[1].encode()).hexdigest()[:10]
     if ("cta", tag) in _libs:
         return _libs[("cta", tag)]
     os.makedirs(BUILD, exist_ok=True)
@@ -245,6 +248,11 @@ def _program_cta(method, rhs, elems, full, user_src=None, n_params=0):
                      "NBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n);\n"
                      '#include "nbk_cta.cuh"\n' + user_src + "\n")
         extra = [f'-DEMUL_USER_PRELUDE="{pre}"']
+    if events:
+        pre_ev = os.path.join(BUILD, f"pre_cta_ev_{tag}.{os.getpid()}.h")
+        with open(pre_ev, "w") as fh:
+            fh.write(f"#define NBK_NEVENTS {events[0]}\n#define NBK_EVENT static inline double\n{events[1]}\n")
+        extra += ["-include", pre_ev]
     deps = [os.path.join(CSRC, f) for f in ("nbk_device.cuh", "nbk_cta.cuh", "nbk_kargs.h", "nbk_program_cta.cu", "nbk_dop853_coeffs.h")]
     deps += [os.path.join(HERE, f) for f in ("nbk_emul_cta.cpp", "cuda_host_shim.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
@@ -278,6 +286,7 @@ class EmulCtaEnsemble:
         user_src = rhs if "nbk_rhs_i" in rhs else None
         if user_src is not None:  # shape rule of csrc/nbk_api.cu for source: a loop means dense coupling
             rhs = "linear" if ("for (" in user_src or "for(" in user_src or "while" in user_src) else "rd1d"
+        self._user_src, self._rhs_name = user_src, rhs
         self.E, self.T, self.full = cta_shape(self.mid, rhs, self.n)
         self.fn = _program_cta(self.mid, "user" if user_src is not None else rhs, self.E, self.full, user_src, self.np_)
         adaptive = self.mid in (23, 45, 853)
@@ -334,6 +343,31 @@ class EmulCtaEnsemble:
         self.counter[:] = 0
         assert self.fn(2, C.byref(a), self.T) == 0
         return t_out, y_out, self.nout.copy()
+
+    def _events_program(self, events):
+        user = getattr(self, "_user_src", None)
+        return _program_cta(self.mid, "user" if user is not None else self._rhs_name, self.E, self.full, user, self.np_,
+                            (events.n_events, events.source))
+
+    def run_events(self, ts, events, cap=64, t_bound=math.inf):
+        """events: nbkode_b200.rhs.CudaEvents (e.g. from rhs.trace_events).  Mirrors Solver.run_events' buffers."""
+        fn = self._events_program(events)
+        ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
+        m, NE = ts.size, events.n_events
+        out = np.full((self.B, m, self.n), np.nan)
+        ev_t = np.full((self.B, NE, cap), np.nan); ev_y = np.full((self.B, NE, cap, self.n), np.nan)
+        ev_c = np.zeros((self.B, NE), np.int32); t_term = np.full(self.B, np.nan)
+        a = KArgs(**self.base)
+        a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
+        a.pristine, self._pristine = int(self._pristine), False
+        a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
+        a.ev_cap, a.ev_terminal = cap, sum(1 << k for k, x in enumerate(events.terminal) if x)
+        for k, d in enumerate(events.direction):
+            a.ev_dir[k] = d
+        a.ev_t, a.ev_y, a.ev_count, a.ev_tterm = ev_t.ctypes.data, ev_y.ctypes.data, ev_c.ctypes.data, t_term.ctypes.data
+        self.counter[:] = 0
+        assert fn(3, C.byref(a), self.T) == 0
+        return out, ev_t, ev_y, ev_c, t_term
 
     t = property(lambda self: self.ts[:, -1].copy())
     y = property(lambda self: self.ys[:, -1].copy())
@@ -421,27 +455,10 @@ class EmulGroupEnsemble(EmulCtaEnsemble):
                                    full=int(self._shape[0] * self._shape[1] == self.n))
         object.__setattr__(self, name, value)
 
-    def run_events(self, ts, events, cap=64, t_bound=math.inf):
-        """events: nbkode_b200.rhs.CudaEvents (e.g. from rhs.trace_events).  Mirrors Solver.run_events' buffers."""
+    def _events_program(self, events):
         user = self._rhs if "nbk_rhs_i" in self._rhs else None
-        fn = _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_,
-                            (events.n_events, events.source), full=int(self._shape[0] * self._shape[1] == self.n))
-        ts = np.ascontiguousarray(np.atleast_1d(np.asarray(ts, float)))
-        m, NE = ts.size, events.n_events
-        out = np.full((self.B, m, self.n), np.nan)
-        ev_t = np.full((self.B, NE, cap), np.nan); ev_y = np.full((self.B, NE, cap, self.n), np.nan)
-        ev_c = np.zeros((self.B, NE), np.int32); t_term = np.full(self.B, np.nan)
-        a = KArgs(**self.base)
-        a.bound, a.tgrid, a.m = t_bound, ts.ctypes.data, m
-        a.pristine, self._pristine = int(self._pristine), False
-        a.y_out, a.o_sb, a.o_sk, a.o_sc = out.ctypes.data, m * self.n, self.n, 1
-        a.ev_cap, a.ev_terminal = cap, sum(1 << k for k, x in enumerate(events.terminal) if x)
-        for k, d in enumerate(events.direction):
-            a.ev_dir[k] = d
-        a.ev_t, a.ev_y, a.ev_count, a.ev_tterm = ev_t.ctypes.data, ev_y.ctypes.data, ev_c.ctypes.data, t_term.ctypes.data
-        self.counter[:] = 0
-        assert fn(3, C.byref(a), 32) == 0
-        return out, ev_t, ev_y, ev_c, t_term
+        return _program_group(self.mid, "user" if user else self._rhs, self._shape[0], self._shape[1], user, self.np_,
+                              (events.n_events, events.source), full=int(self._shape[0] * self._shape[1] == self.n))
 
 
 # --------------------------------------------------------------------------------------------------------------------

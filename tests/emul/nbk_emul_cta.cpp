@@ -44,13 +44,16 @@ void *emul_worker(void *p) {
     gridDim.x = 1;
     if (g->kernel == 0) NBK_KERNEL(init)(*g->a);
     else if (g->kernel == 1) NBK_KERNEL(run)(*g->a);
+#ifdef NBK_NEVENTS
+    else if (g->kernel == 3) NBK_KERNEL(runev)(*g->a);
+#endif
     else NBK_KERNEL(step)(*g->a);
     return nullptr;
 }
 }  // namespace
 
 extern "C" int EMUL_NAME(int kernel, const nbk_kargs *a, int T) {
-    if (kernel < 0 || kernel > 2 || T < 32 || T > 1024 || T % 32) return -1;
+    if (kernel < 0 || kernel > 3 || T < 32 || T > 1024 || T % 32) return -1;
     pthread_barrier_init(&g_bar, nullptr, (unsigned)T);
     pthread_t th[1024];
     emul_arg args[1024];

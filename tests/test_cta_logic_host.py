@@ -264,3 +264,64 @@ def test_failure_paths_of_the_cta_kernels(cls):
         m.base["max_attempts"] = 2
         m.run([5.0])
         assert (m.status == 3).all() and (m.nacc + m.nrej == 2).all()
+
+
+@pytest.mark.parametrize("cls,n,terminal_at", [("RungeKutta45", 140, None), ("RungeKutta45", 128, 0.9), ("DOP853", 100, None),
+                                               ("RungeKutta23", 70, 1.05), ("DOP853", 96, 0.95)])
+def test_run_events_with_one_cta_per_trajectory(cls, n, terminal_at):
+    """run_events in the CTA regime (round 2): the block's threads publish the whole vector in natural order for the event
+    functions (the same nbk_event source as per-thread), every thread evaluates them, detection / bisection / recording
+    are block-uniform; for DOP853 the bisection evaluates the 7th-order dense output whose preparation runs three more
+    stages with block barriers.  Against the NumPy restatement of the reference's run_events; bit-identical across
+    OS-scheduled repetitions (any missing barrier around the event buffer shows as a difference)."""
+    from nbkode_b200 import rhs as nrhs
+
+    def crossing(t, y):
+        return y[0] - 0.5
+
+    def gap(t, y):
+        return y[n // 2] - y[n // 2 + 2]
+
+    gap.direction = -1
+
+    def level(t, y):
+        return y[1] + y[2] - (1.0 if terminal_at is None else terminal_at)
+
+    level.terminal = terminal_at is not None
+    evs = [crossing, gap, level]
+    B = 3
+    y0, p = ensemble(B, n, seed=17, scale=0.4)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    ev = nrhs.trace_events(evs, n, (2,), True)
+    ts = [0.5, 1.5, 3.0]
+    first = None
+    for rep in range(2):
+        g = EmulCtaEnsemble(cls, "rd1d", y0, p, **kw)
+        got = g.run_events(ts, ev)
+        if first is None:
+            first = (g, got)
+        else:
+            for a, b in zip(got, first[1]):
+                assert np.array_equal(a, b, equal_nan=True)
+    g, (out, ev_t, ev_y, ev_c, t_term) = first
+    n_events = 0
+    tol = 1e-6 if cls == "DOP853" else 1e-7
+    for b in range(B):
+        o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **kw)
+        t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, ts, evs)
+        k = int(g.nout[b])
+        assert k == len(t_ref)
+        if g.status[b] == -1:
+            assert rel(t_term[b], t_ref[-1]) < 1e-6 and rel(out[b, k - 1], y_ref[-1]) < 1e-5
+            if k > 1:
+                assert rel(out[b, :k - 1], y_ref[:k - 1]) < tol
+        else:
+            assert g.status[b] == 0 and rel(out[b, :k], y_ref) < tol
+        assert np.isnan(out[b, k:]).all()
+        for j in range(3):
+            assert ev_c[b, j] == len(te_ref[j])
+            n_events += len(te_ref[j])
+            if len(te_ref[j]):
+                assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-6
+                assert rel(ev_y[b, j, :len(te_ref[j])], np.array(ye_ref[j])) < 1e-5
+    assert n_events > 0

@@ -411,3 +411,52 @@ def test_cta_edge_shapes():
     b = nbk.RungeKutta45("rd1d", 0.0, y2[::-1].copy(), p2[::-1].copy(), rtol=1e-6, atol=1e-9)
     _, yb = b.run([0.2])
     assert np.array_equal(ya, yb[::-1])  # position in the ensemble does not change a trajectory's result
+
+
+@pytest.mark.parametrize("cls,rhs,n,B", [("RungeKutta45", "rd1d", 200, 40), ("DOP853", "rd1d", 150, 24), ("RungeKutta23", "rd1d", 2048, 6),
+                                         ("RungeKutta45", "linear", 128, 50)])
+def test_run_events_with_one_cta_per_trajectory(cls, rhs, n, B):
+    """run_events for large systems (round 2): traced event callables through the CTA kernels' run_events variant -- for
+    the shared-matrix linear system the solver's run / step go through the DMMA kernel and run_events through the generic
+    CTA program on the same state -- against the NumPy restatement of the reference's run_events on a prefix: same events
+    in the same order, times to the bisection's resolution, a terminal event truncates the output."""
+    if rhs == "linear":
+        y0, p = onp.linear_ensemble(B, n=n, seed=2)
+        f, shared, ts = onp.rhs_linear, True, [1.0, 4.0, 9.0]
+    else:
+        y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+        p[:, 0] *= 0.4 * (100.0 / n) ** 2
+        f, shared, ts = onp.rhs_rd1d, False, [0.5, 1.5, 3.0]
+
+    def crossing(t, y):
+        return y[0] - 0.5 * y0[0, 0]
+
+    def gap(t, y):
+        return y[n // 2] - y[n // 2 + 2]
+
+    gap.direction = -1
+
+    def level(t, y):
+        return y[1] + y[2] - 0.9 * (y0[0, 1] + y0[0, 2])
+
+    level.terminal = True
+    evs = [crossing, gap, level]
+    s = getattr(nbk, cls)(rhs, 0.0, y0, p, rtol=1e-6, atol=1e-9)
+    assert s._regime == 1 and s._group == 0
+    t, y, te, ye = s.run_events(ts, evs)
+    cnt, st = s.event_counts, s.status
+    assert cnt.shape == (B, 3) and set(np.unique(st)) <= {0, -1}
+    total = 0
+    for b in range(min(B, 5)):
+        o = onp.AdaptiveRK(cls, f, 0.0, y0[b], p if shared else p[b], rtol=1e-6, atol=1e-9)
+        t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, ts, evs)
+        k = len(t_ref)
+        assert int(s._nout[b].item()) == k and (st[b] == -1) == (len(te_ref[2]) > 0)
+        assert np.abs(y[b, :k - 1] - y_ref[:k - 1]).max() <= 2e-6 * max(1.0, np.abs(y_ref).max()) if k > 1 else True
+        for j in range(3):
+            assert cnt[b, j] == len(te_ref[j])
+            total += len(te_ref[j])
+            if len(te_ref[j]):
+                assert np.abs(te[j][b, :len(te_ref[j])] - np.array(te_ref[j])).max() < 1e-5
+                assert np.abs(ye[j][b, :len(te_ref[j])] - np.array(ye_ref[j])).max() < 1e-4 * max(1.0, np.abs(y_ref).max())
+    assert total > 0
