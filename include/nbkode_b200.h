@@ -139,8 +139,9 @@ int nbk_is_jit(const nbk_solver *s);
         (a trajectory's n values are contiguous).  h, counters and status are [B] in both. */
 int nbk_regime(const nbk_solver *s);
 /* Regime 1 only: lanes of a warp that integrate one trajectory in the advance kernels (sub-warp regime for small and
-   mid-size component-wise systems under RungeKutta23 / RungeKutta45: 2, 4, 8, 16 or 32; the reference has one code path
-   for every n, nbkode/runge_kutta/explicit.py:60-79); 0 = the whole CTA (or regime 0). */
+   mid-size component-wise systems, n <= 127: 2, 4, 8, 16 or 32 lanes -- dedicated kernels for RungeKutta23 / RungeKutta45,
+   the CTA regime's source with sub-warp teams for DOP853 (n <= 64), Adams-Bashforth and the fixed-step Runge-Kutta classes;
+   the reference has one code path for every n, nbkode/runge_kutta/explicit.py:60-79); 0 = the whole CTA (or regime 0). */
 int nbk_group_lanes(const nbk_solver *s);
 
 /* Replaces Solver.__init__ / VariableStep.__init__ / Multistep.__init__

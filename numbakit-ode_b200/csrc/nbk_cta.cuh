@@ -25,9 +25,59 @@
 
 namespace nbk {
 
-// Sum over the block; every thread returns the same value (same summation order everywhere).
-// The caller guarantees a __syncthreads between two uses of `red` (the stage barriers do).
+// ---------------------------------------------------------------------------------------------------------------------
+// The TEAM: the kernels of this file are written for T threads that integrate one trajectory together.  By default the
+// team is the whole CTA.  With NBK_TEAM_G = G (2 .. 32) the team is G lanes of a warp and a block of NBK_GRP_BLOCK threads
+// holds NBK_GRP_BLOCK / G teams -- the sub-warp regime for the solver classes that have no dedicated kernel in
+// nbk_group.cuh (DOP853, Adams-Bashforth, the fixed-step Runge-Kutta classes on mid-size systems): the same source, with
+// the barrier a __syncwarp of the team's lanes, the reduction a butterfly over them, and the team's shared memory a
+// slice of the block's.  Teams of one warp run independently (different trajectories, different trip counts); every
+// barrier names exactly the team's lanes.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef NBK_TEAM_G
+#define NBK_TEAM_G 0
+#endif
+#ifndef NBK_GRP_BLOCK
+#define NBK_GRP_BLOCK 128
+#endif
+
+#ifndef NBK_HOST_EMUL  // (tests/emul/nbk_emul_group.cpp provides these for a warp of 32 POSIX threads)
+NBK_DEV void group_sync(unsigned gmask) { __syncwarp(gmask); }
+NBK_DEV double group_shfl_xor(unsigned gmask, double v, int o) { return __shfl_xor_sync(gmask, v, o); }
+NBK_DEV long long group_bcast(unsigned gmask, long long v, int src_lane) { return __shfl_sync(gmask, v, src_lane); }
+NBK_DEV bool warp_all(bool p) { return __all_sync(0xffffffffu, p); }
+#endif
+
+#if NBK_TEAM_G > 0
+NBK_DEV unsigned team_mask() {
+    return NBK_TEAM_G == 32 ? 0xffffffffu : (((1u << NBK_TEAM_G) - 1u) << ((threadIdx.x & 31) & ~(NBK_TEAM_G - 1)));
+}
+NBK_DEV int team_tid() { return (int)(threadIdx.x & (NBK_TEAM_G - 1)); }
+NBK_DEV int team_size() { return NBK_TEAM_G; }
+NBK_DEV void team_sync() { group_sync(team_mask()); }
+NBK_DEV long long team_index() { return (long long)blockIdx.x * (NBK_GRP_BLOCK / NBK_TEAM_G) + threadIdx.x / NBK_TEAM_G; }
+NBK_DEV long long team_count() { return (long long)gridDim.x * (NBK_GRP_BLOCK / NBK_TEAM_G); }
+NBK_DEV double *team_smem(double *sm, int doubles_per_team) { return sm + (size_t)(threadIdx.x / NBK_TEAM_G) * doubles_per_team; }
+#else
+NBK_DEV int team_tid() { return (int)threadIdx.x; }
+NBK_DEV int team_size() { return (int)blockDim.x; }
+NBK_DEV void team_sync() { __syncthreads(); }
+NBK_DEV long long team_index() { return (long long)blockIdx.x; }
+NBK_DEV long long team_count() { return (long long)gridDim.x; }
+NBK_DEV double *team_smem(double *sm, int) { return sm; }
+#endif
+
+// Sum over the team; every thread returns the same value (same summation order everywhere).
+// The caller guarantees a team barrier between two uses of `red` (the stage barriers do).
 NBK_DEV double block_sum(double v, double *red, int nwarps) {
+#if NBK_TEAM_G > 0
+    (void)red;
+    (void)nwarps;
+    const unsigned gmask = team_mask();
+#pragma unroll
+    for (int o = NBK_TEAM_G / 2; o > 0; o >>= 1) v += group_shfl_xor(gmask, v, o);  // (the same pair on both sides: equal totals)
+    return v;
+#else
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31;
@@ -49,6 +99,7 @@ NBK_DEV double block_sum(double v, double *red, int nwarps) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     return tot;
+#endif
 }
 
 // The stage-argument vector in shared memory.  Thread `tid` owns the E consecutive components
@@ -69,7 +120,7 @@ struct smem_vec {
 //   struct prm;  static prm load(const double *p)      -- a trajectory's parameters, fetched ONCE per trajectory
 //                                                         (a pointer for parameter blocks that do not fit registers)
 //   template <int E, bool FULL> static void eval(t, yown[E], ysm (whole vector, shared memory), prm, i0, n, dy[E])
-// `yown` is the thread's slice of the vector that is also in `ysm`.  FULL: n == blockDim.x * E, every thread owns E
+// `yown` is the thread's slice of the vector that is also in `ysm`.  FULL: n == team_size() * E, every thread owns E
 // valid components -- the kernels then compile without any per-component bounds check (branch-free stages whose
 // E dependency chains interleave; with the checks the chains ran one after the other).
 // =====================================================================================
@@ -94,7 +145,7 @@ struct rhs_rd1d_cta {  // periodic 1-D reaction-diffusion: d (y[i+1] - 2 y[i] + 
                              double (&dy)[E]) {
         // only the two halo values come from shared memory, the interior from registers
         if constexpr (FULL) {
-            const int tid = threadIdx.x, T = ysm.T;
+            const int tid = team_tid(), T = ysm.T;
             double left = ysm.at(tid == 0 ? T - 1 : tid - 1, E - 1);
             const double halo_right = ysm.at(tid + 1 == T ? 0 : tid + 1, 0);
 #pragma unroll
@@ -103,7 +154,7 @@ struct rhs_rd1d_cta {  // periodic 1-D reaction-diffusion: d (y[i+1] - 2 y[i] + 
                 left = yown[e];
             }
         } else {
-            // ragged tail (n < blockDim.x * E): no branches either -- slots beyond n are computed from whatever
+            // ragged tail (n < team_size() * E): no branches either -- slots beyond n are computed from whatever
             // finite values sit there and never reach a reduction or a store
             double left = ysm[i0 == 0 ? n - 1 : i0 - 1];
             const int ilast = i0 + E - 1 < n ? i0 + E - 1 : n - 1;
@@ -203,10 +254,10 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
             ys[e] = fma(h, acc, y[e]);
         }
         double *buf = (s & 1) ? buf1 : buf0;
-        const int T = blockDim.x;
+        const int T = team_size();
 #pragma unroll
-        for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = ys[e];  // transposed, conflict-free (see smem_vec)
-        __syncthreads();
+        for (int e = 0; e < E; ++e) buf[e * T + team_tid()] = ys[e];  // transposed, conflict-free (see smem_vec)
+        team_sync();
         Rhs::template eval<E, FULL>(s < S ? fma(h, Tab::cb().c[s < S ? s : 0], t) : t + h, ys, smem_vec<E>{buf, T}, p, i0,
                                     n, K[s]);
         if (s == S) {
@@ -240,7 +291,7 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
         }
         const double hh = h * h * inv_n;
         const double a5 = block_sum(p5, red, nwarps) * hh;
-        __syncthreads();  // `red` is reused
+        team_sync();  // `red` is reused
         const double a3 = block_sum(p3, red, nwarps) * hh;
         const double den = fma(0.01, a3, a5);
         err2 = den > 0.0 ? a5 * a5 / den : a5;  // exact step: the reference divides 0/0 here
@@ -269,10 +320,10 @@ NBK_DEV void cta_attempt(double t, double h, const double (&y)[E], double (&K)[T
 template <class Rhs, int E>
 NBK_DEV void cta_eval(double t, const double (&y)[E], const typename Rhs::prm &p, int i0, int n, double *buf,
                       double (&f)[E]) {
-    const int T = blockDim.x;
+    const int T = team_size();
 #pragma unroll
-    for (int e = 0; e < E; ++e) buf[e * T + threadIdx.x] = y[e];
-    __syncthreads();
+    for (int e = 0; e < E; ++e) buf[e * T + team_tid()] = y[e];
+    team_sync();
 #pragma unroll
     for (int e = 0; e < E; ++e) f[e] = 0.0;
     Rhs::template eval<E>(t, y, smem_vec<E>{buf, T}, p, i0, n, f);
@@ -303,14 +354,14 @@ struct cta_dense {
                             acc = fma(Tab::cb().a[s][j], j < 13 ? K[j < 13 ? j : 0][e] : Ke[j >= 13 ? j - 13 : 0][e], acc);
                     ys[e] = fma(acc, h, y_old[e]);
                 }
-                __syncthreads();  // the previous users of the buffer are done
+                team_sync();  // the previous users of the buffer are done
                 cta_eval<Rhs, E>(fma(Tab::cb().c[s], h, t_old), ys, p, i0, n, (s & 1) ? buf1 : buf0, Ke[s - 13]);
             }
             // the last evaluation read buf1, which the first stage of the NEXT attempt writes without a barrier of its
             // own in between (stages rely on the alternation of the two buffers): close the window here.  Found by the
             // host emulation of the block (tests/test_cta_logic_host.py); real warps run close enough to lock-step
             // that the GPU tests never saw it.
-            __syncthreads();
+            team_sync();
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const double dy = y[e] - y_old[e];
@@ -349,7 +400,7 @@ NBK_DEV double cta_rms_scaled(const double (&x)[E], const double (&sc)[E], int i
             part = fma(v, v, part);
         }
     const double tot = block_sum(part, red, nwarps);
-    __syncthreads();  // `red` is reused by the next norm
+    team_sync();  // `red` is reused by the next norm
     return sqrt(tot) / sqrt((double)n);
 }
 
@@ -359,15 +410,16 @@ NBK_DEV double cta_rms_scaled(const double (&x)[E], const double (&sc)[E], int i
 template <class Tab, class Rhs, int E>
 NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
     constexpr int S = Tab::S;
-    const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
+    const int n = a.n, tid = team_tid(), nwarps = team_size() >> 5, i0 = tid * E, npad = team_size() * E;
+    sm = team_smem(sm, 2 * npad + 34);
     double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
-    for (long long idx = blockIdx.x; idx < a.B; idx += gridDim.x) {
-        __syncthreads();
+    for (long long idx = team_index(); idx < a.B; idx += team_count()) {
+        team_sync();
         // per-trajectory parameters: copy the user's row into the state's [B][np] array
         if (!a.params_shared) {
-            for (int c = tid; c < a.n_params; c += blockDim.x)
+            for (int c = tid; c < a.n_params; c += team_size())
                 a.params[idx * a.n_params + c] = a.p0[idx * a.p0_sb + c * a.p0_sc];
-            __syncthreads();  // made visible to the block before the first right-hand side call
+            team_sync();  // made visible to the block before the first right-hand side call
         }
         const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
         double y[E], f[E], sc[E];
@@ -375,10 +427,10 @@ NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
         for (int e = 0; e < E; ++e) {
             y[e] = i0 + e < n ? a.y0[idx * a.y0_sb + (long long)(i0 + e) * a.y0_sc] : 0.0;
             f[e] = 0.0;
-            buf0[e * blockDim.x + tid] = y[e];
+            buf0[e * team_size() + tid] = y[e];
         }
-        __syncthreads();
-        Rhs::template eval<E>(a.t0, y, smem_vec<E>{buf0, (int)blockDim.x}, p, i0, n, f);
+        team_sync();
+        Rhs::template eval<E>(a.t0, y, smem_vec<E>{buf0, team_size()}, p, i0, n, f);
         double h = a.h0 ? a.h0[idx] : a.h_init;
         if (!(h == h)) {
             // scipy select_initial_step (direction +1, unbounded), SURVEY.md row a4
@@ -392,10 +444,10 @@ NBK_DEV void cta_init_adaptive(const nbk_kargs &a, double *sm) {
             for (int e = 0; e < E; ++e) {
                 y1[e] = y[e] + h0 * f[e];
                 f1[e] = 0.0;
-                buf1[e * blockDim.x + tid] = y1[e];
+                buf1[e * team_size() + tid] = y1[e];
             }
-            __syncthreads();
-            Rhs::template eval<E>(a.t0 + h0, y1, smem_vec<E>{buf1, (int)blockDim.x}, p, i0, n, f1);
+            team_sync();
+            Rhs::template eval<E>(a.t0 + h0, y1, smem_vec<E>{buf1, team_size()}, p, i0, n, f1);
 #pragma unroll
             for (int e = 0; e < E; ++e) f1[e] -= f[e];
             const double d2 = cta_rms_scaled<E>(f1, sc, i0, n, red, nwarps) / h0;
@@ -535,7 +587,7 @@ NBK_DEV bool team_events_after_step(const nbk_kargs &a, long long idx, double t_
 }
 
 struct cta_barrier {
-    NBK_DEV void operator()() const { __syncthreads(); }
+    NBK_DEV void operator()() const { team_sync(); }
 };
 // dense output of the step just accepted, for the whole CTA (prepared lazily; for DOP853 the preparation evaluates three
 // more stages with block barriers -- every thread reaches it at the same call)
@@ -569,9 +621,10 @@ struct cta_step_dense {
 template <class Tab, class Rhs, int E, int MODE, bool FULL = false, bool EV = false>
 NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
     constexpr int S = Tab::S;
-    const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
+    const int n = a.n, tid = team_tid(), nwarps = team_size() >> 5, i0 = tid * E, npad = team_size() * E;
     const long long nn = n;
     const double inv_n = 1.0 / (double)n;
+    sm = team_smem(sm, (EV ? 3 : 2) * npad + 34);
     double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
     long long *s_idx = (long long *)(red + 32);
 #ifdef NBK_NEVENTS
@@ -582,9 +635,9 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
 
     for (;;) {
-        __syncthreads();  // the previous trajectory's last readers of s_idx / the buffers are done
+        team_sync();  // the previous trajectory's last readers of s_idx / the buffers are done
         if (tid == 0) *s_idx = (long long)atomicAdd(a.work_counter, 1ULL);
-        __syncthreads();
+        team_sync();
         const long long idx = *s_idx;
         if (idx >= a.B) break;
 
@@ -681,7 +734,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
                         done = true;
                         stopped_by_event = true;
                     }
-                    __syncthreads();  // the event path's last readers of the stage buffers (DOP853 dense output) are done
+                    team_sync();  // the event path's last readers of the stage buffers (DOP853 dense output) are done
                 }
             }
 #endif
@@ -819,7 +872,7 @@ NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)
     double y1[E], f1[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) y1[e] = y0[e] + h0 * f0[e];
-    __syncthreads();
+    team_sync();
     cta_eval<Rhs, E>(t0 + h0, y1, p, i0, n, buf1, f1);
 #pragma unroll
     for (int e = 0; e < E; ++e) f1[e] -= f0[e];
@@ -839,7 +892,7 @@ NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)
                 for (int e = 0; e < E; ++e) K[0][e] = K[S][e];
             }
             double ynew[E], err2;
-            __syncthreads();
+            team_sync();
             cta_attempt<Tab, Rhs, E>(t, h, y, K, p, i0, n, inv_n, buf0, buf1, red, nwarps, ynew, err2, rtol, atol);
             const bool accept = pos_less(err2, 1.0);
             const double t_new = t + h;
@@ -858,7 +911,7 @@ NBK_DEV bool cta_rk_startup(double t0, const double (&y0)[E], const double (&f0)
         }
         double out[E], fo[E];
         rk_dense<Tab, E>(ti, t_old, t, y_old, y, K, out);
-        __syncthreads();
+        team_sync();
         cta_eval<Rhs, E>(ti, out, p, i0, n, (j & 1) ? buf0 : buf1, fo);
         // push(ti, out, fo)
 #pragma unroll
@@ -892,15 +945,16 @@ template <int METHOD, class Rhs, int E>
 NBK_DEV void cta_init_fixed(const nbk_kargs &a, double *sm) {
     using TR = cta_fixed_traits<METHOD>;
     constexpr int L = TR::L, S = TR::S;
-    const int n = a.n, tid = threadIdx.x, nwarps = blockDim.x >> 5, i0 = tid * E, npad = blockDim.x * E;
+    const int n = a.n, tid = team_tid(), nwarps = team_size() >> 5, i0 = tid * E, npad = team_size() * E;
     const long long nn = n;
+    sm = team_smem(sm, 2 * npad + 34);
     double *buf0 = sm, *buf1 = sm + npad, *red = sm + 2 * npad;
-    for (long long idx = blockIdx.x; idx < a.B; idx += gridDim.x) {
-        __syncthreads();
+    for (long long idx = team_index(); idx < a.B; idx += team_count()) {
+        team_sync();
         if (!a.params_shared) {
-            for (int c = tid; c < a.n_params; c += blockDim.x)
+            for (int c = tid; c < a.n_params; c += team_size())
                 a.params[idx * a.n_params + c] = a.p0[idx * a.p0_sb + c * a.p0_sc];
-            __syncthreads();
+            team_sync();
         }
         const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
         double y[E], f[E];
@@ -982,7 +1036,7 @@ NBK_DEV void cta_store_window(const nbk_kargs &a, long long idx, int n, int i0, 
             }
         }
     }
-    if (threadIdx.x == 0) {
+    if (team_tid() == 0) {
 #pragma unroll
         for (int l = 0; l < L; ++l) a.ts[idx * L + l] = ts[(l + ROT) % L];
     }
@@ -993,11 +1047,12 @@ NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
     using TR = cta_fixed_traits<METHOD>;
     constexpr int L = TR::L, S = TR::S;
     constexpr int KS = S > 0 ? S : 1;
-    const int n = a.n, tid = threadIdx.x, i0 = tid * E, npad = blockDim.x * E;
+    const int n = a.n, tid = team_tid(), i0 = tid * E, npad = team_size() * E;
     const long long nn = n;
+    sm = team_smem(sm, 2 * npad + 34);
     double *buf0 = sm, *buf1 = sm + npad;
-    for (long long idx = blockIdx.x; idx < a.B; idx += gridDim.x) {
-        __syncthreads();
+    for (long long idx = team_index(); idx < a.B; idx += team_count()) {
+        team_sync();
         const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
         double ts[L], ys[L][E], fs[L][E], K[KS][E];
 #pragma unroll

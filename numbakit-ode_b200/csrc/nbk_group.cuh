@@ -26,23 +26,13 @@
 
 #include "nbk_cta.cuh"
 
-#ifndef NBK_GRP_BLOCK
-#define NBK_GRP_BLOCK 128
-#endif
 #ifndef NBK_GRP_INNER
 #define NBK_GRP_INNER 4  // attempts between two looks at the queue / retire code
 #endif
 
 namespace nbk {
 
-#ifdef NBK_HOST_EMUL
-// tests/emul/nbk_emul_group.cpp provides the warp primitives for a warp of 32 POSIX threads
-#else
-NBK_DEV void group_sync(unsigned gmask) { __syncwarp(gmask); }
-NBK_DEV double group_shfl_xor(unsigned gmask, double v, int o) { return __shfl_xor_sync(gmask, v, o); }
-NBK_DEV long long group_bcast(unsigned gmask, long long v, int src_lane) { return __shfl_sync(gmask, v, src_lane); }
-NBK_DEV bool warp_all(bool p) { return __all_sync(0xffffffffu, p); }
-#endif
+// (group_sync / group_shfl_xor / group_bcast / warp_all: nbk_cta.cuh; tests/emul/nbk_emul_group.cpp on the host)
 
 // Sum over the G lanes of a group; the xor butterfly gives every lane the same value (each round adds the same pair
 // of numbers on both sides).

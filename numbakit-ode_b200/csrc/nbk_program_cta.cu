@@ -4,8 +4,14 @@
 // launch: ceil(n / NBK_E) rounded up to a warp; dynamic shared memory = (2*T*E + 34) doubles.
 // NBK_GROUP = G > 0: sub-warp regime (nbk_group.cuh) -- the run / step kernels are persistent 128-thread blocks in which
 // G lanes integrate one trajectory (RungeKutta23 / RungeKutta45, n <= G * NBK_E); the construction kernel stays the CTA one.
+// Classes without a dedicated sub-warp kernel (DOP853, Adams-Bashforth, the fixed-step Runge-Kutta classes) run the CTA
+// regime's source with the team = G lanes of a warp (NBK_TEAM_G, see nbk_cta.cuh): all three kernels then use
+// NBK_GRP_BLOCK-thread blocks.
 #ifndef NBK_GROUP
 #define NBK_GROUP 0
+#endif
+#if NBK_GROUP > 0 && NBK_METHOD != 23 && NBK_METHOD != 45 && !defined(NBK_TEAM_G)
+#define NBK_TEAM_G NBK_GROUP
 #endif
 #if NBK_GROUP > 0
 #include "nbk_group.cuh"
@@ -48,19 +54,31 @@ typedef nbk::tab_dop853 nbk_tab_t;  // 13 stage vectors per thread: one or two c
 #ifndef NBK_CTA_FULL
 #define NBK_CTA_FULL 0
 #endif
-#if NBK_GROUP > 0
-#if !NBK_CTA_ADAPTIVE || NBK_METHOD == 853
-#error "the sub-warp regime implements RungeKutta23 / RungeKutta45"
-#endif
+#if NBK_GROUP > 0 && NBK_TEAM_G == 0
 #ifndef NBK_GRP_MINB
 #define NBK_GRP_MINB 4
 #endif
 #define NBK_ADV_BOUNDS __launch_bounds__(NBK_GRP_BLOCK, NBK_GRP_MINB)
+#define NBK_INIT_BOUNDS __launch_bounds__(NBK_CTA_MAXT)
 template <int MODE>
 __device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *sm) {
     nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, MODE, false, NBK_CTA_FULL != 0>(a, sm);
 }
+#elif NBK_TEAM_G > 0
+// the CTA regime's source with sub-warp teams: resident blocks by register budget (DOP853 holds 15 vectors per lane)
+#ifndef NBK_GRP_MINB
+#define NBK_GRP_MINB (NBK_METHOD == 853 ? 3 : 4)
+#endif
+#define NBK_ADV_BOUNDS __launch_bounds__(NBK_GRP_BLOCK, NBK_GRP_MINB)
+#define NBK_INIT_BOUNDS __launch_bounds__(NBK_GRP_BLOCK)
+#if NBK_CTA_ADAPTIVE
+template <int MODE>
+__device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *sm) {
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, MODE, false>(a, sm);
+}
+#endif
 #else
+#define NBK_INIT_BOUNDS __launch_bounds__(NBK_CTA_MAXT)
 #define NBK_ADV_BOUNDS __launch_bounds__(NBK_CTA_MAXT, NBK_CTA_MINB)
 #if NBK_CTA_ADAPTIVE
 template <int MODE>
@@ -70,7 +88,7 @@ __device__ __forceinline__ void nbk_cta_advance_any(const nbk_kargs &a, double *
 #endif
 #endif
 
-extern "C" __global__ void __launch_bounds__(NBK_CTA_MAXT) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void NBK_INIT_BOUNDS NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ __align__(16) double nbk_smem[];
 #if NBK_CTA_ADAPTIVE
     nbk::cta_init_adaptive<nbk_tab_t, nbk_rhs_t, NBK_E>(a, nbk_smem);
@@ -99,8 +117,10 @@ extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(step)(const __grid_constant
 // for the event functions -- sub-warp regime 3 * NBK_GRP_BLOCK * NBK_E doubles, one CTA per trajectory 3 * T * NBK_E + 34.
 extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ __align__(16) double nbk_smem[];
-#if NBK_GROUP > 0
+#if NBK_GROUP > 0 && NBK_TEAM_G == 0
     nbk::group_advance<nbk_tab_t, nbk_rhs_t, NBK_GROUP, NBK_E, NBK_MODE_RUN, true, NBK_CTA_FULL != 0>(a, nbk_smem);
+#elif NBK_TEAM_G > 0
+    nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_RUN, false, true>(a, nbk_smem);
 #else
     nbk::cta_advance<nbk_tab_t, nbk_rhs_t, NBK_E, NBK_MODE_RUN, NBK_CTA_FULL != 0, true>(a, nbk_smem);
 #endif

@@ -381,10 +381,11 @@ class EmulCtaEnsemble:
 GROUP_RHS_TYPES = {"rd1d": "nbk::rhs_rd1d_cta", "decay": "nbk::rhs_decay_cta<false>", "decay1": "nbk::rhs_decay_cta<true>"}
 
 
-def group_shape(n, lanes=None):
-    """Mirror of group_shape() in csrc/nbk_api.cu -> (lanes per trajectory, components per lane, construction block)."""
+def group_shape(n, lanes=None, emax=4):
+    """Mirror of group_shape() in csrc/nbk_api.cu -> (lanes per trajectory, components per lane, construction block);
+    emax: components per lane, 4 (2 under DOP853)."""
     g = 2
-    while g < 32 and (n + g - 1) // g > 4:
+    while g < 32 and (n + g - 1) // g > emax:
         g *= 2
     g = lanes or g
     e = (n + g - 1) // g
@@ -426,7 +427,7 @@ def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0, events=
         subprocess.check_call([
             "g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-ffp-contract=off",
             "-I", CSRC, "-I", HERE, "-D__CUDACC_RTC__", f"-DNBK_METHOD={method}", f"-DNBK_TAG={tag}", f"-DNBK_E={elems}",
-            f"-DNBK_GROUP={lanes}", "-DNBK_CTA_MAXT=128", f"-DNBK_CTA_FULL={int(full)}", *extra,
+            f"-DNBK_GROUP={lanes}", "-DNBK_GRP_BLOCK=32", "-DNBK_CTA_MAXT=128", f"-DNBK_CTA_FULL={int(full)}", *extra,
             os.path.join(HERE, "nbk_emul_group.cpp"), "-o", so + f".{os.getpid()}.tmp",
         ])
         os.replace(so + f".{os.getpid()}.tmp", so)  # atomic: pytest-xdist workers may build the same program
@@ -437,12 +438,14 @@ def _program_group(method, rhs, lanes, elems, user_src=None, n_params=0, events=
 
 
 class EmulGroupEnsemble(EmulCtaEnsemble):
-    """RungeKutta23 / RungeKutta45 through the sub-warp kernels: up to 32 / G trajectories are in flight in the one emulated
-    warp and the rest is pulled from the queue.  `rhs`: "rd1d", "decay" (n rates), "decay1" (one rate) or nbk_rhs_i source."""
+    """The sub-warp regime in one emulated warp: up to 32 / G trajectories in flight, the rest pulled from the queue (or, for
+    the fixed-step classes, taken in turn).  RungeKutta23 / RungeKutta45 run the dedicated kernels of nbk_group.cuh, every
+    other class of the CTA regime its source with sub-warp teams (NBK_TEAM_G).  `rhs`: "rd1d", "decay" (n rates), "decay1"
+    (one rate) or nbk_rhs_i source."""
 
     def __init__(self, method, rhs, y0, params, lanes=None, **kw):
         n = np.atleast_2d(np.asarray(y0)).shape[1]
-        self._shape = group_shape(n, lanes)
+        self._shape = group_shape(n, lanes, emax=2 if method == "DOP853" else 4)
         self._rhs = rhs
         super().__init__(method, rhs if "nbk_rhs_i" in rhs else "rd1d", y0, params, **kw)
 

@@ -93,7 +93,7 @@ void *emul_worker(void *p) {
 // kernel 0: construction with a block of T threads; 1 / 2 / 3: run / step / run_events with one warp (T is ignored)
 extern "C" int EMUL_NAME(int kernel, const nbk_kargs *a, int T) {
     if (kernel < 0 || kernel > 3) return -1;
-    if (kernel != 0) T = 32;
+    if (kernel != 0 || NBK_TEAM_G > 0) T = 32;  // (with sub-warp teams in every kernel the construction runs in the warp too)
     if (T < 32 || T > 1024 || T % 32) return -1;
     g_group = NBK_GROUP;
     pthread_barrier_init(&g_bar, nullptr, (unsigned)T);

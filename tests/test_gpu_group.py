@@ -220,3 +220,41 @@ def test_run_events_in_the_sub_warp_regime():
     for b in np.nonzero(cnt[:, 0] > 0)[0][:20]:
         for i in range(cnt[b, 0]):
             assert abs(yer[0][b, i, 5] - yer[0][b, i, 17]) < 1e-7  # the recorded state is a root of the event function
+
+
+@pytest.mark.parametrize("cls,n,kw", [("AdamsBashforth4", 24, dict(h=0.002)), ("AdamsBashforth2", 100, dict(h=0.002)), ("ForwardEuler", 50, dict(h=0.001)),
+                                      ("RungeKutta4", 20, dict(h=0.005)), ("Heun3", 64, dict(h=0.005)),
+                                      ("DOP853", 32, dict(rtol=1e-7, atol=1e-10)), ("DOP853", 13, dict(rtol=1e-6, atol=1e-9))])
+def test_other_classes_as_sub_warp_teams(cls, n, kw):
+    """The classes without a dedicated sub-warp kernel (DOP853, Adams-Bashforth, ForwardEuler, fixed-step Runge-Kutta) run
+    the CTA regime's source with G lanes per trajectory (NBK_TEAM_G): against the C port, and against the same classes
+    with one CTA per trajectory (NBK_NO_TEAM=1) -- fixed step 1e-12 (against both), DOP853 within the tolerance with step
+    counts within +-1."""
+    B = 1500
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+    p[:, 0] *= 0.05 * (100.0 / n) ** 2
+    ts = [0.05, 0.2, 0.5]
+    adaptive = cls == "DOP853"
+    ref = oc.run_ensemble(cls, "rd1d", y0, p, ts, nthreads=8, **kw)
+    s = getattr(nbk, cls)("rd1d", 0.0, y0, p, **kw)
+    t, y = s.run(ts)
+    assert s._regime == 1 and s._group in (4, 8, 16, 32) and s.last_launch()["block"] == 128
+    os.environ["NBK_NO_TEAM"] = "1"
+    try:
+        c = getattr(nbk, cls)("rd1d", 0.0, y0, p, **kw)
+    finally:
+        del os.environ["NBK_NO_TEAM"]
+    _, yc = c.run(ts)
+    assert c._group == 0
+    if adaptive:
+        parity_bar(f"group/team/{cls}/n{n}/gpu_vs_c_port", y, ref["ys"], kw["rtol"], kw["atol"], 1.0)
+        parity_bar(f"group/team/{cls}/n{n}/team_vs_cta", y, yc, kw["rtol"], kw["atol"], 1.0)
+        assert np.abs(s.n_accepted - ref["n_accepted"]).max() <= 1 and np.abs(s.n_accepted - c.n_accepted).max() <= 1
+    else:
+        scale = max(1.0, np.abs(ref["ys"]).max())
+        assert np.abs(y - ref["ys"]).max() <= 1e-12 * scale
+        assert np.abs(y - yc).max() <= 1e-12 * scale and np.abs(s.y - c.y).max() <= 1e-12 * scale and np.abs(s.f - c.f).max() <= 1e-11 * scale
+    # step / resumed run on top
+    t1, y1 = s.step(n=3)
+    tc, yc1 = c.step(n=3)
+    assert t1.shape == (B, 3) and np.abs(y1 - yc1).max() < (1e-6 if adaptive else 1e-12 * max(1.0, np.abs(yc1).max()))

@@ -214,3 +214,84 @@ def test_run_events_in_the_group_kernels(cls, n, terminal_at):
                 assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-6
                 assert rel(ev_y[b, j, :len(te_ref[j])], np.array(ye_ref[j])) < 1e-5
     assert n_events > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The classes without a dedicated sub-warp kernel run the CTA regime's source with the team = G lanes of a warp
+# (NBK_TEAM_G, csrc/nbk_cta.cuh): construction, run and step kernels all in the emulated warp.
+# ---------------------------------------------------------------------------------------------------------------------
+def _reference(cls, y0, p, kw):
+    if cls in ("RungeKutta23", "RungeKutta45", "DOP853"):
+        return onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0, p, **kw)
+    if cls in ("RungeKutta4", "Heun3", "Runge2", "Runge3", "RungeKutta3_8"):
+        return onp.FixedRK(cls, onp.rhs_rd1d, 0.0, y0, p, h=kw["h"])
+    order = 1 if cls == "ForwardEuler" else int(cls[-1])
+    return onp.AdamsBashforth(order, onp.rhs_rd1d, 0.0, y0, p, h=kw["h"],
+                              first_stepper={45: "RungeKutta45", 23: "RungeKutta23", 0: None}[kw.get("first_stepper", 45)])
+
+
+@pytest.mark.parametrize("cls,n,kw", [("AdamsBashforth4", 24, dict(h=0.01, first_stepper=45)), ("AdamsBashforth5", 13, dict(h=0.01, first_stepper=23)),
+                                      ("AdamsBashforth2", 50, dict(h=0.01, first_stepper=45)), ("ForwardEuler", 32, dict(h=0.01, first_stepper=0)),
+                                      ("RungeKutta4", 20, dict(h=0.01)), ("Heun3", 7, dict(h=0.01)),
+                                      ("DOP853", 20, dict(rtol=1e-6, atol=1e-9)), ("DOP853", 64, dict(rtol=1e-7, atol=1e-10))])
+def test_team_mode_classes_vs_numpy_restatement(cls, n, kw):
+    """Adams-Bashforth (ring-buffered window, RungeKutta45 / RungeKutta23 / no start-up), ForwardEuler, fixed-step Runge-
+    Kutta and DOP853 (two-norm error estimate, dense output with three extra stages behind team barriers) as sub-warp
+    teams: dense output on a grid that straddles steps, a resumed run, step(); more trajectories than teams in the warp;
+    fixed step to 1e-12, DOP853 to 1e-3 of the tolerance with identical step counts."""
+    B = 11
+    y0, p = ensemble(B, n, seed=33)
+    adaptive = cls == "DOP853"
+    g = EmulGroupEnsemble(cls, "rd1d", y0, p, **kw)
+    assert g._shape[0] * g._shape[1] >= n and g._shape[1] <= (2 if adaptive else 4)
+    ts = np.array([0.005, 0.0312, 0.1, 0.1049, 0.25])
+    out = np.concatenate([g.run(ts[:3]), g.run(ts[3:])], axis=1)
+    tq, yq, counts = g.step(5)
+    assert (g.status == 0).all() and (counts == 5).all()
+    for b in range(B):
+        o = _reference(cls, y0[b], p[b], kw)
+        _, yo = onp.run(o, ts)
+        to, ys = onp.steps(o, n=5)
+        if adaptive:
+            assert np.all(np.abs(out[b] - yo) <= 1e-3 * (kw["rtol"] * np.abs(yo) + kw["atol"]))
+            assert g.nacc[b] == o.n_accepted and rel(tq[b], to) < 1e-6 and rel(yq[b], ys) < 1e-6
+        else:
+            assert rel(out[b], yo) < 1e-12, (cls, n, b, rel(out[b], yo))
+            assert rel(tq[b], to) < 1e-12 and rel(yq[b], ys) < 1e-12
+            assert rel(g.t[b], o.t) < 1e-12 and rel(g.y[b], o.y) < 1e-12 and rel(g.f[b], o.f) < 1e-11
+
+
+@pytest.mark.parametrize("cls,n,kw", [("AdamsBashforth4", 24, dict(h=0.01, first_stepper=45)), ("RungeKutta4", 13, dict(h=0.01)),
+                                      ("DOP853", 20, dict(rtol=1e-6, atol=1e-9))])
+def test_team_mode_is_race_free_and_dop853_events(cls, n, kw):
+    """Repetitions under OS scheduling are bit-identical (every barrier names exactly the team's lanes); DOP853 also runs
+    run_events through the team routine (its dense output prepares three extra stages inside the bisection)."""
+    B = 9
+    y0, p = ensemble(B, n, seed=5, scale=0.4 if cls == "DOP853" else 0.05)
+    ref = None
+    for rep in range(3):
+        g = EmulGroupEnsemble(cls, "rd1d", y0, p, **kw)
+        got = [g.run([0.1, 0.11, 0.5]), g.run([0.9]), *g.step(3)[:2], g.t, g.y, g.f]
+        if ref is None:
+            ref = got
+        else:
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b)
+    if cls == "DOP853":
+        from nbkode_b200 import rhs as nrhs
+
+        evs = _events(n, 0.95)
+        ev = nrhs.trace_events(evs, n, (2,), True)
+        g = EmulGroupEnsemble(cls, "rd1d", y0, p, **kw)
+        out, ev_t, ev_y, ev_c, t_term = g.run_events([0.5, 1.5, 3.0], ev)
+        total = 0
+        for b in range(B):
+            o = onp.AdaptiveRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], **kw)
+            t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, [0.5, 1.5, 3.0], evs)
+            assert int(g.nout[b]) == len(t_ref) and (g.status[b] == -1) == (len(te_ref[2]) > 0)
+            for j in range(3):
+                assert ev_c[b, j] == len(te_ref[j])
+                total += len(te_ref[j])
+                if len(te_ref[j]):
+                    assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-6
+        assert total > 0

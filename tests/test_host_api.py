@@ -253,8 +253,12 @@ def test_nvrtc_compiles_event_programs_and_traces_events():
         assert sz.value > 10_000
     with pytest.raises(ValueError):
         _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(45, 3, 3, rhs_name=b"lorenz")), 9, ev.source.encode(), C.byref(sz)))
-    with pytest.raises(ValueError):  # CTA regime: not implemented
-        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(45, 2048, 2, rhs_name=b"rd1d")), 1, ev.source.encode(), C.byref(sz)))
+    # component-wise right-hand sides: the adaptive classes have run_events as sub-warp teams and with one CTA per trajectory
+    for method, n in ((45, 2048), (45, 24), (853, 40), (853, 300), (23, 200)):
+        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(method, n, 2, rhs_name=b"rd1d")), 3, ev.source.encode(), C.byref(sz)))
+        assert sz.value > 10_000
+    with pytest.raises(ValueError):  # ... the fixed-step classes only per thread
+        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(4, 200, 2, rhs_name=b"rd1d")), 1, ev.source.encode(), C.byref(sz)))
     with pytest.raises(rhs.TraceError):
         rhs.trace_events(lambda t, y: 1.0 if y[0] > 0 else -1.0, 3, (3,), True)
 
