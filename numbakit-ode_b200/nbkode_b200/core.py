@@ -210,7 +210,7 @@ class Solver(ABC):
         # one, e.g. "thread" to use run_events or DOP853 on a mid-size system)
         cta_ok = self.METHOD_ID in _CTA_METHODS and not (2 <= self.METHOD_ID <= 5 and 1 <= _first_stepper <= 5)
         name, src = _rhs.resolve(rhs, self.n, p_shape if p_shape else (self.n_params,), params is not None, regime, cta_ok,
-                                 group_ok=self.METHOD_ID in (23, 45))
+                                 group_ok=self.METHOD_ID in (23, 45), auto_n=_rhs.AUTO_N_BY_METHOD.get(self.METHOD_ID))
         if name in ("decay", "decay:thread") and self.n_params not in (1, self.n):
             raise ValueError("built-in 'decay' needs 1 or n parameters")
         self.rhs = name if name is not None else _rhs.CudaRHS(src)

@@ -756,9 +756,13 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
 # n = 64: 202 vs 22.5 ms, per-thread vs CTA).
 CTA_AUTO_N = 16
 GROUP_AUTO_N = 10
+# largest n a traced callable still runs per thread, by method id (tools/bench_group.py, tools/bench_team_decay.py: the
+# component-wise form then runs as sub-warp groups / teams, csrc/nbk_group.cuh, nbk_cta.cuh)
+AUTO_N_BY_METHOD = {23: 10, 45: 10, 853: 5, 1: 17, 2: 17, 3: 17, 4: 17, 5: 17, 202: 20, 203: 20, 213: 20, 204: 20, 238: 20}
 
 
-def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", cta_ok: bool = True, group_ok: bool = False):
+def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", cta_ok: bool = True, group_ok: bool = False,
+            auto_n=None):
     """-> (builtin_name or None, cuda_source or None).  ``regime``: "auto" | "thread" | "cta" (Python callables only:
     built-ins and CUDA C source fix their regime themselves)."""
     if isinstance(rhs, CudaRHS):
@@ -778,7 +782,8 @@ def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", c
             raise ValueError("regime must be 'auto', 'thread' or 'cta'")
         # RungeKutta23 / RungeKutta45 have the sub-warp kernels (csrc/nbk_group.cuh) for component-wise right-hand sides:
         # they overtake the per-thread kernels from n = 11 on (decay, n = 12 / 16: 1.4x / 2.2x)
-        auto_n = GROUP_AUTO_N if group_ok else CTA_AUTO_N
+        # (`auto_n`: the solver class's own measured crossover, see AUTO_N_BY_METHOD)
+        auto_n = auto_n if auto_n is not None else (GROUP_AUTO_N if group_ok else CTA_AUTO_N)
         if regime == "thread" or (regime == "auto" and (n <= auto_n or not cta_ok)):
             if n > MAX_TRACED_N:
                 raise ValueError(f"n = {n} needs the CTA regime, which this solver class does not have "
