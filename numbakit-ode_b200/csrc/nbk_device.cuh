@@ -39,7 +39,12 @@
 #define NBK_BLOCK 128
 #endif
 #ifndef NBK_INNER
-#define NBK_INNER 8  // attempts between two looks at the trajectory queue (measured: 1 -> 7.48 ms, 4 -> 7.31, 8 -> 7.26)
+#define NBK_INNER 16  // attempts between two looks at the trajectory queue (measured, round 1: 1 -> 7.48 ms, 4 -> 7.31, 8 -> 7.26;
+                      // round 2, with the tail compaction: 4 -> 6.95, 8 -> 6.85, 12 -> 6.82, 16 -> 6.80, 24 -> 6.79, 32 -> 6.80;
+                      // 125 000 trajectories: 8 -> 1.117, 16 -> 1.106, 32 -> 1.127)
+#endif
+#ifndef NBK_INNER_ADAPT
+#define NBK_INNER_ADAPT 1
 #endif
 #ifdef NBK_HOST_EMUL
 #define NBK_LOG2F(x) log2f(x)
@@ -889,6 +894,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     int kout = 0;            // RUN: next grid index
     bool fresh = true;       // the next attempt opens a new step (K[S] holds f(t, y))
     int status = NBK_TRAJ_OK;
+    int inner = NBK_INNER;   // attempts until the next look at the queue (adapted per warp, NBK_INNER_ADAPT)
 
     // ---- tail compaction (see NBK_COMPACT above).  A parked trajectory is its loop-carried state: t, h, te_next, y, K,
     // p (NFD doubles), its index and four counters.  The pool holds at most CAP of them, field-major so that the lanes
@@ -954,6 +960,18 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
         }
         // ---------------------------------------------------------------- (2) refill
         const unsigned idle = __ballot_sync(FULL, !running);
+#if NBK_INNER_ADAPT
+        // The number of attempts between two looks at the queue follows the workload (per warp): long trajectories want
+        // few looks (vote / branch overhead, refills batched over more lanes), short ones more (a finished lane idles
+        // until the next look) -- but never fewer than 8 attempts apart: measured on 29-attempt trajectories (Lorenz to
+        // t = 0.5, 1 M) 2..4 apart 0.724 ms, 8 apart 0.664, 16 apart 0.687; on 484-attempt ones 8 / 16: 6.845 / 6.796.
+        if (!queue_empty) {
+            const int nid = __popc(idle);
+            inner = nid >= 8 ? NBK_INNER / 2 : (nid <= 2 ? NBK_INNER : inner);
+        } else {
+            inner = NBK_INNER;
+        }
+#endif
         if (idle) {
             if (queue_empty) {
 #if NBK_COMPACT
@@ -1166,7 +1184,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
         // NBK_INNER attempts per queue check: a finished lane waits at most NBK_INNER-1 attempts
         // (of ~500 per trajectory) and the vote/branch overhead is paid once per NBK_INNER.
 #pragma unroll 1
-        for (int rep = 0; rep < NBK_INNER; ++rep) {
+        for (int rep = 0; rep < inner; ++rep) {
 #ifdef NBK_DEBUG_COMPACT
             if (queue_empty) ++dbg_reps;
 #endif

@@ -13,6 +13,7 @@ method = os.environ.get("NBK_TUNE_METHOD", "RungeKutta45")
 FLOP = {"RungeKutta45": 264, "RungeKutta23": 123, "DOP853": 635}[method]
 B = int(os.environ.get("NBK_TUNE_B", 1_000_000)); reps = int(os.environ.get("NBK_TUNE_REPS", 6))
 rtol, atol = float(os.environ.get("NBK_TUNE_RTOL", 1e-6)), float(os.environ.get("NBK_TUNE_ATOL", 1e-9))
+T_END = float(os.environ.get("NBK_TUNE_T", 10.0))  # a short horizon = short trajectories (few attempts each)
 y0, p = onp.lorenz_ensemble(B, 0)
 
 
@@ -26,11 +27,11 @@ for it in range(reps + 3):
     # NBK_TUNE_JIT=1: the same right-hand side as a Python callable (traced -> CUDA C -> NVRTC) instead of the catalogue kernel
     s = getattr(nbk, method)(rhs_lorenz if os.environ.get("NBK_TUNE_JIT") else "lorenz", 0.0, y0d, pd, rtol=rtol, atol=atol)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); s.run([10.0]); e1.record(); torch.cuda.synchronize()
+    e0.record(); s.run([T_END]); e1.record(); torch.cuda.synchronize()
     if it >= 3: times.append(e0.elapsed_time(e1))
     att = int((s._nacc.sum() + s._nrej.sum()).item()); acc = int(s._nacc.sum().item())
 ms = float(np.median(times))
-print(json.dumps({"lib": os.path.basename(os.environ.get("NBK_LIB_PATH", "default")), "method": method, "rtol": rtol,
+print(json.dumps({"lib": os.path.basename(os.environ.get("NBK_LIB_PATH", "default")), "method": method, "rtol": rtol, "t_end": T_END,
                   "ms_median": ms, "ms_min": min(times), "attempts": att, "accepted": acc,
                   "attempts_per_s": att / ms * 1e3, "accepted_per_s": acc / ms * 1e3, "tflops": att * FLOP / ms * 1e3 / 1e12,
                   "launch": s.last_launch()}))
