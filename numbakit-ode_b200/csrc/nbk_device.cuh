@@ -967,7 +967,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
         // t = 0.5, 1 M) 2..4 apart 0.724 ms, 8 apart 0.664, 16 apart 0.687; on 484-attempt ones 8 / 16: 6.845 / 6.796.
         if (!queue_empty) {
             const int nid = __popc(idle);
-            inner = nid >= 8 ? NBK_INNER / 2 : (nid <= 2 ? NBK_INNER : inner);
+            inner = nid >= 4 ? NBK_INNER / 2 : (nid <= 2 ? NBK_INNER : inner);  // (DOP853 / Lorenz, ~75 attempts: 8 apart 6.21 ms, 16 apart 6.27)
         } else {
             inner = NBK_INNER;
         }
