@@ -464,16 +464,31 @@ def main():
         import collections
 
         live = collections.deque(maxlen=len(inputs))  # keeps the last R states alive: the allocator hands out other memory
-        for i in range(warmup):
+        # Warm-up: at least `warmup` untimed passes, and on until the device has settled -- three consecutive passes within
+        # 3 % of each other (observed on one box of the pool: the first 0.3-0.5 s of GPU work of a fresh process ran at a
+        # third of the speed, with the SM clock reading its maximum and no throttle reason; later passes of the same
+        # process were normal) -- but no longer than 3 s.  The count actually done is reported as "warmup".
+        wu_ms, t_wu, i = [], time.perf_counter(), 0
+        while True:
             s = nbk.RungeKutta45("lorenz", 0.0, *inputs[i % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
             s.run([T_END])
+            w1.record()
             live.append(s)
+            torch.cuda.synchronize(dev)
+            wu_ms.append(w0.elapsed_time(w1))
+            i += 1
+            settled = len(wu_ms) >= 3 and max(wu_ms[-3:]) <= 1.03 * min(wu_ms[-3:])
+            if (i >= warmup and settled) or time.perf_counter() - t_wu > 3.0:
+                break
+        kernel_arm.warmup_done = i
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         run_ev = []
         barrier()
         ev[0].record()
         for i in range(steps):
-            s = nbk.RungeKutta45("lorenz", 0.0, *inputs[i % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
+            s = nbk.RungeKutta45("lorenz", 0.0, *inputs[(i + kernel_arm.warmup_done) % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             t, y = s.run([T_END])
@@ -486,12 +501,16 @@ def main():
         # every step integrates the same ensemble (deterministic kernels): count once, after the clock stopped
         acc = float(s._nacc.sum().item())
         att = acc + float(s._nrej.sum().item())
-        return s, y, ev[0].elapsed_time(ev[1]), sum(a.elapsed_time(b) for a, b in run_ev), acc * steps, att * steps
+        per_step = [a.elapsed_time(b) for a, b in run_ev]
+        if os.environ.get("NBK_BENCH_DEBUG"):
+            print("run-kernel ms per step:", [round(x, 3) for x in per_step], file=sys.stderr)
+        return s, y, ev[0].elapsed_time(ev[1]), sum(per_step), acc * steps, att * steps
 
     # ------------------------------------------------------------ kernel-only arm
     sampler = ClockSampler(local_rank)
     sampler.start()
     s, y_dev, ms_total, ms_run, steps_acc, attempts = kernel_arm(inputs, args.steps, max(args.warmup, 3))
+    warmup_done = kernel_arm.warmup_done
     clocks = sampler.finish()
     launch = s.last_launch()
     # device-timed, max over ranks; work summed over ranks (the driver computes efficiency itself)
@@ -522,14 +541,32 @@ def main():
     # warm-up with the same two-deep pattern (pinned result buffers of two passes are alive at once)
     # and the same variable lifetimes as the timed loop: the pinned-host caching allocator then already owns every
     # buffer the steady state needs (a fresh cudaHostAlloc of 24 MB costs ~14 ms and synchronises the device)
-    pending = None
-    for i in range(max(args.warmup, 3) + 3):
+    # ... and on until the pipeline has settled (three consecutive passes within 5 % of each other, at most 3 s): the
+    # first passes also pay for the pinned buffers and, on some boxes, a slow first few hundred milliseconds (see kernel_arm)
+    pending, wall, t_wu, i = None, [], time.perf_counter(), 0
+    while True:
+        t_p = time.perf_counter()
         item = e2e_pass(i)
         if pending is not None:
             n_i, y, nacc = e2e_finish(pending)
         pending = item
+        wall.append(time.perf_counter() - t_p)
+        i += 1
+        settled = len(wall) >= 4 and max(wall[-3:]) <= 1.05 * min(wall[-3:])
+        if (i >= max(args.warmup, 3) + 3 and settled) or time.perf_counter() - t_wu > 3.0:
+            break
     n_i, y, nacc = e2e_finish(pending)
+    # no stale reference may keep a warm-up solver (416 MB of device state) alive into the timed region: its blocks would be
+    # missing from the stream's pool and the first timed pass would cudaMalloc nine new ones (measured: 3.5-35 ms)
+    item = pending = None
     barrier()
+    dbg = os.environ.get("NBK_BENCH_DEBUG")
+    hstat = (lambda: dict(torch.cuda.host_memory_stats()).get("num_host_alloc")) if hasattr(torch.cuda, "host_memory_stats") else (lambda: None)
+    h_before, d_before, marks = hstat(), torch.cuda.memory_stats(dev).get("num_device_alloc"), []
+    import gc
+
+    gc.collect()
+    gc.disable()  # (a generation-2 collection inside a 35 ms timed region is a 10 ms outlier)
     t0 = time.perf_counter()
     e2e_steps, pending = 0, None
     for i in range(args.steps):
@@ -538,10 +575,17 @@ def main():
             n_i, y, nacc = e2e_finish(pending)
             e2e_steps += n_i
         pending = item
+        item = None
+        marks.append(time.perf_counter())
     n_i, y, nacc = e2e_finish(pending)
     e2e_steps += n_i
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    gc.enable()
+    if dbg:
+        print("e2e warm-up passes:", len(wall), "timed pass marks (ms):", [round(1e3 * (m - t0), 2) for m in marks], "total",
+              round(1e3 * e2e_s, 2), "host allocs", h_before, "->", hstat(), "device allocs", d_before, "->",
+              torch.cuda.memory_stats(dev).get("num_device_alloc"), file=sys.stderr)
     h2d = y0_host.numel() * 8 + p_host.numel() * 8
     d2h = y.numel() * 8 + 2 * nacc.numel() * 8
     # latency of ONE pass, nothing overlapped: host buffers -> result in host memory, wall clock
@@ -605,7 +649,7 @@ def main():
     if rank == 0:
         achieved_tf = (total_attempts / world) * FLOP_PER_ATTEMPT / (ms_run * 1e-3) / 1e12  # per GPU
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup_done,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, B_total, l2_note),
             "clocks": clocks,
