@@ -632,6 +632,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
     double ev_last[NBK_NEVENTS];
 #endif
     const double rtol = a.rtol, atol = a.atol, bound = a.bound;
+    const bool bounded = a.bound < 1.7976931348623157e308;  // (usually not: skips the guard of every accepted step)
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
 
     for (;;) {
@@ -771,7 +772,7 @@ NBK_DEV void cta_advance(const nbk_kargs &a, double *sm) {
                 status = NBK_TRAJ_MAXATTEMPTS;
                 done = true;
             }
-            if (accept && !done && (t_new + h > bound)) {  // guard of the next step
+            if (bounded && accept && !done && (t_new + h > bound)) {  // guard of the next step
                 status = NBK_TRAJ_BOUND;
                 done = true;
             }

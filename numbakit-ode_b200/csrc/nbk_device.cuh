@@ -881,6 +881,8 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     const double rtol = a.rtol, atol = a.atol;
     const double safety = a.safety, min_factor = a.min_factor, max_factor = a.max_factor;
     const double bound = a.bound;
+    // t_bound / upto_t is usually infinite: a kernel-uniform flag skips the guard of every accepted step (DADD + DSETP + LDC)
+    const bool bounded = a.bound < 1.7976931348623157e308;
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
 
     // Loop-carried per-lane state: t, h, y, K (K[0] = f at the start of the step, K[S] = f at its
@@ -1292,7 +1294,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
                     done = true;
                 }
                 // t_bound / upto_t guard of the NEXT step, with the proposed h (core.py:176-184)
-                if (accept && !done && (t_new + h > bound)) {
+                if (bounded && accept && !done && (t_new + h > bound)) {
                     status = NBK_TRAJ_BOUND;
                     done = true;
                 }

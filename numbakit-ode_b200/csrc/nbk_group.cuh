@@ -203,6 +203,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
     const double *pp = a.params;
 #endif
     const double rtol = a.rtol, atol = a.atol, bound = a.bound;
+    const bool bounded = a.bound < 1.7976931348623157e308;  // (usually not: skips the guard of every accepted step)
     const double safety = a.safety, min_factor = a.min_factor, max_factor = a.max_factor;
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
 
@@ -402,7 +403,7 @@ NBK_DEV void group_advance(const nbk_kargs &a, double *sm) {
                     status = NBK_TRAJ_MAXATTEMPTS;
                     done = true;
                 }
-                if (accept && !done && (t_new + h > bound)) {  // guard of the next step
+                if (bounded && accept && !done && (t_new + h > bound)) {  // guard of the next step
                     status = NBK_TRAJ_BOUND;
                     done = true;
                 }
