@@ -882,7 +882,7 @@ NBK_DEV void advance_adaptive(const nbk_kargs &a) {
     const double safety = a.safety, min_factor = a.min_factor, max_factor = a.max_factor;
     const double bound = a.bound;
     // t_bound / upto_t is usually infinite: a kernel-uniform flag skips the guard of every accepted step (DADD + DSETP + LDC)
-    const bool bounded = a.bound < 1.7976931348623157e308;
+    const bool bounded = (__double2hiint(a.bound) & 0x7fffffff) < 0x7ff00000;  // finite (an integer test: stays off the FP64 pipe)
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
 
     // Loop-carried per-lane state: t, h, y, K (K[0] = f at the start of the step, K[S] = f at its
