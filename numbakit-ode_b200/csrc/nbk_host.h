@@ -9,6 +9,7 @@ struct nbk_static_program {
     int cta_full;          // CTA regime: 1 = compiled without bounds checks, needs n == block * E; 0 = any n
     int group;             // CTA regime: G > 0 = sub-warp run / step kernels (G lanes per trajectory, 128-thread persistent blocks)
     int mma_tile;          // > 0: K4, one CTA integrates a tile of that many trajectories (shared-matrix linear)
+    int mma_block;         // K4: threads per CTA (32 x warps of the tile kernel)
     unsigned long mma_smem;  // dynamic shared memory of the K4 run/step kernels
     const void *k_init;    // host stubs of the __global__ kernels (cudaLaunchKernel)
     const void *k_run;

@@ -28,8 +28,13 @@
 
 namespace nbk {
 
+#ifndef NBK_MMA_MT
+#define NBK_MMA_MT 2  // 8-row accumulator tiles per warp: 2 -> 8 warps of 16 rows (256 threads), 1 -> 16 warps of 8 rows (512)
+#endif
 constexpr int MMA_NT = 16;       // trajectories per tile
-constexpr int MMA_WARPS = 8;     // warps per CTA; warp w owns rows [16w, 16w+16)
+constexpr int MMA_MT = NBK_MMA_MT;
+constexpr int MMA_ROWS = 8 * MMA_MT;      // rows of the tile a warp owns: warp w owns rows [MMA_ROWS w, MMA_ROWS (w + 1))
+constexpr int MMA_WARPS = 128 / MMA_ROWS; // warps per CTA
 constexpr int MMA_LD = MMA_NT + 4;  // padded row length of the staged Y (doubles)
 constexpr int MMA_LDA = 128 + 4;    // padded row length of the matrix staged in shared memory: a fragment load touches
                                     // (k, row) = (k0 + lane % 4, r0 + lane / 4); LDA = 4 mod 16 puts the 16 lanes of a
@@ -58,12 +63,12 @@ struct mma_cols {
     long long tile;
 };
 
-// Element (i, c) of a thread's 8 values v[mt][nt][q]: row = 16 w + 8 mt + lane/4, column = 8 nt + 2 (lane%4) + q
+// Element (i, c) of a thread's values v[mt][nt][q]: row = MMA_ROWS w + 8 mt + lane/4, column = 8 nt + 2 (lane%4) + q
 #define NBK_MMA_FOR_ELEMS(...)                                                    \
-    _Pragma("unroll") for (int mt = 0; mt < 2; ++mt)                              \
+    _Pragma("unroll") for (int mt = 0; mt < MMA_MT; ++mt)                         \
     _Pragma("unroll") for (int nt = 0; nt < 2; ++nt)                              \
     _Pragma("unroll") for (int q = 0; q < 2; ++q) {                               \
-        const int row = 16 * warp + 8 * mt + (lane >> 2);                         \
+        const int row = MMA_ROWS * warp + 8 * mt + (lane >> 2);                   \
         const int col = 8 * nt + 2 * (lane & 3) + q;                              \
         (void)row; (void)col;                                                     \
         __VA_ARGS__                                                               \
@@ -72,7 +77,7 @@ struct mma_cols {
 template <class Tab, int NPAD, int MODE>
 NBK_DEV void mma_advance(const nbk_kargs &a, double *sm) {
     constexpr int S = Tab::S;
-    static_assert(NPAD == 16 * MMA_WARPS, "8 warps x 16 rows");
+    static_assert(NPAD == MMA_ROWS * MMA_WARPS, "the warps' row blocks cover the padded matrix");
     const int n = a.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long nn = n;
     double *ybuf0 = sm, *ybuf1 = sm + NPAD * MMA_LD;
@@ -140,7 +145,7 @@ NBK_DEV void mma_advance(const nbk_kargs &a, double *sm) {
             }
         }
         __syncthreads();
-        double y[2][2][2], K[S + 1][2][2][2];
+        double y[MMA_MT][2][2], K[S + 1][MMA_MT][2][2];
         NBK_MMA_FOR_ELEMS({
             const long long idx = cs->idx[col];
             const bool ok = idx >= 0 && row < n;
@@ -170,7 +175,7 @@ _Pragma("unroll")
         // ---------------------------------------------------------------- lock-step attempts
         while (any_running) {
             // columns that already finished keep their registers frozen until the tile retires
-            double hcol[2][2], ynew[2][2][2];
+            double hcol[2][2], ynew[MMA_MT][2][2];
             bool runc[2][2];
 _Pragma("unroll")
             for (int nt = 0; nt < 2; ++nt)
@@ -204,24 +209,25 @@ _Pragma("unroll")
                     ybuf[row * MMA_LD + col] = v;
                 })
                 __syncthreads();
-                // K_s = A . Y_s on the FP64 tensor pipe: 4 accumulator tiles per warp
-                double acc[2][2][2];
+                // K_s = A . Y_s on the FP64 tensor pipe: 2 MMA_MT accumulator tiles per warp
+                double acc[MMA_MT][2][2];
 _Pragma("unroll")
-                for (int mt = 0; mt < 2; ++mt)
+                for (int mt = 0; mt < MMA_MT; ++mt)
 _Pragma("unroll")
                     for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-                const int arow = 16 * warp + (lane >> 2), kk = lane & 3;
+                const int arow = MMA_ROWS * warp + (lane >> 2), kk = lane & 3;
                 const double *ap = As + kk * MMA_LDA + arow, *bp = ybuf + kk * MMA_LD + (lane >> 2);
 _Pragma("unroll 8")
                 for (int k0 = 0; k0 < NPAD; k0 += 4) {
-                    // A fragment (8x4, row-major): element (row, k) = As[k][row] (zero beyond n)
-                    const double a0 = ap[k0 * MMA_LDA], a1 = ap[k0 * MMA_LDA + 8];
                     // B fragment (4x8, "col"): element (k, col) = Y[k][col]
                     const double b0 = bp[k0 * MMA_LD], b1 = bp[k0 * MMA_LD + 8];
-                    dmma_8x8x4(acc[0][0][0], acc[0][0][1], a0, b0);
-                    dmma_8x8x4(acc[0][1][0], acc[0][1][1], a0, b1);
-                    dmma_8x8x4(acc[1][0][0], acc[1][0][1], a1, b0);
-                    dmma_8x8x4(acc[1][1][0], acc[1][1][1], a1, b1);
+_Pragma("unroll")
+                    for (int mt = 0; mt < MMA_MT; ++mt) {
+                        // A fragment (8x4, row-major): element (row, k) = As[k][row] (zero beyond n)
+                        const double am = ap[k0 * MMA_LDA + 8 * mt];
+                        dmma_8x8x4(acc[mt][0][0], acc[mt][0][1], am, b0);
+                        dmma_8x8x4(acc[mt][1][0], acc[mt][1][1], am, b1);
+                    }
                 }
                 NBK_MMA_FOR_ELEMS({ if (runc[nt][q]) K[s][mt][nt][q] = acc[mt][nt][q]; })
             }

@@ -137,6 +137,7 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->cta_full = NBK_CTA_FULL;
     out->group = NBK_GROUP;
     out->mma_tile = 0;
+    out->mma_block = 0;
     out->mma_smem = 0;
     out->k_init = (const void *)&NBK_KERNEL(init);
     out->k_run = (const void *)&NBK_KERNEL(run);

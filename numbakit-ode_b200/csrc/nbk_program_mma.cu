@@ -16,15 +16,15 @@ typedef nbk::tab_rk23 nbk_tab_t;
 #endif
 
 // construction is the CTA regime's (same trajectory-major state): one CTA per trajectory, E = 1
-extern "C" __global__ void __launch_bounds__(256) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(32 * nbk::MMA_WARPS) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
     nbk::cta_init_adaptive<nbk_tab_t, nbk::rhs_linear_cta, 1>(a, nbk_smem);
 }
-extern "C" __global__ void __launch_bounds__(256, 1) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(32 * nbk::MMA_WARPS, 1) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
     nbk::mma_advance<nbk_tab_t, 128, NBK_MODE_RUN>(a, nbk_smem);
 }
-extern "C" __global__ void __launch_bounds__(256, 1) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(32 * nbk::MMA_WARPS, 1) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
     nbk::mma_advance<nbk_tab_t, 128, NBK_MODE_STEP>(a, nbk_smem);
 }
@@ -39,6 +39,7 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->cta_full = 0;
     out->group = 0;
     out->mma_tile = nbk::MMA_NT;
+    out->mma_block = 32 * nbk::MMA_WARPS;
     out->mma_smem = sizeof(double) * (2 * 128 * nbk::MMA_LD + nbk::MMA_WARPS * nbk::MMA_NT) + sizeof(nbk::mma_cols) + 16 +
                     sizeof(double) * 128 * nbk::MMA_LDA;  // Y staging (2 buffers), reduction scratch, columns, the matrix
     out->k_init = (const void *)&NBK_KERNEL(init);
