@@ -31,6 +31,10 @@ namespace nbk {
 #ifndef NBK_MMA_MT
 #define NBK_MMA_MT 2  // 8-row accumulator tiles per warp: 2 -> 8 warps of 16 rows (256 threads), 1 -> 16 warps of 8 rows (512)
 #endif
+#ifndef NBK_MMA_KSPLIT
+#define NBK_MMA_KSPLIT 4  // interleaved partial sums per accumulator tile (independent DMMA chains; measured C4: 1 -> 114.0 ms, 2 -> 115.0, 4 -> 110.4)
+#endif
+constexpr int MMA_KSPLIT = NBK_MMA_KSPLIT;
 constexpr int MMA_NT = 16;       // trajectories per tile
 constexpr int MMA_MT = NBK_MMA_MT;
 constexpr int MMA_ROWS = 8 * MMA_MT;      // rows of the tile a warp owns: warp w owns rows [MMA_ROWS w, MMA_ROWS (w + 1))
@@ -209,27 +213,45 @@ _Pragma("unroll")
                     ybuf[row * MMA_LD + col] = v;
                 })
                 __syncthreads();
-                // K_s = A . Y_s on the FP64 tensor pipe: 2 MMA_MT accumulator tiles per warp
-                double acc[MMA_MT][2][2];
+                // K_s = A . Y_s on the FP64 tensor pipe: 2 MMA_MT accumulator tiles per warp, each summed as MMA_KSPLIT
+                // interleaved partial sums over k (a DMMA into an accumulator waits for the previous one into it: with
+                // 2 warps per scheduler and 4 accumulators per warp only 8 are in flight; two partial sums per
+                // accumulator double that -- see DESIGN.md section 9, K4)
+                double acc[MMA_KSPLIT][MMA_MT][2][2];
 _Pragma("unroll")
-                for (int mt = 0; mt < MMA_MT; ++mt)
+                for (int ks = 0; ks < MMA_KSPLIT; ++ks)
 _Pragma("unroll")
-                    for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+                    for (int mt = 0; mt < MMA_MT; ++mt)
+_Pragma("unroll")
+                        for (int nt = 0; nt < 2; ++nt) acc[ks][mt][nt][0] = acc[ks][mt][nt][1] = 0.0;
                 const int arow = MMA_ROWS * warp + (lane >> 2), kk = lane & 3;
                 const double *ap = As + kk * MMA_LDA + arow, *bp = ybuf + kk * MMA_LD + (lane >> 2);
-_Pragma("unroll 8")
-                for (int k0 = 0; k0 < NPAD; k0 += 4) {
-                    // B fragment (4x8, "col"): element (k, col) = Y[k][col]
-                    const double b0 = bp[k0 * MMA_LD], b1 = bp[k0 * MMA_LD + 8];
+_Pragma("unroll 4")
+                for (int k0 = 0; k0 < NPAD; k0 += 4 * MMA_KSPLIT) {
 _Pragma("unroll")
-                    for (int mt = 0; mt < MMA_MT; ++mt) {
-                        // A fragment (8x4, row-major): element (row, k) = As[k][row] (zero beyond n)
-                        const double am = ap[k0 * MMA_LDA + 8 * mt];
-                        dmma_8x8x4(acc[mt][0][0], acc[mt][0][1], am, b0);
-                        dmma_8x8x4(acc[mt][1][0], acc[mt][1][1], am, b1);
+                    for (int ks = 0; ks < MMA_KSPLIT; ++ks) {
+                        const int k1 = k0 + 4 * ks;
+                        // B fragment (4x8, "col"): element (k, col) = Y[k][col]
+                        const double b0 = bp[k1 * MMA_LD], b1 = bp[k1 * MMA_LD + 8];
+_Pragma("unroll")
+                        for (int mt = 0; mt < MMA_MT; ++mt) {
+                            // A fragment (8x4, row-major): element (row, k) = As[k][row] (zero beyond n)
+                            const double am = ap[k1 * MMA_LDA + 8 * mt];
+                            dmma_8x8x4(acc[ks][mt][0][0], acc[ks][mt][0][1], am, b0);
+                            dmma_8x8x4(acc[ks][mt][1][0], acc[ks][mt][1][1], am, b1);
+                        }
                     }
                 }
-                NBK_MMA_FOR_ELEMS({ if (runc[nt][q]) K[s][mt][nt][q] = acc[mt][nt][q]; })
+_Pragma("unroll")
+                for (int ks = 1; ks < MMA_KSPLIT; ++ks)
+_Pragma("unroll")
+                    for (int mt = 0; mt < MMA_MT; ++mt)
+_Pragma("unroll")
+                        for (int nt = 0; nt < 2; ++nt) {
+                            acc[0][mt][nt][0] += acc[ks][mt][nt][0];
+                            acc[0][mt][nt][1] += acc[ks][mt][nt][1];
+                        }
+                NBK_MMA_FOR_ELEMS({ if (runc[nt][q]) K[s][mt][nt][q] = acc[0][mt][nt][q]; })
             }
             // ---- scaled error per column: partial over this thread's 2 rows, then lanes sharing the column
             double part[2][2];
