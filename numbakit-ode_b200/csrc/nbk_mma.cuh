@@ -28,17 +28,33 @@
 
 namespace nbk {
 
+// Shape of the tile kernel.  NBK_MMA_GROUPS = 1 (shipped): one group of 8 warps, tiles of 16 trajectories (a warp owns 16
+// rows x 16 columns = 4 accumulator tiles), everything between two CTA-wide barriers in lock-step.  NBK_MMA_GROUPS = 2: the
+// CTA's 8 warps form TWO independent groups of 4; each group integrates its own tiles of 8 trajectories (a warp owns 32
+// rows x 8 columns) behind its own named barrier, so that one group's element-wise stage algebra, error norm and serial
+// controller section overlap the other group's DMMA stream -- both share the one copy of the matrix in shared memory.
+// Measured on C4 (262 144 x n = 128): one group 110.4 ms, two groups 113.2 ms; 16 warps of 8 rows 112.8 ms; fragments
+// fetched as 16-byte pairs 113.1-115.3 ms -- every shape lands within 4 %: with 8 warps per SM a DMMA stream fed from
+// shared memory tops out at 27 of the 37 TFLOP/s the pipe delivers from registers (tools/micro/dmma_occ.cu), and the
+// kernel runs at 24.4 including everything that is not the GEMM.
+#ifndef NBK_MMA_GROUPS
+#define NBK_MMA_GROUPS 1
+#endif
 #ifndef NBK_MMA_MT
-#define NBK_MMA_MT 2  // 8-row accumulator tiles per warp: 2 -> 8 warps of 16 rows (256 threads), 1 -> 16 warps of 8 rows (512)
+#define NBK_MMA_MT (NBK_MMA_GROUPS == 2 ? 4 : 2)  // 8-row accumulator tiles per warp
 #endif
 #ifndef NBK_MMA_KSPLIT
-#define NBK_MMA_KSPLIT 4  // interleaved partial sums per accumulator tile (independent DMMA chains; measured C4: 1 -> 114.0 ms, 2 -> 115.0, 4 -> 110.4)
+#define NBK_MMA_KSPLIT (NBK_MMA_GROUPS == 2 ? 2 : 4)  // interleaved partial sums per accumulator tile (independent DMMA chains)
 #endif
+constexpr int MMA_GROUPS = NBK_MMA_GROUPS;
 constexpr int MMA_KSPLIT = NBK_MMA_KSPLIT;
-constexpr int MMA_NT = 16;       // trajectories per tile
+constexpr int MMA_NTN = MMA_GROUPS == 2 ? 1 : 2;  // 8-column accumulator tiles across a tile of trajectories
+constexpr int MMA_NT = 8 * MMA_NTN;       // trajectories per tile
 constexpr int MMA_MT = NBK_MMA_MT;
 constexpr int MMA_ROWS = 8 * MMA_MT;      // rows of the tile a warp owns: warp w owns rows [MMA_ROWS w, MMA_ROWS (w + 1))
-constexpr int MMA_WARPS = 128 / MMA_ROWS; // warps per CTA
+constexpr int MMA_WARPS = 128 / MMA_ROWS; // warps per group
+constexpr int MMA_GTHREADS = 32 * MMA_WARPS;            // threads per group
+constexpr int MMA_THREADS = MMA_GTHREADS * MMA_GROUPS;  // threads per CTA
 constexpr int MMA_LD = MMA_NT + 4;  // padded row length of the staged Y (doubles)
 constexpr int MMA_LDA = 128 + 4;    // padded row length of the matrix staged in shared memory: a fragment load touches
                                     // (k, row) = (k0 + lane % 4, r0 + lane / 4); LDA = 4 mod 16 puts the 16 lanes of a
@@ -51,6 +67,30 @@ NBK_DEV void dmma_8x8x4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+#endif
+}
+
+// The group's barrier: the whole CTA when there is one group, a named barrier of the group's threads otherwise (ids 1, 2;
+// id 0 stays the CTA-wide one).  mma_bar_or also ORs a predicate over the group (bar.red).
+NBK_DEV void mma_bar(int grp) {
+#ifdef NBK_HOST_EMUL
+    nbk_emul_bar(grp);
+#else
+    if (MMA_GROUPS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(MMA_GTHREADS) : "memory");
+#endif
+}
+NBK_DEV int mma_bar_or(int grp, int pred) {
+#ifdef NBK_HOST_EMUL
+    return nbk_emul_bar_or(grp, pred);
+#else
+    if (MMA_GROUPS == 1) return __syncthreads_or(pred);
+    unsigned r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r)
+                 : "r"((unsigned)pred), "r"(grp + 1), "r"(MMA_GTHREADS)
+                 : "memory");
+    return (int)r;
 #endif
 }
 
@@ -70,7 +110,7 @@ struct mma_cols {
 // Element (i, c) of a thread's values v[mt][nt][q]: row = MMA_ROWS w + 8 mt + lane/4, column = 8 nt + 2 (lane%4) + q
 #define NBK_MMA_FOR_ELEMS(...)                                                    \
     _Pragma("unroll") for (int mt = 0; mt < MMA_MT; ++mt)                         \
-    _Pragma("unroll") for (int nt = 0; nt < 2; ++nt)                              \
+    _Pragma("unroll") for (int nt = 0; nt < MMA_NTN; ++nt)                        \
     _Pragma("unroll") for (int q = 0; q < 2; ++q) {                               \
         const int row = MMA_ROWS * warp + 8 * mt + (lane >> 2);                   \
         const int col = 8 * nt + 2 * (lane & 3) + q;                              \
@@ -82,28 +122,33 @@ template <class Tab, int NPAD, int MODE>
 NBK_DEV void mma_advance(const nbk_kargs &a, double *sm) {
     constexpr int S = Tab::S;
     static_assert(NPAD == MMA_ROWS * MMA_WARPS, "the warps' row blocks cover the padded matrix");
-    const int n = a.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // tid / warp are relative to the thread's GROUP from here on: leaders, row blocks and the reduction scratch are per group
+    const int n = a.n, grp = (int)threadIdx.x / MMA_GTHREADS, tid = (int)threadIdx.x - grp * MMA_GTHREADS, warp = tid >> 5, lane = tid & 31;
     const long long nn = n;
-    double *ybuf0 = sm, *ybuf1 = sm + NPAD * MMA_LD;
-    double *red = sm + 2 * NPAD * MMA_LD;                      // [MMA_WARPS][MMA_NT]
+    constexpr int COLS_WORDS = (int)((sizeof(mma_cols) + 7) / 8);
+    constexpr int GROUP_WORDS = 2 * NPAD * MMA_LD + MMA_WARPS * MMA_NT + COLS_WORDS + 2;  // a group's slice of shared memory (even)
+    double *gsm = sm + (size_t)grp * GROUP_WORDS;
+    double *ybuf0 = gsm, *ybuf1 = gsm + NPAD * MMA_LD;
+    double *red = gsm + 2 * NPAD * MMA_LD;                     // [MMA_WARPS][MMA_NT]
     mma_cols *cs = (mma_cols *)(red + MMA_WARPS * MMA_NT);
     const double *At = a.params;  // A transposed: At[k*n + i] = A[i][k]
-    // The matrix lives in shared memory for the whole (persistent) kernel, zero-padded to NPAD x NPAD: fragment loads
-    // need no bounds checks, and a shared-memory load of 8 rows x 4 k costs 2 wavefronts where the same load from
-    // global memory touched 4 cache lines (the L1 data path was 83 % busy, ahead of the DMMA pipe at 61 %).
-    double *As = (double *)(((unsigned long long)(cs + 1) + 15ULL) & ~15ULL);
-    for (int i = tid; i < NPAD * NPAD; i += blockDim.x) {
+    // The matrix lives in shared memory for the whole (persistent) kernel -- one copy for all groups --, zero-padded to
+    // NPAD x NPAD: fragment loads need no bounds checks, and a shared-memory load of 8 rows x 4 k costs 2 wavefronts where
+    // the same load from global memory touched 4 cache lines (the L1 data path was 83 % busy, ahead of the DMMA pipe at 61 %).
+    double *As = (double *)(((unsigned long long)(sm + (size_t)MMA_GROUPS * GROUP_WORDS) + 15ULL) & ~15ULL);
+    for (int i = (int)threadIdx.x; i < NPAD * NPAD; i += (int)blockDim.x) {
         const int k = i / NPAD, r = i % NPAD;
         As[k * MMA_LDA + r] = (k < n && r < n) ? At[(long long)k * n + r] : 0.0;
     }
+    __syncthreads();  // the last CTA-wide barrier: from here on the groups run on their own
     const double rtol = a.rtol, atol = a.atol, bound = a.bound;
     const int max_att = a.max_attempts > 2147483647LL ? 2147483647 : (int)a.max_attempts;
     const long long n_tiles = (a.B + MMA_NT - 1) / MMA_NT;
 
     for (;;) {
-        __syncthreads();
+        mma_bar(grp);
         if (tid == 0) cs->tile = (long long)atomicAdd(a.work_counter, 1ULL);
-        __syncthreads();
+        mma_bar(grp);
         const long long tile = cs->tile;
         if (tile >= n_tiles) break;
 
@@ -148,8 +193,8 @@ NBK_DEV void mma_advance(const nbk_kargs &a, double *sm) {
                 cs->emit_from[c] = 0;
             }
         }
-        __syncthreads();
-        double y[MMA_MT][2][2], K[S + 1][MMA_MT][2][2];
+        mma_bar(grp);
+        double y[MMA_MT][MMA_NTN][2], K[S + 1][MMA_MT][MMA_NTN][2];
         NBK_MMA_FOR_ELEMS({
             const long long idx = cs->idx[col];
             const bool ok = idx >= 0 && row < n;
@@ -174,15 +219,15 @@ _Pragma("unroll")
             }
         })
         // (the barrier doubles as the OR over the columns' running flags)
-        int any_running = __syncthreads_or(tid < MMA_NT ? cs->running[tid] : 0);
+        int any_running = mma_bar_or(grp, tid < MMA_NT ? cs->running[tid] : 0);
 
         // ---------------------------------------------------------------- lock-step attempts
         while (any_running) {
             // columns that already finished keep their registers frozen until the tile retires
-            double hcol[2][2], ynew[MMA_MT][2][2];
-            bool runc[2][2];
+            double hcol[MMA_NTN][2], ynew[MMA_MT][MMA_NTN][2];
+            bool runc[MMA_NTN][2];
 _Pragma("unroll")
-            for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < MMA_NTN; ++nt)
 _Pragma("unroll")
                 for (int q = 0; q < 2; ++q) {
                     hcol[nt][q] = cs->h[8 * nt + 2 * (lane & 3) + q];
@@ -212,18 +257,18 @@ _Pragma("unroll")
                     if (s == S) ynew[mt][nt][q] = v;
                     ybuf[row * MMA_LD + col] = v;
                 })
-                __syncthreads();
+                mma_bar(grp);
                 // K_s = A . Y_s on the FP64 tensor pipe: 2 MMA_MT accumulator tiles per warp, each summed as MMA_KSPLIT
                 // interleaved partial sums over k (a DMMA into an accumulator waits for the previous one into it: with
                 // 2 warps per scheduler and 4 accumulators per warp only 8 are in flight; two partial sums per
                 // accumulator double that -- see DESIGN.md section 9, K4)
-                double acc[MMA_KSPLIT][MMA_MT][2][2];
+                double acc[MMA_KSPLIT][MMA_MT][MMA_NTN][2];
 _Pragma("unroll")
                 for (int ks = 0; ks < MMA_KSPLIT; ++ks)
 _Pragma("unroll")
                     for (int mt = 0; mt < MMA_MT; ++mt)
 _Pragma("unroll")
-                        for (int nt = 0; nt < 2; ++nt) acc[ks][mt][nt][0] = acc[ks][mt][nt][1] = 0.0;
+                        for (int nt = 0; nt < MMA_NTN; ++nt) acc[ks][mt][nt][0] = acc[ks][mt][nt][1] = 0.0;
                 const int arow = MMA_ROWS * warp + (lane >> 2), kk = lane & 3;
                 const double *ap = As + kk * MMA_LDA + arow, *bp = ybuf + kk * MMA_LD + (lane >> 2);
 _Pragma("unroll 4")
@@ -231,14 +276,16 @@ _Pragma("unroll 4")
 _Pragma("unroll")
                     for (int ks = 0; ks < MMA_KSPLIT; ++ks) {
                         const int k1 = k0 + 4 * ks;
-                        // B fragment (4x8, "col"): element (k, col) = Y[k][col]
-                        const double b0 = bp[k1 * MMA_LD], b1 = bp[k1 * MMA_LD + 8];
+                        // B fragments (4x8, "col"): element (k, col) = Y[k][col]
+                        double bf[MMA_NTN];
+_Pragma("unroll")
+                        for (int nt = 0; nt < MMA_NTN; ++nt) bf[nt] = bp[k1 * MMA_LD + 8 * nt];
 _Pragma("unroll")
                         for (int mt = 0; mt < MMA_MT; ++mt) {
                             // A fragment (8x4, row-major): element (row, k) = As[k][row] (zero beyond n)
                             const double am = ap[k1 * MMA_LDA + 8 * mt];
-                            dmma_8x8x4(acc[ks][mt][0][0], acc[ks][mt][0][1], am, b0);
-                            dmma_8x8x4(acc[ks][mt][1][0], acc[ks][mt][1][1], am, b1);
+_Pragma("unroll")
+                            for (int nt = 0; nt < MMA_NTN; ++nt) dmma_8x8x4(acc[ks][mt][nt][0], acc[ks][mt][nt][1], am, bf[nt]);
                         }
                     }
                 }
@@ -247,16 +294,16 @@ _Pragma("unroll")
 _Pragma("unroll")
                     for (int mt = 0; mt < MMA_MT; ++mt)
 _Pragma("unroll")
-                        for (int nt = 0; nt < 2; ++nt) {
+                        for (int nt = 0; nt < MMA_NTN; ++nt) {
                             acc[0][mt][nt][0] += acc[ks][mt][nt][0];
                             acc[0][mt][nt][1] += acc[ks][mt][nt][1];
                         }
                 NBK_MMA_FOR_ELEMS({ if (runc[nt][q]) K[s][mt][nt][q] = acc[0][mt][nt][q]; })
             }
             // ---- scaled error per column: partial over this thread's 2 rows, then lanes sharing the column
-            double part[2][2];
+            double part[MMA_NTN][2];
 _Pragma("unroll")
-            for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < MMA_NTN; ++nt)
 _Pragma("unroll")
                 for (int q = 0; q < 2; ++q) part[nt][q] = 0.0;
             NBK_MMA_FOR_ELEMS({
@@ -276,7 +323,7 @@ _Pragma("unroll")
                 }
             })
 _Pragma("unroll")
-            for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < MMA_NTN; ++nt)
 _Pragma("unroll")
                 for (int q = 0; q < 2; ++q) {
                     double v = part[nt][q];
@@ -285,7 +332,7 @@ _Pragma("unroll")
                     v += __shfl_xor_sync(0xffffffffu, v, 16);
                     if (lane < 4) red[warp * MMA_NT + 8 * nt + 2 * lane + q] = v;
                 }
-            __syncthreads();
+            mma_bar(grp);
             // ---- controller: one leader thread per column
             if (tid < MMA_NT) {
                 const int c = tid;
@@ -352,7 +399,7 @@ _Pragma("unroll")
                     cs->done[c] = 0;
                 }
             }
-            any_running = __syncthreads_or(tid < MMA_NT ? cs->running[tid] : 0);
+            any_running = mma_bar_or(grp, tid < MMA_NT ? cs->running[tid] : 0);
             // ---- emission, history stash, commit (every thread for its own elements)
             NBK_MMA_FOR_ELEMS({
                 const long long idx = cs->idx[col];

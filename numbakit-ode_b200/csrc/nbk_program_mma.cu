@@ -16,15 +16,15 @@ typedef nbk::tab_rk23 nbk_tab_t;
 #endif
 
 // construction is the CTA regime's (same trajectory-major state): one CTA per trajectory, E = 1
-extern "C" __global__ void __launch_bounds__(32 * nbk::MMA_WARPS) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(nbk::MMA_THREADS) NBK_KERNEL(init)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
     nbk::cta_init_adaptive<nbk_tab_t, nbk::rhs_linear_cta, 1>(a, nbk_smem);
 }
-extern "C" __global__ void __launch_bounds__(32 * nbk::MMA_WARPS, 1) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(nbk::MMA_THREADS, 1) NBK_KERNEL(run)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
     nbk::mma_advance<nbk_tab_t, 128, NBK_MODE_RUN>(a, nbk_smem);
 }
-extern "C" __global__ void __launch_bounds__(32 * nbk::MMA_WARPS, 1) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
+extern "C" __global__ void __launch_bounds__(nbk::MMA_THREADS, 1) NBK_KERNEL(step)(const __grid_constant__ nbk_kargs a) {
     extern __shared__ double nbk_smem[];
     nbk::mma_advance<nbk_tab_t, 128, NBK_MODE_STEP>(a, nbk_smem);
 }
@@ -39,9 +39,10 @@ extern "C" void NBK_KERNEL(program)(nbk_static_program *out) {
     out->cta_full = 0;
     out->group = 0;
     out->mma_tile = nbk::MMA_NT;
-    out->mma_block = 32 * nbk::MMA_WARPS;
-    out->mma_smem = sizeof(double) * (2 * 128 * nbk::MMA_LD + nbk::MMA_WARPS * nbk::MMA_NT) + sizeof(nbk::mma_cols) + 16 +
-                    sizeof(double) * 128 * nbk::MMA_LDA;  // Y staging (2 buffers), reduction scratch, columns, the matrix
+    out->mma_block = nbk::MMA_THREADS;
+    // per group: Y staging (2 buffers), reduction scratch, columns; then the one copy of the matrix (see mma_advance)
+    out->mma_smem = sizeof(double) * nbk::MMA_GROUPS * (2 * 128 * nbk::MMA_LD + nbk::MMA_WARPS * nbk::MMA_NT + (sizeof(nbk::mma_cols) + 7) / 8 + 2) +
+                    16 + sizeof(double) * 128 * nbk::MMA_LDA;
     out->k_init = (const void *)&NBK_KERNEL(init);
     out->k_run = (const void *)&NBK_KERNEL(run);
     out->k_step = (const void *)&NBK_KERNEL(step);

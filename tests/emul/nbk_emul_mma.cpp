@@ -37,6 +37,22 @@ static inline double __shfl_xor_sync(unsigned, double v, int o) {
     pthread_barrier_wait(&g_wbar[t >> 5]);
     return r;
 }
+// the groups' named barriers (csrc/nbk_mma.cuh, NBK_MMA_GROUPS = 2): 128 threads each; with one group = the block barrier
+static pthread_barrier_t g_gbar[2];
+static int g_gor[2][2];
+static thread_local unsigned g_gor_phase;
+static int g_gthreads = 256;
+static inline void nbk_emul_bar(int grp) { pthread_barrier_wait(g_gthreads == 256 ? &g_bar : &g_gbar[grp]); }
+static inline int nbk_emul_bar_or(int grp, int p) {
+    if (g_gthreads == 256) return __syncthreads_or(p);
+    const unsigned k = g_gor_phase++ & 1u;
+    if (p) __atomic_store_n(&g_gor[grp][k], 1, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&g_gbar[grp]);
+    const int r = __atomic_load_n(&g_gor[grp][k], __ATOMIC_SEQ_CST);
+    if ((int)threadIdx.x % g_gthreads == 0) __atomic_store_n(&g_gor[grp][k ^ 1u], 0, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&g_gbar[grp]);
+    return r;
+}
 static inline void nbk_emul_dmma(double &c0, double &c1, double a, double b) {
     const int t = (int)threadIdx.x, w = t & ~31, lane = t & 31, row = lane >> 2, cq = 2 * (lane & 3);
     g_ma[t] = a;
@@ -72,6 +88,11 @@ extern "C" int EMUL_NAME(int kernel, const nbk_kargs *a) {
     if (kernel < 0 || kernel > 2) return -1;
     pthread_barrier_init(&g_bar, nullptr, 256);
     g_or[0] = g_or[1] = 0;
+    g_gthreads = nbk::MMA_GTHREADS;
+    for (int g = 0; g < 2; ++g) {
+        pthread_barrier_init(&g_gbar[g], nullptr, (unsigned)nbk::MMA_GTHREADS);
+        g_gor[g][0] = g_gor[g][1] = 0;
+    }
     for (int w = 0; w < 8; ++w) pthread_barrier_init(&g_wbar[w], nullptr, 32);
     pthread_t th[256];
     emul_arg args[256];
