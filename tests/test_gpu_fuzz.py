@@ -100,13 +100,16 @@ def test_random_call_sequences_cta_regime(seed):
     assert g._regime == 1
 
 
-def _drive(rng, cls, rname, y0, p):
+def _drive(rng, cls, rname, y0, p, step_slack=1.0):
     g, o, kind = make_pair(cls, rname, y0, p, rng)
     # step times of the adaptive pairs: the controller feeds the rounding of the error estimate back into h.  E.K cancels
     # down to the local error (8+ digits at rtol 1e-8; more for DOP853's E5.K / E3.K), so an FMA-contracted and a plain
     # evaluation differ by up to ~1e-8 (RungeKutta23/45) and ~1e-7 (DOP853) in h -- not part of the parity bar, which
     # is values within rtol |y| + atol and step counts within 1
     tkind = kind if kind[0] == "fixed" else ("adaptive", 1e-6 if cls == "DOP853" else 1e-7, 0.0)
+    # states AFTER a step are compared at the two implementations' own step times, which differ by the figure above: the
+    # caller may widen the bar of those comparisons (not of run(), which interpolates at given times)
+    skind = kind if kind[0] == "fixed" else ("adaptive", kind[1] * step_slack, kind[2] * step_slack)
     for _ in range(int(rng.integers(3, 7))):
         op = str(rng.choice(["run", "step", "skip", "step_upto", "skip_upto"]))
         tmax = max(float(s.t) for s in o)
@@ -125,7 +128,7 @@ def _drive(rng, cls, rname, y0, p):
                 for b, s in enumerate(o):
                     to, yo = osteps(s, n=k)
                     close(tkind, tg[b], to, (cls, rname, "step t", b))
-                    close(kind, yg[b], yo, (cls, rname, "step y", b))
+                    close(skind, yg[b], yo, (cls, rname, "step y", b))
             else:
                 g.skip(n=k)
                 for s in o:
@@ -139,7 +142,7 @@ def _drive(rng, cls, rname, y0, p):
                     k = len(to)  # batched step(upto_t=) pads with NaN
                     assert np.isnan(tg[b, k:]).all(), (cls, rname, op, b)
                     close(tkind, tg[b, :k], to, (cls, rname, "upto t", b))
-                    close(kind, yg[b, :k], yo, (cls, rname, "upto y", b))
+                    close(skind, yg[b, :k], yo, (cls, rname, "upto y", b))
             else:
                 g.skip(upto_t=upto)
                 for s in o:
@@ -156,3 +159,22 @@ def _drive(rng, cls, rname, y0, p):
                 assert (np.abs(np.atleast_2d(g.y)[b] - s.y) <= lim).all(), (cls, rname, op, "y", b)
     assert (np.asarray(g.status) <= 1).all()
     return g
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_random_call_sequences_sub_warp_regime(seed):
+    """The same for small and mid-size component-wise systems: sub-warp groups (RungeKutta23 / RungeKutta45: dedicated
+    kernels) and sub-warp teams (DOP853, Adams-Bashforth, fixed-step Runge-Kutta: the CTA regime's source with G lanes per
+    trajectory), 2 .. 32 lanes per trajectory, ragged and full groups, more trajectories than groups in a warp."""
+    rng = np.random.default_rng(9000 + seed)
+    cls = str(rng.choice(ADAPTIVE + FIXED_RK + AB))
+    n = int(rng.choice([5, 8, 13, 16, 24, 32, 50, 64, 100]))
+    B = int(rng.integers(2, 40))
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=int(rng.integers(0, 1 << 30)))
+    p[:, 0] *= 0.05 * (100.0 / n) ** 2
+    # (DOP853's error estimate is a sum over the team: another summation order than the oracle's moves its step times by
+    # ~1e-7 relative -- measured 1.75 x the state bar after a step on one of these sequences)
+    g = _drive(rng, cls, "rd1d", y0, p, step_slack=3.0 if cls == "DOP853" else 1.0)
+    assert g._regime == 1
+    if not (cls == "DOP853" and n > 64):
+        assert g._group in (2, 4, 8, 16, 32)
