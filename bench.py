@@ -95,6 +95,25 @@ def l2_policy(per_gpu):
 
 
 # ----------------------------------------------------------------------------------------
+class no_gc:
+    """Timed regions run with the cyclic garbage collector off (after one full collection), so that no collection pass
+    lands between two launches while the host has not yet run ahead of the device."""
+
+    def __enter__(self):
+        import gc
+
+        gc.collect()
+        self.was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+
+        if self.was:
+            gc.enable()
+        return False
+
+
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU while the timed region runs, with the
     profiling guide's recipe: `nvidia-smi --query-gpu=... -lms 200` in a separate process (NVML
@@ -294,10 +313,11 @@ def extra_configs(nbk, torch, dev, peak_tf, sizes=None):
             s = make()
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = run(s)
-            e1.record()
-            torch.cuda.synchronize(dev)
+            with no_gc():
+                e0.record()
+                out = run(s)
+                e1.record()
+                torch.cuda.synchronize(dev)
             ms = e0.elapsed_time(e1)
             best = ms if best is None else min(best, ms)
             acc, att = int(s._nacc.sum().item()), int((s._nacc.sum() + s._nrej.sum()).item())
@@ -465,48 +485,58 @@ def main():
         import collections
 
         live = collections.deque(maxlen=len(inputs))  # keeps the last R states alive: the allocator hands out other memory
-        # Warm-up: at least `warmup` untimed passes, and on until the device has settled -- three consecutive passes within
-        # 3 % of each other (observed on one box of the pool: the first 0.3-0.5 s of GPU work of a fresh process ran at a
-        # third of the speed, with the SM clock reading its maximum and no throttle reason; later passes of the same
-        # process were normal) -- but no longer than 3 s.  The count actually done is reported as "warmup".
+        # Warm-up: at least `warmup` untimed passes, at least WARMUP_MIN_S seconds, and on until three consecutive passes
+        # are within 3 % of each other (at most 3 s); the count actually done is reported as "warmup".  The warm-up loop
+        # has to have the SAME object lifetimes as the timed loop: an earlier version dropped the result of a warm-up pass
+        # at once while the timed loop keeps it bound until the next pass returns -- the second timed pass then needed one
+        # more 24 MB output block, and that cudaMalloc, issued while the previous pass's kernel occupied the GPU, took
+        # anywhere from 0.8 to 140 ms (per-step CUDA events showed a single 45-140 ms "kernel" among 6.7 ms ones, always at
+        # timed step 1; NBK_BENCH_DEBUG=1 prints per-step device and host times and the allocator's cudaMalloc count).
         wu_ms, t_wu, i = [], time.perf_counter(), 0
         while True:
             s = nbk.RungeKutta45("lorenz", 0.0, *inputs[i % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
             w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             w0.record()
-            s.run([T_END])
-            w1.record()
+            t, y = s.run([T_END])  # (bound to the same names as in the timed loop: the result of the previous pass stays alive
+            w1.record()            # while the next one is allocated, so the second output block exists before the clock starts)
             live.append(s)
             torch.cuda.synchronize(dev)
             wu_ms.append(w0.elapsed_time(w1))
             i += 1
             settled = len(wu_ms) >= 3 and max(wu_ms[-3:]) <= 1.03 * min(wu_ms[-3:])
             elapsed = time.perf_counter() - t_wu
-            # (the slow phase seen on that box was itself steady -- 20 ms per pass for about half a second -- hence the floor)
             if (i >= warmup and settled and elapsed >= WARMUP_MIN_S) or elapsed > 3.0:
                 break
         kernel_arm.warmup_done = i
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        run_ev = []
+        run_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        gc_off = no_gc()
+        gc_off.__enter__()
         barrier()
         ev[0].record()
+        host_marks, alloc0 = [], torch.cuda.memory_stats(dev).get("num_device_alloc")
         for i in range(steps):
+            h0 = time.perf_counter()
             s = nbk.RungeKutta45("lorenz", 0.0, *inputs[(i + kernel_arm.warmup_done) % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h1 = time.perf_counter()
+            e0, e1 = run_ev[i]
             e0.record()
             t, y = s.run([T_END])
             e1.record()
-            run_ev.append((e0, e1))
+            h2 = time.perf_counter()
             live.append(s)
+            host_marks.append((round(1e3 * (h1 - h0), 3), round(1e3 * (h2 - h1), 3), round(1e3 * (time.perf_counter() - h2), 3)))
         ev[1].record()
         barrier()
+        gc_off.__exit__()
         s.raise_for_status()  # device-resident results are checked lazily: once, outside the timed region
         # every step integrates the same ensemble (deterministic kernels): count once, after the clock stopped
         acc = float(s._nacc.sum().item())
         att = acc + float(s._nrej.sum().item())
         per_step = [a.elapsed_time(b) for a, b in run_ev]
         if os.environ.get("NBK_BENCH_DEBUG"):
-            print("run-kernel ms per step:", [round(x, 3) for x in per_step], file=sys.stderr)
+            print("run-kernel ms per step:", [round(x, 3) for x in per_step], "host ms (ctor, run, append):", host_marks,
+                  "device allocs", alloc0, "->", torch.cuda.memory_stats(dev).get("num_device_alloc"), file=sys.stderr)
         return s, y, ev[0].elapsed_time(ev[1]), sum(per_step), acc * steps, att * steps
 
     # ------------------------------------------------------------ kernel-only arm
@@ -603,6 +633,43 @@ def main():
 
     # ------------------------------------------------------------ weak-scaling figure of the same run (N > 1)
     extra = {}
+    if not args.no_extra:
+        # The same passes (device-resident inputs) issued alternately on two streams: the tail of one pass -- the last
+        # trajectories of a shard run with most lanes idle -- overlaps the head of the next.  This is the throughput of a
+        # SEQUENCE of ensembles, not the time of one; `value` above stays the single-stream figure.
+        t2, acc2, n2, err2 = 0.0, 0.0, max(args.steps, 10), None
+        try:  # (no collective inside: a failing rank must not leave the others waiting)
+            st2 = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+            keep = []
+
+            def two_stream(n_pass):
+                for i in range(n_pass):
+                    with torch.cuda.stream(st2[i % 2]):
+                        s2 = nbk.RungeKutta45("lorenz", 0.0, *inputs[i % len(inputs)], rtol=RTOL, atol=ATOL, device=local_rank)
+                        s2.run([T_END])
+                    keep.append(s2)
+                    del keep[:-4]
+
+            two_stream(6)
+            torch.cuda.synchronize(dev)
+            with no_gc():
+                t2 = time.perf_counter()
+                two_stream(n2)
+                torch.cuda.synchronize(dev)
+                t2 = time.perf_counter() - t2
+            keep[-1].raise_for_status()
+            acc2 = float(keep[-1]._nacc.sum().item())
+            del keep[:]
+        except Exception as exc:  # noqa: BLE001
+            err2 = f"{type(exc).__name__}: {exc}"[:300]
+        (t2, bad2), (acc2,) = nd.reduce_max_sum([t2, 1.0 if err2 else 0.0], [acc2], device=dev)
+        if bad2 or t2 <= 0:
+            extra["two_stream_throughput"] = {"error": err2 or "failed on another rank"}
+        else:
+            extra["two_stream_throughput"] = {
+                "value": acc2 * n2 / t2, "unit": UNIT, "ms_per_step": 1e3 * t2 / n2, "passes": n2,
+                "note": "device-resident inputs, consecutive passes alternate between two CUDA streams (wall clock around the "
+                        "whole sequence, max over ranks): one pass's tail overlaps the next pass's head"}
     if world > 1 and not args.no_extra:
         yw, pw = ensembles.lorenz_ensemble(B_TOTAL, seed=rank)
         w_in = [(torch.from_numpy(yw).to(dev), torch.from_numpy(pw).to(dev))]
@@ -626,10 +693,11 @@ def main():
                 s5 = nbk.RungeKutta45("rd1d", 0.0, y5d, p5d, rtol=RTOL, atol=ATOL, device=local_rank)
                 torch.cuda.synchronize(dev)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                s5.run([1.0])
-                e1.record()
-                torch.cuda.synchronize(dev)
+                with no_gc():
+                    e0.record()
+                    s5.run([1.0])
+                    e1.record()
+                    torch.cuda.synchronize(dev)
                 t5 = e0.elapsed_time(e1)
                 best = t5 if best is None else min(best, t5)
             s5.raise_for_status()
