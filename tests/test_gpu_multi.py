@@ -112,3 +112,32 @@ def test_sharded_events_and_errors():
         nbk.RungeKutta45("lorenz", 0.0, y0, p, devices=[0, 0])            # duplicate device
     with pytest.raises(ValueError):
         nbk.RungeKutta45("lorenz", 0.0, y0, p, devices=[0, NDEV + 3])     # out of range
+
+
+@multi
+@pytest.mark.parametrize("cls,n,kw", [("RungeKutta45", 24, dict(rtol=1e-6, atol=1e-9)), ("DOP853", 20, dict(rtol=1e-7, atol=1e-10)),
+                                      ("AdamsBashforth4", 32, dict(h=0.002)), ("RungeKutta45", 300, dict(rtol=1e-6, atol=1e-9))])
+def test_sharded_component_wise_regimes(cls, n, kw):
+    """devices=[...] over the sub-warp groups / teams and the CTA regime (trajectory-major state): bit-identical to one GPU,
+    incl. run_events for the adaptive classes."""
+    devs = list(range(min(NDEV, 8)))
+    B = 1003
+    y0, p = ensembles.rd1d_ensemble(B, n=n, seed=3)
+    p[:, 0] *= 0.3 * (100.0 / n) ** 2
+    one = getattr(nbk, cls)("rd1d", 0.0, y0, p, **kw)
+    many = getattr(nbk, cls)("rd1d", 0.0, y0, p, devices=devs, **kw)
+    ts = [0.1, 0.3]
+    assert np.array_equal(one.run(ts)[1], many.run(ts)[1])
+    assert np.array_equal(one.y, many.y) and np.array_equal(one.n_accepted, many.n_accepted)
+    a1, b1 = one.step(n=2)
+    am, bm = many.step(n=2)
+    assert np.array_equal(a1, am) and np.array_equal(b1, bm)
+    if cls != "AdamsBashforth4":
+        def crossing(t, y):
+            return y[0] - 0.5
+
+        e1 = getattr(nbk, cls)("rd1d", 0.0, y0, p, **kw)
+        em = getattr(nbk, cls)("rd1d", 0.0, y0, p, devices=devs, **kw)
+        r1, rm = e1.run_events([0.5, 1.5], [crossing]), em.run_events([0.5, 1.5], [crossing])
+        assert np.array_equal(r1[1], rm[1], equal_nan=True) and np.array_equal(e1.event_counts, em.event_counts)
+        assert np.array_equal(r1[2][0], rm[2][0], equal_nan=True)
