@@ -401,3 +401,18 @@ def test_implicit_multistep_ensemble_api_and_failure():
     # n > 8 is rejected with a clear message
     with pytest.raises(ValueError, match="n <= 8"):
         nbk.BDF2("decay", 0.0, np.ones(9), np.array([0.1]), h=0.1)
+
+
+@pytest.mark.parametrize("cls", ["RungeKutta45", "RungeKutta23"])
+def test_grid_point_exactly_at_a_step_end(cls):
+    """A grid time equal to the end of a step returns y_new itself (RkInterpolator, explicit.py:371-403): the kernels patch
+    that point after the per-point loop."""
+    y0, p = onp.lorenz_ensemble(64, seed=4)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    a = getattr(nbk, cls)("lorenz", 0.0, y0, p, **kw)
+    a.run([0.7])
+    t_end, y_end = a.t, a.y
+    for b in (0, 17, 63):
+        g = getattr(nbk, cls)("lorenz", 0.0, y0[b], p[b], **kw)
+        _, out = g.run([0.3, 0.5 * (0.3 + t_end[b]), t_end[b]])
+        assert np.array_equal(out[2], y_end[b])

@@ -288,3 +288,22 @@ def test_implicit_step_flow_vs_reference(c):
     ya = e.run(np.linspace(0, 4, 9))
     yb = e.run(c["resume_b_t"])
     assert rel(ya[0], c["resume_a"]) < 5e-7 and rel(yb[0], c["resume_b"]) < 5e-7
+
+
+@pytest.mark.parametrize("cls", ["RungeKutta45", "RungeKutta23"])
+def test_grid_point_exactly_at_a_step_end_is_the_step_end(cls):
+    """RkInterpolator returns y_new itself for a time equal to the end of the step (explicit.py:371-403); the kernels
+    evaluate the interpolant inside the per-point loop and patch such a point after it -- only the last point of a
+    step can be one."""
+    y0, p = onp.lorenz_ensemble(3, seed=4)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    a = EmulEnsemble(cls, "lorenz", y0, p, **kw)
+    a.run([0.7])
+    t_end, y_end = a.t, a.y          # ends of the steps that crossed 0.7, one per trajectory
+    for b in range(3):
+        g = EmulEnsemble(cls, "lorenz", y0[b:b + 1], p[b:b + 1], **kw)
+        out = g.run([0.3, 0.5 * (0.3 + t_end[b]), t_end[b]])
+        assert np.array_equal(out[0, 2], y_end[b])                  # bit for bit
+        o = onp.AdaptiveRK(cls, onp.rhs_lorenz, 0.0, y0[b], p[b], **kw)
+        _, yo = onp.run(o, [0.3, 0.5 * (0.3 + t_end[b]), t_end[b]])
+        assert np.abs(out[0] - yo).max() < 1e-9 * np.abs(yo).max()
