@@ -13,7 +13,12 @@ inlined into the integrator kernel, so it can be given as
 * a Python callable with the reference's signature: it is *traced* once with symbolic
   arguments and translated to CUDA C (no Python runs on the device, nothing falls back to
   the CPU).  Tracing supports arithmetic, ``**``, indexing/slicing, ``@`` and the NumPy
-  ufuncs listed in ``_UNARY``; data-dependent Python control flow is not traceable.
+  ufuncs listed in ``_UNARY``.  Data-dependent Python control flow (``if`` / ``elif`` / ``while`` /
+  ``and`` / ``or`` / ``min`` / ``max`` on the state, the time or the parameters) is traced by
+  *path exploration*: the callable is re-run once per control-flow path with the outcome of every
+  comparison dictated by the tracer, and the paths are emitted as nested ``if`` / ``else`` (per-thread
+  form) or selects (component-wise form) -- the branch is taken at run time on the device, as numba
+  takes it on the CPU.  A callable with more than ``MAX_TRACED_PATHS`` paths is refused.
 """
 
 from __future__ import annotations
@@ -75,23 +80,138 @@ def _lit(v) -> str:
     return s
 
 
+MAX_TRACED_PATHS = 64   # control-flow paths of one traced callable (each is one re-run and one emitted leaf)
+MAX_TRACED_DEPTH = 256  # decisions along one path (a `while` on the state that never settles ends here)
+
+
+class _Paths:
+    """The decisions of ONE run of a callable under path exploration: comparisons that are asked for their truth
+    value take the outcome the plan dictates, and True beyond the plan (`_explore` comes back for the False arms)."""
+
+    def __init__(self, plan):
+        self.plan = list(plan)
+        self.taken = []  # (condition as C code, outcome, mark = position in the statement list)
+
+    def decide(self, code: str, mark: int = 0) -> bool:
+        k = len(self.taken)
+        if k >= MAX_TRACED_DEPTH:
+            raise TraceError(f"more than {MAX_TRACED_DEPTH} data-dependent decisions along one path (a loop on the state "
+                             "that does not terminate under tracing?); write the right-hand side as CUDA C")
+        outcome = self.plan[k] if k < len(self.plan) else True
+        self.taken.append((code, outcome, mark))
+        return outcome
+
+
+class _Node:
+    """Decision tree of a traced callable: a leaf carries the payload of its run, a branch the condition."""
+
+    __slots__ = ("cond", "mark", "true", "false", "payload")
+
+    def __init__(self, payload, cond=None, mark=0, true=None, false=None):
+        self.payload, self.cond, self.mark, self.true, self.false = payload, cond, mark, true, false
+
+    @property
+    def is_leaf(self):
+        return self.cond is None
+
+
+def _explore(run, what="right-hand side"):
+    """Depth-first exploration of the control-flow paths of a callable.  ``run(paths)`` executes it once under the
+    decision plan of ``paths`` and returns the payload of that path; the result is the decision tree.  A run with the
+    plan ``prefix`` takes True at every later decision, so it is the all-True leaf under ``prefix`` and its decisions
+    name the branch nodes above that leaf; the False arm of each of them is one more run."""
+    count = [0]
+
+    def build(prefix, conds=()):
+        count[0] += 1
+        if count[0] > MAX_TRACED_PATHS:
+            raise TraceError(f"the {what} has more than {MAX_TRACED_PATHS} control-flow paths (element-wise branches on a "
+                             "vector multiply them: use np.where / np.maximum on whole arrays, or CUDA C)")
+        paths = _Paths(prefix)
+        payload = run(paths)
+        taken = paths.taken
+        if [c for c, _, _ in taken[:len(prefix)]] != list(conds):  # the same questions in the same order as the parent run
+            raise TraceError(f"the {what} is not deterministic under tracing (its control flow changed between runs)")
+        node = _Node(payload)
+        for j in range(len(taken) - 1, len(prefix) - 1, -1):
+            code, _, mark = taken[j]
+            other = build([o for _, o, _ in taken[:j]] + [False], [c for c, _, _ in taken[:j + 1]])
+            node = _Node(payload, cond=code, mark=mark, true=node, false=other)
+        return node
+
+    return build([])
+
+
 class _Trace:
-    def __init__(self):
+    def __init__(self, paths=None):
         self.stmts = []
         self.count = 0
+        self.paths = paths
 
     def new(self, code: str) -> "Expr":
         name = f"v{self.count}"
         self.count += 1
-        self.stmts.append(f"    const double {name} = {code};")
+        self.stmts.append(f"const double {name} = {code};")
         return Expr(self, name)
+
+    def decide(self, code: str) -> bool:
+        if self.paths is None:
+            raise TraceError("data-dependent control flow (if/while on the state) cannot be traced here; "
+                             "write it as CUDA C instead")
+        return self.paths.decide(code, len(self.stmts))
+
+
+class Cond:
+    """A comparison inside the traced right-hand side.  Asked for its truth value (``if``, ``and``, ``min`` ...) it
+    becomes a run-time branch of the emitted code (path exploration, `_explore`); used in arithmetic it is 1.0 / 0.0
+    as a Python bool would be; ``&``, ``|`` and ``~`` combine conditions without branching."""
+
+    __slots__ = ("tr", "code")
+    __hash__ = None
+
+    def __init__(self, tr, code):
+        self.tr, self.code = tr, code
+
+    def __bool__(self):
+        return self.tr.decide(self.code)
+
+    @staticmethod
+    def _code(x):
+        if isinstance(x, Cond):
+            return x.code
+        if isinstance(x, (bool, np.bool_)):
+            return "true" if x else "false"
+        if isinstance(x, Expr):
+            return f"({x.name} != 0.0)"
+        raise TraceError(f"cannot combine a traced comparison with {type(x).__name__}")
+
+    def __and__(self, o): return Cond(self.tr, f"({self.code} && {Cond._code(o)})")
+    def __or__(self, o): return Cond(self.tr, f"({self.code} || {Cond._code(o)})")
+    def __xor__(self, o): return Cond(self.tr, f"({self.code} != {Cond._code(o)})")
+    __rand__, __ror__, __rxor__ = __and__, __or__, __xor__
+    def __invert__(self): return Cond(self.tr, f"(!{self.code})")
+
+    def as_expr(self) -> "Expr":
+        return self.tr.new(f"({self.code} ? 1.0 : 0.0)")
+
+    def __add__(self, o): return self.as_expr() + o
+    def __radd__(self, o): return o + self.as_expr()
+    def __sub__(self, o): return self.as_expr() - o
+    def __rsub__(self, o): return o - self.as_expr()
+    def __mul__(self, o): return self.as_expr() * o
+    def __rmul__(self, o): return o * self.as_expr()
+    def __neg__(self): return -self.as_expr()
+
+    def __float__(self):
+        raise TraceError("a traced comparison cannot be converted to float")
 
 
 class Expr:
     """A scalar double value inside the traced right-hand side."""
 
     __slots__ = ("tr", "name")
-    __array_priority__ = 1000.0
+    # no __array_priority__ / __array_ufunc__: to NumPy an Expr is an object scalar, so `y * p[0]` and `-y + t` (array on
+    # the left) broadcast element by element through the operators below, like `p[0] * y` does
 
     def __init__(self, tr, name):
         self.tr, self.name = tr, name
@@ -100,6 +220,8 @@ class Expr:
     def _c(x):
         if isinstance(x, Expr):
             return x.name
+        if isinstance(x, Cond):
+            return x.as_expr().name
         if isinstance(x, (numbers.Real, np.floating, np.integer, np.bool_)):
             return _lit(x)
         raise TraceError(f"cannot use {type(x).__name__} inside a traced right-hand side")
@@ -137,18 +259,25 @@ class Expr:
         return self.tr.new(f"pow({Expr._c(base)}, {self.name})")
 
     def __bool__(self):
-        raise TraceError("data-dependent control flow (if/while on the state) cannot be traced; "
-                         "write the right-hand side as CUDA C (CudaRHS) instead")
+        # `if y[0]:` / `while x:` -- Python's truth of a float, decided at run time (path exploration)
+        return self.tr.decide(f"({self.name} != 0.0)")
 
     def __float__(self):
-        raise TraceError("a traced value cannot be converted to float")
+        raise TraceError("a traced value cannot be converted to float (math.* functions need one: use the numpy ones)")
 
-    def _cmp(self, *_):
-        raise TraceError("comparisons on traced values are not supported; use CudaRHS for branching right-hand sides")
+    # Comparisons are symbolic conditions (`Cond`); `==` / `!=` too: Python's default identity comparison would
+    # evaluate `if y[0] == 0.0:` to a constant at trace time and freeze one arm of the branch into the CUDA source
+    def _cmp(self, other, op):
+        if isinstance(other, np.ndarray):
+            return NotImplemented
+        return Cond(self.tr, f"({self.name} {op} {Expr._c(other)})")
 
-    # == and != too: Python's default identity comparison would evaluate `if y[0] == 0.0:` to a constant at trace
-    # time and freeze one arm of the branch into the CUDA source without any error
-    __lt__ = __le__ = __gt__ = __ge__ = __eq__ = __ne__ = _cmp
+    def __lt__(self, o): return self._cmp(o, "<")
+    def __le__(self, o): return self._cmp(o, "<=")
+    def __gt__(self, o): return self._cmp(o, ">")
+    def __ge__(self, o): return self._cmp(o, ">=")
+    def __eq__(self, o): return self._cmp(o, "==")
+    def __ne__(self, o): return self._cmp(o, "!=")
     __hash__ = None
 
     def __getattr__(self, item):
@@ -158,37 +287,66 @@ class Expr:
         raise AttributeError(item)
 
 
-def trace(func, n: int, params_shape, has_params: bool) -> CudaRHS:
-    """Run ``func`` once on symbolic (t, y, p) and emit the equivalent ``nbk_rhs`` CUDA C."""
-    tr = _Trace()
+def _symbolic_args(tr, n, params_shape, with_params):
     t = Expr(tr, "t")
     y = np.empty(n, dtype=object)
     for i in range(n):
         y[i] = Expr(tr, f"y[{i}]")
-    try:
-        if has_params:
-            p = np.empty(int(np.prod(params_shape, dtype=int)), dtype=object)
-            for i in range(p.size):
-                p[i] = Expr(tr, f"p[{i}]")
-            out = func(t, y, p.reshape(params_shape))
-        else:
-            out = func(t, y)
-    except TraceError:
-        raise
-    except Exception as exc:  # noqa: BLE001
-        raise TraceError(
-            f"could not trace {getattr(func, '__name__', func)!r} into CUDA C ({type(exc).__name__}: {exc}); "
-            "pass a built-in name or CUDA C source (nbkode_b200.CudaRHS) instead"
-        ) from exc
-    out = np.asarray(out, dtype=object).ravel()
-    if out.size != n:
-        raise TraceError(f"right-hand side returned {out.size} values for a state of size {n}")
+    if not with_params:
+        return (t, y)
+    p = np.empty(int(np.prod(params_shape, dtype=int)), dtype=object)
+    for i in range(p.size):
+        p[i] = Expr(tr, f"p[{i}]")
+    return (t, y, p.reshape(params_shape))
+
+
+def _count_leaves(node) -> int:
+    return 1 if node.is_leaf else _count_leaves(node.true) + _count_leaves(node.false)
+
+
+def _emit_tree(node, leaf, lines, start=0, depth=1):
+    """Statements of a decision tree: what a run computed between two decisions is emitted once, above the `if`
+    whose arms continue it (all runs below a node share the statements up to the node's mark, name for name)."""
+    pad = "    " * depth
+    tr = node.payload[0]
+    if node.is_leaf:
+        lines += [pad + st for st in tr.stmts[start:]]
+        lines += [pad + st for st in leaf(node.payload)]
+        return
+    lines += [pad + st for st in tr.stmts[start:node.mark]]
+    lines.append(f"{pad}if {node.cond} {{")
+    _emit_tree(node.true, leaf, lines, node.mark, depth + 1)
+    lines.append(f"{pad}}} else {{")
+    _emit_tree(node.false, leaf, lines, node.mark, depth + 1)
+    lines.append(f"{pad}}}")
+
+
+def trace(func, n: int, params_shape, has_params: bool) -> CudaRHS:
+    """Run ``func`` on symbolic (t, y, p) -- once per control-flow path -- and emit the equivalent ``nbk_rhs`` CUDA C."""
+
+    def run(paths):
+        tr = _Trace(paths)
+        try:
+            out = func(*_symbolic_args(tr, n, params_shape, has_params))
+        except TraceError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            raise TraceError(
+                f"could not trace {getattr(func, '__name__', func)!r} into CUDA C ({type(exc).__name__}: {exc}); "
+                "pass a built-in name or CUDA C source (nbkode_b200.CudaRHS) instead"
+            ) from exc
+        out = np.asarray(out, dtype=object).ravel()
+        if out.size != n:
+            raise TraceError(f"right-hand side returned {out.size} values for a state of size {n}")
+        return tr, [Expr._c(e) for e in out]  # (Cond outputs append their 1.0 / 0.0 statement here, before emission)
+
+    tree = _explore(run)
     lines = ["NBK_RHS nbk_rhs(double t, const double* y, const double* p, double* dy) {"]
-    lines += tr.stmts
-    for i, e in enumerate(out):
-        lines.append(f"    dy[{i}] = {Expr._c(e)};")
+    _emit_tree(tree, lambda payload: [f"dy[{i}] = {e};" for i, e in enumerate(payload[1])], lines)
     lines.append("}")
-    return CudaRHS("\n".join(lines) + "\n", name=getattr(func, "__name__", "traced"))
+    out = CudaRHS("\n".join(lines) + "\n", name=getattr(func, "__name__", "traced"))
+    out.paths = _count_leaves(tree)
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -332,8 +490,8 @@ class Sc:
 
     __array_priority__ = 1001.0
 
-    def __init__(self, code):
-        self.c = code
+    def __init__(self, code, boolean=False):
+        self.c, self.boolean = code, boolean
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         if any(isinstance(x, Vec) or (isinstance(x, np.ndarray) and x.ndim == 1) for x in inputs):
@@ -371,20 +529,46 @@ class Sc:
     def __abs__(self): return Sc(f"fabs({self.c})")
     def __pow__(self, e): return Sc(_pow_code(self.c, e))
 
-    def _cmp(self, o):
-        if isinstance(o, Vec):
+    # Comparisons of scalars (time, parameters, single elements) are boolean scalars: a mask for np.where, 1 / 0 in
+    # arithmetic, and -- asked for their truth value by `if` / `and` / `min` -- a run-time select between the
+    # control-flow paths of the callable (path exploration, `_explore`).  `==` / `!=` too: Python's identity
+    # comparison would freeze an `if t == 0:` at trace time.
+    def _cmp(self, o, op):
+        if isinstance(o, (Vec, np.ndarray)):
             return NotImplemented  # scalar (x) vector comparison: the vector builds the mask
-        raise TraceError("comparisons on traced scalars are not supported (an `if t == 0:` would be frozen at trace "
-                         "time); use np.where on vectors, or write the right-hand side as CUDA C")
+        return Sc(f"({self.c} {op} {_sc(o)})", boolean=True)
 
-    __lt__ = __le__ = __gt__ = __ge__ = __eq__ = __ne__ = _cmp
+    def __lt__(self, o): return self._cmp(o, "<")
+    def __le__(self, o): return self._cmp(o, "<=")
+    def __gt__(self, o): return self._cmp(o, ">")
+    def __ge__(self, o): return self._cmp(o, ">=")
+    def __eq__(self, o): return self._cmp(o, "==")
+    def __ne__(self, o): return self._cmp(o, "!=")
     __hash__ = None
 
+    def _logic(self, o, op):
+        if isinstance(o, (Vec, np.ndarray)):
+            return NotImplemented
+        return Sc(f"({self._truth()} {op} {o._truth() if isinstance(o, Sc) else ('true' if o else 'false')})", boolean=True)
+
+    def __and__(self, o): return self._logic(o, "&&")
+    def __or__(self, o): return self._logic(o, "||")
+    __rand__, __ror__ = __and__, __or__
+    def __invert__(self): return Sc(f"(!{self._truth()})", boolean=True)
+
+    def _truth(self) -> str:
+        return self.c if self.boolean else f"({self.c} != 0.0)"
+
     def __bool__(self):
-        raise TraceError("data-dependent control flow cannot be traced; write the right-hand side as CUDA C")
+        if _SC_PATHS is None:
+            raise TraceError("data-dependent control flow cannot be traced here; write the right-hand side as CUDA C")
+        return _SC_PATHS.decide(self._truth())
 
     def __float__(self):
-        raise TraceError("a traced value cannot be converted to float")
+        raise TraceError("a traced value cannot be converted to float (math.* functions need one: use the numpy ones)")
+
+
+_SC_PATHS: "_Paths | None" = None
 
 
 def _sc(x) -> str:
@@ -413,9 +597,14 @@ class _Tables:
     def __init__(self):
         self.arrays = []
         self.functions = []
+        self._function_formats = []
 
     def add(self, arr) -> str:
-        self.arrays.append(np.ascontiguousarray(arr, dtype=np.float64))
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        for k, a in enumerate(self.arrays):  # the runs of a path exploration capture the same constants again
+            if a.shape == arr.shape and a.tobytes() == arr.tobytes():
+                return f"nbk_tab{k}"
+        self.arrays.append(arr)
         return f"nbk_tab{len(self.arrays) - 1}"
 
     def source(self) -> str:
@@ -428,7 +617,11 @@ class _Tables:
         """A helper device function (used for matrix-vector products: one row per component)."""
         if not hasattr(self, "functions"):
             self.functions = []
+        for k, (fmt, _) in enumerate(self._function_formats):
+            if fmt == body_fmt:
+                return f"nbk_fn{k}"
         name = f"nbk_fn{len(self.functions)}"
+        self._function_formats.append((body_fmt, name))
         self.functions.append(body_fmt.format(name=name))
         return name
 
@@ -649,10 +842,15 @@ def _np_gradient(a, *args, **kw):
 
 
 def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
-    """Trace a NumPy-style whole-vector right-hand side into the component-wise ``nbk_rhs_i`` of the CTA regime."""
-    global _TABLES
+    """Trace a NumPy-style whole-vector right-hand side into the component-wise ``nbk_rhs_i`` of the CTA regime.
+    Control flow on scalars (``if t < t_on:``, ``if p[0] > 0:``) is explored path by path like in :func:`trace`; the
+    paths become one nested select around the component expressions."""
+    global _TABLES, _SC_PATHS
     _TABLES = _Tables()
-    try:
+
+    def run(paths):
+        global _SC_PATHS
+        _SC_PATHS = paths
         y = Vec(n, lambda j: f"y[{j}]")
         t = Sc("t")
         try:
@@ -673,11 +871,19 @@ def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
                 "nbk_rhs_i(t, y, p, i, n)") from exc
         if isinstance(out, (list, tuple)) or (isinstance(out, np.ndarray) and out.dtype == object):
             out = _np_concatenate([[e] if not isinstance(e, Vec) else e for e in np.asarray(out, dtype=object).ravel()])
-        out = _as_vec(out, n)
-        body = out.code("i")
+        return (_as_vec(out, n).code("i"),)
+
+    def select(node):
+        if node.is_leaf:
+            return node.payload[0]
+        return f"({node.cond} ? {select(node.true)} : {select(node.false)})"
+
+    try:
+        body = select(_explore(run))
         src = _TABLES.source()
     finally:
         _TABLES = None
+        _SC_PATHS = None
     src += ("\nNBK_RHS_I nbk_rhs_i(double t, nbk_vec y, const double* p, int i, int n) {\n"
             f"    return {body};\n}}\n")
     return CudaRHS(src, name=getattr(func, "__name__", "traced"))
@@ -716,34 +922,28 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
     for k, ev in enumerate(events):
         terminal.append(bool(getattr(ev, "terminal", False)))
         direction.append(int(np.sign(getattr(ev, "direction", 0))))
-        tr = _Trace()
-        t = Expr(tr, "t")
-        y = np.empty(n, dtype=object)
-        for i in range(n):
-            y[i] = Expr(tr, f"y[{i}]")
         try:
             nargs = len(inspect.signature(ev).parameters)
         except (TypeError, ValueError):
             nargs = 2
-        try:
-            if nargs >= 3 and has_params:
-                p = np.empty(int(np.prod(params_shape, dtype=int)), dtype=object)
-                for i in range(p.size):
-                    p[i] = Expr(tr, f"p[{i}]")
-                out = ev(t, y, p.reshape(params_shape))
-            else:
-                out = ev(t, y)
-        except TraceError:
-            raise
-        except Exception as exc:  # noqa: BLE001
-            raise TraceError(f"could not trace event {getattr(ev, '__name__', ev)!r} into CUDA C "
-                             f"({type(exc).__name__}: {exc}); pass nbkode_b200.CudaEvents instead") from exc
-        out = np.asarray(out, dtype=object).ravel()
-        if out.size != 1:
-            raise TraceError("an event function must return one float")
+
+        def run(paths, ev=ev, nargs=nargs):
+            tr = _Trace(paths)
+            try:
+                out = ev(*_symbolic_args(tr, n, params_shape, nargs >= 3 and has_params))
+            except TraceError:
+                raise
+            except Exception as exc:  # noqa: BLE001
+                raise TraceError(f"could not trace event {getattr(ev, '__name__', ev)!r} into CUDA C "
+                                 f"({type(exc).__name__}: {exc}); pass nbkode_b200.CudaEvents instead") from exc
+            out = np.asarray(out, dtype=object).ravel()
+            if out.size != 1:
+                raise TraceError("an event function must return one float")
+            return tr, Expr._c(out[0])
+
+        tree = _explore(run, "event function")
         lines.append(f"  if (k == {k}) {{")
-        lines += tr.stmts
-        lines.append(f"    return {Expr._c(out[0])};")
+        _emit_tree(tree, lambda payload: [f"return {payload[1]};"], lines)
         lines.append("  }")
     lines.append("  return 0.0;")
     lines.append("}")
@@ -755,6 +955,7 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
 # RungeKutta45, 1 M decay trajectories: n = 16: 7.9 vs 11.4 ms, n = 24: 28 vs 11.8 ms, n = 32: 73 vs 11.8 ms,
 # n = 64: 202 vs 22.5 ms, per-thread vs CTA).
 CTA_AUTO_N = 16
+SELECT_OVER_PATHS = 8  # a per-thread trace with more control-flow paths than this tries the select form first
 GROUP_AUTO_N = 10
 # largest n a traced callable still runs per thread, by method id (tools/bench_group.py, tools/bench_team_decay.py: the
 # component-wise form then runs as sub-warp groups / teams, csrc/nbk_group.cuh, nbk_cta.cuh)
@@ -789,12 +990,20 @@ def resolve(rhs, n: int, params_shape, has_params: bool, regime: str = "auto", c
                 raise ValueError(f"n = {n} needs the CTA regime, which this solver class does not have "
                                  "(RungeKutta23/45, AdamsBashforth*, ForwardEuler and the fixed-step Runge-Kutta classes do)")
             try:
-                return None, trace(rhs, n, params_shape, has_params).source
+                traced = trace(rhs, n, params_shape, has_params)
             except TraceError:
-                # e.g. np.where / comparisons: only the whole-vector tracer can express them (as selects)
+                # e.g. element-wise branches beyond MAX_TRACED_PATHS: the whole-vector tracer expresses them as selects
                 if regime != "auto" or not cta_ok:
                     raise
                 return None, trace_cta(rhs, n, params_shape, has_params).source
+            if traced.paths > SELECT_OVER_PATHS and regime == "auto" and cta_ok:
+                # np.where / np.maximum on the object array of a small system branch element by element (2 ** n paths
+                # per thread); as a whole-vector expression the same callable is one select per component
+                try:
+                    return None, trace_cta(rhs, n, params_shape, has_params).source
+                except TraceError:
+                    pass
+            return None, traced.source
         # large (and mid-size) systems run one CTA per trajectory: the right-hand side is traced as a whole-vector
         # expression; a function the vector tracer cannot handle falls back to the per-thread form while it can
         try:

@@ -710,6 +710,30 @@ def rhs_rd1d(t, y, p):
     return d * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + r * y * (1 - y)
 
 
+def rhs_pwl(t, y, p):
+    """Oscillator with run-time branches on the state and the time (the reference compiles them with numba): a
+    spring that is four times stiffer beyond a stop at |x| = p[1], a saturated damper written with Python's
+    min / max, a forcing ramp that ends at t = 6.  Every piece joins continuously, so that a branch decided
+    differently in the last bit next to a kink moves the result by rounding error only."""
+    x, v = y[0], y[1]
+    if x > p[1]:
+        f = -p[0] * p[1] - 4.0 * p[0] * (x - p[1])
+    elif x < -p[1]:
+        f = p[0] * p[1] - 4.0 * p[0] * (x + p[1])
+    else:
+        f = -p[0] * x
+    u = min(max(-p[2] * v, -0.5), 0.5)
+    g = 0.3 * (6.0 - t) if t < 6.0 else 0.0
+    return np.array([v, f + u + g])
+
+
+def ev_switch(t, y):
+    """An event function with a branch: the level it watches moves at t = 3."""
+    if t < 3.0:
+        return y[0] - 0.5
+    return y[0] + 0.25
+
+
 # event functions shared by the golden-vector generator and the tests (SciPy convention: optional
 # ``terminal`` / ``direction`` attributes, nbkode/core.py:343-366)
 def ev_y0(t, y):
@@ -749,9 +773,9 @@ def ev_y0_up_terminal(t, y):
 ev_y0_up_terminal.terminal = True
 ev_y0_up_terminal.direction = 1
 
-EVENTS = {"y0_up_terminal": ev_y0_up_terminal, "y0": ev_y0, "y1_down": ev_y1_down, "z25_up": ev_z25_up, "x_m8_terminal": ev_x_m8_terminal, "time": ev_time}
+EVENTS = {"switch": ev_switch, "y0_up_terminal": ev_y0_up_terminal, "y0": ev_y0, "y1_down": ev_y1_down, "z25_up": ev_z25_up, "x_m8_terminal": ev_x_m8_terminal, "time": ev_time}
 
-RHS = {"decay": rhs_decay, "lorenz": rhs_lorenz, "vdp": rhs_vdp, "linear": rhs_linear, "rd1d": rhs_rd1d}
+RHS = {"decay": rhs_decay, "lorenz": rhs_lorenz, "vdp": rhs_vdp, "linear": rhs_linear, "rd1d": rhs_rd1d, "pwl": rhs_pwl}
 
 
 # input generators of the BASELINE configurations: defined in the package (so that the product harness never

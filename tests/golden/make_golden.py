@@ -239,7 +239,40 @@ def implicit_section():
     dump("implicit_extra.json", extra)
 
 
+def branching_section():
+    """Right-hand sides and event functions with run-time branches (`if` on the state and the time, Python's
+    min / max): the reference compiles them as they are; nbkode_b200 explores their control-flow paths
+    (tests/test_trace_branches.py).  Single trajectories of the live reference."""
+    pw = ([1.6, -0.4], [2.0, 0.8, 0.7])
+    adaptive = [
+        adaptive_case("RungeKutta45", "pwl", *pw, np.linspace(0.5, 12, 24), rtol=1e-6, atol=1e-9),
+        adaptive_case("RungeKutta23", "pwl", *pw, np.linspace(0.5, 12, 24), rtol=1e-6, atol=1e-9),
+        adaptive_case("DOP853", "pwl", *pw, [3.0, 6.0, 12.0], rtol=1e-6, atol=1e-9),
+        adaptive_case("RungeKutta45", "pwl", [0.2, 0.1], [1.0, 0.5, 2.5], [4.0, 8.0], rtol=1e-8, atol=1e-10),
+    ]
+    fixed = [
+        fixed_case("RungeKutta4", "pwl", *pw, np.linspace(0.5, 12, 24), 0.01),
+        fixed_case("AdamsBashforth3", "pwl", *pw, np.linspace(0.5, 12, 24), 0.005),
+        fixed_case("ForwardEuler", "pwl", *pw, [1.0, 2.0], 0.001),
+    ]
+    events = []
+    for cls, kw in (("RungeKutta45", dict(rtol=1e-6, atol=1e-9)), ("RungeKutta23", dict(rtol=1e-6, atol=1e-9)),
+                    ("RungeKutta4", dict(h=0.01))):
+        ts = np.linspace(0.5, 12, 24)
+        s = getattr(nbkode, cls)(onp.RHS["pwl"], 0.0, np.array(pw[0]), params=np.array(pw[1]), **kw)
+        t, y, te, ye = s.run_events(ts, [onp.EVENTS["switch"], onp.EVENTS["y1_down"]])
+        alias = [[bool(getattr(x, "base", None) is not None) for x in lst] for lst in ye]
+        events.append({"cls": cls, "rhs": "pwl", "y0": L(pw[0]), "p": L(pw[1]), "kw": kw, "ts": L(ts),
+                       "events": ["switch", "y1_down"], "t": L(t), "y": L(y), "t_events": [L(x) for x in te],
+                       "y_events": [L(x) for x in ye], "y_events_aliased": alias, "t_end": float(s.t)})
+        assert len(te[0]) >= 2 and len(te[1]) >= 2
+    dump("branching.json", {"adaptive": adaptive, "fixed": fixed, "events": events})
+
+
 def main():
+    if sys.argv[1:] == ["branching"]:
+        return branching_section()
+    branching_section()
     if sys.argv[1:] == ["implicit"]:
         return implicit_section()
     implicit_section()

@@ -1,0 +1,130 @@
+"""GPU parity of right-hand sides and event functions with run-time branches (`if` on the state and the time,
+Python's min / max) -- the reference compiles them with numba as they are (nbkode/core.py:125-132); here the tracer
+explores their control-flow paths (nbkode_b200/rhs.py, tests/test_trace_branches.py) and the branch is taken on
+the device.
+
+Checked against tests/golden/branching.json (single trajectories of the LIVE reference, make_golden.py
+`branching`) and, for ensembles, against the bit-exact NumPy restatement running the same Python callable.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():  # pragma: no cover
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import nbkode_b200 as nbk  # noqa: E402
+from oracle import nbk_oracle_np as onp  # noqa: E402
+
+G = load_golden("branching.json")
+FIXED_TOL = 1e-12
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b))) / max(1.0, float(np.max(np.abs(b)))) if a.size else 0.0
+
+
+def within(y, ref, rtol, atol, slack=1.0):
+    return np.abs(np.asarray(y) - np.asarray(ref)) <= slack * (rtol * np.abs(ref) + atol)
+
+
+@pytest.mark.parametrize("c", G["adaptive"], ids=lambda c: f"{c['cls']}-{len(c['ts'])}-{c['kw']['rtol']}")
+def test_branching_adaptive_single_vs_reference(c):
+    kw = dict(c["kw"])
+    s = getattr(nbk, c["cls"])(onp.RHS[c["rhs"]], 0.0, np.array(c["y0"]), np.array(c["p"]), **kw)
+    assert s.is_jit
+    assert rel(float(s.h), c["h0"]) < 1e-13 and rel(s.f, c["f0"]) < 1e-14
+    t, y = s.run(c["ts"])
+    assert abs(s.n_accepted - c["n_accepted"]) <= 1
+    assert within(y, c["ys"], kw["rtol"], kw["atol"]).all()
+    assert within(s.y, c["y_end"], kw["rtol"], kw["atol"]).all()
+    if s.n_accepted == c["n_accepted"]:  # same step sequence: the dense output agrees far inside the bar
+        assert rel(y, c["ys"]) < 1e-9
+
+
+@pytest.mark.parametrize("c", G["fixed"], ids=lambda c: c["cls"])
+def test_branching_fixed_single_vs_reference(c):
+    s = getattr(nbk, c["cls"])(onp.RHS[c["rhs"]], 0.0, np.array(c["y0"]), np.array(c["p"]), h=c["h"])
+    t, y = s.run(c["ts"])
+    assert rel(y, c["ys"]) <= FIXED_TOL and s.t == c["t_end"]
+    assert rel(s.y, c["y_end"]) <= FIXED_TOL and rel(s.f, c["f_end"]) <= FIXED_TOL
+
+
+@pytest.mark.parametrize("c", G["events"], ids=lambda c: c["cls"])
+def test_branching_events_vs_reference(c):
+    s = getattr(nbk, c["cls"])(onp.RHS[c["rhs"]], 0.0, np.array(c["y0"]), np.array(c["p"]), **c["kw"])
+    t, y, te, ye = s.run_events(c["ts"], [onp.EVENTS[e] for e in c["events"]])
+    assert rel(t, c["t"]) < 1e-7 and rel(y, c["y"]) < 1e-7
+    assert [len(x) for x in te] == [len(x) for x in c["t_events"]]
+    for a, b in zip(te, c["t_events"]):
+        assert rel(a, b) < 1e-6
+
+
+def _ensemble(B, seed=7):
+    rng = np.random.default_rng(seed)
+    y0 = np.stack([rng.uniform(-2, 2, B), rng.uniform(-1, 1, B)], 1)
+    p = np.stack([rng.uniform(1, 3, B), rng.uniform(0.3, 1.2, B), rng.uniform(0.2, 1.5, B)], 1)
+    return y0, p
+
+
+def test_branching_ensemble_vs_oracle():
+    """1024 trajectories take different arms at the same time inside one warp; 48 of them against the restatement."""
+    B = 1024
+    y0, p = _ensemble(B)
+    ts = np.linspace(0.5, 10, 20)
+    rows = np.r_[0:24, B - 24:B]
+    for cls, kw in (("RungeKutta45", dict(rtol=1e-6, atol=1e-9)), ("RungeKutta23", dict(rtol=1e-6, atol=1e-9))):
+        s = getattr(nbk, cls)(onp.rhs_pwl, 0.0, y0, p, **kw)
+        t, y = s.run(ts)
+        assert y.shape == (B, ts.size, 2) and np.isfinite(y).all()
+        nacc = np.asarray(s.n_accepted)
+        worst = 0.0
+        for i in rows:
+            o = onp.AdaptiveRK(cls, onp.rhs_pwl, 0.0, y0[i], p[i], **kw)
+            _, yo = onp.run(o, ts)
+            assert abs(int(nacc[i]) - o.n_accepted) <= 1, (cls, i)
+            worst = max(worst, float(np.max(np.abs(y[i] - yo) / (kw["rtol"] * np.abs(yo) + kw["atol"]))))
+        assert worst <= 1.0, (cls, worst)
+    for cls, h in (("RungeKutta4", 0.01), ("AdamsBashforth4", 0.005)):
+        s = getattr(nbk, cls)(onp.rhs_pwl, 0.0, y0, p, h=h)
+        t, y = s.run(ts)
+        for i in rows[::6]:
+            o = onp.FixedRK(cls, onp.rhs_pwl, 0.0, y0[i], p[i], h=h) if cls == "RungeKutta4" else \
+                onp.AdamsBashforth(4, onp.rhs_pwl, 0.0, y0[i], p[i], h=h)
+            _, yo = onp.run(o, ts)
+            assert rel(y[i], yo) <= FIXED_TOL, (cls, i)
+
+
+def test_branching_vector_rhs_in_the_componentwise_regimes():
+    """Scalar decisions (time, parameters, single elements) around a whole-vector expression become selects of
+    nbk_rhs_i: sub-warp groups (n = 24) and one CTA per trajectory (n = 300) against the restatement."""
+
+    def switched(t, y, p):
+        d = p[0] if t < 0.5 else 2 * p[0]
+        out = d * (np.roll(y, -1) - 2 * y + np.roll(y, 1))
+        if p[1] > 1.0 and t >= 0.25:
+            out = out + p[1] * y * (1 - y)
+        if y[0] > y[-1]:           # one element against another; the extra term joins continuously
+            out = out - 0.25 * (y[0] - y[-1]) * y
+        return out
+
+    rng = np.random.default_rng(2)
+    for n, B in ((24, 96), (300, 24)):
+        x = np.arange(n) / n
+        y0 = 0.5 + 0.4 * np.sin(2 * np.pi * x[None, :] + rng.uniform(0, 6, B)[:, None])
+        p = np.stack([rng.uniform(0.5, 2, B), rng.uniform(0.5, 2, B)], 1)
+        s = nbk.RungeKutta45(switched, 0.0, y0, p, rtol=1e-6, atol=1e-9)
+        t, y = s.run([0.3, 0.6, 1.0])
+        nacc = np.asarray(s.n_accepted)
+        for i in (0, 1, B // 2, B - 1):
+            o = onp.AdaptiveRK("RungeKutta45", switched, 0.0, y0[i], p[i], rtol=1e-6, atol=1e-9)
+            _, yo = onp.run(o, [0.3, 0.6, 1.0])
+            assert abs(int(nacc[i]) - o.n_accepted) <= 1
+            assert within(y[i], yo, 1e-6, 1e-9).all(), (n, i)

@@ -130,14 +130,15 @@ def test_trace_arithmetic_and_ufuncs():
 
 
 def test_trace_rejects_untraceable():
+    # comparisons are run-time branches of the emitted source (tests/test_trace_branches.py) ...
     def branching(t, y):
         return y if y[0] > 0 else -y
 
-    with pytest.raises(rhs.TraceError):
-        rhs.trace(branching, 1, (), False)
+    src = rhs.trace(branching, 1, (), False).source
+    assert "if (y[0] > 0.0) {" in src and "} else {" in src and src.count("dy[0]") == 2
 
-    # == / != must not fall back to Python's identity comparison (that would freeze one arm of the branch into the
-    # CUDA source at trace time, silently diverging from the reference, which branches at run time)
+    # ... and so are == / !=: they must not fall back to Python's identity comparison (that would freeze one arm of
+    # the branch into the CUDA source at trace time, silently diverging from the reference, which branches at run time)
     def eq_branch(t, y):
         if y[0] == 0.0:
             return np.array([1.0 + 0 * y[0]])
@@ -148,16 +149,20 @@ def test_trace_rejects_untraceable():
             return -y
         return y
 
-    for fn in (eq_branch, ne_time):
-        with pytest.raises(rhs.TraceError):
-            rhs.trace(fn, 1, (), False)
-        with pytest.raises(rhs.TraceError):
-            rhs.trace_cta(fn, 1, (), False)
+    for fn, cond in ((eq_branch, "y[0] == 0.0"), (ne_time, "t != 0.0")):
+        src = rhs.trace(fn, 1, (), False).source
+        assert f"if ({cond})" in src and src.count("dy[0]") == 2
+        src = rhs.trace_cta(fn, 1, (), False).source
+        assert f"({cond}) ?" in src
     with pytest.raises(TypeError):
         hash(rhs.Sc("t"))
-    # vectors: == builds a mask for np.where, like the other comparisons
+    with pytest.raises(TypeError):
+        hash(rhs.Expr(None, "t"))
+    # vectors: == builds a mask for np.where, like the other comparisons; the truth of a whole vector is refused
     src = rhs.trace_cta(lambda t, y: np.where(y == 0.0, 1.0, -y), 128, (), False).source
     assert "==" in src
+    with pytest.raises(rhs.TraceError):
+        rhs.trace_cta(lambda t, y: (y if y > 0 else -y), 128, (), False)
 
     def wrong_size(t, y):
         return np.array([y[0], y[0]])
@@ -259,8 +264,12 @@ def test_nvrtc_compiles_event_programs_and_traces_events():
         assert sz.value > 10_000
     with pytest.raises(ValueError):  # ... the fixed-step classes only per thread
         _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(4, 200, 2, rhs_name=b"rd1d")), 1, ev.source.encode(), C.byref(sz)))
+    # a branching event function is a run-time branch of nbk_event (tests/test_trace_branches.py)
+    ev = rhs.trace_events(lambda t, y: 1.0 if y[0] > 0 else -1.0, 3, (3,), True)
+    assert "if (y[0] > 0.0) {" in ev.source and "return 1.0;" in ev.source and "return -1.0;" in ev.source
+    _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(45, 3, 3, rhs_name=b"lorenz")), 1, ev.source.encode(), C.byref(sz)))
     with pytest.raises(rhs.TraceError):
-        rhs.trace_events(lambda t, y: 1.0 if y[0] > 0 else -1.0, 3, (3,), True)
+        rhs.trace_events(lambda t, y: float(y[0]), 3, (3,), True)
 
 
 def test_vector_tracer_emits_componentwise_cuda_and_compiles():
@@ -302,8 +311,9 @@ def test_vector_tracer_emits_componentwise_cuda_and_compiles():
     # comparisons / np.where are selects in the whole-vector tracer only: a small system that uses them is traced
     # that way (CTA regime) instead of failing in the component-by-component tracer
     relu = lambda t, y, p: np.where(y > 0, -y, p[0] * y) + np.diff(np.append(y, 0.0)).sum()  # noqa: E731
+    assert rhs.trace(relu, 6, (1,), True).paths == 64  # per thread: one branch per element, 2 ** 6 paths
     with pytest.raises(rhs.TraceError):
-        rhs.trace(relu, 6, (1,), True)
+        rhs.trace(relu, 7, (1,), True)
     s3 = rhs.resolve(relu, 6, (1,), True)[1]
     assert "nbk_rhs_i" in s3 and "?" in s3
     _lib.check(lib.nbk_jit_compile_only(C.byref(_cfg(45, 6, 1, src=s3.encode())), C.byref(sz)))

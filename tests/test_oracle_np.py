@@ -254,3 +254,28 @@ def test_implicit_api_semantics(c):
     _eq(y, c["resume_a"])
     t, y = onp.run(s, c["resume_b_t"])
     _eq(y, c["resume_b"])
+
+
+# ---------------------------------------------------------------- right-hand sides / events with run-time branches
+_BR = load_golden("branching.json")
+
+
+@pytest.mark.parametrize("c", _BR["adaptive"], ids=lambda c: f"{c['cls']}-{c['rhs']}-{len(c['ts'])}")
+def test_branching_adaptive_bitexact(c):
+    test_adaptive_single_bitexact(c)
+
+
+@pytest.mark.parametrize("c", _BR["fixed"], ids=lambda c: f"{c['cls']}-{c['rhs']}")
+def test_branching_fixed_bitexact(c):
+    s = _mk_any({**c, "kw": {"h": c["h"]}})
+    _eq(s.cache.ys, c["init_ys"])
+    t, y = onp.run(s, c["ts"])
+    _eq(y, c["ys"], "run(ts)")
+    assert s.t == c["t_end"]
+    _eq(s.y, c["y_end"])
+    _eq(s.f, c["f_end"])
+
+
+@pytest.mark.parametrize("c", _BR["events"], ids=lambda c: f"{c['cls']}-{'+'.join(c['events'])}")
+def test_branching_events_bitexact(c):
+    test_events_bitexact(c)

@@ -1,0 +1,275 @@
+"""Data-dependent control flow in Python right-hand sides and event functions (path exploration in
+nbkode_b200/rhs.py).
+
+The reference compiles the user's callable with numba (nbkode/core.py:125-132), so an ``if y[0] > 0:`` inside it is
+a run-time branch.  The tracer re-runs the callable once per control-flow path and emits nested ``if`` / ``else``
+(per-thread form, ``nbk_rhs``) or selects (component-wise form, ``nbk_rhs_i``).  CPU-only checks:
+
+ * the emitted source, compiled for the HOST with g++ behind a three-line shim, returns bit for bit what the Python
+   callable returns on random inputs that visit every path (the arithmetic is + - * / fabs sqrt only, so the
+   comparison is exact; ``-ffp-contract=off`` keeps g++ from fusing what Python does not);
+ * NVRTC compiles the same source into the sm_100a integrator kernels (no GPU needed to compile);
+ * the bounds (paths, depth) and the determinism check raise ``TraceError``.
+"""
+
+import ctypes as C
+import subprocess
+
+import numpy as np
+import pytest
+
+from nbkode_b200 import _lib, rhs
+
+SHIM = r"""
+#include <cmath>
+namespace nbk { inline double d_nan() { return NAN; } inline double d_inf() { return INFINITY; } }
+#define NBK_RHS extern "C" void
+#define NBK_EVENT extern "C" double
+#define NBK_RHS_I extern "C" double
+#define __device__
+typedef const double* nbk_vec;
+"""
+
+
+def _host_build(tmp_path, source, tag):
+    cpp = tmp_path / f"{tag}.cpp"
+    so = tmp_path / f"{tag}.so"
+    cpp.write_text(SHIM + source)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cpp)], check=True)
+    return C.CDLL(str(so))
+
+
+def _call_rhs(lib, t, y, p):
+    dy = np.empty_like(y)
+    dp = C.POINTER(C.c_double)
+    lib.nbk_rhs.restype = None
+    lib.nbk_rhs.argtypes = [C.c_double, dp, dp, dp]
+    pp = np.ascontiguousarray(p, dtype=np.float64).ravel() if p is not None else np.zeros(1)
+    lib.nbk_rhs(float(t), y.ctypes.data_as(dp), pp.ctypes.data_as(dp), dy.ctypes.data_as(dp))
+    return dy
+
+
+# ------------------------------------------------------------------ right-hand sides with branches
+def piecewise(t, y, p):
+    # if / elif / else with `and`, Python's min / max, abs, an early return
+    if y[0] > 1.0:
+        a = -p[0] * y[0]
+    elif y[0] < -1 and t > 2:
+        a = p[0] * y[1]
+    else:
+        a = min(y[0], y[1])
+    if t >= 4.5:
+        return np.array([a, -y[1]])
+    return np.array([a, max(abs(y[1]), 0.5) - t])
+
+
+def friction(t, y, p):
+    # Coulomb friction: the sign of the velocity picks the arm; `==` must be a run-time test as well
+    v = y[1]
+    if v == 0.0:
+        f = 0.0
+    elif v > 0:
+        f = -p[1]
+    else:
+        f = p[1]
+    return np.array([v, -p[0] * y[0] + f])
+
+
+def helper_clip(x, lo, hi):
+    if x < lo:
+        return lo
+    if x > hi:
+        return hi
+    return x
+
+
+def with_helper_and_loop(t, y):
+    # a nested helper, a chained comparison, a bounded `while` on the state, truth of a float, `not`
+    a = helper_clip(y[0], -0.5, 0.5)
+    b = y[1]
+    k = 0
+    while k < 2 and b > 1.0:
+        b = b * 0.5
+        k += 1
+    c = 1.0 if 0.0 < y[2] < 1.0 else -1.0
+    if not (y[2] * 0.0 + t):   # t == 0
+        c = c * 2.0
+    return np.array([a - b, b * c, (y[0] > 0) * y[2] + ((y[1] > 0) & (y[2] > 0)) * 1.5])
+
+
+CASES = [
+    (piecewise, 2, (1,), True),
+    (friction, 2, (2,), True),
+    (with_helper_and_loop, 3, (), False),
+]
+
+
+@pytest.mark.parametrize("func,n,pshape,has_p", CASES, ids=[c[0].__name__ for c in CASES])
+def test_branching_rhs_host_compiled_source_equals_python(tmp_path, func, n, pshape, has_p):
+    src = rhs.trace(func, n, pshape, has_p).source
+    assert "if (" in src and "else" in src
+    lib = _host_build(tmp_path, src, func.__name__)
+    rng = np.random.default_rng(5)
+    seen = set()
+    for k in range(600):
+        y = rng.uniform(-3, 3, n)
+        if k % 7 == 0:
+            y[rng.integers(n)] = 0.0  # the `==` arm
+        t = float(rng.choice([0.0, rng.uniform(0, 5)]))
+        p = rng.uniform(0.1, 2, pshape) if has_p else None
+        want = np.asarray(func(t, y, p) if has_p else func(t, y), dtype=np.float64)
+        got = _call_rhs(lib, t, y, p)
+        assert np.array_equal(got, want), (t, y, p, got, want)
+        seen.add(tuple(np.sign(want)))
+    assert len(seen) >= 3  # the sample visits different arms
+
+
+def test_branching_rhs_compiles_into_the_kernels():
+    lib = _lib.lib()
+    sz = C.c_longlong(0)
+
+    def cfg(method, n, npar, src):
+        return _lib.NbkConfig(method, n, npar, 0, 16, None, src, 1e-6, 1e-9, 0.2, 10.0, 0.9, 0, 0)
+
+    src = rhs.trace(piecewise, 2, (1,), True).source.encode()
+    for method in (45, 23, 853, 4, 204):
+        _lib.check(lib.nbk_jit_compile_only(C.byref(cfg(method, 2, 1, src)), C.byref(sz)))
+        assert sz.value > 10_000
+    src = rhs.trace(with_helper_and_loop, 3, (), False).source.encode()
+    _lib.check(lib.nbk_jit_compile_only(C.byref(cfg(45, 3, 0, src)), C.byref(sz)))
+
+
+def test_path_count_depth_and_determinism_are_checked():
+    def many(t, y):
+        return np.array([(e if e > 0 else -e) for e in y])   # 2 ** 7 element-wise paths
+
+    with pytest.raises(rhs.TraceError, match="control-flow paths"):
+        rhs.trace(many, 7, (), False)
+    assert rhs.trace(many, 6, (), False).source.count("dy[0]") == 64
+
+    def endless(t, y):
+        x = y[0]
+        while x > 0:       # never settles when every comparison is taken as True
+            x = x - 1.0
+        return np.array([x])
+
+    with pytest.raises(rhs.TraceError, match="decisions along one path"):
+        rhs.trace(endless, 1, (), False)
+
+    calls = []
+
+    def flaky(t, y):
+        calls.append(1)
+        if len(calls) > 1 and t > 1:
+            return -y
+        if y[0] > 0:
+            return y
+        return -y
+
+    with pytest.raises(rhs.TraceError, match="not deterministic"):
+        rhs.trace(flaky, 1, (), False)
+
+    # math.* needs a real float: refused with a pointer to numpy, not silently evaluated
+    import math
+
+    with pytest.raises(rhs.TraceError):
+        rhs.trace(lambda t, y: np.array([math.sin(y[0])]), 1, (), False)
+    with pytest.raises(TypeError):
+        hash(rhs.trace.__globals__["Cond"](None, "(a < b)"))
+
+
+def test_array_on_the_left_of_a_traced_scalar(tmp_path):
+    """`y * p[0]`, `-y + t`, `y / np.float64(2) - y.sum()`: NumPy broadcasts the traced scalar over the object array
+    whichever side it stands on (an Expr is an object scalar to NumPy, it claims no array priority)."""
+    A = np.arange(9.0).reshape(3, 3) / 7.0
+
+    def f(t, y, p):
+        a = y * p[0] + (-y + t) * p[1]
+        b = y / np.float64(2.0) - y.sum() + np.float64(0.5) * y[0]
+        return a - b + A @ y * (t > 1) + (y > 0) * y[::-1]
+
+    src = rhs.trace(f, 3, (2,), True).source
+    lib = _host_build(tmp_path, src, "left")
+    rng = np.random.default_rng(9)
+    for _ in range(100):
+        t, y, p = float(rng.uniform(0, 2)), rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 2)
+        # (A @ y and y.sum() add in BLAS / pairwise order in NumPy, left to right in the trace: last-bit differences)
+        np.testing.assert_allclose(_call_rhs(lib, t, y, p), f(t, y, p), rtol=1e-13, atol=1e-15)
+    for g in (lambda t, y: y * t, lambda t, y: y - y.sum(), lambda t, y: y / np.sin(t), lambda t, y: -y + t):
+        assert rhs.trace(g, 4, (), False).source.count("dy[") == 4
+
+
+# ------------------------------------------------------------------ events
+def test_branching_event_functions(tmp_path):
+    def ev0(t, y):
+        return y[0] - 1.0 if t < 3 else y[0] + 1.0
+
+    def ev1(t, y, p):
+        if p[0] > 1.0 or y[1] < 0:
+            return y[1] * p[0]
+        return y[1] - p[0]
+
+    ev0.terminal = True
+    ev1.direction = -1
+    ev = rhs.trace_events([ev0, ev1], 2, (1,), True)
+    assert ev.terminal == [True, False] and ev.direction == [0, -1] and ev.n_events == 2
+    lib = _host_build(tmp_path, ev.source, "events")
+    dp = C.POINTER(C.c_double)
+    lib.nbk_event.restype = C.c_double
+    lib.nbk_event.argtypes = [C.c_int, C.c_double, dp, dp]
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        t, y, p = float(rng.uniform(0, 6)), rng.uniform(-2, 2, 2), rng.uniform(0.2, 2, 1)
+        assert lib.nbk_event(0, t, y.ctypes.data_as(dp), p.ctypes.data_as(dp)) == ev0(t, y)
+        assert lib.nbk_event(1, t, y.ctypes.data_as(dp), p.ctypes.data_as(dp)) == ev1(t, y, p)
+
+
+# ------------------------------------------------------------------ component-wise form (CTA / sub-warp regimes)
+def switched_diffusion(t, y, p):
+    d = p[0] if t < 1.0 else 2 * p[0]
+    out = d * (np.roll(y, -1) - 2 * y + np.roll(y, 1))
+    if p[1] > 0 and t >= 0.5:
+        out = out + p[1] * y * (1 - y)
+    if y[0] > y[-1]:           # one element against another: a per-trajectory decision
+        out = out - 0.25 * y
+    return np.where(t < 0.1, out, np.maximum(out, -1.0))
+
+
+def test_branching_vector_rhs_host_compiled_source_equals_python(tmp_path):
+    n = 48
+    src = rhs.trace_cta(switched_diffusion, n, (2,), True).source
+    assert "nbk_rhs_i" in src and "?" in src
+    lib = _host_build(tmp_path, src, "vec")
+    dp = C.POINTER(C.c_double)
+    lib.nbk_rhs_i.restype = C.c_double
+    lib.nbk_rhs_i.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int]
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        t = float(rng.uniform(0, 1.5))
+        y = rng.uniform(0, 1, n)
+        p = np.array([rng.uniform(0.5, 2), rng.uniform(-1, 1)])
+        want = switched_diffusion(t, y, p)
+        got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, n) for i in range(n)])
+        assert np.array_equal(got, want)
+    # captured constant arrays are emitted once, however many paths capture them
+    grid = np.linspace(0, 1, n)
+    src = rhs.trace_cta(lambda t, y: (grid * y if t < 1 else (grid * y) * -1.0), n, (), False).source
+    assert src.count("nbk_tab") == 3 and "nbk_tab1" not in src  # one definition + one use per path
+    sz = C.c_longlong(0)
+    cfg = _lib.NbkConfig(45, n, 2, 0, 16, None, rhs.trace_cta(switched_diffusion, n, (2,), True).source.encode(),
+                         1e-6, 1e-9, 0.2, 10.0, 0.9, 0, 0)
+    _lib.check(_lib.lib().nbk_jit_compile_only(C.byref(cfg), C.byref(sz)))
+    assert sz.value > 10_000
+
+
+def test_resolve_prefers_selects_for_elementwise_branches():
+    relu = lambda t, y, p: np.where(y > 0, -y, p[0] * y)  # noqa: E731
+    # 2 ** 6 paths per thread: within the bound, but the whole-vector tracer says the same with one select
+    name, src = rhs.resolve(relu, 6, (1,), True)
+    assert name is None and "nbk_rhs_i" in src and src.count("?") == 1
+    # a solver class without the component-wise regimes still gets the branching per-thread form
+    name, src = rhs.resolve(relu, 3, (1,), True, "auto", False)
+    assert "nbk_rhs(" in src and "if (" in src
+    # scalar branches stay per thread for small systems
+    name, src = rhs.resolve(friction, 2, (2,), True)
+    assert "nbk_rhs(" in src and "if (" in src
