@@ -955,7 +955,7 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
 # RungeKutta45, 1 M decay trajectories: n = 16: 7.9 vs 11.4 ms, n = 24: 28 vs 11.8 ms, n = 32: 73 vs 11.8 ms,
 # n = 64: 202 vs 22.5 ms, per-thread vs CTA).
 CTA_AUTO_N = 16
-SELECT_OVER_PATHS = 8  # a per-thread trace with more control-flow paths than this tries the select form first
+SELECT_OVER_PATHS = 32  # a per-thread trace with more control-flow paths than this tries the select form first
 GROUP_AUTO_N = 10
 # largest n a traced callable still runs per thread, by method id (tools/bench_group.py, tools/bench_team_decay.py: the
 # component-wise form then runs as sub-warp groups / teams, csrc/nbk_group.cuh, nbk_cta.cuh)

@@ -728,8 +728,8 @@ def rhs_pwl(t, y, p):
 
 
 def ev_switch(t, y):
-    """An event function with a branch: the level it watches moves at t = 3."""
-    if t < 3.0:
+    """An event function with a branch: the level it watches moves at t = 0.9."""
+    if t < 0.9:
         return y[0] - 0.5
     return y[0] + 0.25
 

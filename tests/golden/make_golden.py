@@ -242,13 +242,21 @@ def implicit_section():
 def branching_section():
     """Right-hand sides and event functions with run-time branches (`if` on the state and the time, Python's
     min / max): the reference compiles them as they are; nbkode_b200 explores their control-flow paths
-    (tests/test_trace_branches.py).  Single trajectories of the live reference."""
+    (tests/test_trace_branches.py).  Single trajectories of the live reference.
+
+    Horizons: a kink of the right-hand side makes the error estimate of the step that crosses it depend on where
+    the step starts, so an adaptive step sequence amplifies a last-bit difference by about 10 x per crossing (the
+    NumPy restatement with the right-hand side scaled by 1 + 2.3e-16 leaves the golden run by 80 x the tolerance at
+    t = 10, with the same number of accepted steps).  The adaptive cases therefore end at t = 1.2 (two crossings:
+    the spring's stop and the damper's saturation), where one ulp moves the result by 0.005 of the tolerance; the
+    fixed-step cases, which have no controller to amplify anything, run to t = 12 through some twenty crossings."""
     pw = ([1.6, -0.4], [2.0, 0.8, 0.7])
+    short = np.linspace(0.1, 1.2, 12)
     adaptive = [
-        adaptive_case("RungeKutta45", "pwl", *pw, np.linspace(0.5, 12, 24), rtol=1e-6, atol=1e-9),
-        adaptive_case("RungeKutta23", "pwl", *pw, np.linspace(0.5, 12, 24), rtol=1e-6, atol=1e-9),
-        adaptive_case("DOP853", "pwl", *pw, [3.0, 6.0, 12.0], rtol=1e-6, atol=1e-9),
-        adaptive_case("RungeKutta45", "pwl", [0.2, 0.1], [1.0, 0.5, 2.5], [4.0, 8.0], rtol=1e-8, atol=1e-10),
+        adaptive_case("RungeKutta45", "pwl", *pw, short, rtol=1e-6, atol=1e-9),
+        adaptive_case("RungeKutta23", "pwl", *pw, short, rtol=1e-6, atol=1e-9),
+        adaptive_case("DOP853", "pwl", *pw, [0.4, 0.8, 1.2], rtol=1e-4, atol=1e-7),  # (at 1e-6 one ulp already moves it by 1.1 x the bar)
+        adaptive_case("RungeKutta45", "pwl", [0.9, 0.6], [1.0, 0.5, 2.5], [0.5, 1.0], rtol=1e-5, atol=1e-8),
     ]
     fixed = [
         fixed_case("RungeKutta4", "pwl", *pw, np.linspace(0.5, 12, 24), 0.01),
@@ -256,16 +264,15 @@ def branching_section():
         fixed_case("ForwardEuler", "pwl", *pw, [1.0, 2.0], 0.001),
     ]
     events = []
-    for cls, kw in (("RungeKutta45", dict(rtol=1e-6, atol=1e-9)), ("RungeKutta23", dict(rtol=1e-6, atol=1e-9)),
-                    ("RungeKutta4", dict(h=0.01))):
-        ts = np.linspace(0.5, 12, 24)
+    for cls, kw, ts in (("RungeKutta45", dict(rtol=1e-6, atol=1e-9), short), ("RungeKutta23", dict(rtol=1e-6, atol=1e-9), short),
+                        ("RungeKutta4", dict(h=0.01), np.linspace(0.5, 12, 24))):
         s = getattr(nbkode, cls)(onp.RHS["pwl"], 0.0, np.array(pw[0]), params=np.array(pw[1]), **kw)
-        t, y, te, ye = s.run_events(ts, [onp.EVENTS["switch"], onp.EVENTS["y1_down"]])
+        t, y, te, ye = s.run_events(ts, [onp.EVENTS["switch"], onp.EVENTS["y0"]])
         alias = [[bool(getattr(x, "base", None) is not None) for x in lst] for lst in ye]
         events.append({"cls": cls, "rhs": "pwl", "y0": L(pw[0]), "p": L(pw[1]), "kw": kw, "ts": L(ts),
-                       "events": ["switch", "y1_down"], "t": L(t), "y": L(y), "t_events": [L(x) for x in te],
+                       "events": ["switch", "y0"], "t": L(t), "y": L(y), "t_events": [L(x) for x in te],
                        "y_events": [L(x) for x in ye], "y_events_aliased": alias, "t_end": float(s.t)})
-        assert len(te[0]) >= 2 and len(te[1]) >= 2
+        assert len(te[0]) >= 2 and len(te[1]) >= 1, [len(x) for x in te]
     dump("branching.json", {"adaptive": adaptive, "fixed": fixed, "events": events})
 
 

@@ -262,6 +262,13 @@ def test_nvrtc_compiles_event_programs_and_traces_events():
     for method, n in ((45, 2048), (45, 24), (853, 40), (853, 300), (23, 200)):
         _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(method, n, 2, rhs_name=b"rd1d")), 3, ev.source.encode(), C.byref(sz)))
         assert sz.value > 10_000
+    # ... also when the right-hand side is user code too (it pulls the kernel header in ahead of the events source)
+    rd = lambda t, y, p: p[0] * (np.roll(y, -1) - 2 * y + np.roll(y, 1)) + p[1] * y * (1 - y)  # noqa: E731
+    ev2 = rhs.trace_events([lambda t, y: y[0] - 0.5, lambda t, y, p: (y[3] - p[1] if t < 1 else y[3])], 24, (2,), True)
+    for method, n in ((45, 24), (853, 40), (23, 300)):
+        cfg = _cfg(method, n, 2, src=rhs.trace_cta(rd, n, (2,), True).source.encode())
+        _lib.check(lib.nbk_jit_compile_events_only(C.byref(cfg), 2, ev2.source.encode(), C.byref(sz)))
+        assert sz.value > 10_000
     with pytest.raises(ValueError):  # ... the fixed-step classes only per thread
         _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(4, 200, 2, rhs_name=b"rd1d")), 1, ev.source.encode(), C.byref(sz)))
     # a branching event function is a run-time branch of nbk_event (tests/test_trace_branches.py)
