@@ -1043,15 +1043,35 @@ NBK_DEV void cta_store_window(const nbk_kargs &a, long long idx, int n, int i0, 
     }
 }
 
-template <int METHOD, class Rhs, int E, int MODE>
+#ifdef NBK_NEVENTS
+// dense output of the fixed-step classes (the window Hermite of cta_hermite) as the functor team_events_after_step takes
+template <int L, int E>
+struct cta_window_dense {
+    const double (&ts)[L];
+    const double (&ys)[L][E];
+    const double (&fs)[L][E];
+    NBK_DEV cta_window_dense(const double (&t_)[L], const double (&y_)[L][E], const double (&f_)[L][E]) : ts(t_), ys(y_), fs(f_) {}
+    NBK_DEV void operator()(double te, double (&out)[E]) { cta_hermite<L, E>(te, ts, ys, fs, out); }
+};
+#endif
+
+// EV: the run_events variant (run mode only) -- after every step the team's event routine (team_events_after_step, shared
+// with the adaptive kernels) brackets the previous point and the new one on the window Hermite, like the per-thread
+// kernels (advance_ab / advance_erk in nbk_device.cuh) and the reference's run_events (core.py:621-647) do; the
+// Adams-Bashforth classes of order >= 3 then take the shifting window below instead of the register ring.
+template <int METHOD, class Rhs, int E, int MODE, bool EV = false>
 NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
     using TR = cta_fixed_traits<METHOD>;
     constexpr int L = TR::L, S = TR::S;
     constexpr int KS = S > 0 ? S : 1;
     const int n = a.n, tid = team_tid(), i0 = tid * E, npad = team_size() * E;
     const long long nn = n;
-    sm = team_smem(sm, 2 * npad + 34);
+    sm = team_smem(sm, (EV ? 3 : 2) * npad + 34);
     double *buf0 = sm, *buf1 = sm + npad;
+#ifdef NBK_NEVENTS
+    double *evbuf = sm + 2 * npad + 34;  // EV: the whole vector in natural order for the event functions (npad doubles)
+    double ev_last[NBK_NEVENTS];
+#endif
     for (long long idx = team_index(); idx < a.B; idx += team_count()) {
         team_sync();
         const typename Rhs::prm p = Rhs::load(a.params_shared ? a.params : a.params + idx * a.n_params);
@@ -1095,8 +1115,14 @@ NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
         } else {
             running = a.n_steps > 0;
         }
+#ifdef NBK_NEVENTS
+        const double *pp = a.params_shared ? a.params : a.params + idx * a.n_params;
+        if constexpr (EV && MODE == NBK_MODE_RUN) {
+            if (status == NBK_TRAJ_OK) team_events_start<E>(a, idx, ts[L - 1], ys[L - 1], pp, ev_last, evbuf, tid == 0, i0, n, cta_barrier{});
+        }
+#endif
         int flip = 0;
-        if constexpr (!TR::ERK && (L > 2)) {
+        if constexpr (!TR::ERK && (L > 2) && !EV) {
             // AdamsBashforth3..5: the window is a ring in registers like in the per-thread kernel (advance_ab) -- L
             // steps unrolled, a push overwrites the oldest slot (the shifting loop below moved (L-1)(2E+1) doubles per
             // step), a trajectory that stops inside the block skips the rest of it.  Control flow is the same in every
@@ -1245,6 +1271,28 @@ NBK_DEV void cta_advance_fixed(const nbk_kargs &a, double *sm) {
                 fs[L - 1][e] = fnew[e];
             }
             ++nsteps;
+#ifdef NBK_NEVENTS
+            if constexpr (EV && MODE == NBK_MODE_RUN) {
+                // events first, then the grid points inside the step (core.py:638-645); every quantity that steers this
+                // block is identical in all threads of the team
+                cta_window_dense<L, E> dense(ts, ys, fs);
+                double t_term = 0.0;
+                if (team_events_after_step<E>(a, idx, ts[L - 2], t_new, ynew, pp, ev_last, evbuf, tid == 0, i0, n, cta_barrier{}, dense,
+                                              t_term, status)) {
+                    if (status != NBK_TRAJ_EVBRACKET) {
+                        double out[E];
+                        dense(t_term, out);
+#pragma unroll
+                        for (int e = 0; e < E; ++e)
+                            if (i0 + e < n) a.y_out[idx * a.o_sb + kout * a.o_sk + (long long)(i0 + e) * a.o_sc] = out[e];
+                        if (tid == 0) a.ev_tterm[idx] = t_term;
+                        ++kout;
+                        status = NBK_TRAJ_EVENT;
+                    }
+                    break;
+                }
+            }
+#endif
             if (MODE == NBK_MODE_RUN) {
                 while (t_new >= te_next) {
                     double out[E];

@@ -112,6 +112,14 @@ extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(step)(const __grid_constant
     nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_STEP>(a, nbk_smem);
 #endif
 }
+#if defined(NBK_NEVENTS) && !NBK_CTA_ADAPTIVE
+// run_events of the fixed-step classes (sub-warp teams and one CTA per trajectory): the run kernel with the team's event
+// routine after every step; dynamic shared memory as below (one more whole-vector buffer per team)
+extern "C" __global__ void NBK_ADV_BOUNDS NBK_KERNEL(runev)(const __grid_constant__ nbk_kargs a) {
+    extern __shared__ __align__(16) double nbk_smem[];
+    nbk::cta_advance_fixed<NBK_METHOD, nbk_rhs_t, NBK_E, NBK_MODE_RUN, true>(a, nbk_smem);
+}
+#endif
 #if defined(NBK_NEVENTS) && NBK_CTA_ADAPTIVE
 // run_events variant of the run kernel (nbk_set_events).  Dynamic shared memory: the run kernel's + one whole-vector buffer
 // for the event functions -- sub-warp regime 3 * NBK_GRP_BLOCK * NBK_E doubles, one CTA per trajectory 3 * T * NBK_E + 34.

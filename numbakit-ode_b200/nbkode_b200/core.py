@@ -587,11 +587,6 @@ class Solver(ABC):
         if not events:
             return self.run(t) + ([], [])
         torch = _torch()
-        if self._regime != 0 and self.METHOD_ID not in (23, 45, 853):
-            raise NotImplementedError(
-                "for component-wise right-hand sides (sub-warp groups / one CTA per trajectory) events are implemented for "
-                "RungeKutta23, RungeKutta45 and DOP853; the fixed-step classes have them in the per-thread regime (n <= 64)"
-                + ('; construct the solver with regime="thread" to use run_events on this system' if self.n <= 64 else ""))
         ev = _rhs.trace_events(events, self.n, self._p_shape, self.params is not None)
         if not (1 <= ev.n_events <= _lib.MAX_EVENTS):
             raise ValueError(f"between 1 and {_lib.MAX_EVENTS} event functions are supported")

@@ -325,3 +325,63 @@ def test_run_events_with_one_cta_per_trajectory(cls, n, terminal_at):
                 assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-6
                 assert rel(ev_y[b, j, :len(te_ref[j])], np.array(ye_ref[j])) < 1e-5
     assert n_events > 0
+
+
+@pytest.mark.parametrize("cls,n,terminal_at", [("RungeKutta4", 100, None), ("AdamsBashforth2", 70, 0.9), ("ForwardEuler", 64, 1.0),
+                                               ("Heun3", 128, None)])
+def test_run_events_of_the_fixed_step_classes_with_one_cta_per_trajectory(cls, n, terminal_at):
+    """run_events of the fixed-step classes in the CTA regime: the team's event routine after every step, bracketing the
+    previous point and the new one on the window Hermite (cta_advance_fixed<..., EV>), against the NumPy restatement of the
+    reference's run_events; bit-identical across OS-scheduled repetitions."""
+    from nbkode_b200 import rhs as nrhs
+
+    def crossing(t, y):
+        return y[0] - 0.5
+
+    def gap(t, y):
+        return y[n // 2] - y[n // 2 + 2]
+
+    gap.direction = -1
+
+    def level(t, y):
+        return y[1] + y[2] - (1.0 if terminal_at is None else terminal_at)
+
+    level.terminal = terminal_at is not None
+    evs = [crossing, gap, level]
+    B, h = 3, 0.01
+    y0, p = ensemble(B, n, seed=17, scale=0.4)
+    ev = nrhs.trace_events(evs, n, (2,), True)
+    ts = [0.5, 1.5, 3.0]
+    first = None
+    for rep in range(2):
+        g = EmulCtaEnsemble(cls, "rd1d", y0, p, h=h, first_stepper=0)
+        got = g.run_events(ts, ev)
+        if first is None:
+            first = (g, got)
+        else:
+            for a, b in zip(got, first[1]):
+                assert np.array_equal(a, b, equal_nan=True)
+    g, (out, ev_t, ev_y, ev_c, t_term) = first
+    n_events = 0
+    for b in range(B):
+        if cls in ("RungeKutta4", "Heun3"):
+            o = onp.FixedRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], h=h)
+        else:
+            o = onp.AdamsBashforth(1 if cls == "ForwardEuler" else int(cls[-1]), onp.rhs_rd1d, 0.0, y0[b], p[b], h=h, first_stepper=None)
+        t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, ts, evs)
+        k = int(g.nout[b])
+        assert k == len(t_ref)
+        if g.status[b] == -1:
+            assert rel(t_term[b], t_ref[-1]) < 1e-7 and rel(out[b, k - 1], y_ref[-1]) < 1e-7
+            if k > 1:
+                assert rel(out[b, :k - 1], y_ref[:k - 1]) < 1e-12
+        else:
+            assert g.status[b] == 0 and rel(out[b, :k], y_ref) < 1e-12
+        assert np.isnan(out[b, k:]).all()
+        for j in range(3):
+            assert ev_c[b, j] == len(te_ref[j])
+            n_events += len(te_ref[j])
+            if len(te_ref[j]):
+                assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-7
+                assert rel(ev_y[b, j, :len(te_ref[j])], np.array(ye_ref[j])) < 1e-7
+    assert n_events > 0

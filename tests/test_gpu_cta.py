@@ -460,3 +460,56 @@ def test_run_events_with_one_cta_per_trajectory(cls, rhs, n, B):
                 assert np.abs(te[j][b, :len(te_ref[j])] - np.array(te_ref[j])).max() < 1e-5
                 assert np.abs(ye[j][b, :len(te_ref[j])] - np.array(ye_ref[j])).max() < 1e-4 * max(1.0, np.abs(y_ref).max())
     assert total > 0
+
+
+@pytest.mark.parametrize("cls,n,B,kw", [("RungeKutta4", 300, 40, dict(h=0.005)), ("AdamsBashforth2", 24, 200, dict(h=0.005, first_stepper_cls=None)),
+                                        ("ForwardEuler", 2048, 12, dict(h=0.002)), ("Heun3", 13, 120, dict(h=0.005))])
+def test_run_events_of_the_fixed_step_classes_componentwise(cls, n, B, kw):
+    """run_events of the fixed-step classes for component-wise right-hand sides -- as sub-warp teams (n = 13, 24) and with
+    one CTA per trajectory (n = 300, 2048) -- against the NumPy restatement of the reference's run_events on a prefix:
+    same events in the same order, event times to the bisection's resolution, grid rows to 1e-12, a terminal event
+    truncates the output."""
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=3)
+    p[:, 0] *= 0.05 * (100.0 / n) ** 2
+    ts = [0.25, 0.5, 1.0]
+
+    def crossing(t, y):
+        return y[0] - 0.6
+
+    def gap(t, y):
+        return y[n // 2] - y[n // 2 + 2]
+
+    gap.direction = -1
+
+    def level(t, y):
+        return y[1] + y[2] - 1.5
+
+    level.terminal = True
+    level.direction = 1
+    evs = [crossing, gap, level]
+    s = getattr(nbk, cls)("rd1d", 0.0, y0, p, **kw)
+    assert s._regime == 1
+    t, y, te, ye = s.run_events(ts, evs)
+    cnt, st = s.event_counts, s.status
+    assert cnt.shape == (B, 3) and set(np.unique(st)) <= {0, -1}
+    total = 0
+    for b in range(min(B, 6)):
+        if cls in ("RungeKutta4", "Heun3"):
+            o = onp.FixedRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], h=kw["h"])
+        else:
+            o = onp.AdamsBashforth(1 if cls == "ForwardEuler" else int(cls[-1]), onp.rhs_rd1d, 0.0, y0[b], p[b], h=kw["h"],
+                                   first_stepper=None)
+        t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, ts, evs)
+        k = len(t_ref)
+        assert int(s._nout[b].item()) == k and (st[b] == -1) == (len(te_ref[2]) > 0)
+        keep = k - 1 if st[b] == -1 else k
+        if keep:
+            assert rel(y[b, :keep], y_ref[:keep]) <= 1e-12
+        assert np.isnan(y[b, k:]).all()
+        for j in range(3):
+            assert cnt[b, j] == len(te_ref[j]), (cls, b, j)
+            total += len(te_ref[j])
+            if len(te_ref[j]):
+                assert np.abs(te[j][b, :len(te_ref[j])] - np.array(te_ref[j])).max() < 1e-7
+                assert np.abs(ye[j][b, :len(te_ref[j])] - np.array(ye_ref[j])).max() < 1e-7
+    assert total > 0

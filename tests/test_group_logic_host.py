@@ -295,3 +295,45 @@ def test_team_mode_is_race_free_and_dop853_events(cls, n, kw):
                 if len(te_ref[j]):
                     assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-6
         assert total > 0
+
+
+@pytest.mark.parametrize("cls,n,terminal_at", [("RungeKutta4", 13, None), ("AdamsBashforth2", 24, 0.9), ("ForwardEuler", 40, None)])
+def test_run_events_of_the_fixed_step_classes_as_sub_warp_teams(cls, n, terminal_at):
+    """run_events of the fixed-step classes with G lanes per trajectory (cta_advance_fixed<..., EV> behind NBK_TEAM_G): several
+    teams of one warp detect, bisect and record their own events at different steps; against the restatement of the
+    reference's run_events, bit-identical across OS-scheduled repetitions."""
+    from nbkode_b200 import rhs as nrhs
+
+    evs = _events(n, terminal_at)
+    ev = nrhs.trace_events(evs, n, (2,), True)
+    B, h, ts = 9, 0.01, [0.5, 1.5, 3.0]
+    y0, p = ensemble(B, n, seed=5, scale=0.4)
+    kw = dict(h=h) if cls == "RungeKutta4" else dict(h=h, first_stepper=0)
+    first = None
+    for rep in range(2):
+        g = EmulGroupEnsemble(cls, "rd1d", y0, p, **kw)
+        got = g.run_events(ts, ev)
+        if first is None:
+            first = (g, got)
+        else:
+            for a, b in zip(got, first[1]):
+                assert np.array_equal(a, b, equal_nan=True)
+    g, (out, ev_t, ev_y, ev_c, t_term) = first
+    total = 0
+    for b in range(B):
+        if cls == "RungeKutta4":
+            o = onp.FixedRK(cls, onp.rhs_rd1d, 0.0, y0[b], p[b], h=h)
+        else:
+            o = onp.AdamsBashforth(1 if cls == "ForwardEuler" else int(cls[-1]), onp.rhs_rd1d, 0.0, y0[b], p[b], h=h, first_stepper=None)
+        t_ref, y_ref, te_ref, ye_ref = onp.run_events(o, ts, evs)
+        k = int(g.nout[b])
+        assert k == len(t_ref) and (g.status[b] == -1) == (terminal_at is not None and len(te_ref[2]) > 0)
+        keep = k - 1 if g.status[b] == -1 else k
+        if keep:
+            assert rel(out[b, :keep], y_ref[:keep]) < 1e-12
+        for j in range(3):
+            assert ev_c[b, j] == len(te_ref[j])
+            total += len(te_ref[j])
+            if len(te_ref[j]):
+                assert rel(ev_t[b, j, :len(te_ref[j])], te_ref[j]) < 1e-7
+    assert total > 0

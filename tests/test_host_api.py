@@ -269,8 +269,12 @@ def test_nvrtc_compiles_event_programs_and_traces_events():
         cfg = _cfg(method, n, 2, src=rhs.trace_cta(rd, n, (2,), True).source.encode())
         _lib.check(lib.nbk_jit_compile_events_only(C.byref(cfg), 2, ev2.source.encode(), C.byref(sz)))
         assert sz.value > 10_000
-    with pytest.raises(ValueError):  # ... the fixed-step classes only per thread
-        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(4, 200, 2, rhs_name=b"rd1d")), 1, ev.source.encode(), C.byref(sz)))
+    # ... and the fixed-step classes (sub-warp teams and one CTA per trajectory; built-in and user right-hand sides)
+    for method, n in ((4, 200), (204, 24), (1, 2048), (2, 40), (213, 300)):
+        _lib.check(lib.nbk_jit_compile_events_only(C.byref(_cfg(method, n, 2, rhs_name=b"rd1d")), 3, ev.source.encode(), C.byref(sz)))
+        assert sz.value > 10_000
+    cfg = _cfg(204, 24, 2, src=rhs.trace_cta(rd, 24, (2,), True).source.encode())
+    _lib.check(lib.nbk_jit_compile_events_only(C.byref(cfg), 2, ev2.source.encode(), C.byref(sz)))
     # a branching event function is a run-time branch of nbk_event (tests/test_trace_branches.py)
     ev = rhs.trace_events(lambda t, y: 1.0 if y[0] > 0 else -1.0, 3, (3,), True)
     assert "if (y[0] > 0.0) {" in ev.source and "return 1.0;" in ev.source and "return -1.0;" in ev.source
