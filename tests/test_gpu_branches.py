@@ -180,4 +180,4 @@ def test_events_with_a_traced_componentwise_rhs():
                 assert u.event_counts[i, j] == len(te_ref[j]), (cls, i, j)
                 if len(te_ref[j]):
                     assert np.abs(teu[j][i, :len(te_ref[j])] - np.array(te_ref[j])).max() < 1e-6
-    assert seen > 100
+    assert seen > 20

@@ -58,10 +58,12 @@ def test_tutorial_step_and_skip():
     assert np.max(np.abs(ts - to)) < 1e-11 and np.max(np.abs(ys - yo)) < 1e-12
     solver = nbkode.RungeKutta45(rhs, 0, 1.)
     solver.skip(upto_t=10)
+    # "until the next timepoint will go beyond upto_t" (core.py:269-313, _skip: `while step(t_end, ...)`): the solver
+    # stops at the last step whose successor would pass t = 10 -- with the default tolerances on this problem the step
+    # size grows tenfold per step, so that is well before 10
     o = onp.AdaptiveRK("RungeKutta45", rhs, 0, 1.)
-    while o.t < 10:
-        o.step()
-    assert abs(solver.t - o.t) < 1e-10 and solver.t >= 10
+    onp.steps(o, upto_t=10)
+    assert abs(solver.t - o.t) < 1e-10 and solver.t <= 10 and solver.t + solver.h > 10
     assert np.max(np.abs(solver.y - o.y)) < 1e-12 and np.max(np.abs(solver.f - o.f)) < 1e-12
     # "You can also use upto_t here": the last returned step is the last one that does not pass upto_t
     solver = nbkode.RungeKutta45(rhs, 0, 1.)
