@@ -214,7 +214,7 @@ def cta_shape(mid, rhs, n):
     if n > 2048:
         e = (n + 255) // 256
     elif mid == 853:
-        e = 1 if n <= 512 else 2
+        e = 1 if n <= 512 else (2 if n <= 1024 else 4)
     elif rhs == "linear":
         e = 1 if n <= 512 else (2 if n <= 1024 else 4)
     else:

@@ -40,6 +40,7 @@ def test_shape_rule_matches_the_launcher():
     assert cta_shape(45, "rd1d", 2048) == (4, 512, 1)
     assert cta_shape(4, "rd1d", 2048) == (4, 512, 0)      # fixed step: the any-n program
     assert cta_shape(853, "rd1d", 512) == (1, 512, 1) and cta_shape(853, "rd1d", 700) == (2, 352, 0)
+    assert cta_shape(853, "rd1d", 2048) == (4, 512, 1) and cta_shape(853, "rd1d", 1100) == (4, 288, 0)
     assert cta_shape(45, "linear", 128) == (1, 128, 1)
     assert cta_shape(45, "rd1d", 3000) == (12, 256, 0)
 
@@ -204,10 +205,12 @@ def test_dmma_tile_kernel_k4_on_the_host():
         assert runs[0][4][b] == o.n_accepted and rel(runs[0][2][b], o.y) < 1e-7 and rel(runs[0][3][b], o.h) < 1e-6  # summation order of A.y
 
 
-@pytest.mark.parametrize("cls,n", [("RungeKutta45", 130), ("RungeKutta45", 300), ("RungeKutta23", 2100), ("AdamsBashforth3", 300)])
+@pytest.mark.parametrize("cls,n", [("RungeKutta45", 130), ("RungeKutta45", 300), ("RungeKutta23", 2100), ("AdamsBashforth3", 300),
+                                   ("DOP853", 1100), ("DOP853", 2100)])
 def test_more_cta_shapes_on_the_host(cls, n):
     """Further shapes: four components per thread with a ragged last thread (n = 130, 300), the large-n shape
-    (n = 2100: nine components per thread, 256 threads), against the NumPy restatement and repeated for determinism."""
+    (n = 2100: nine components per thread, 256 threads), DOP853 beyond n = 1024 (four components per thread, and the
+    large-n shape), against the NumPy restatement and repeated for determinism."""
     B = 2
     y0, p = ensemble(B, n, seed=13)
     kw = dict(h=0.01) if cls.startswith("Adams") else dict(rtol=1e-6, atol=1e-9)

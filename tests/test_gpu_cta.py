@@ -284,12 +284,36 @@ def test_fixed_step_cta_api_linear_and_traced_python():
     a = nbk.RungeKutta4(rd, 0.0, y0, p, h=1e-3)
     b = nbk.RungeKutta4("rd1d", 0.0, y0, p, h=1e-3)
     assert rel(a.run([0.02])[1], b.run([0.02])[1]) <= 1e-11
-    # the implicit families are per-thread only, DOP853 stops at n = 1024: clear errors
+    # the implicit families are per-thread only: a clear error
     with pytest.raises(ValueError, match="per-thread"):
         nbk.BDF2("rd1d", 0.0, y0, p, h=1e-3)
-    y0b, pb = onp.rd1d_ensemble(2, n=2048, seed=2)
-    with pytest.raises(ValueError, match="1024"):
-        nbk.DOP853("rd1d", 0.0, y0b, pb)
+
+
+@pytest.mark.parametrize("n,B", [(1500, 12), (2048, 10), (3000, 6)])
+def test_dop853_beyond_1024_components(n, B):
+    """DOP853 with one CTA per trajectory beyond n = 1024: four components per thread up to 2048 (the stage vectors then
+    spill past the register file), the 256-thread shape above -- against the C port: within the tolerance, accepted steps
+    within +-1; run_events on the same systems."""
+    y0, p = onp.rd1d_ensemble(B, n=n, seed=2)
+    p[:, 0] *= 0.05 * (100.0 / n) ** 2  # a non-stiff grid: rounding differences stay at rounding level
+    ts = [1.0, 3.0, 6.0]
+    kw = dict(rtol=1e-8, atol=1e-11)   # 7 to 14 accepted steps per trajectory
+    ref = oc.run_ensemble("DOP853", "rd1d", y0, p, ts, nthreads=8, **kw)
+    s = nbk.DOP853("rd1d", 0.0, y0, p, **kw)
+    assert s._regime == 1 and s._group == 0
+    t, y = s.run(ts)
+    assert np.all(np.abs(np.asarray(s.n_accepted) - ref["n_accepted"]) <= 1)
+    parity_bar(f"dop853_large/n{n}/gpu_vs_c_port", y, ref["ys"], 1e-8, 1e-11, 1.0)
+
+    def level(t, yv):
+        return yv[n // 3] - 0.7
+
+    s2 = nbk.DOP853("rd1d", 0.0, y0, p, **kw)
+    t2, y2, te, ye = s2.run_events(ts, [level])
+    assert np.array_equal(y2, y)  # a non-terminal event does not change the trajectory
+    cnt = s2.event_counts
+    for b in np.nonzero(cnt[:, 0] > 0)[0][:4]:
+        assert abs(ye[0][b, 0, n // 3] - 0.7) < 1e-7
 
 
 def test_auto_regime_for_mid_size_traced_systems():
