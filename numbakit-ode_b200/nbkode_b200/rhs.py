@@ -68,6 +68,15 @@ _UNARY = {
 }
 
 
+_BINARY = {"arctan2": "atan2", "hypot": "hypot", "fmod": "fmod", "copysign": "copysign", "fmax": "fmax", "fmin": "fmin"}
+# math.<name> -> C function (the numba-style spelling of a scalar right-hand side: `from math import sin`)
+_MATH_UNARY = {"sin": "sin", "cos": "cos", "tan": "tan", "asin": "asin", "acos": "acos", "atan": "atan", "sinh": "sinh",
+               "cosh": "cosh", "tanh": "tanh", "asinh": "asinh", "acosh": "acosh", "atanh": "atanh", "exp": "exp",
+               "expm1": "expm1", "log10": "log10", "log2": "log2", "log1p": "log1p", "sqrt": "sqrt", "fabs": "fabs",
+               "erf": "erf", "erfc": "erfc", "cbrt": "cbrt", "exp2": "exp2"}
+_MATH_BINARY = {"atan2": "atan2", "hypot": "hypot", "pow": "pow", "fmod": "fmod", "copysign": "copysign"}
+
+
 def _lit(v) -> str:
     v = float(v)
     if math.isnan(v):
@@ -281,10 +290,155 @@ class Expr:
     __hash__ = None
 
     def __getattr__(self, item):
-        # NumPy's object-dtype ufunc loops call a method named like the ufunc (np.sin -> .sin())
+        # NumPy's object-dtype ufunc loops call a method named like the ufunc (np.sin -> .sin(), np.arctan2 -> .arctan2(b))
         if item in _UNARY:
             return lambda: self.tr.new(f"{_UNARY[item]}({self.name})")
+        if item in _BINARY:
+            return lambda other: self.tr.new(f"{_BINARY[item]}({self.name}, {Expr._c(other)})")
+        if item == "sign":
+            return lambda: self.tr.new(f"(({self.name}) > 0.0 ? 1.0 : (({self.name}) < 0.0 ? -1.0 : 0.0))")
         raise AttributeError(item)
+
+
+class _tracing:
+    """While a callable is traced: `math.sin(x)` & co. accept traced values (math's own functions insist on a real
+    float), and `np.zeros(n)` / `np.empty(n)` / `np.ones(n)` / `np.full(n, v)` return containers that can hold them --
+    the numba spelling of a right-hand side is
+
+        from math import sin
+        def rhs(t, y, p):
+            dy = np.empty(2)
+            dy[0] = y[1]
+            dy[1] = -p[0] * sin(y[0])
+            return dy
+
+    The wrappers replace the attributes of the `math` / `numpy` modules and the names the callable's module imported
+    from `math` for the duration of the trace (a few milliseconds, under a lock) and pass everything that is not a
+    traced value through to the originals.  ``vector``: the whole-vector tracer (containers are `Vec`s)."""
+
+    _lock = __import__("threading").RLock()
+
+    def __init__(self, funcs, vector=False):
+        self.funcs, self.vector, self.saved = [f for f in funcs if f is not None], vector, []
+
+    @staticmethod
+    def _traced(x):
+        return isinstance(x, (Expr, Cond, Sc, Vec)) or (isinstance(x, np.ndarray) and x.dtype == object)
+
+    def _math_wrappers(self):
+        out = {}
+        for name, cname in _MATH_UNARY.items():
+            orig = getattr(math, name, None)
+            if orig is None:
+                continue
+
+            def un(x, orig=orig, cname=cname):
+                if isinstance(x, Cond):
+                    x = x.as_expr()
+                if isinstance(x, Expr):
+                    return x.tr.new(f"{cname}({x.name})")
+                if isinstance(x, Sc):
+                    return Sc(f"{cname}({x.c})")
+                return orig(x)
+
+            out[name] = (orig, un)
+        for name, cname in _MATH_BINARY.items():
+            orig = getattr(math, name)
+
+            def bi(a, b, orig=orig, cname=cname):
+                tr = next((v.tr for v in (a, b) if isinstance(v, (Expr, Cond))), None)
+                if tr is not None:
+                    return tr.new(f"{cname}({Expr._c(a)}, {Expr._c(b)})")
+                if isinstance(a, Sc) or isinstance(b, Sc):
+                    return Sc(f"{cname}({_sc(a)}, {_sc(b)})")
+                return orig(a, b)
+
+            out[name] = (orig, bi)
+        orig_log = math.log
+
+        def log(x, *base):
+            if not any(isinstance(v, (Expr, Cond, Sc)) for v in (x, *base)):
+                return orig_log(x, *base)
+            if isinstance(x, (Expr, Cond)):
+                num = x.tr.new(f"log({Expr._c(x)})")
+            elif isinstance(x, Sc):
+                num = Sc(f"log({x.c})")
+            else:
+                num = orig_log(x)
+            return num / log(base[0]) if base else num
+
+        out["log"] = (orig_log, log)
+        return out
+
+    def _numpy_wrappers(self):
+        vector = self.vector
+
+        def container(fill):
+            def make(orig):
+                def f(shape, *args, **kw):
+                    dtype = kw.get("dtype", args[0] if args and fill != "full" else None)
+                    if fill == "full":
+                        value = args[0] if args else kw.get("fill_value")
+                        dtype = kw.get("dtype", args[1] if len(args) > 1 else None)
+                    floaty = dtype is None or dtype in (float, np.float64, "float64", "f8", "d")
+                    one_d = isinstance(shape, (int, np.integer)) or (isinstance(shape, tuple) and len(shape) == 1)
+                    if not floaty:
+                        return orig(shape, *args, **kw)
+                    if vector:
+                        if not one_d:
+                            return orig(shape, *args, **kw)
+                        length = int(shape if not isinstance(shape, tuple) else shape[0])
+                        code = _sc(value) if fill == "full" else ("1.0" if fill == "ones" else "0.0")
+                        return Vec(length, lambda j, code=code: code)
+                    arr = np.ndarray(shape, dtype=object)  # (np.ndarray: not one of the wrapped constructors)
+                    arr[...] = value if fill == "full" else (1.0 if fill == "ones" else 0.0)
+                    return arr
+                return f
+            return make
+
+        return {"zeros": container("zeros"), "empty": container("empty"), "ones": container("ones"), "full": container("full")}
+
+    def __enter__(self):
+        self._lock.acquire()
+        try:
+            wrappers = self._math_wrappers()
+            originals = {id(orig): fn for orig, fn in wrappers.values()}
+            for name, (orig, fn) in wrappers.items():
+                self.saved.append((math, name, orig, "attr"))
+                setattr(math, name, fn)
+            for name, make in self._numpy_wrappers().items():
+                orig = getattr(np, name)
+                self.saved.append((np, name, orig, "attr"))
+                setattr(np, name, make(orig))
+            # `from math import sin` / `from numpy import zeros` in the callable's module: rebind those names as well
+            np_originals = {id(orig): getattr(np, name) for mod, name, orig, _ in self.saved if mod is np}
+            seen = set()
+            for f in self.funcs:
+                g = getattr(f, "__globals__", None)
+                if g is None or id(g) in seen or g is globals():
+                    continue
+                seen.add(id(g))
+                for key, val in list(g.items()):
+                    repl = originals.get(id(val)) or np_originals.get(id(val))
+                    if repl is not None and callable(val):
+                        self.saved.append((g, key, val, "item"))
+                        g[key] = repl
+        except BaseException:
+            self.__exit__(None, None, None)
+            raise
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            for target, name, orig, kind in reversed(self.saved):
+                if kind == "attr":
+                    setattr(target, name, orig)
+                else:
+                    target[name] = orig
+            self.saved = []
+        finally:
+            self._lock.release()
+        return False
 
 
 def _symbolic_args(tr, n, params_shape, with_params):
@@ -340,7 +494,8 @@ def trace(func, n: int, params_shape, has_params: bool) -> CudaRHS:
             raise TraceError(f"right-hand side returned {out.size} values for a state of size {n}")
         return tr, [Expr._c(e) for e in out]  # (Cond outputs append their 1.0 / 0.0 statement here, before emission)
 
-    tree = _explore(run)
+    with _tracing([func]):
+        tree = _explore(run)
     lines = ["NBK_RHS nbk_rhs(double t, const double* y, const double* p, double* dy) {"]
     _emit_tree(tree, lambda payload: [f"dy[{i}] = {e};" for i, e in enumerate(payload[1])], lines)
     lines.append("}")
@@ -879,7 +1034,8 @@ def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
         return f"({node.cond} ? {select(node.true)} : {select(node.false)})"
 
     try:
-        body = select(_explore(run))
+        with _tracing([func], vector=True):
+            body = select(_explore(run))
         src = _TABLES.source()
     finally:
         _TABLES = None
@@ -941,7 +1097,8 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
                 raise TraceError("an event function must return one float")
             return tr, Expr._c(out[0])
 
-        tree = _explore(run, "event function")
+        with _tracing([ev]):
+            tree = _explore(run, "event function")
         lines.append(f"  if (k == {k}) {{")
         _emit_tree(tree, lambda payload: [f"return {payload[1]};"], lines)
         lines.append("  }")

@@ -13,10 +13,13 @@ a run-time branch.  The tracer re-runs the callable once per control-flow path a
 """
 
 import ctypes as C
+import math
 import subprocess
+from math import exp, sin  # noqa: F401  (the numba spelling: names imported from math, used by the callables below)
 
 import numpy as np
 import pytest
+from numpy import zeros
 
 from nbkode_b200 import _lib, rhs
 
@@ -169,11 +172,12 @@ def test_path_count_depth_and_determinism_are_checked():
     with pytest.raises(rhs.TraceError, match="not deterministic"):
         rhs.trace(flaky, 1, (), False)
 
-    # math.* needs a real float: refused with a pointer to numpy, not silently evaluated
-    import math
-
+    # float() of a traced value is refused, not silently evaluated (math.* functions are wrapped while tracing, see
+    # test_math_functions_and_float_containers; anything else that insists on a real float ends here)
     with pytest.raises(rhs.TraceError):
-        rhs.trace(lambda t, y: np.array([math.sin(y[0])]), 1, (), False)
+        rhs.trace(lambda t, y: np.array([float(y[0]) * 2.0]), 1, (), False)
+    with pytest.raises(rhs.TraceError):
+        rhs.trace(lambda t, y: np.array([math.floor(y[0])]), 1, (), False)
     with pytest.raises(TypeError):
         hash(rhs.trace.__globals__["Cond"](None, "(a < b)"))
 
@@ -273,3 +277,81 @@ def test_resolve_prefers_selects_for_elementwise_branches():
     # scalar branches stay per thread for small systems
     name, src = rhs.resolve(friction, 2, (2,), True)
     assert "nbk_rhs(" in src and "if (" in src
+
+
+# ------------------------------------------------------------------ the numba spelling of a right-hand side
+def pendulum(t, y, p):
+    dy = np.empty(2)                       # a float container, filled element by element
+    dy[0] = y[1]
+    dy[1] = -p[0] * sin(y[0]) - p[1] * y[1] + math.cos(t) * exp(-t / 10)
+    return dy
+
+
+def ring_loop(t, y, p):
+    n = len(y)
+    dy = zeros(n)                          # `from numpy import zeros`
+    for i in range(n):
+        left = y[i - 1] if i > 0 else y[n - 1]
+        right = y[i + 1] if i < n - 1 else y[0]
+        dy[i] = p[0] * (left - 2.0 * y[i] + right) + math.atan2(y[i], 1.0 + math.fabs(t)) + math.log(1.0 + y[i] * y[i], 2.0)
+    if math.hypot(y[0], y[1]) > 1.5:       # a branch on a math.* value
+        dy[0] = dy[0] - math.sqrt(y[0] * y[0] + 1.0)
+    return dy
+
+
+def assembled(t, y, p):
+    out = np.zeros(len(y))
+    out[1:-1] = p[0] * (y[2:] - 2 * y[1:-1] + y[:-2])
+    out[0] = -y[0] * math.exp(-t)
+    out[-1] = math.sin(t) - y[-1]
+    return out + np.full(len(y), 0.25) * p[1] + np.ones(len(y))
+
+
+def test_math_functions_and_float_containers(tmp_path):
+    """`from math import sin`, `math.cos(t)`, `np.empty(2)` / `zeros(n)` filled element by element, `np.zeros(n)` with
+    slice assembly in the whole-vector form: the way right-hand sides are written for numba.  While a callable is traced
+    the math functions accept traced values and the float constructors return containers that hold them
+    (rhs._tracing); afterwards every patched name is the original again -- also when tracing fails."""
+    for func, n, pshape in ((pendulum, 2, (2,)), (ring_loop, 5, (1,))):
+        src = rhs.trace(func, n, pshape, True).source
+        lib = _host_build(tmp_path, src, func.__name__)
+        rng = np.random.default_rng(4)
+        for _ in range(200):
+            t, y, p = float(rng.uniform(0, 3)), rng.uniform(-2, 2, n), rng.uniform(0.1, 2, pshape)
+            np.testing.assert_allclose(_call_rhs(lib, t, y, p), func(t, y, p), rtol=1e-14, atol=1e-16)
+    n = 40
+    src = rhs.trace_cta(assembled, n, (2,), True).source
+    lib = _host_build(tmp_path, src, "assembled")
+    dp = C.POINTER(C.c_double)
+    lib.nbk_rhs_i.restype = C.c_double
+    lib.nbk_rhs_i.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int]
+    rng = np.random.default_rng(6)
+    for _ in range(20):
+        t, y, p = float(rng.uniform(0, 3)), rng.uniform(-1, 1, n), rng.uniform(0.1, 2, 2)
+        got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, n) for i in range(n)])
+        np.testing.assert_allclose(got, assembled(t, y, p), rtol=1e-14, atol=1e-16)
+    # an event function in the same spelling
+    ev = rhs.trace_events([lambda t, y: sin(y[0]) - 0.5 * math.exp(-t)], 2, (), False)
+    assert "sin(y[0])" in ev.source and "exp(" in ev.source
+
+    def failing(t, y):
+        np.zeros(2)[0] = y[0]
+        raise RuntimeError("boom")
+
+    with pytest.raises(rhs.TraceError, match="boom"):
+        rhs.trace(failing, 2, (), False)
+    g = globals()
+    assert g["sin"] is math.sin and g["exp"] is math.exp and g["zeros"] is np.zeros
+    assert math.sin(0.5) == 0.479425538604203 and np.zeros(2).dtype == np.float64 and np.empty(3).dtype == np.float64
+    assert np.full(2, 1.5).dtype == np.float64 and math.log(8.0, 2.0) == 3.0 and math.atan2(1.0, 1.0) == math.pi / 4
+    # integer / explicit dtypes and non-traced arguments pass through while tracing
+    seen = {}
+
+    def probe(t, y):
+        seen["int"] = np.zeros(3, dtype=int).dtype
+        seen["sin"] = math.sin(0.5)
+        seen["two_d"] = np.zeros((2, 2)).shape
+        return -y
+
+    rhs.trace(probe, 2, (), False)
+    assert seen == {"int": np.dtype(int), "sin": math.sin(0.5), "two_d": (2, 2)}
