@@ -300,6 +300,13 @@ class Expr:
         raise AttributeError(item)
 
 
+def _python_function(func):
+    """A callable that numba already compiled (`@numba.njit def rhs(...)`; the reference accepts those and skips its own
+    njit, core.py:125-132) is traced through the Python function it wraps."""
+    inner = getattr(func, "py_func", None)
+    return inner if callable(inner) else func
+
+
 class _tracing:
     """While a callable is traced: `math.sin(x)` & co. accept traced values (math's own functions insist on a real
     float), and `np.zeros(n)` / `np.empty(n)` / `np.ones(n)` / `np.full(n, v)` return containers that can hold them --
@@ -319,7 +326,7 @@ class _tracing:
     _lock = __import__("threading").RLock()
 
     def __init__(self, funcs, vector=False):
-        self.funcs, self.vector, self.saved = [f for f in funcs if f is not None], vector, []
+        self.funcs, self.vector, self.saved = [_python_function(f) for f in funcs if f is not None], vector, []
 
     @staticmethod
     def _traced(x):
@@ -410,16 +417,31 @@ class _tracing:
                 orig = getattr(np, name)
                 self.saved.append((np, name, orig, "attr"))
                 setattr(np, name, make(orig))
-            # `from math import sin` / `from numpy import zeros` in the callable's module: rebind those names as well
-            np_originals = {id(orig): getattr(np, name) for mod, name, orig, _ in self.saved if mod is np}
-            seen = set()
-            for f in self.funcs:
-                g = getattr(f, "__globals__", None)
+            orig_norm = np.linalg.norm
+
+            def norm(x, *args, **kw):  # the Euclidean norm of a traced vector (np.linalg.norm casts to float first)
+                if isinstance(x, Vec) and not args and not kw:
+                    return np.sqrt(_vec_sum(x * x))
+                if isinstance(x, np.ndarray) and x.dtype == object and x.ndim == 1 and not args and not kw:
+                    return np.sqrt((x * x).sum())
+                return orig_norm(x, *args, **kw)
+
+            self.saved.append((np.linalg, "norm", orig_norm, "attr"))
+            np.linalg.norm = norm
+            # `from math import sin` / `from numpy import zeros` in the callable's module: rebind those names as well;
+            # helpers the callable's module decorated with numba.njit run as the Python functions they wrap
+            np_originals = {id(orig): getattr(mod, name) for mod, name, orig, _ in self.saved if mod is np or mod is np.linalg}
+            seen, work = set(), list(self.funcs)
+            while work:
+                g = getattr(work.pop(), "__globals__", None)
                 if g is None or id(g) in seen or g is globals():
                     continue
                 seen.add(id(g))
                 for key, val in list(g.items()):
                     repl = originals.get(id(val)) or np_originals.get(id(val))
+                    if repl is None and callable(val) and hasattr(val, "py_func") and callable(getattr(val, "py_func", None)):
+                        repl = val.py_func
+                        work.append(repl)
                     if repl is not None and callable(val):
                         self.saved.append((g, key, val, "item"))
                         g[key] = repl
@@ -477,6 +499,7 @@ def _emit_tree(node, leaf, lines, start=0, depth=1):
 
 def trace(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     """Run ``func`` on symbolic (t, y, p) -- once per control-flow path -- and emit the equivalent ``nbk_rhs`` CUDA C."""
+    func = _python_function(func)
 
     def run(paths):
         tr = _Trace(paths)
@@ -551,6 +574,8 @@ class Vec:
         if name in ("maximum", "minimum") and len(inputs) == 2:
             fn = "fmax" if name == "maximum" else "fmin"
             return _vec_binary(inputs[0], inputs[1], None, lambda a, b: f"{fn}({a}, {b})")
+        if name in _BINARY and len(inputs) == 2:
+            return _vec_binary(inputs[0], inputs[1], None, lambda a, b, fn=_BINARY[name]: f"{fn}({a}, {b})")
         if name == "matmul" and len(inputs) == 2:
             return _vec_matmul(inputs[0], inputs[1]) if isinstance(inputs[1], Vec) and not isinstance(inputs[0], Vec) \
                 else _vec_dot(inputs[0], inputs[1])
@@ -661,6 +686,10 @@ class Sc:
             return Sc(f"(-{_sc(inputs[0])})")
         if name in _UNARY and len(inputs) == 1:
             return Sc(f"{_UNARY[name]}({_sc(inputs[0])})")
+        if name in _BINARY and len(inputs) == 2:
+            return Sc(f"{_BINARY[name]}({_sc(inputs[0])}, {_sc(inputs[1])})")
+        if name in ("maximum", "minimum") and len(inputs) == 2:
+            return Sc(f"{'fmax' if name == 'maximum' else 'fmin'}({_sc(inputs[0])}, {_sc(inputs[1])})")
         if name in ("power", "float_power"):
             return Sc(_pow_code(_sc(inputs[0]), inputs[1]))
         raise TraceError(f"numpy.{name} cannot be traced")
@@ -1002,6 +1031,7 @@ def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     paths become one nested select around the component expressions."""
     global _TABLES, _SC_PATHS
     _TABLES = _Tables()
+    func = _python_function(func)
 
     def run(paths):
         global _SC_PATHS
@@ -1078,6 +1108,7 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
     for k, ev in enumerate(events):
         terminal.append(bool(getattr(ev, "terminal", False)))
         direction.append(int(np.sign(getattr(ev, "direction", 0))))
+        ev = _python_function(ev)
         try:
             nargs = len(inspect.signature(ev).parameters)
         except (TypeError, ValueError):

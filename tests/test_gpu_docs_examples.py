@@ -6,6 +6,9 @@ lists for y0 / params, tuple-returning right-hand sides, run(scalar), run resume
 step(upto_t=), skip(upto_t=), the state properties, get_solvers / get_groups queries.
 """
 
+import math
+from math import sin
+
 import numpy as np
 import pytest
 
@@ -165,3 +168,39 @@ def test_readme_example():
         ts, ys = solver.run([0, 5, 10])
         _, yo = onp.run(ref(), [0, 5, 10])
         assert ys.shape == (3, 1) and np.max(np.abs(ys - yo)) < 1e-12
+
+
+def _pendulum(t, y, p):
+    dy = np.empty(2)
+    dy[0] = y[1]
+    dy[1] = -p[0] * sin(y[0]) - p[1] * y[1] + 0.2 * math.cos(t)
+    return dy
+
+
+def test_numba_spelling_and_njit_dispatchers():
+    """A right-hand side written the way numba users write them (`from math import sin`, `np.empty(2)` filled element by
+    element) and the same function already wrapped by `numba.njit` -- the reference accepts both (core.py:125-132) --
+    give the same ensemble results as the NumPy restatement calling the very same callables."""
+    numba = pytest.importorskip("numba")
+    jitted = numba.njit(_pendulum)
+    rng = np.random.default_rng(12)
+    B = 300
+    y0 = np.stack([rng.uniform(-2, 2, B), rng.uniform(-1, 1, B)], 1)
+    p = np.stack([rng.uniform(0.5, 2, B), rng.uniform(0.05, 0.5, B)], 1)
+    ts = np.linspace(0.5, 10, 20)
+    kw = dict(rtol=1e-6, atol=1e-9)
+    a = nbkode.RungeKutta45(_pendulum, 0.0, y0, p, **kw)
+    b = nbkode.RungeKutta45(jitted, 0.0, y0, p, **kw)
+    _, ya = a.run(ts)
+    _, yb = b.run(ts)
+    assert np.array_equal(ya, yb)
+    for i in (0, 1, 150, 299):
+        o = onp.AdaptiveRK("RungeKutta45", _pendulum, 0.0, y0[i], p[i], **kw)
+        _, yo = onp.run(o, ts)
+        assert abs(int(np.asarray(a.n_accepted)[i]) - o.n_accepted) <= 1
+        assert np.all(np.abs(ya[i] - yo) <= 1e-6 * np.abs(yo) + 1e-9)
+    s = nbkode.RungeKutta4(jitted, 0.0, y0[0], p[0], h=0.01)
+    _, y4 = s.run(ts)
+    o = onp.FixedRK("RungeKutta4", _pendulum, 0.0, y0[0], p[0], h=0.01)
+    _, yo = onp.run(o, ts)
+    assert np.max(np.abs(y4 - yo)) < 1e-12

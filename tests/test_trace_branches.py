@@ -30,6 +30,7 @@ namespace nbk { inline double d_nan() { return NAN; } inline double d_inf() { re
 #define NBK_EVENT extern "C" double
 #define NBK_RHS_I extern "C" double
 #define __device__
+#define __forceinline__ inline
 typedef const double* nbk_vec;
 """
 
@@ -355,3 +356,56 @@ def test_math_functions_and_float_containers(tmp_path):
 
     rhs.trace(probe, 2, (), False)
     assert seen == {"int": np.dtype(int), "sin": math.sin(0.5), "two_d": (2, 2)}
+
+
+# ------------------------------------------------------------------ callables that numba already compiled
+numba = pytest.importorskip("numba")
+
+
+@numba.njit
+def _grav(r2):
+    return -1.0 / (r2 * math.sqrt(r2))
+
+
+@numba.njit
+def kepler_njit(t, y, p):
+    dy = np.empty(4)
+    r = np.linalg.norm(y[:2])
+    g = _grav(r * r) * p[0]
+    dy[0] = y[2]
+    dy[1] = y[3]
+    dy[2] = g * y[0]
+    dy[3] = g * y[1] + 0.01 * np.arctan2(y[1], y[0])
+    return dy
+
+
+@numba.njit
+def _crossing_njit(t, y):
+    return y[1] if t < 2.0 else y[1] - 0.1
+
+
+def test_numba_compiled_callables_are_traced_through_their_python_functions(tmp_path):
+    """The reference accepts a right-hand side that is already an njit dispatcher (core.py:125-132).  Here the dispatcher
+    -- and every njit helper of its module that it calls -- is traced through the Python function it wraps; afterwards
+    the module's names are the dispatchers again."""
+    src = rhs.trace(kepler_njit, 4, (1,), True).source
+    assert "atan2(y[1], y[0])" in src and src.count("sqrt(") == 2
+    lib = _host_build(tmp_path, src, "kepler")
+    rng = np.random.default_rng(8)
+    for _ in range(100):
+        t, y, p = float(rng.uniform(0, 3)), rng.uniform(0.3, 2, 4), rng.uniform(0.5, 2, 1)
+        np.testing.assert_allclose(_call_rhs(lib, t, y, p), kepler_njit(t, y, p), rtol=1e-14, atol=1e-16)
+    ev = rhs.trace_events([_crossing_njit], 4, (1,), True)
+    assert "if (t < 2.0)" in ev.source
+    assert type(_grav).__name__ == "CPUDispatcher" and globals()["_grav"] is _grav and np.linalg.norm([3.0, 4.0]) == 5.0
+    assert rhs.resolve(kepler_njit, 4, (1,), True)[1] == src
+    # whole-vector form: binary ufuncs and the norm of the traced vector
+    v = rhs.trace_cta(lambda t, y: np.arctan2(y, 1.0 + t) + np.linalg.norm(y) * np.hypot(y, np.roll(y, 1)), 32, (), False).source
+    lib = _host_build(tmp_path, v, "vecnorm")
+    dp = C.POINTER(C.c_double)
+    lib.nbk_rhs_i.restype = C.c_double
+    lib.nbk_rhs_i.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int]
+    y = rng.uniform(-1, 1, 32)
+    p = np.zeros(1)
+    got = np.array([lib.nbk_rhs_i(0.5, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, 32) for i in range(32)])
+    np.testing.assert_allclose(got, np.arctan2(y, 1.5) + np.linalg.norm(y) * np.hypot(y, np.roll(y, 1)), rtol=1e-13)
