@@ -409,3 +409,90 @@ def test_numba_compiled_callables_are_traced_through_their_python_functions(tmp_
     p = np.zeros(1)
     got = np.array([lib.nbk_rhs_i(0.5, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, 32) for i in range(32)])
     np.testing.assert_allclose(got, np.arctan2(y, 1.5) + np.linalg.norm(y) * np.hypot(y, np.roll(y, 1)), rtol=1e-13)
+
+
+# ------------------------------------------------------------------ random branching programs
+def _gen_expr(r, depth, names):
+    if depth == 0 or r.random() < 0.25:
+        c = r.random()
+        if c < 0.6: return r.choice(names)
+        return repr(round(r.uniform(-2, 2), 3))
+    op = r.choice(["+", "-", "*", "abs", "min", "max", "neg", "sq"])
+    a = _gen_expr(r, depth-1, names); b = _gen_expr(r, depth-1, names)
+    if op in "+-*": return f"({a} {op} {b})"
+    if op == "abs": return f"abs({a})"
+    if op == "neg": return f"(-{a})"
+    if op == "sq": return f"({a} * {a})"
+    return f"{op}({a}, {b})"
+
+def _gen_cond(r, names):
+    a = _gen_expr(r, 1, names); b = _gen_expr(r, 1, names)
+    c = f"{a} {r.choice(['<','>','<=','>='])} {b}"
+    k = r.random()
+    if k < 0.2: return f"({c}) and ({_gen_expr(r,1,names)} > 0.1)"
+    if k < 0.4: return f"({c}) or ({_gen_expr(r,1,names)} < -0.3)"
+    if k < 0.5: return f"not ({c})"
+    return c
+
+def _gen_block(r, indent, names, nvars, budget):
+    lines = []
+    pad = "    " * indent
+    for _ in range(r.randint(1, 3)):
+        k = r.random()
+        if k < 0.45 or budget[0] <= 0 or indent > 3:
+            v = f"v{nvars[0]}"; nvars[0] += 1
+            lines.append(f"{pad}{v} = {_gen_expr(r, 2, names)}")
+            names = names + [v]
+        elif k < 0.8:
+            budget[0] -= 1
+            tgt = r.choice([n for n in names if n.startswith('v')] or [None])
+            if tgt is None:
+                tgt = f"v{nvars[0]}"; nvars[0] += 1
+                lines.append(f"{pad}{tgt} = 0.5"); names = names + [tgt]
+            lines.append(f"{pad}if {_gen_cond(r, names)}:")
+            lines.append(f"{pad}    {tgt} = {_gen_expr(r, 2, names)}")
+            if r.random() < 0.6:
+                lines.append(f"{pad}else:")
+                lines.append(f"{pad}    {tgt} = {_gen_expr(r, 2, names)}")
+        else:
+            budget[0] -= 1
+            lines.append(f"{pad}if {_gen_cond(r, names)}:")
+            sub, _ = _gen_block(r, indent+1, names, nvars, budget)
+            lines += sub
+            if r.random() < 0.3:
+                lines.append(f"{pad}    return np.array([{_gen_expr(r,1,names)}, {_gen_expr(r,1,names)}])")
+    return lines, names
+
+def _gen_func(seed):
+    import random
+
+    r = random.Random(seed)
+    names = ["t", "y[0]", "y[1]", "p[0]"]
+    nvars = [0]; budget = [4]
+    lines, names = _gen_block(r, 1, names, nvars, budget)
+    src = "def f(t, y, p):\n" + "\n".join(lines) + f"\n    return np.array([{_gen_expr(r,2,names)}, {_gen_expr(r,2,names)}])\n"
+    return src
+
+
+
+def test_random_branching_programs(tmp_path):
+    """40 generated right-hand sides (nested if / else, early returns, and / or / not, min / max / abs, variables
+    reassigned inside branches): the emitted source compiled for the host equals the Python function bit for bit on 60
+    random inputs each."""
+    checked = 0
+    for seed in range(40):
+        ns = {"np": np}
+        exec(_gen_func(seed), ns)
+        f = ns["f"]
+        try:
+            traced = rhs.trace(f, 2, (1,), True)
+        except rhs.TraceError as exc:
+            assert "control-flow paths" in str(exc), (seed, exc)
+            continue
+        lib = _host_build(tmp_path, traced.source, f"f{seed}")
+        rng = np.random.default_rng(seed)
+        for _ in range(60):
+            t, y, p = float(rng.uniform(-1, 2)), rng.uniform(-2, 2, 2), rng.uniform(-1, 1, 1)
+            assert np.array_equal(_call_rhs(lib, t, y, p), np.asarray(f(t, y, p), float)), (seed, t, y, p)
+        checked += 1
+    assert checked >= 30
