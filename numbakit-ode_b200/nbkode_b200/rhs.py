@@ -395,8 +395,9 @@ class _tracing:
                         if not one_d:
                             return orig(shape, *args, **kw)
                         length = int(shape if not isinstance(shape, tuple) else shape[0])
-                        code = _sc(value) if fill == "full" else ("1.0" if fill == "ones" else "0.0")
-                        return Vec(length, lambda j, code=code: code)
+                        if fill == "full" and isinstance(value, Sc):
+                            return Vec(length, lambda j, code=value.c: code)
+                        return _ConstVec(orig(shape, *args, **kw))
                     arr = np.ndarray(shape, dtype=object)  # (np.ndarray: not one of the wrapped constructors)
                     arr[...] = value if fill == "full" else (1.0 if fill == "ones" else 0.0)
                     return arr
@@ -663,6 +664,41 @@ class Vec:
         old = self.code
         self.code = lambda j, a=a, b=b, old=old, v=val.code: (
             f"(({j}) >= {a} && ({j}) < {b} ? {v(f'(({j}) - {a})' if a else j)} : {old(j)})")
+
+
+class _ConstVec(Vec):
+    """What `np.zeros(n)` / `np.ones(n)` / `np.full(n, v)` return while a whole-vector callable is traced: a float array
+    as long as only numbers are stored into it (a coefficient profile filled in a loop stays ONE constant table), a
+    traced vector from the first traced value stored into it or the first use in an expression on."""
+
+    def __init__(self, values):
+        self.values = np.array(values, dtype=np.float64).ravel()
+        self.length = self.values.size
+        self._code = None
+
+    @property
+    def code(self):
+        if self._code is None:
+            v = self.values
+            if v.size and np.all(v == v[0]):
+                self._code = lambda j, c=_lit(v[0]): c
+            else:
+                self._code = lambda j, name=_TABLES.add(v.copy()): f"{name}[{j}]"
+        return self._code
+
+    @code.setter
+    def code(self, fn):
+        self._code = fn
+
+    def __setitem__(self, key, value):
+        numeric = isinstance(value, (numbers.Real, np.floating, np.integer)) or (isinstance(value, np.ndarray) and value.dtype != object)
+        if self._code is None and numeric and isinstance(key, (numbers.Integral, np.integer, slice)):
+            self.values[key] = value
+            return
+        Vec.__setitem__(self, key, value)
+
+    def copy(self):
+        return _ConstVec(self.values) if self._code is None else Vec(self.length, self._code)
 
 
 class Sc:

@@ -331,6 +331,15 @@ def test_math_functions_and_float_containers(tmp_path):
         t, y, p = float(rng.uniform(0, 3)), rng.uniform(-1, 1, n), rng.uniform(0.1, 2, 2)
         got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, n) for i in range(n)])
         np.testing.assert_allclose(got, assembled(t, y, p), rtol=1e-14, atol=1e-16)
+    # a constant profile filled element by element stays ONE table (not a chain of selects)
+    def profiled(t, y):
+        w = np.zeros(n)
+        for i in range(n):
+            w[i] = math.sin(i / n)
+        return w * y + np.ones(n) * 0.5
+
+    src = rhs.trace_cta(profiled, n, (), False).source
+    assert src.count("nbk_tab0[") == 2 and "?" not in src and len(src) < 2500
     # an event function in the same spelling
     ev = rhs.trace_events([lambda t, y: sin(y[0]) - 0.5 * math.exp(-t)], 2, (), False)
     assert "sin(y[0])" in ev.source and "exp(" in ev.source
