@@ -505,3 +505,62 @@ def test_random_branching_programs(tmp_path):
             assert np.array_equal(_call_rhs(lib, t, y, p), np.asarray(f(t, y, p), float)), (seed, t, y, p)
         checked += 1
     assert checked >= 30
+
+
+# ------------------------------------------------------------------ random whole-vector programs
+N = 16
+def _vgen_vec(r, d):
+    if d == 0 or r.random() < 0.2:
+        return r.choice(["y", "np.roll(y, 1)", "np.roll(y, -2)", "y[::-1]", "G", "np.ones(N)", "np.concatenate([y[3:], y[:3]])"])
+    k = r.choice(["+","-","*","where","max","min","abs","sc*","neg","sq","clip","diff","sin","sum*","sl"])
+    a = _vgen_vec(r, d-1); b = _vgen_vec(r, d-1)
+    if k in "+-*": return f"({a} {k} {b})"
+    if k == "where": return f"np.where({a} {r.choice(['<','>','>='])} {_vgen_sc(r)}, {a}, {b})"
+    if k == "max": return f"np.maximum({a}, {b})"
+    if k == "min": return f"np.minimum({a}, {_vgen_sc(r)})"
+    if k == "abs": return f"np.abs({a})"
+    if k == "sc*": return f"({_vgen_sc(r)} * {a})"
+    if k == "neg": return f"(-{a})"
+    if k == "sq": return f"({a} ** 2)"
+    if k == "clip": return f"np.clip({a}, -1.0, 1.5)"
+    if k == "diff": return f"np.append(np.diff({a}), 0.0)"
+    if k == "sin": return f"np.tanh({a})"
+    if k == "sum*": return f"({a} * ({b}).sum() * 0.01)"
+    return f"np.concatenate([({a})[:5], ({b})[5:]])"
+def _vgen_sc(r):
+    return r.choice(["t", "p[0]", "p[1]", "0.5", "(t * p[0])", "(p[1] - 0.3)", "y[2]", "y[-1]"])
+def _vgen_func(seed):
+    import random
+
+    r = random.Random(seed)
+    body = []
+    body.append(f"    a = {_vgen_vec(r, 2)}")
+    if r.random() < 0.6:
+        body.append(f"    if {_vgen_sc(r)} {r.choice(['<','>'])} {_vgen_sc(r)}:")
+        body.append(f"        a = a + {_vgen_vec(r, 1)}")
+        if r.random() < 0.5:
+            body.append("    else:"); body.append(f"        a = {_vgen_vec(r, 1)} - a")
+    if r.random() < 0.4:
+        body.append("    out = np.zeros(N)"); body.append("    out[1:-1] = a[2:] - a[:-2]"); body.append("    out[0] = a[0]"); body.append("    a = out + a")
+    body.append(f"    return a + {_vgen_vec(r, 1)}")
+    return "def f(t, y, p):\n" + "\n".join(body) + "\n"
+
+
+def test_random_whole_vector_programs(tmp_path):
+    """30 generated whole-vector right-hand sides (np.roll, reversed / shifted slices, concatenate, where / maximum /
+    minimum / clip, diff, reductions, scalar branches on t / p / single elements, slice assembly into np.zeros): the
+    emitted nbk_rhs_i compiled for the host equals NumPy on 25 random inputs each."""
+    G = np.linspace(-1, 1, N)
+    dp = C.POINTER(C.c_double)
+    for seed in range(30):
+        ns = {"np": np, "N": N, "G": G}
+        exec(_vgen_func(seed), ns)
+        f = ns["f"]
+        lib = _host_build(tmp_path, rhs.trace_cta(f, N, (2,), True).source, f"v{seed}")
+        lib.nbk_rhs_i.restype = C.c_double
+        lib.nbk_rhs_i.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int]
+        rng = np.random.default_rng(seed)
+        for _ in range(25):
+            t, y, p = float(rng.uniform(-1, 2)), rng.uniform(-2, 2, N), rng.uniform(-1, 1, 2)
+            got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, N) for i in range(N)])
+            np.testing.assert_allclose(got, np.asarray(f(t, y, p), float), rtol=1e-12, atol=1e-13, err_msg=f"seed {seed}")
