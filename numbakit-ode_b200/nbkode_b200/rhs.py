@@ -57,6 +57,10 @@ class TraceError(TypeError):
     pass
 
 
+class PathBudgetError(TraceError):
+    """More control-flow paths than MAX_TRACED_PATHS: the tracers retry with the if-converted callable (_ifconv.py)."""
+
+
 # --------------------------------------------------------------------------------------
 # symbolic tracer
 # --------------------------------------------------------------------------------------
@@ -134,7 +138,7 @@ def _explore(run, what="right-hand side"):
     def build(prefix, conds=()):
         count[0] += 1
         if count[0] > MAX_TRACED_PATHS:
-            raise TraceError(f"the {what} has more than {MAX_TRACED_PATHS} control-flow paths (element-wise branches on a "
+            raise PathBudgetError(f"the {what} has more than {MAX_TRACED_PATHS} control-flow paths (element-wise branches on a "
                              "vector multiply them: use np.where / np.maximum on whole arrays, or CUDA C)")
         paths = _Paths(prefix)
         payload = run(paths)
@@ -498,10 +502,31 @@ def _emit_tree(node, leaf, lines, start=0, depth=1):
     lines.append(f"{pad}}}")
 
 
+def _retry_if_converted(tracer, func, *args):
+    """``tracer(func, *args)``; when the callable has more control-flow paths than the budget, once more with its
+    if-converted twin (independent branches become selects, _ifconv.py).  A failure of the retry reports the first one."""
+    try:
+        return tracer(func, *args)
+    except PathBudgetError as first:
+        from . import _ifconv
+
+        twin = _ifconv.convert(func)
+        if twin is None:
+            raise
+        try:
+            out = tracer(twin, *args)
+        except TraceError:
+            raise first from None
+        out.if_converted = True
+        return out
+
+
 def trace(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     """Run ``func`` on symbolic (t, y, p) -- once per control-flow path -- and emit the equivalent ``nbk_rhs`` CUDA C."""
-    func = _python_function(func)
+    return _retry_if_converted(_trace_paths, _python_function(func), n, params_shape, has_params)
 
+
+def _trace_paths(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     def run(paths):
         tr = _Trace(paths)
         try:
@@ -1065,9 +1090,12 @@ def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     """Trace a NumPy-style whole-vector right-hand side into the component-wise ``nbk_rhs_i`` of the CTA regime.
     Control flow on scalars (``if t < t_on:``, ``if p[0] > 0:``) is explored path by path like in :func:`trace`; the
     paths become one nested select around the component expressions."""
+    return _retry_if_converted(_trace_cta_paths, _python_function(func), n, params_shape, has_params)
+
+
+def _trace_cta_paths(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     global _TABLES, _SC_PATHS
     _TABLES = _Tables()
-    func = _python_function(func)
 
     def run(paths):
         global _SC_PATHS

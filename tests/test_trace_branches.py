@@ -564,3 +564,108 @@ def test_random_whole_vector_programs(tmp_path):
             t, y, p = float(rng.uniform(-1, 2)), rng.uniform(-2, 2, N), rng.uniform(-1, 1, 2)
             got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, N) for i in range(N)])
             np.testing.assert_allclose(got, np.asarray(f(t, y, p), float), rtol=1e-12, atol=1e-13, err_msg=f"seed {seed}")
+
+
+# ------------------------------------------------------------------ if-conversion (beyond the path budget)
+def relu_loop(t, y, p):
+    n = len(y)
+    dy = np.empty(n)
+    for i in range(n):
+        if y[i] > 0:
+            dy[i] = -y[i]
+        elif y[i] < -1 and t > 0.5:
+            dy[i] = p[0] * y[i] * y[i]
+        else:
+            dy[i] = p[0] * y[i]
+            dy[i] = dy[i] + 0.1
+    s = 0.0
+    for i in range(n):
+        s = s + (y[i] if 0.0 < y[i] < 1.0 else 0.25 * min(y[i], 0.5))
+    dy[0] = dy[0] + s
+    return dy
+
+
+def staged_switches(t, y, p):
+    out = p[0] * (np.roll(y, -1) - 2 * y + np.roll(y, 1))
+    for k in range(8):                      # eight independent scalar switches: 256 paths
+        if t > 0.1 * k and not y[k] < 0.0:
+            out = out + 0.01 * (k + 1) * y
+        else:
+            out = out - p[1] * 0.001
+    return out
+
+
+def one_armed(t, y):
+    for i in range(8):
+        if y[i] > 0:
+            z = -y[i]                       # bound in one arm only, unbound before: nothing a select can express
+    return np.array([z] * 8)
+
+
+def test_if_conversion_beyond_the_path_budget(tmp_path):
+    """n independent element-wise branches are 2 ** n paths; beyond the budget the tracers retry with the if-converted
+    callable (nbkode_b200/_ifconv.py): both arms run, the assigned values merge into selects.  Bit for bit the Python
+    function, per thread and in the whole-vector form; what a select cannot express reports the path budget."""
+    from nbkode_b200 import _ifconv
+
+    n = 12
+    traced = rhs.trace(relu_loop, n, (1,), True)
+    assert traced.if_converted and traced.paths == 1 and "if (" not in traced.source and traced.source.count("?") >= 3 * n
+    lib = _host_build(tmp_path, traced.source, "relu_loop")
+    rng = np.random.default_rng(21)
+    for _ in range(300):
+        t, y, p = float(rng.uniform(0, 1)), rng.uniform(-2, 2, n), rng.uniform(0.1, 2, 1)
+        assert np.array_equal(_call_rhs(lib, t, y, p), relu_loop(t, y, p))
+    sz = C.c_longlong(0)
+    cfg = _lib.NbkConfig(45, n, 1, 0, 16, None, traced.source.encode(), 1e-6, 1e-9, 0.2, 10.0, 0.9, 0, 0)
+    _lib.check(_lib.lib().nbk_jit_compile_only(C.byref(cfg), C.byref(sz)))
+    # small systems keep the exact branches (no retry below the budget)
+    one = rhs.trace(relu_loop, 1, (1,), True)
+    assert not getattr(one, "if_converted", False) and one.paths > 8 and "if (" in one.source
+
+    m = 24
+    v = rhs.trace_cta(staged_switches, m, (2,), True)
+    assert v.if_converted
+    lib = _host_build(tmp_path, v.source, "staged")
+    dp = C.POINTER(C.c_double)
+    lib.nbk_rhs_i.restype = C.c_double
+    lib.nbk_rhs_i.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int]
+    for _ in range(40):
+        t, y, p = float(rng.uniform(0, 1)), rng.uniform(-1, 1, m), rng.uniform(0.1, 2, 2)
+        got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, m) for i in range(m)])
+        np.testing.assert_allclose(got, staged_switches(t, y, p), rtol=1e-13, atol=1e-15)
+
+    with pytest.raises(rhs.PathBudgetError):
+        rhs.trace(one_armed, 8, (), False)
+    with pytest.raises(rhs.PathBudgetError):  # no source to rewrite: a lambda built at run time
+        rhs.trace(eval("lambda t, y: np.array([(e if e > 0 else -e) for e in y])", {"np": np}), 7, (), False)
+    assert _ifconv.convert(pendulum) is None  # nothing to convert
+
+
+def test_if_converted_random_programs(tmp_path):
+    """The generated branching programs again, forced through the if-conversion: every program it accepts equals the Python
+    function bit for bit; what it refuses (a name bound in one arm only, early returns mixed in) is refused loudly."""
+    from nbkode_b200 import _ifconv
+
+    checked = 0
+    for seed in range(60):
+        path = tmp_path / f"prog{seed}.py"
+        path.write_text("import numpy as np\n" + _gen_func(seed))
+        ns = {}
+        exec(compile(path.read_text(), str(path), "exec"), ns)  # a real file, so that inspect.getsource finds it
+        f = ns["f"]
+        twin = _ifconv.convert(f)
+        if twin is None:
+            continue
+        try:
+            traced = rhs._trace_paths(twin, 2, (1,), True)
+        except rhs.TraceError as exc:
+            assert "NoConvert" in str(exc) or "control-flow paths" in str(exc), (seed, exc)
+            continue
+        lib = _host_build(tmp_path, traced.source, f"c{seed}")
+        rng = np.random.default_rng(seed)
+        for _ in range(60):
+            t, y, p = float(rng.uniform(-1, 2)), rng.uniform(-2, 2, 2), rng.uniform(-1, 1, 1)
+            assert np.array_equal(_call_rhs(lib, t, y, p), np.asarray(f(t, y, p), float)), (seed, t, y, p)
+        checked += 1
+    assert checked >= 30
