@@ -147,9 +147,12 @@ def test_path_count_depth_and_determinism_are_checked():
     def many(t, y):
         return np.array([(e if e > 0 else -e) for e in y])   # 2 ** 7 element-wise paths
 
-    with pytest.raises(rhs.TraceError, match="control-flow paths"):
-        rhs.trace(many, 7, (), False)
     assert rhs.trace(many, 6, (), False).source.count("dy[0]") == 64
+    # beyond the budget: retried if-converted (test_if_conversion_beyond_the_path_budget) -- one select per element
+    seven = rhs.trace(many, 7, (), False)
+    assert seven.if_converted and seven.paths == 1 and seven.source.count("?") == 7
+    with pytest.raises(rhs.TraceError, match="control-flow paths"):  # the same without source to rewrite
+        rhs.trace(eval("lambda t, y: np.array([(e if e > 0 else -e) for e in y])", {"np": np}), 7, (), False)
 
     def endless(t, y):
         x = y[0]
