@@ -181,3 +181,41 @@ def test_events_with_a_traced_componentwise_rhs():
                 if len(te_ref[j]):
                     assert np.abs(teu[j][i, :len(te_ref[j])] - np.array(te_ref[j])).max() < 1e-6
     assert seen > 20
+
+
+def _relu_loop(t, y, p):
+    n = len(y)
+    dy = np.empty(n)
+    for i in range(n):
+        if y[i] > 0:
+            dy[i] = -p[0] * y[i]
+        else:
+            dy[i] = -p[1] * y[i] + 0.05 * (y[(i + 1) % n] - y[i])
+    return dy
+
+
+def test_if_converted_elementwise_branches_on_the_device():
+    """Twelve independent element-wise branches (4096 control-flow paths) are traced if-converted (nbkode_b200/_ifconv.py,
+    one select each): per-thread kernels (regime="thread") and the default regime against the NumPy restatement running the
+    Python function -- the pieces join continuously at y = 0, fixed step to 1e-12."""
+    from nbkode_b200 import rhs as nrhs
+
+    n, B = 12, 256
+    assert nrhs.trace(_relu_loop, n, (2,), True).if_converted
+    rng = np.random.default_rng(31)
+    y0 = rng.uniform(-1, 1, (B, n))
+    p = np.stack([rng.uniform(0.5, 2, B), rng.uniform(0.5, 2, B)], 1)
+    ts = np.linspace(0.2, 2, 10)
+    for regime in ("thread", "auto"):
+        s = nbk.RungeKutta4(_relu_loop, 0.0, y0, p, h=0.01, regime=regime)
+        _, y = s.run(ts)
+        for i in (0, 100, 255):
+            o = onp.FixedRK("RungeKutta4", _relu_loop, 0.0, y0[i], p[i], h=0.01)
+            _, yo = onp.run(o, ts)
+            assert rel(y[i], yo) <= FIXED_TOL, (regime, i)
+    s = nbk.RungeKutta45(_relu_loop, 0.0, y0, p, rtol=1e-6, atol=1e-9, regime="thread")
+    _, y = s.run(ts[:3])
+    for i in (0, 255):
+        o = onp.AdaptiveRK("RungeKutta45", _relu_loop, 0.0, y0[i], p[i], rtol=1e-6, atol=1e-9)
+        _, yo = onp.run(o, ts[:3])
+        assert within(y[i], yo, 1e-6, 1e-9, slack=2.0).all()
