@@ -99,6 +99,17 @@ def merge(c, a, b):
         if not _is_traced(a) and not _is_traced(b) and float(a) == float(b):
             return a
         return _select(c, a, b)
+    if isinstance(a, rhs._ConstVec) and isinstance(b, rhs._ConstVec) and a.assembling and b.assembling and a.length == b.length:
+        # two vectors still being assembled element by element: merged element by element (one select where they differ)
+        out = rhs._ConstVec(a.values)
+        for k in range(a.length):
+            va, vb = a.element(k), b.element(k)
+            if va is vb or (not isinstance(va, rhs.Sc) and not isinstance(vb, rhs.Sc) and va == vb):
+                if isinstance(va, rhs.Sc):
+                    out.traced[k] = va
+                continue
+            out.traced[k] = _select(c, va, vb)
+        return out
     if isinstance(a, rhs.Vec) or isinstance(b, rhs.Vec):
         return _select(c, a, b)
     if isinstance(a, np.ndarray) and isinstance(b, np.ndarray):

@@ -692,38 +692,80 @@ class Vec:
 
 
 class _ConstVec(Vec):
-    """What `np.zeros(n)` / `np.ones(n)` / `np.full(n, v)` return while a whole-vector callable is traced: a float array
-    as long as only numbers are stored into it (a coefficient profile filled in a loop stays ONE constant table), a
-    traced vector from the first traced value stored into it or the first use in an expression on."""
+    """What `np.zeros(n)` / `np.ones(n)` / `np.full(n, v)` return while a whole-vector callable is traced.  It stays a float
+    array as long as only numbers are stored into it (a coefficient profile filled in a loop is ONE constant table);
+    traced scalars stored element by element (`dy[i] = ...` in a `for` loop) are kept per element, so that the vector
+    costs one expression per element however it is assembled or merged (`_ifconv.merge`); the first slice of traced
+    values stored into it, or its first use in an expression, turns it into an ordinary traced vector."""
 
-    def __init__(self, values):
+    def __init__(self, values, traced=None):
         self.values = np.array(values, dtype=np.float64).ravel()
         self.length = self.values.size
+        self.traced = dict(traced or {})  # element index -> Sc
         self._code = None
+
+    @property
+    def assembling(self):
+        return self._code is None
+
+    def element(self, k):
+        """The value of element k while the vector is still assembled: a float or an Sc."""
+        return self.traced.get(k, float(self.values[k]))
 
     @property
     def code(self):
         if self._code is None:
             v = self.values
             if v.size and np.all(v == v[0]):
-                self._code = lambda j, c=_lit(v[0]): c
+                base = lambda j, c=_lit(v[0]): c  # noqa: E731
             else:
-                self._code = lambda j, name=_TABLES.add(v.copy()): f"{name}[{j}]"
+                base = lambda j, name=_TABLES.add(v.copy()): f"{name}[{j}]"  # noqa: E731
+            items = sorted(self.traced.items())
+
+            def code(j, base=base, items=items):
+                expr = base(j)
+                for k, sc in reversed(items):
+                    expr = f"(({j}) == {k} ? {sc.c} : {expr})"
+                return expr
+
+            self._code = code if items else base
         return self._code
 
     @code.setter
     def code(self, fn):
         self._code = fn
 
+    def __getitem__(self, key):
+        if self._code is None and isinstance(key, (numbers.Integral, np.integer)):
+            k = int(key) + (self.length if key < 0 else 0)
+            if not 0 <= k < self.length:
+                raise IndexError(key)
+            v = self.element(k)
+            return v if isinstance(v, Sc) else Sc(_lit(v))
+        return Vec.__getitem__(self, key)
+
     def __setitem__(self, key, value):
+        if self._code is None and isinstance(key, (numbers.Integral, np.integer)):
+            k = int(key) + (self.length if key < 0 else 0)
+            if not 0 <= k < self.length:
+                raise IndexError(key)
+            if isinstance(value, Sc):
+                self.traced[k] = value
+                return
+            if isinstance(value, (numbers.Real, np.floating, np.integer)):
+                self.values[k] = value
+                self.traced.pop(k, None)
+                return
         numeric = isinstance(value, (numbers.Real, np.floating, np.integer)) or (isinstance(value, np.ndarray) and value.dtype != object)
-        if self._code is None and numeric and isinstance(key, (numbers.Integral, np.integer, slice)):
+        if self._code is None and numeric and isinstance(key, slice):
             self.values[key] = value
+            for k in range(*key.indices(self.length)):
+                self.traced.pop(k, None)
             return
         Vec.__setitem__(self, key, value)
 
     def copy(self):
-        return _ConstVec(self.values) if self._code is None else Vec(self.length, self._code)
+        return _ConstVec(self.values, self.traced) if self._code is None else Vec(self.length, self._code)
 
 
 class Sc:

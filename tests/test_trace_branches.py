@@ -638,6 +638,21 @@ def test_if_conversion_beyond_the_path_budget(tmp_path):
         got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, m) for i in range(m)])
         np.testing.assert_allclose(got, staged_switches(t, y, p), rtol=1e-13, atol=1e-15)
 
+    # the element-by-element loop in the whole-vector form (what regime="auto" picks for n = 12): the container is merged
+    # element by element, one select per element -- linear in n, not one copy of the vector per arm
+    for nn in (12, 40):
+        w = rhs.trace_cta(relu_loop, nn, (1,), True)
+        assert w.if_converted and len(w.source) < 700 * nn
+        lib = _host_build(tmp_path, w.source, f"relu_vec{nn}")
+        lib.nbk_rhs_i.restype = C.c_double
+        lib.nbk_rhs_i.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int]
+        for _ in range(20):
+            t, y, p = float(rng.uniform(0, 1)), rng.uniform(-2, 2, nn), rng.uniform(0.1, 2, 1)
+            got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, nn) for i in range(nn)])
+            assert np.array_equal(got, relu_loop(t, y, p))
+    cfg = _lib.NbkConfig(45, 12, 1, 0, 16, None, rhs.trace_cta(relu_loop, 12, (1,), True).source.encode(), 1e-6, 1e-9, 0.2, 10.0, 0.9, 0, 0)
+    _lib.check(_lib.lib().nbk_jit_compile_only(C.byref(cfg), C.byref(sz)))
+
     with pytest.raises(rhs.PathBudgetError):
         rhs.trace(one_armed, 8, (), False)
     with pytest.raises(rhs.PathBudgetError):  # no source to rewrite: a lambda built at run time
