@@ -502,6 +502,13 @@ def _emit_tree(node, leaf, lines, start=0, depth=1):
     lines.append(f"{pad}}}")
 
 
+class _Explored:
+    """A decision tree as the result of a tracer (what `_retry_if_converted` hands back and marks)."""
+
+    def __init__(self, tree):
+        self.tree = tree
+
+
 def _retry_if_converted(tracer, func, *args):
     """``tracer(func, *args)``; when the callable has more control-flow paths than the budget, once more with its
     if-converted twin (independent branches become selects, _ifconv.py).  A failure of the retry reports the first one."""
@@ -1220,22 +1227,25 @@ def trace_events(events, n: int, params_shape, has_params: bool) -> CudaEvents:
         except (TypeError, ValueError):
             nargs = 2
 
-        def run(paths, ev=ev, nargs=nargs):
-            tr = _Trace(paths)
-            try:
-                out = ev(*_symbolic_args(tr, n, params_shape, nargs >= 3 and has_params))
-            except TraceError:
-                raise
-            except Exception as exc:  # noqa: BLE001
-                raise TraceError(f"could not trace event {getattr(ev, '__name__', ev)!r} into CUDA C "
-                                 f"({type(exc).__name__}: {exc}); pass nbkode_b200.CudaEvents instead") from exc
-            out = np.asarray(out, dtype=object).ravel()
-            if out.size != 1:
-                raise TraceError("an event function must return one float")
-            return tr, Expr._c(out[0])
+        def explore(ev, nargs=nargs):
+            def run(paths):
+                tr = _Trace(paths)
+                try:
+                    out = ev(*_symbolic_args(tr, n, params_shape, nargs >= 3 and has_params))
+                except TraceError:
+                    raise
+                except Exception as exc:  # noqa: BLE001
+                    raise TraceError(f"could not trace event {getattr(ev, '__name__', ev)!r} into CUDA C "
+                                     f"({type(exc).__name__}: {exc}); pass nbkode_b200.CudaEvents instead") from exc
+                out = np.asarray(out, dtype=object).ravel()
+                if out.size != 1:
+                    raise TraceError("an event function must return one float")
+                return tr, Expr._c(out[0])
 
-        with _tracing([ev]):
-            tree = _explore(run, "event function")
+            with _tracing([ev]):
+                return _Explored(_explore(run, "event function"))
+
+        tree = _retry_if_converted(explore, ev).tree
         lines.append(f"  if (k == {k}) {{")
         _emit_tree(tree, lambda payload: [f"return {payload[1]};"], lines)
         lines.append("  }")

@@ -598,6 +598,16 @@ def staged_switches(t, y, p):
     return out
 
 
+def _many_sided_event(t, y):
+    g = -2.5
+    for i in range(8):
+        if y[i] > 0.25:
+            g = g + y[i]
+        else:
+            g = g + 0.25
+    return g
+
+
 def one_armed(t, y):
     for i in range(8):
         if y[i] > 0:
@@ -652,6 +662,15 @@ def test_if_conversion_beyond_the_path_budget(tmp_path):
             assert np.array_equal(got, relu_loop(t, y, p))
     cfg = _lib.NbkConfig(45, 12, 1, 0, 16, None, rhs.trace_cta(relu_loop, 12, (1,), True).source.encode(), 1e-6, 1e-9, 0.2, 10.0, 0.9, 0, 0)
     _lib.check(_lib.lib().nbk_jit_compile_only(C.byref(cfg), C.byref(sz)))
+
+    # event functions take the same second chance
+    ev = rhs.trace_events([_many_sided_event], 8, (), False)
+    lib = _host_build(tmp_path, ev.source, "ev_many")
+    lib.nbk_event.restype = C.c_double
+    lib.nbk_event.argtypes = [C.c_int, C.c_double, dp, dp]
+    for _ in range(50):
+        y = rng.uniform(-1, 1, 8)
+        assert lib.nbk_event(0, 0.5, y.ctypes.data_as(dp), y.ctypes.data_as(dp)) == _many_sided_event(0.5, y)
 
     with pytest.raises(rhs.PathBudgetError):
         rhs.trace(one_armed, 8, (), False)
