@@ -541,6 +541,10 @@ def _trace_paths(func, n: int, params_shape, has_params: bool) -> CudaRHS:
         except TraceError:
             raise
         except Exception as exc:  # noqa: BLE001
+            if isinstance(exc, TypeError) and "unorderable types" in str(exc) and paths.taken and not any(o for _, o, _ in paths.taken[-3:]):
+                # np.sign on a traced scalar compares three times (< 0, > 0, == 0); the path on which all three are false
+                # is the NaN input, for which NumPy's float loop returns NaN: that leaf is all-NaN
+                return tr, ["nbk::d_nan()"] * n
             raise TraceError(
                 f"could not trace {getattr(func, '__name__', func)!r} into CUDA C ({type(exc).__name__}: {exc}); "
                 "pass a built-in name or CUDA C source (nbkode_b200.CudaRHS) instead"
@@ -640,6 +644,7 @@ class Vec:
     def __pos__(self): return self
     def __abs__(self): return _vec_unary(self, lambda a: f"fabs({a})")
     def __pow__(self, e): return _vec_pow(self, e)
+    def __rpow__(self, base): return _vec_pow(base, self)
     def __rmatmul__(self, m): return _vec_matmul(m, self)
     def __matmul__(self, o): return _vec_dot(self, o)
     def __lt__(self, o): return _vec_binary(self, o, "<")
@@ -800,13 +805,20 @@ class Sc:
             return Sc(f"{_BINARY[name]}({_sc(inputs[0])}, {_sc(inputs[1])})")
         if name in ("maximum", "minimum") and len(inputs) == 2:
             return Sc(f"{'fmax' if name == 'maximum' else 'fmin'}({_sc(inputs[0])}, {_sc(inputs[1])})")
+        if name == "sign" and len(inputs) == 1:
+            a = _sc(inputs[0])
+            return Sc(f"(({a}) > 0.0 ? 1.0 : (({a}) < 0.0 ? -1.0 : 0.0))")
+        if name == "square" and len(inputs) == 1:
+            return Sc(_pow_code(_sc(inputs[0]), 2))
+        if name == "reciprocal" and len(inputs) == 1:
+            return Sc(f"(1.0 / ({_sc(inputs[0])}))")
         if name in ("power", "float_power"):
             return Sc(_pow_code(_sc(inputs[0]), inputs[1]))
         raise TraceError(f"numpy.{name} cannot be traced")
 
     def _b(self, o, op, swap=False):
-        if isinstance(o, Vec):
-            return NotImplemented
+        if isinstance(o, Vec) or (isinstance(o, np.ndarray) and o.ndim > 0):
+            return NotImplemented  # scalar (x) vector / constant array: the array side builds the vector (`p[0] * grid`)
         a, b = (_sc(o), self.c) if swap else (self.c, _sc(o))
         return Sc(f"({a} {op} {b})")
 
@@ -821,7 +833,12 @@ class Sc:
     def __neg__(self): return Sc(f"(-{self.c})")
     def __pos__(self): return self
     def __abs__(self): return Sc(f"fabs({self.c})")
-    def __pow__(self, e): return Sc(_pow_code(self.c, e))
+    def __pow__(self, e):
+        if isinstance(e, Vec) or (isinstance(e, np.ndarray) and e.ndim > 0):
+            return NotImplemented  # scalar ** vector: the array side builds the vector
+        return Sc(_pow_code(self.c, e))
+
+    def __rpow__(self, base): return Sc(f"pow({_sc(base)}, {self.c})")
 
     # Comparisons of scalars (time, parameters, single elements) are boolean scalars: a mask for np.where, 1 / 0 in
     # arithmetic, and -- asked for their truth value by `if` / `and` / `min` -- a run-time select between the
