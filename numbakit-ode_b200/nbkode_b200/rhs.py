@@ -397,6 +397,9 @@ class _tracing:
                         return orig(shape, *args, **kw)
                     if vector:
                         if not one_d:
+                            if isinstance(shape, tuple) and all(isinstance(d, (int, np.integer)) for d in shape) and not (
+                                    fill == "full" and isinstance(value, Sc)):
+                                return Grid(_ConstVec(orig(shape, *args, **kw)), shape)
                             return orig(shape, *args, **kw)
                         length = int(shape if not isinstance(shape, tuple) else shape[0])
                         if fill == "full" and isinstance(value, Sc):
@@ -594,6 +597,8 @@ class Vec:
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         if method != "__call__" or kwargs.get("out") is not None:
             return NotImplemented
+        if any(isinstance(x, Grid) for x in inputs):
+            return NotImplemented  # the grid's own __array_ufunc__ takes it
         name = ufunc.__name__
         binary = {"add": "+", "subtract": "-", "multiply": "*", "true_divide": "/", "divide": "/"}
         if name in binary and len(inputs) == 2:
@@ -789,6 +794,12 @@ class Sc:
         self.c, self.boolean = code, boolean
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if any(isinstance(x, Grid) for x in inputs):
+            return NotImplemented  # the grid's own __array_ufunc__ takes it
+        nd = next((x for x in inputs if isinstance(x, np.ndarray) and x.ndim >= 2), None)
+        if nd is not None:  # scalar (x) constant N-d array: a grid of constants
+            const = Grid(_as_vec(np.ascontiguousarray(nd, dtype=np.float64).ravel(), nd.size), nd.shape)
+            return const.__array_ufunc__(ufunc, method, *[const if x is nd else x for x in inputs], **kwargs)
         if any(isinstance(x, Vec) or (isinstance(x, np.ndarray) and x.ndim == 1) for x in inputs):
             return Vec.__array_ufunc__(None, ufunc, method, *inputs, **kwargs)  # vector (x) scalar
         if method != "__call__":
@@ -817,7 +828,7 @@ class Sc:
         raise TraceError(f"numpy.{name} cannot be traced")
 
     def _b(self, o, op, swap=False):
-        if isinstance(o, Vec) or (isinstance(o, np.ndarray) and o.ndim > 0):
+        if isinstance(o, (Vec, Grid)) or (isinstance(o, np.ndarray) and o.ndim > 0):
             return NotImplemented  # scalar (x) vector / constant array: the array side builds the vector (`p[0] * grid`)
         a, b = (_sc(o), self.c) if swap else (self.c, _sc(o))
         return Sc(f"({a} {op} {b})")
@@ -834,7 +845,7 @@ class Sc:
     def __pos__(self): return self
     def __abs__(self): return Sc(f"fabs({self.c})")
     def __pow__(self, e):
-        if isinstance(e, Vec) or (isinstance(e, np.ndarray) and e.ndim > 0):
+        if isinstance(e, (Vec, Grid)) or (isinstance(e, np.ndarray) and e.ndim > 0):
             return NotImplemented  # scalar ** vector: the array side builds the vector
         return Sc(_pow_code(self.c, e))
 
@@ -845,7 +856,7 @@ class Sc:
     # control-flow paths of the callable (path exploration, `_explore`).  `==` / `!=` too: Python's identity
     # comparison would freeze an `if t == 0:` at trace time.
     def _cmp(self, o, op):
-        if isinstance(o, (Vec, np.ndarray)):
+        if isinstance(o, (Vec, Grid, np.ndarray)):
             return NotImplemented  # scalar (x) vector comparison: the vector builds the mask
         return Sc(f"({self.c} {op} {_sc(o)})", boolean=True)
 
@@ -858,7 +869,7 @@ class Sc:
     __hash__ = None
 
     def _logic(self, o, op):
-        if isinstance(o, (Vec, np.ndarray)):
+        if isinstance(o, (Vec, Grid, np.ndarray)):
             return NotImplemented
         return Sc(f"({self._truth()} {op} {o._truth() if isinstance(o, Sc) else ('true' if o else 'false')})", boolean=True)
 
@@ -941,6 +952,8 @@ _TABLES: "_Tables | None" = None
 
 
 def _as_vec(x, length) -> Vec:
+    if isinstance(x, Grid):
+        x = x.flat
     if isinstance(x, Vec):
         if x.length != length:
             raise TraceError(f"shape mismatch in a traced right-hand side: ({x.length},) vs ({length},)")
@@ -963,6 +976,10 @@ def _len_of(x):
 
 
 def _vec_binary(a, b, op, fn=None):
+    if isinstance(a, Grid):
+        return a._bin(b, op, False, fn)
+    if isinstance(b, Grid):
+        return b._bin(a, op, True, fn)
     length = _len_of(a) if _len_of(a) is not None else _len_of(b)
     va, vb = _as_vec(a, length), _as_vec(b, length)
     if fn is None:
@@ -1152,6 +1169,345 @@ def _np_gradient(a, *args, **kw):
     raise TraceError("np.gradient is not traceable; write the stencil with slices or np.roll")
 
 
+
+# --------------------------------------------------------------------------------------
+# N-d views of a traced vector: method-of-lines right-hand sides on 2-D / 3-D grids
+# --------------------------------------------------------------------------------------
+# ``u = y.reshape(N, N)``, ``np.roll(u, 1, axis=0)``, ``u[1:-1, 2:]``, ``out[1:-1, 1:-1] = ...``, ``out.ravel()``: a
+# `Grid` is a shape on top of a flat `Vec` (C order).  Element-wise arithmetic works on the flat vectors; rolls, slices
+# and slice assignment turn the flat index j into the multi-index of the shape with integer division / modulo by
+# compile-time constants (which the compiler strength-reduces) and back.
+
+
+def _unravel(j: str, shape):
+    """C expressions of the multi-index of flat index ``j`` in ``shape`` (C order)."""
+    out, stride = [], 1
+    strides = []
+    for dim in reversed(shape):
+        strides.append(stride)
+        stride *= dim
+    strides.reverse()
+    for k, (dim, st) in enumerate(zip(shape, strides)):
+        e = f"({j})" if st == 1 else f"(({j}) / {st})"
+        out.append(e if k == 0 else f"({e} % {dim})")
+    return out, strides
+
+
+def _prod(shape) -> int:
+    return int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+
+
+class Grid:
+    """A traced N-d array: ``flat`` (a `Vec` of prod(shape) elements, C order) seen with ``shape``."""
+
+    __array_priority__ = 1002.0
+
+    def __init__(self, flat, shape):
+        shape = tuple(int(d) for d in shape)
+        if not isinstance(flat, Vec) or flat.length != _prod(shape):
+            raise TraceError(f"cannot view {getattr(flat, 'length', '?')} elements as shape {shape}")
+        self.flat, self.shape = flat, shape
+
+    ndim = property(lambda self: len(self.shape))
+    size = property(lambda self: self.flat.length)
+    dtype = np.dtype(np.float64)
+    T = property(lambda self: self.transpose())
+
+    def __len__(self):
+        return self.shape[0]
+
+    def _like(self, flat):
+        return Grid(flat, self.shape)
+
+    # ---- shape
+    def reshape(self, *shape, **kw):
+        return _reshape(self.flat, shape)
+
+    def ravel(self, *a, **kw):
+        return self.flat
+
+    flatten = ravel
+
+    def copy(self):
+        return Grid(self.flat.copy(), self.shape)
+
+    def transpose(self, *axes):
+        axes = tuple(axes[0]) if len(axes) == 1 and isinstance(axes[0], (tuple, list)) else (axes or tuple(reversed(range(self.ndim))))
+        new_shape = tuple(self.shape[a] for a in axes)
+        _, src_strides = _unravel("0", self.shape)
+
+        def code(j, base=self.flat.code):
+            idx, _ = _unravel(j, new_shape)
+            return base(" + ".join(f"{e} * {src_strides[a]}" for e, a in zip(idx, axes)))
+
+        return Grid(Vec(self.size, code), new_shape)
+
+    # ---- element-wise arithmetic: on the flat vectors
+    def _operand(self, o):
+        if isinstance(o, Grid):
+            if o.shape != self.shape:
+                raise TraceError(f"shape mismatch in a traced right-hand side: {o.shape} vs {self.shape}")
+            return o.flat
+        if isinstance(o, Vec):
+            if self.ndim >= 1 and o.length == self.shape[-1]:  # a row vector against every row
+                return Vec(self.size, lambda j, c=o.code, m=o.length: c(f"(({j}) % {m})"))
+            raise TraceError(f"shape mismatch in a traced right-hand side: ({o.length},) vs {self.shape}")
+        if isinstance(o, np.ndarray) and o.ndim > 0:
+            try:
+                return np.ascontiguousarray(np.broadcast_to(o, self.shape), dtype=np.float64).ravel()
+            except ValueError as exc:
+                raise TraceError(f"shape mismatch in a traced right-hand side: {o.shape} vs {self.shape}") from exc
+        return o
+
+    def _bin(self, o, op, swap=False, fn=None):
+        a, b = (self._operand(o), self.flat) if swap else (self.flat, self._operand(o))
+        return self._like(_vec_binary(a, b, op, fn))
+
+    def __add__(self, o): return self._bin(o, "+")
+    def __radd__(self, o): return self._bin(o, "+", True)
+    def __sub__(self, o): return self._bin(o, "-")
+    def __rsub__(self, o): return self._bin(o, "-", True)
+    def __mul__(self, o): return self._bin(o, "*")
+    def __rmul__(self, o): return self._bin(o, "*", True)
+    def __truediv__(self, o): return self._bin(o, "/")
+    def __rtruediv__(self, o): return self._bin(o, "/", True)
+    def __lt__(self, o): return self._bin(o, "<")
+    def __le__(self, o): return self._bin(o, "<=")
+    def __gt__(self, o): return self._bin(o, ">")
+    def __ge__(self, o): return self._bin(o, ">=")
+    def __eq__(self, o): return self._bin(o, "==")
+    def __ne__(self, o): return self._bin(o, "!=")
+    __hash__ = None
+    def __neg__(self): return self._like(-self.flat)
+    def __pos__(self): return self
+    def __abs__(self): return self._like(abs(self.flat))
+    def __pow__(self, e): return self._like(_vec_pow(self.flat, self._operand(e)))
+    def __rpow__(self, b): return self._like(_vec_pow(self._operand(b), self.flat))
+    def sum(self, axis=None):
+        if axis is not None:
+            raise TraceError("sums along one axis of a traced grid cannot be traced; sum the whole grid or write CUDA C")
+        return _vec_sum(self.flat)
+    def mean(self, axis=None): return self.sum(axis) / float(self.size)
+
+    def __bool__(self):
+        raise TraceError("data-dependent control flow on a whole grid cannot be traced; write the right-hand side as CUDA C")
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs.get("out") is not None:
+            return NotImplemented
+        ref = next(x for x in inputs if isinstance(x, Grid))
+        out = Vec.__array_ufunc__(None, ufunc, method, *[ref._operand(x) if x is not ref else ref.flat for x in inputs], **kwargs)
+        return ref._like(out) if isinstance(out, Vec) and out.length == ref.size else out
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func in _GRID_HANDLED:
+            return _GRID_HANDLED[func](*args, **kwargs)
+        raise TraceError(f"numpy.{func.__name__} cannot be traced on an N-d grid; write the right-hand side as CUDA C "
+                         "defining nbk_rhs_i(t, y, p, i, n)")
+
+    # ---- indexing
+    def _region(self, key):
+        """-> per dimension (start, step, count or None for an integer index)"""
+        if not isinstance(key, tuple):
+            key = (key,)
+        if any(k is Ellipsis for k in key):
+            pos = next(i for i, k in enumerate(key) if k is Ellipsis)
+            key = key[:pos] + (slice(None),) * (self.ndim - len(key) + 1) + key[pos + 1:]
+        if len(key) > self.ndim:
+            raise IndexError("too many indices for a traced grid")
+        key = key + (slice(None),) * (self.ndim - len(key))
+        region = []
+        for k, dim in zip(key, self.shape):
+            if isinstance(k, (numbers.Integral, np.integer)):
+                i = int(k) + (dim if k < 0 else 0)
+                if not 0 <= i < dim:
+                    raise IndexError(k)
+                region.append((i, 1, None))
+            elif isinstance(k, slice):
+                a, b, st = k.indices(dim)
+                region.append((a, st, len(range(a, b, st))))
+            else:
+                raise TraceError("only integers and slices can index a traced grid")
+        return region
+
+    def __getitem__(self, key):
+        region = self._region(key)
+        out_shape = tuple(c for _, _, c in region if c is not None)
+        _, strides = _unravel("0", self.shape)
+        if not out_shape:
+            return Sc(self.flat.code(str(sum(a * st for (a, _, _), st in zip(region, strides)))))
+
+        def code(j, base=self.flat.code):
+            idx, _ = _unravel(j, out_shape)
+            terms, it = [], iter(idx)
+            for (a, step, count), st in zip(region, strides):
+                if count is None:
+                    terms.append(str(a * st))
+                else:
+                    terms.append(f"({a} + ({step}) * {next(it)}) * {st}")
+            return base(" + ".join(terms))
+
+        flat = Vec(_prod(out_shape), code)
+        return flat if len(out_shape) == 1 else Grid(flat, out_shape)
+
+    def __setitem__(self, key, value):
+        region = self._region(key)
+        if any(step != 1 for _, step, c in region if c is not None):
+            raise TraceError("only unit-stride slice assignments can be traced")
+        sub_shape = tuple(c for _, _, c in region if c is not None)
+        n_sub = _prod(sub_shape)
+        if isinstance(value, Grid):
+            if value.shape != sub_shape:
+                raise TraceError(f"shape mismatch in a traced right-hand side: {value.shape} vs {sub_shape}")
+            val = value.flat
+        elif isinstance(value, np.ndarray) and value.ndim > 0:
+            val = _as_vec(np.ascontiguousarray(np.broadcast_to(value, sub_shape), dtype=np.float64).ravel(), n_sub)
+        else:
+            val = _as_vec(value, n_sub)
+        old = self.flat.code
+
+        def code(j, old=old, v=val.code):
+            idx, _ = _unravel(j, self.shape)
+            conds, sub_idx = [], []
+            for e, (a, _, count) in zip(idx, region):
+                if count is None:
+                    conds.append(f"{e} == {a}")
+                else:
+                    conds.append(f"{e} >= {a} && {e} < {a + count}")
+                    sub_idx.append(f"({e} - {a})")
+            flat_sub, stride = [], 1
+            for e, dim in zip(reversed(sub_idx), reversed(sub_shape)):
+                flat_sub.append(e if stride == 1 else f"{e} * {stride}")
+                stride *= dim
+            inner = " + ".join(reversed(flat_sub)) if flat_sub else "0"
+            return f"(({' && '.join(conds)}) ? {v(inner)} : {old(j)})"
+
+        self.flat = Vec(self.size, code)
+
+
+def _reshape(flat, shape):
+    if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+        shape = tuple(shape[0])
+    shape = [int(d) for d in shape]
+    if shape.count(-1) == 1:
+        known = _prod([d for d in shape if d != -1])
+        shape[shape.index(-1)] = flat.length // known if known else 0
+    if _prod(shape) != flat.length:
+        raise TraceError(f"cannot reshape {flat.length} elements into shape {tuple(shape)}")
+    return flat if len(shape) == 1 else Grid(flat, shape)
+
+
+Vec.reshape = lambda self, *shape, **kw: _reshape(self, shape)
+Vec.ravel = lambda self, *a, **kw: self
+Vec.flatten = Vec.ravel
+
+_GRID_HANDLED = {}
+_NP_ZEROS, _NP_ONES = np.zeros, np.ones  # the originals (`_tracing` replaces the module attributes while a callable runs)
+
+
+def _grid_implements(np_func):
+    def deco(f):
+        _GRID_HANDLED[np_func] = f
+        return f
+    return deco
+
+
+@_grid_implements(np.roll)
+def _grid_roll(a, shift, axis=None):
+    if axis is None:
+        return Grid(_np_roll(a.flat, shift), a.shape)
+    if isinstance(axis, (tuple, list)):
+        shifts = shift if isinstance(shift, (tuple, list)) else [shift] * len(axis)
+        for sh, ax in zip(shifts, axis):
+            a = _grid_roll(a, sh, ax)
+        return a
+    ax = int(axis) + (a.ndim if axis < 0 else 0)
+    dim = a.shape[ax]
+    k = int(shift) % dim
+    if k == 0:
+        return a
+    _, strides = _unravel("0", a.shape)
+
+    def code(j, base=a.flat.code):
+        idx, _ = _unravel(j, a.shape)
+        idx[ax] = f"(({idx[ax]} + {dim - k}) % {dim})"
+        return base(" + ".join(f"{e} * {st}" for e, st in zip(idx, strides)))
+
+    return a._like(Vec(a.size, code))
+
+
+@_grid_implements(np.where)
+def _grid_where(cond, a=None, b=None):
+    ref = next(x for x in (cond, a, b) if isinstance(x, Grid))
+    return ref._like(_np_where(ref._operand(cond) if cond is not ref else ref.flat,
+                               ref._operand(a) if a is not ref else ref.flat, ref._operand(b) if b is not ref else ref.flat))
+
+
+@_grid_implements(np.zeros_like)
+def _grid_zeros_like(a, **kw):
+    return Grid(_ConstVec(_NP_ZEROS(a.size)), a.shape)
+
+
+@_grid_implements(np.empty_like)
+def _grid_empty_like(a, **kw):
+    return Grid(_ConstVec(_NP_ZEROS(a.size)), a.shape)
+
+
+@_grid_implements(np.ones_like)
+def _grid_ones_like(a, **kw):
+    return Grid(_ConstVec(_NP_ONES(a.size)), a.shape)
+
+
+@_grid_implements(np.reshape)
+def _grid_reshape(a, shape, **kw):
+    return _reshape(a.flat, shape if isinstance(shape, (tuple, list)) else (shape,))
+
+
+@_grid_implements(np.ravel)
+def _grid_ravel(a, **kw):
+    return a.flat
+
+
+@_grid_implements(np.transpose)
+def _grid_transpose(a, axes=None):
+    return a.transpose(*(axes,) if axes is not None else ())
+
+
+@_grid_implements(np.sum)
+def _grid_sum(a, axis=None, **kw):
+    return a.sum(axis)
+
+
+@_grid_implements(np.mean)
+def _grid_mean(a, axis=None, **kw):
+    return a.mean(axis)
+
+
+@_grid_implements(np.clip)
+def _grid_clip(a, a_min=None, a_max=None, **kw):
+    return a._like(_np_clip(a.flat, a._operand(a_min) if a_min is not None else None, a._operand(a_max) if a_max is not None else None))
+
+
+@_grid_implements(np.copy)
+def _grid_copy(a, *args, **kw):
+    return a.copy()
+
+
+@_grid_implements(np.asarray)
+def _grid_asarray(a, *args, **kw):
+    return a
+
+
+@_implements(np.reshape)
+def _np_reshape(a, shape, **kw):
+    return _reshape(a, shape if isinstance(shape, (tuple, list)) else (shape,))
+
+
+@_implements(np.ravel)
+def _np_ravel(a, **kw):
+    return a
+
+
 def trace_cta(func, n: int, params_shape, has_params: bool) -> CudaRHS:
     """Trace a NumPy-style whole-vector right-hand side into the component-wise ``nbk_rhs_i`` of the CTA regime.
     Control flow on scalars (``if t < t_on:``, ``if p[0] > 0:``) is explored path by path like in :func:`trace`; the
@@ -1184,6 +1540,8 @@ def _trace_cta_paths(func, n: int, params_shape, has_params: bool) -> CudaRHS:
                 f"could not trace {getattr(func, '__name__', func)!r} into a component-wise CUDA right-hand side "
                 f"({type(exc).__name__}: {exc}); pass a CTA built-in ('rd1d', 'linear') or CUDA C source defining "
                 "nbk_rhs_i(t, y, p, i, n)") from exc
+        if isinstance(out, Grid):
+            out = out.flat
         if isinstance(out, (list, tuple)) or (isinstance(out, np.ndarray) and out.dtype == object):
             out = _np_concatenate([[e] if not isinstance(e, Vec) else e for e in np.asarray(out, dtype=object).ravel()])
         return (_as_vec(out, n).code("i"),)
