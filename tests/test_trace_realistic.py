@@ -81,7 +81,7 @@ def heaviside_drive(t, y, p):
 
 
 CASES = [
-    (robertson, 3, (1,), "both"), (nbody, 12, (2,), "thread"), (hh_gate, 2, (1,), "both"), (sir, 3, (3,), "both"),
+    (robertson, 3, (1,), "both"), (nbody, 12, (2,), "both"), (hh_gate, 2, (1,), "both"), (sir, 3, (3,), "both"),
     (friction_sign, 2, (2,), "both"), (lv_clamped, 2, (4,), "both"), (kuramoto, 5, (2,), "thread"),
     (kuramoto_loop, 5, (2,), "both"), (matrix_form, 2, (2,), "both"), (with_tuple_unpack, 2, (2,), "both"),
     (heaviside_drive, 2, (1,), "both"),
