@@ -8,13 +8,12 @@ assigned into selects (``x = c ? x_then : x_else``), so independent branches cos
 arms are evaluated and the select picks one -- the same result as the branch numba compiles for the reference
 (nbkode/core.py:125-132), since the arms of a right-hand side have no side effects beyond their assignments.
 
-What is rewritten (``convert``): ``if`` / ``elif`` / ``else`` statements whose arms contain only assignments, expression
-statements, ``pass``, ``for`` loops and nested convertible ``if`` statements; conditional expressions (``a if c else b``);
+What is rewritten (``convert``): ``if`` / ``elif`` / ``else`` statements whose arms contain only assignments, ``pass``,
+``for`` loops and nested convertible ``if`` statements (no calls made for their side effect); conditional expressions (``a if c else b``);
 ``and`` / ``or`` / ``not`` and chained comparisons inside the tests (Python would ask the traced condition for its truth
 value); the builtins ``min`` / ``max``.  Arms with ``return`` / ``break`` / ``continue`` / ``while`` / ``try`` ... are left
-alone and keep being explored path by path.  If an arm binds a name that the other leaves unbound, or the arms disagree
-on something that is not a number (an index, a shape), ``NoConvert`` is raised at trace time and the caller falls
-back to (and reports the failure of) plain path exploration.
+alone and keep being explored path by path.  If the arms disagree on something that is not a number (an index, a flag, a
+shape), ``NoConvert`` is raised at trace time and the caller reports the failure of plain path exploration.
 """
 
 from __future__ import annotations
@@ -85,7 +84,9 @@ def merge(c, a, b):
     if a is b:
         return a
     if a is UNSET or b is UNSET:
-        raise NoConvert("a name is bound in one arm of a traced `if` only")
+        # bound in one arm only and unbound before the `if` (a temporary of that arm): a correct program reads it again
+        # only where that arm was taken, so the arm's value is the value
+        return b if a is UNSET else a
     if isinstance(a, (bool, np.bool_)) and isinstance(b, (bool, np.bool_)):
         if bool(a) == bool(b):
             return a
@@ -229,6 +230,8 @@ def _convertible(stmts) -> bool:
     for st in stmts:
         if not isinstance(st, _SIMPLE):
             return False
+        if isinstance(st, ast.Expr) and not isinstance(st.value, ast.Constant):
+            return False  # a call for its side effect (`terms.append(...)`): both arms would run it
         for node in ast.walk(st):
             if isinstance(node, _FORBIDDEN):
                 return False
@@ -348,9 +351,17 @@ class _Rewriter(ast.NodeTransformer):
             """)
             merge_back += _stmts(f"""
                 try:
-                    {name} = __nbk_merge({c}, {a}, {name})
+                    {p} = {name}
                 except NameError:
-                    {name} = __nbk_merge({c}, {a}, __NBK_UNSET)
+                    {p} = __NBK_UNSET
+                {p} = __nbk_merge({c}, {a}, {p})
+                if {p} is __NBK_UNSET:
+                    try:
+                        del {name}
+                    except NameError:
+                        pass
+                else:
+                    {name} = {p}
             """)
         both = pre + node.body + then_grab + restore + (node.orelse or [ast.Pass()]) + merge_back
         plain = ast.If(test=ast.Name(id=c, ctx=ast.Load()), body=node.body, orelse=node.orelse)

@@ -609,10 +609,30 @@ def _many_sided_event(t, y):
 
 
 def one_armed(t, y):
+    z = 0.0 * y[0]
     for i in range(8):
         if y[i] > 0:
-            z = -y[i]                       # bound in one arm only, unbound before: nothing a select can express
+            half = 0.5 * y[i]               # a temporary of this arm only
+            z = z - half - half
     return np.array([z] * 8)
+
+
+def index_switch(t, y):
+    k = 0
+    for i in range(8):
+        if y[i] > 0:
+            k = i                           # the arms disagree on an INDEX: nothing a select can express
+    return np.array([y[k]] * 8)
+
+
+def side_effects(t, y):
+    terms = []
+    for i in range(8):
+        if y[i] > 0:
+            terms.append(y[i])              # a call for its side effect: running both arms would append twice
+        else:
+            terms.append(-y[i])
+    return np.array(terms)
 
 
 def test_if_conversion_beyond_the_path_budget(tmp_path):
@@ -672,8 +692,15 @@ def test_if_conversion_beyond_the_path_budget(tmp_path):
         y = rng.uniform(-1, 1, 8)
         assert lib.nbk_event(0, 0.5, y.ctypes.data_as(dp), y.ctypes.data_as(dp)) == _many_sided_event(0.5, y)
 
-    with pytest.raises(rhs.PathBudgetError):
-        rhs.trace(one_armed, 8, (), False)
+    # a temporary bound in one arm only is that arm's business
+    lib = _host_build(tmp_path, rhs.trace(one_armed, 8, (), False).source, "one_armed")
+    for _ in range(50):
+        y = rng.uniform(-1, 1, 8)
+        assert np.array_equal(_call_rhs(lib, 0.0, y, None), one_armed(0.0, y))
+    # what a select cannot express, and calls made for their side effect, stay under path exploration: the budget error
+    for refused in (index_switch, side_effects):
+        with pytest.raises(rhs.PathBudgetError):
+            rhs.trace(refused, 8, (), False)
     with pytest.raises(rhs.PathBudgetError):  # no source to rewrite: a lambda built at run time
         rhs.trace(eval("lambda t, y: np.array([(e if e > 0 else -e) for e in y])", {"np": np}), 7, (), False)
     assert _ifconv.convert(pendulum) is None  # nothing to convert
