@@ -94,3 +94,62 @@ def test_grid_shape_errors_are_trace_errors():
         rhs.trace_cta(lambda t, y: (y.reshape(4, 6) + y.reshape(6, 4)).ravel(), 24, (), False)
     with pytest.raises(rhs.TraceError):
         rhs.trace_cta(lambda t, y: y.reshape(4, 6).sum(axis=0).repeat(4), 24, (), False)
+
+
+# ------------------------------------------------------------------ random grid programs
+SHAPES = [(6, 8), (8, 6), (4, 3, 4), (2, 4, 6)]
+def _gen_grid_program(seed):
+    import random
+
+    r = random.Random(seed)
+    shape = r.choice(SHAPES); nd = len(shape); n = int(np.prod(shape))
+    L = [f"    u = y.reshape{shape}"]
+    cur = "u"
+    for step in range(r.randint(2, 5)):
+        k = r.choice(["roll", "arith", "where", "slice_set", "transpose", "scal", "row", "pad"])
+        if k == "roll":
+            ax = r.randrange(nd); sh = r.randint(-3, 3)
+            L.append(f"    {cur} = np.roll({cur}, {sh}, axis={ax}) + 0.5 * {cur}")
+        elif k == "arith":
+            L.append(f"    {cur} = {cur} * {cur} - p[0] * np.abs({cur}) + t")
+        elif k == "where":
+            L.append(f"    {cur} = np.where({cur} > 0.3, {cur}, -0.5 * np.roll({cur}, 1, axis={r.randrange(nd)}))")
+        elif k == "slice_set":
+            sl = ", ".join(r.choice(["1:-1", ":", "0:2", "1:"]) for _ in range(nd))
+            L.append(f"    z = np.zeros_like({cur})")
+            L.append(f"    z[{sl}] = ({cur} * 2.0)[{sl}]")
+            L.append(f"    {cur} = z + 0.1 * {cur}")
+        elif k == "transpose" and shape[0] == shape[-1]:
+            L.append(f"    {cur} = {cur} + {cur}.T")
+        elif k == "scal":
+            idx = ", ".join(str(r.randrange(d)) for d in shape)
+            L.append(f"    {cur} = {cur} + {cur}[{idx}] * p[1]")
+        elif k == "row":
+            L.append(f"    {cur} = {cur} - 0.25 * np.linspace(0, 1, {shape[-1]})")
+        elif k == "pad":
+            L.append(f"    w = np.zeros({shape})")
+            L.append(f"    w[{', '.join(['0'] + [':'] * (nd - 1))}] = {cur}[{', '.join(['-1'] + [':'] * (nd - 1))}]")
+            L.append(f"    {cur} = {cur} + w")
+    if r.random() < 0.5:
+        L.append(f"    if p[0] > p[1]:\n        {cur} = {cur} * 0.5\n    else:\n        {cur} = {cur} + 1.0")
+    L.append(f"    return {cur}.ravel() - 0.1 * y")
+    return "def f(t, y, p):\n" + "\n".join(L) + "\n", n
+
+
+def test_random_grid_programs(tmp_path):
+    """25 generated programs on 2-D / 3-D views (rolls along axes, N-d slice assignment, transposes, row broadcasts, single
+    elements, a scalar branch): the emitted nbk_rhs_i compiled for the host equals NumPy."""
+    dp = C.POINTER(C.c_double)
+    for seed in range(25):
+        src, n = _gen_grid_program(seed)
+        ns = {"np": np}
+        exec(src, ns)
+        f = ns["f"]
+        lib = _host_build(tmp_path, rhs.trace_cta(f, n, (2,), True).source, f"g{seed}")
+        lib.nbk_rhs_i.restype = C.c_double
+        lib.nbk_rhs_i.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int]
+        rng = np.random.default_rng(seed)
+        for _ in range(5):
+            t, y, p = float(rng.uniform(0, 1)), rng.uniform(-1, 1, n), rng.uniform(0, 1, 2)
+            got = np.array([lib.nbk_rhs_i(t, y.ctypes.data_as(dp), p.ctypes.data_as(dp), i, n) for i in range(n)])
+            np.testing.assert_allclose(got, np.asarray(f(t, y, p), float), rtol=1e-12, atol=1e-13, err_msg=f"seed {seed}\n{src}")
