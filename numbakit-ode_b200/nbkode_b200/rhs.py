@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import math
 import numbers
+import threading
 
 import numpy as np
 
@@ -325,12 +326,13 @@ class _tracing:
 
     The wrappers replace the attributes of the `math` / `numpy` modules and the names the callable's module imported
     from `math` for the duration of the trace (a few milliseconds, under a lock) and pass everything that is not a
-    traced value through to the originals.  ``vector``: the whole-vector tracer (containers are `Vec`s)."""
+    traced value -- and every call from another thread -- through to the originals.  ``vector``: the whole-vector tracer (containers are `Vec`s)."""
 
-    _lock = __import__("threading").RLock()
+    _lock = threading.RLock()
 
     def __init__(self, funcs, vector=False):
         self.funcs, self.vector, self.saved = [_python_function(f) for f in funcs if f is not None], vector, []
+        self.owner = None  # the tracing thread: other threads calling np.zeros & co. meanwhile get the originals
 
     @staticmethod
     def _traced(x):
@@ -387,6 +389,8 @@ class _tracing:
         def container(fill):
             def make(orig):
                 def f(shape, *args, **kw):
+                    if threading.get_ident() != self.owner:
+                        return orig(shape, *args, **kw)
                     dtype = kw.get("dtype", args[0] if args and fill != "full" else None)
                     if fill == "full":
                         value = args[0] if args else kw.get("fill_value")
@@ -415,6 +419,7 @@ class _tracing:
 
     def __enter__(self):
         self._lock.acquire()
+        self.owner = threading.get_ident()
         try:
             wrappers = self._math_wrappers()
             originals = {id(orig): fn for orig, fn in wrappers.values()}

@@ -19,6 +19,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 from . import distributed as _dist
+from . import rhs as _rhs
 
 
 def _torch():
@@ -165,6 +166,10 @@ class ShardedSolver:
         return self._gather(self._map(lambda s: s.interpolate(t)))
 
     def run_events(self, t, events, max_events: int = 64):
+        if events and not isinstance(events, _rhs.CudaEvents):
+            # traced once, here (the tracer is not re-entrant); the shards get the CUDA C
+            s0 = self.shards[0]
+            events = _rhs.trace_events(events, s0.n, s0._p_shape, s0.params is not None)
         parts = self._map(lambda s: s.run_events(t, events, max_events))
         if not events:
             return parts[0][0], self._gather([p[1] for p in parts]), [], []

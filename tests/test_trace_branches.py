@@ -357,6 +357,32 @@ def test_math_functions_and_float_containers(tmp_path):
     assert g["sin"] is math.sin and g["exp"] is math.exp and g["zeros"] is np.zeros
     assert math.sin(0.5) == 0.479425538604203 and np.zeros(2).dtype == np.float64 and np.empty(3).dtype == np.float64
     assert np.full(2, 1.5).dtype == np.float64 and math.log(8.0, 2.0) == 3.0 and math.atan2(1.0, 1.0) == math.pi / 4
+    # another thread that calls np.zeros while a callable is traced (the shards of a devices=[...] solver do) gets floats
+    import threading
+    import time
+
+    seen, stop = [], []
+
+    def other():
+        while not stop:
+            seen.append(np.zeros(3).dtype)
+            seen.append(np.full(2, 1.0).dtype)
+
+    def slow(t, y):
+        dy = np.empty(2)
+        time.sleep(0.02)
+        dy[0], dy[1] = y[1], -y[0]
+        return dy
+
+    th = threading.Thread(target=other)
+    th.start()
+    try:
+        for _ in range(3):
+            rhs.trace(slow, 2, (), False)
+    finally:
+        stop.append(1)
+        th.join()
+    assert len(seen) > 10 and set(seen) == {np.dtype(np.float64)}
     # integer / explicit dtypes and non-traced arguments pass through while tracing
     seen = {}
 
